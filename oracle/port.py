@@ -1,0 +1,70 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end to oracle/_ref/liboracle_port.so (the CPU
+restatement, oracle/port.cpp).  Same calling convention as dada2_b200.dada_uniques."""
+import ctypes as C
+import os
+import numpy as np
+from dada2_b200 import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "liboracle_port.so"))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(os.path.join(_HERE, "_ref", "liboracle_port.so"))
+        L.port_run.argtypes = [C.POINTER(_abi.In), C.POINTER(_abi.Opts), C.POINTER(C.POINTER(_abi.Out)), C.c_char_p]
+        L.port_free.argtypes = [C.POINTER(_abi.Out)]
+        L.port_calc_pA.restype = C.c_double
+        L.port_calc_pA.argtypes = [C.c_int, C.c_double, C.c_int]
+        L.port_ppois_upper.restype = C.c_double
+        L.port_ppois_upper.argtypes = [C.c_int, C.c_double]
+        _LIB = L
+    return _LIB
+
+
+def dada_uniques(seqs, abundances, priors, err, quals, **opts):
+    L = lib()
+    pin = _abi.PackedIn(seqs, abundances, priors, err, quals)
+    o = _abi.make_opts(**opts)
+    out = C.POINTER(_abi.Out)()
+    eb = C.create_string_buffer(_abi.ERRLEN)
+    rc = L.port_run(C.byref(pin.struct), C.byref(o), C.byref(out), eb)
+    if rc:
+        raise RuntimeError(eb.value.decode())
+    try:
+        return _abi.unpack_out(out.contents)
+    finally:
+        L.port_free(out)
+
+
+def pair(seq0, q0, seq1, q1, err, use_kmers=True, kdist_cutoff=0.42, **opts):
+    L = lib()
+    o = _abi.make_opts(**opts)
+    l0, l1 = len(seq0), len(seq1)
+    err_rm = np.ascontiguousarray(err, dtype=np.float64)
+    lam, ns = C.c_double(), C.c_int()
+    mp = np.zeros(l0 + 1, dtype=np.uint16)
+    pos = np.zeros(l0 + l1 + 1, dtype=np.uint16)
+    nt0, nt1 = C.create_string_buffer(l0 + l1 + 1), C.create_string_buffer(l0 + l1 + 1)
+    sq0, sq1 = np.zeros(l0 + l1 + 1, dtype=np.uint8), np.zeros(l0 + l1 + 1, dtype=np.uint8)
+    al0, al1 = C.create_string_buffer(l0 + l1 + 2), C.create_string_buffer(l0 + l1 + 2)
+    eb = C.create_string_buffer(256)
+    q0a = np.ascontiguousarray(q0, dtype=np.uint8) if q0 is not None else None
+    q1a = np.ascontiguousarray(q1, dtype=np.uint8) if q1 is not None else None
+    kind = L.port_pair(seq0.encode(), q0a.ctypes.data_as(C.c_void_p) if q0a is not None else None,
+                       seq1.encode(), q1a.ctypes.data_as(C.c_void_p) if q1a is not None else None,
+                       err_rm.ctypes.data_as(C.c_void_p), C.c_int(err_rm.shape[1]), C.byref(o),
+                       C.c_int(use_kmers), C.c_double(kdist_cutoff), C.byref(lam), C.byref(ns),
+                       mp.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p), nt0, nt1,
+                       sq0.ctypes.data_as(C.c_void_p), sq1.ctypes.data_as(C.c_void_p), al0, al1, eb)
+    if kind < 0:
+        raise RuntimeError(eb.value.decode())
+    n = max(ns.value, 0)
+    return dict(kind=kind, shrouded=(kind == 0), lam=lam.value, nsubs=ns.value, map=mp[:l0].copy(),
+                pos=pos[:n].copy(), nt0=bytes(nt0.raw[:n]), nt1=bytes(nt1.raw[:n]), q0=sq0[:n].copy(),
+                q1=sq1[:n].copy(), al0=al0.value.decode(), al1=al1.value.decode())
