@@ -1,0 +1,76 @@
+// Shared host/device declarations for libdada2b.so (product code).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dd2 {
+
+constexpr int KMER = 5;              // KMER_SIZE, /root/reference/src/dada.h:27
+constexpr int NKMER = 1 << (2 * KMER);
+constexpr unsigned HAM_NULL = 0xFFFFFFFFu;  // hamming=-1 of a NULL sub (cluster.cpp:142)
+
+enum PairKind : int { KIND_SHROUD = 0, KIND_GAPLESS = 1, KIND_NW = 2, KIND_SKIP = 3 };
+
+// Resident, immutable inputs (packed once per dada2b_upload).
+struct DevIn {
+  int nraw, maxlen, minlen;
+  int SW;             // uint32 words of 2-bit bases per raw (multiple of 4 -> 16 B rows)
+  int QS;             // bytes of quality per raw (multiple of 16)
+  uint32_t *seq2;     // [nraw][SW]  base b of raw r: (seq2[r*SW + b/16] >> 2*(b%16)) & 3, A,C,G,T = 0..3
+  uint8_t *qual;      // [nraw][QS]  (uint8_t)round(mean quality), containers.cpp:34
+  uint16_t *len;      // [nraw]
+  uint32_t *reads;    // [nraw]
+  uint8_t *prior;     // [nraw]
+};
+
+// Alignment / screen parameters (Rmain.cpp:35-47 subset used by raw_align).
+struct AlnParams {
+  int match, mismatch, gap, hgap;
+  int band;           // BAND_SIZE; <0 unbanded
+  int homo;           // 1 => homopolymer gap penalties (nwalign_endsfree_homo)
+  int sentinel;       // out-of-band fill: -9999 (nwalign_endsfree.cpp:116) or int16 fill (nwalign_vectorized.cpp:106)
+  int use_kmers, gapless, sse;
+  double kdist_cutoff;
+  int use_quals;
+  int ncol;           // columns of err
+};
+
+// Mutable per-run state.
+struct DevState {
+  // per raw
+  uint8_t *lock, *is_center, *slot0, *correct;
+  double *E_minmax, *p, *comp_lambda;
+  uint32_t *comp_ham, *cluster_of;
+  // comparison store (Bi::comp of every cluster, appended round by round)
+  uint32_t *cs_index, *cs_i, *cs_ham;
+  double *cs_lambda;
+  unsigned long long cs_cap;
+  // per cluster
+  uint32_t *cl_reads, *cl_center;
+  uint8_t *cl_update_e, *cl_check_locks;
+  // shuffle scratch (per raw)
+  unsigned long long *emax_bits;
+  uint32_t *best_entry;
+  // job lists
+  uint32_t *nw_list, *gl_list;
+  // device counters / flags (see enum Ctr)
+  unsigned long long *ctr;
+  // error matrix, row-major 16 x ncol (cluster.cpp:162-170)
+  double *err;
+  // final-pass accumulators
+  int *trans;                       // [16][ncol] row-major
+  unsigned long long *cq_sum, *cq_cnt;  // [nclust][maxlen]
+  uint32_t *nsubs_final;            // per raw
+};
+
+enum Ctr : int {
+  CTR_CS_COUNT = 0,   // entries in the comparison store
+  CTR_NW, CTR_GL,     // job list lengths
+  CTR_ALIGN, CTR_SHROUD, CTR_NWTOT, CTR_GLTOT, CTR_CELLS,
+  CTR_NMOVE, CTR_ERR, CTR_PMIN, CTR_RMAX, CTR_NTIE, CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR,
+  CTR_N
+};
+
+enum ErrCode : int { ERR_NONE = 0, ERR_LAMBDA = 1, ERR_QUAL = 2, ERR_TRACE = 3 };
+
+}  // namespace dd2

@@ -1,0 +1,891 @@
+// Host driver of libdada2b.so: the C-ABI of include/dada2b.h.  Product code.
+//
+// Restates the control flow of dada_uniques()/run_dada() (/root/reference/src/Rmain.cpp:30-336)
+// around device kernels (dd_kernels.cu).  The only state kept on the host is what the
+// reference's tie-breaks depend on and what is O(moves), not O(nraw): the per-cluster member
+// arrays with their slot order (Bi::raw; swap-with-last pops, containers.cpp:183-197) and the
+// per-cluster birth records.  Every O(nraw) / O(pairs) computation runs on the GPU.
+// There is NO CPU fallback: without a CUDA device every entry point returns an error.
+#include "../../include/dada2b.h"
+#include "../../include/dada2b_test.h"
+#include <memory>
+#include "dd_common.h"
+#include "dd_kernels.h"
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace dd2;
+
+namespace {
+
+struct Err { std::string msg; };
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw Err{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x}; } while (0)
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+double na_real() { union { double d; uint64_t u; } v; v.u = 0x7FF00000000007A2ULL; return v.d; }
+
+template <typename T> struct DBuf {   // device buffer
+  T *p = nullptr; size_t n = 0;
+  void alloc(size_t count) { free(); n = count; if (count) CK(cudaMalloc(&p, count * sizeof(T))); }
+  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void zero(cudaStream_t s) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  ~DBuf() { free(); }
+};
+template <typename T> struct PBuf {   // pinned host buffer
+  T *p = nullptr; size_t n = 0;
+  void alloc(size_t count) { free(); n = count; if (count) CK(cudaMallocHost(&p, count * sizeof(T))); }
+  void free() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+  ~PBuf() { free(); }
+};
+
+template <typename F> void parallel_for(size_t n, F f) {
+  unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (n < 4096 || nt == 1) { f(0, n); return; }
+  std::vector<std::thread> th;
+  size_t chunk = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; t++) {
+    size_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([=]() { f(b, e); });
+  }
+  for (auto &t : th) t.join();
+}
+
+}  // namespace
+
+struct dada2b_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevIn in{};
+  int maxq = 0;            // largest rounded quality present
+  bool has_quals = false;
+  bool bad_nt = false;
+  unsigned total_reads = 0;
+  std::vector<uint16_t> len;
+  std::vector<uint32_t> reads;
+  std::vector<uint8_t> prior;
+  std::string seq_concat;
+  std::vector<int64_t> seq_off;
+  DBuf<uint32_t> d_seq2, d_reads;
+  DBuf<uint8_t> d_qual, d_prior;
+  DBuf<uint16_t> d_len;
+  int num_sms = 148;
+};
+
+// ------------------------------------------------------------------------------------
+// upload: validation of Rmain.cpp:52-78, raw_new (containers.cpp:19-43) and packing
+// ------------------------------------------------------------------------------------
+static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
+  const unsigned nraw = in->nraw;
+  if (in->nraw <= 0) throw Err{"Zero input sequences."};
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw Err{"dada2b: no CUDA device available (this library has no CPU path)."};
+  CK(cudaSetDevice(device));
+  std::unique_ptr<dada2b_ctx> cx(new dada2b_ctx());
+  cx->device = device;
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  cx->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
+  unsigned maxlen = 0, minlen = 9999;
+  cx->len.resize(nraw);
+  for (unsigned i = 0; i < nraw; i++) {
+    int64_t l = in->seq_off[i + 1] - in->seq_off[i];
+    if (l < 0) throw Err{"Bad sequence offsets."};
+    if (l >= 9999) throw Err{"Input sequences exceed the maximum allowed string length."};
+    cx->len[i] = (uint16_t)l;
+    maxlen = std::max<unsigned>(maxlen, (unsigned)l); minlen = std::min<unsigned>(minlen, (unsigned)l);
+  }
+  if (maxlen >= 9999) throw Err{"Input sequences exceed the maximum allowed string length."};
+  if (minlen <= (unsigned)KMER) throw Err{"Input sequences must all be longer than the kmer-size (5)."};
+  cx->has_quals = in->maxlen > 0 && in->quals != nullptr;
+  if (!cx->has_quals)
+    throw Err{"A quality matrix is required (the reference dereferences raw->qual unconditionally, error.cpp:160)."};
+  if ((unsigned)in->maxlen != maxlen) throw Err{"Sequence must have associated qualities for each nucleotide position."};
+  DevIn &d = cx->in;
+  d.nraw = nraw; d.maxlen = maxlen; d.minlen = minlen;
+  d.SW = (((int)maxlen + 15) / 16 + 3) & ~3;
+  d.QS = ((int)maxlen + 15) & ~15;
+  cx->seq_off.assign(in->seq_off, in->seq_off + nraw + 1);
+  cx->seq_concat.assign(in->seq_concat + in->seq_off[0], in->seq_concat + in->seq_off[nraw]);
+  const int64_t off0 = in->seq_off[0];
+  for (auto &o : cx->seq_off) o -= off0;
+  cx->reads.resize(nraw); cx->prior.resize(nraw);
+  unsigned tot = 0;
+  for (unsigned i = 0; i < nraw; i++) {
+    cx->reads[i] = (uint32_t)in->abund[i];
+    cx->prior[i] = in->prior ? (in->prior[i] != 0) : 0;
+    tot += cx->reads[i];                                      // unsigned int accumulation, containers.cpp:100
+  }
+  cx->total_reads = tot;
+  // pack on the host into pinned staging, then one H2D per array
+  PBuf<uint32_t> h_seq; h_seq.alloc((size_t)nraw * d.SW);
+  PBuf<uint8_t> h_qual; h_qual.alloc((size_t)nraw * d.QS);
+  std::vector<int> tmaxq(64, 0), tbad(64, 0);
+  const char *sc = cx->seq_concat.data();
+  const double *qd = in->quals;
+  const int SW = d.SW, QS = d.QS, ML = in->maxlen;
+  unsigned slot = 0;
+  std::vector<std::pair<size_t, size_t>> ranges;
+  {
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    size_t chunk = (nraw + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) {
+      size_t b = t * chunk, e = std::min<size_t>(nraw, b + chunk);
+      if (b >= e) break;
+      th.emplace_back([&, b, e, t]() {
+        int mq = 0, bad = 0;
+        for (size_t r = b; r < e; r++) {
+          const char *s = sc + cx->seq_off[r];
+          const int L = cx->len[r];
+          uint32_t *row = h_seq.p + r * SW;
+          for (int w = 0; w < SW; w++) row[w] = 0;
+          for (int p = 0; p < L; p++) {
+            unsigned code;
+            switch (s[p]) { case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break;
+                            case 'T': code = 3; break; default: code = 0; bad = 1; }
+            row[p >> 4] |= code << (2 * (p & 15));
+          }
+          uint8_t *q = h_qual.p + r * QS;
+          const double *src = qd + (size_t)ML * r;
+          for (int p = 0; p < L; p++) { uint8_t v = (uint8_t)round(src[p]); q[p] = v; if (v > mq) mq = v; }   // containers.cpp:34
+          for (int p = L; p < QS; p++) q[p] = 0;
+        }
+        tmaxq[t] = mq; tbad[t] = bad;
+      });
+    }
+    for (auto &x : th) x.join();
+    (void)slot;
+  }
+  for (int v : tmaxq) cx->maxq = std::max(cx->maxq, v);
+  for (int v : tbad) cx->bad_nt |= (v != 0);
+  cx->d_seq2.alloc((size_t)nraw * d.SW); cx->d_qual.alloc((size_t)nraw * d.QS);
+  cx->d_len.alloc(nraw); cx->d_reads.alloc(nraw); cx->d_prior.alloc(nraw);
+  CK(cudaMemcpyAsync(cx->d_seq2.p, h_seq.p, (size_t)nraw * d.SW * 4, cudaMemcpyHostToDevice, cx->stream));
+  CK(cudaMemcpyAsync(cx->d_qual.p, h_qual.p, (size_t)nraw * d.QS, cudaMemcpyHostToDevice, cx->stream));
+  CK(cudaMemcpyAsync(cx->d_len.p, cx->len.data(), nraw * 2, cudaMemcpyHostToDevice, cx->stream));
+  CK(cudaMemcpyAsync(cx->d_reads.p, cx->reads.data(), nraw * 4, cudaMemcpyHostToDevice, cx->stream));
+  CK(cudaMemcpyAsync(cx->d_prior.p, cx->prior.data(), nraw, cudaMemcpyHostToDevice, cx->stream));
+  CK(cudaStreamSynchronize(cx->stream));
+  d.seq2 = cx->d_seq2.p; d.qual = cx->d_qual.p; d.len = cx->d_len.p; d.reads = cx->d_reads.p; d.prior = cx->d_prior.p;
+  return cx.release();
+}
+
+// ------------------------------------------------------------------------------------
+namespace {
+
+struct Birth {                     // Bi birth_* fields, dada.h:99-104
+  char type = 'I';
+  uint32_t from = 0;
+  double pval = 0, fold = 1, e = 0;
+  uint32_t comp_i = 0, comp_index = 0, comp_ham = 0;
+  double comp_lambda = 0;
+};
+
+struct Run {
+  dada2b_ctx *cx;
+  const dada2b_opts *o;
+  cudaStream_t s;
+  DevIn in;
+  AlnParams P{};
+  DevState st{};
+  int nraw, ncol;
+  // device state buffers
+  DBuf<uint8_t> lock, is_center, slot0, correct, cl_update_e, cl_check_locks, b_nt0, b_nt1, b_q1, b_ops, kind_out;
+  DBuf<double> E_minmax, p, comp_lambda, cs_lambda, err, b_lambda, trip_v, pa_E, pa_out;
+  DBuf<uint32_t> comp_ham, cluster_of, cs_index, cs_i, cs_ham, cl_reads, cl_center, best_entry, nw_list, gl_list,
+      moves, ties, ties_pr, nsubs_final, ptr_scratch, pair_centre, pair_raw, b_nsubs, b_nops, trip_ij;
+  DBuf<uint16_t> b_pos;
+  DBuf<unsigned long long> emax_bits, ctr, cq_sum, cq_cnt;
+  DBuf<int> trans, center_cluster, pa_reads, pa_prior;
+  PBuf<unsigned long long> h_ctr;
+  PBuf<uint32_t> h_moves, h_ties, h_ties_pr;
+  unsigned move_cap = 0, tie_cap = 4096;
+  size_t cl_cap = 0;
+  unsigned long long cs_count = 0;
+  // host membership (Bi::raw with slot order) and cluster records
+  std::vector<std::vector<uint32_t>> members;
+  std::vector<uint32_t> slot_of, cluster_of_h, cl_center_h, cl_reads_h;
+  std::vector<uint8_t> upd_e, chk_locks;
+  std::vector<Birth> birth;
+  // align launch geometry
+  int warp_words = 0, seq_bytes = 0, H_words = 0, ops_words = 0, ptr_in_smem = 0, align_grid = 0;
+  unsigned long long ptr_words = 0;
+  size_t align_smem = 0, align_smem_final = 0, classify_smem = 0;
+  int kord_words = 0;
+  // stats
+  int n_rounds = 0, n_shuffles = 0;
+
+  void setup_params();
+  void alloc_state();
+  void ensure_cluster_cap(size_t n);
+  void ensure_cs_cap(unsigned long long need);
+  void upload_cluster_arrays(bool flags);
+  void read_ctr() { CK(cudaMemcpyAsync(h_ctr.p, ctr.p, CTR_N * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
+  void check_dev_error();
+  void compare(uint32_t i, double kdist_cutoff);
+  bool shuffle_pass();
+  void p_update();
+  int bud();
+  void finish(dada2b_out *out);
+  AlignArgs align_args(int mode, int kind);
+  void launch_align_jobs(int mode, AlignArgs &a, unsigned long long upper);
+};
+
+void Run::setup_params() {
+  const dada2b_opts &op = *o;
+  P.match = op.match; P.mismatch = op.mismatch; P.gap = op.gap; P.hgap = op.homo_gap; P.band = op.band_size;
+  // raw_align dispatch, nwalign_endsfree.cpp:57-66
+  P.homo = (!op.vectorized_alignment && op.homo_gap != op.gap && op.homo_gap <= 0) ? 1 : 0;
+  if (op.vectorized_alignment) {
+    int m = std::min(std::min(op.mismatch, op.gap), std::min(op.match, 0));
+    P.sentinel = (int)(int16_t)(INT16_MIN - m);                  // nwalign_vectorized.cpp:106
+  } else P.sentinel = -9999;                                     // nwalign_endsfree.cpp:116-117
+  P.use_kmers = op.use_kmers != 0; P.gapless = op.gapless != 0; P.sse = op.SSE;
+  P.kdist_cutoff = op.kdist_cutoff; P.use_quals = op.use_quals != 0; P.ncol = ncol;
+  // ---- k_align shared-memory layout
+  const int maxlen = in.maxlen, minlen = in.minlen;
+  int lbmax, rbmax;
+  if (P.band < 0) { lbmax = rbmax = maxlen; }
+  else { lbmax = rbmax = std::min(P.band + (maxlen - minlen), maxlen); }
+  const int Wmax = lbmax + rbmax + 1;
+  const int nchunk = (((Wmax + 1) >> 1) + 31) >> 5;
+  seq_bytes = (maxlen + 15) & ~15;
+  H_words = (Wmax + 2 + 3) & ~3;
+  ops_words = ((2 * maxlen) / 16 + 2 + 3) & ~3;
+  ptr_words = (unsigned long long)(2 * maxlen + 2) * 2 * nchunk;
+  const int base_words = 2 * (seq_bytes / 4) + H_words + ops_words;
+  const size_t fixed = (size_t)16 * ncol * 8 + (size_t)16 * ncol * 4;
+  ptr_in_smem = (fixed + 4 * (size_t)(base_words + ptr_words) * 4 <= 56 * 1024) ? 1 : 0;
+  warp_words = base_words + (ptr_in_smem ? (int)ptr_words : 0);
+  align_smem = fixed + (size_t)4 * warp_words * 4;
+  if (align_smem > 200 * 1024) throw Err{"dada2b: band/sequence length too large for the alignment kernel's shared memory."};
+  CK(align_set_smem(std::max<size_t>(align_smem, 48 * 1024)));
+  align_grid = cx->num_sms * 8;
+  kord_words = ((maxlen + 1) / 2 + 3) & ~3;
+  classify_smem = (size_t)(512 + kord_words + 8 * 512 + 8 * in.SW) * 4;
+  if (classify_smem > 100 * 1024) throw Err{"dada2b: sequences too long for the k-mer screen kernel."};
+}
+
+void Run::ensure_cluster_cap(size_t n) {
+  if (n <= cl_cap) return;
+  size_t nc = std::max<size_t>(256, cl_cap * 2);
+  while (nc < n) nc *= 2;
+  DBuf<uint32_t> r2, c2; DBuf<uint8_t> u2, k2;
+  r2.alloc(nc); c2.alloc(nc); u2.alloc(nc); k2.alloc(nc);
+  r2.zero(s); c2.zero(s); u2.zero(s); k2.zero(s);
+  std::swap(cl_reads.p, r2.p); std::swap(cl_reads.n, r2.n);
+  std::swap(cl_center.p, c2.p); std::swap(cl_center.n, c2.n);
+  std::swap(cl_update_e.p, u2.p); std::swap(cl_update_e.n, u2.n);
+  std::swap(cl_check_locks.p, k2.p); std::swap(cl_check_locks.n, k2.n);
+  cl_cap = nc;
+  st.cl_reads = cl_reads.p; st.cl_center = cl_center.p; st.cl_update_e = cl_update_e.p; st.cl_check_locks = cl_check_locks.p;
+  CK(cudaStreamSynchronize(s));
+}
+
+void Run::ensure_cs_cap(unsigned long long need) {
+  if (need <= st.cs_cap) return;
+  unsigned long long nc = std::max<unsigned long long>(need, st.cs_cap * 2);
+  DBuf<uint32_t> a, b, c; DBuf<double> l;
+  a.alloc(nc); b.alloc(nc); c.alloc(nc); l.alloc(nc);
+  if (cs_count) {
+    CK(cudaMemcpyAsync(a.p, cs_index.p, cs_count * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(b.p, cs_i.p, cs_count * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(c.p, cs_ham.p, cs_count * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(l.p, cs_lambda.p, cs_count * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  std::swap(cs_index.p, a.p); std::swap(cs_index.n, a.n);
+  std::swap(cs_i.p, b.p); std::swap(cs_i.n, b.n);
+  std::swap(cs_ham.p, c.p); std::swap(cs_ham.n, c.n);
+  std::swap(cs_lambda.p, l.p); std::swap(cs_lambda.n, l.n);
+  st.cs_index = cs_index.p; st.cs_i = cs_i.p; st.cs_ham = cs_ham.p; st.cs_lambda = cs_lambda.p; st.cs_cap = nc;
+}
+
+void Run::alloc_state() {
+  const size_t n = nraw;
+  lock.alloc(n); is_center.alloc(n); slot0.alloc(n); correct.alloc(n);
+  E_minmax.alloc(n); p.alloc(n); comp_lambda.alloc(n); comp_ham.alloc(n); cluster_of.alloc(n);
+  emax_bits.alloc(n); best_entry.alloc(n); nw_list.alloc(n); gl_list.alloc(n); nsubs_final.alloc(n);
+  ctr.alloc(CTR_N); h_ctr.alloc(CTR_N);
+  move_cap = (unsigned)n; moves.alloc(2 * n); h_moves.alloc(2 * n);
+  ties.alloc(tie_cap * 3); ties_pr.alloc(tie_cap * 3); h_ties.alloc(tie_cap * 3); h_ties_pr.alloc(tie_cap * 3);
+  err.alloc((size_t)16 * ncol);
+  lock.zero(s); is_center.zero(s); slot0.zero(s); correct.zero(s); p.zero(s); comp_lambda.zero(s); comp_ham.zero(s);
+  cluster_of.zero(s); ctr.zero(s);
+  std::vector<double> em(n, -999.0);                               // containers.cpp:39
+  CK(cudaMemcpyAsync(E_minmax.p, em.data(), n * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  st.lock = lock.p; st.is_center = is_center.p; st.slot0 = slot0.p; st.correct = correct.p;
+  st.E_minmax = E_minmax.p; st.p = p.p; st.comp_lambda = comp_lambda.p; st.comp_ham = comp_ham.p; st.cluster_of = cluster_of.p;
+  st.emax_bits = emax_bits.p; st.best_entry = best_entry.p; st.nw_list = nw_list.p; st.gl_list = gl_list.p;
+  st.ctr = ctr.p; st.err = err.p; st.nsubs_final = nsubs_final.p;
+  st.cs_cap = 0;
+  ensure_cs_cap(2ull * n + 1024);
+  ensure_cluster_cap(256);
+  if (!ptr_in_smem) {
+    ptr_scratch.alloc((size_t)ptr_words * align_grid * 4);
+  }
+}
+
+void Run::check_dev_error() {
+  unsigned long long e = h_ctr.p[CTR_ERR];
+  if (e == ERR_LAMBDA) throw Err{"Lambda out-of-range error."};                       // cluster.cpp:184
+  if (e == ERR_QUAL) throw Err{"Rounded quality exceeded range of err lookup table."};  // pval.cpp:170
+  if (e == ERR_TRACE) throw Err{"N-W Align out of range."};                           // nwalign_endsfree.cpp:184
+}
+
+AlignArgs Run::align_args(int mode, int kind) {
+  AlignArgs a{};
+  a.in = in; a.P = P; a.st = st; a.kind = kind;
+  a.warp_words = warp_words; a.seq_bytes = seq_bytes; a.H_words = H_words; a.ops_words = ops_words;
+  a.ptr_in_smem = ptr_in_smem; a.ptr_scratch = ptr_scratch.p; a.ptr_words = ptr_words;
+  (void)mode;
+  return a;
+}
+
+void Run::launch_align_jobs(int mode, AlignArgs &a, unsigned long long upper) {
+  if (upper == 0) return;
+  int grid = (int)std::min<unsigned long long>((upper + 3) / 4, (unsigned long long)align_grid);
+  launch_align(mode, a, grid, 128, align_smem, s);
+}
+
+// b_compare_parallel (cluster.cpp:152-204) for seed cluster i
+void Run::compare(uint32_t i, double kdist_cutoff) {
+  const uint32_t c = cl_center_h[i];
+  ensure_cs_cap(cs_count + (unsigned long long)nraw + 1024);
+  CK(cudaMemsetAsync(ctr.p + CTR_NW, 0, 2 * 8, s));
+  ClassifyArgs ca{};
+  ca.in = in; ca.P = P; ca.P.kdist_cutoff = kdist_cutoff; ca.mode = 0; ca.centre_idx = c; ca.centre_reads = cx->reads[c];
+  ca.greedy = o->greedy != 0; ca.lock = st.lock; ca.nw_list = st.nw_list; ca.gl_list = st.gl_list; ca.ctr = st.ctr;
+  ca.kind_out = nullptr; ca.kord_words = kord_words;
+  int cgrid = std::min((nraw + 7) / 8, cx->num_sms * 4);
+  launch_classify(ca, cgrid, 256, classify_smem, s);
+  for (int kind : {KIND_NW, KIND_GAPLESS}) {
+    AlignArgs a = align_args(MODE_LOOP, kind);
+    a.jobs = kind == KIND_NW ? st.nw_list : st.gl_list;
+    a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
+    a.centre_idx = c; a.centre_reads = cx->reads[c]; a.cluster_i = i; a.total_reads = cx->total_reads;
+    launch_align_jobs(MODE_LOOP, a, (unsigned long long)nraw);
+  }
+  if (i == 0) {
+    unsigned long long n = nraw;
+    CK(cudaMemcpyAsync(ctr.p + CTR_CS_COUNT, &n, 8, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  read_ctr();
+  check_dev_error();
+  cs_count = h_ctr.p[CTR_CS_COUNT];
+  if (cs_count > st.cs_cap) throw Err{"dada2b: comparison store overflow"};
+}
+
+void Run::upload_cluster_arrays(bool flags) {
+  const size_t nc = members.size();
+  ensure_cluster_cap(nc);
+  CK(cudaMemcpyAsync(cl_reads.p, cl_reads_h.data(), nc * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(cl_center.p, cl_center_h.data(), nc * 4, cudaMemcpyHostToDevice, s));
+  if (flags) {
+    CK(cudaMemcpyAsync(cl_update_e.p, upd_e.data(), nc, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(cl_check_locks.p, chk_locks.data(), nc, cudaMemcpyHostToDevice, s));
+  }
+}
+
+// b_shuffle2 (cluster.cpp:210-266): device finds each raw's best cluster, host replays the moves on the
+// member arrays in the reference's order (clusters ascending, slots descending, swap-with-last pops).
+bool Run::shuffle_pass() {
+  CK(cudaMemsetAsync(ctr.p + CTR_NMOVE, 0, 8, s));
+  launch_shuffle_pass(st, nraw, cs_count, moves.p, move_cap, s);
+  read_ctr();
+  const unsigned long long nm = h_ctr.p[CTR_NMOVE];
+  n_shuffles++;
+  if (nm == 0) return false;
+  CK(cudaMemcpyAsync(h_moves.p, moves.p, nm * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  struct Mv { uint32_t from, slot, r, to; };
+  std::vector<Mv> mv(nm);
+  for (unsigned long long k = 0; k < nm; k++) {
+    uint32_t r = h_moves.p[2 * k], to = h_moves.p[2 * k + 1];
+    mv[k] = Mv{cluster_of_h[r], slot_of[r], r, to};
+  }
+  std::sort(mv.begin(), mv.end(), [](const Mv &a, const Mv &b) { return a.from != b.from ? a.from < b.from : a.slot > b.slot; });
+  bool slot0_changed = false;
+  std::vector<std::pair<uint32_t, uint8_t>> slot0_updates;
+  for (const Mv &m : mv) {
+    std::vector<uint32_t> &src = members[m.from];
+    const uint32_t sl = slot_of[m.r];                          // still valid: pops only disturb higher slots' tail
+    const uint32_t last = src.back();                          // bi_pop_raw: slot <- last
+    src[sl] = last; slot_of[last] = sl; src.pop_back();
+    if (sl == 0) { slot0_updates.push_back({m.r, 0}); if (last != m.r) slot0_updates.push_back({last, 1}); slot0_changed = true; }
+    cl_reads_h[m.from] -= cx->reads[m.r];
+    std::vector<uint32_t> &dst = members[m.to];                // bi_add_raw: append
+    if (dst.empty()) { slot0_updates.push_back({m.r, 1}); slot0_changed = true; }
+    slot_of[m.r] = (uint32_t)dst.size(); dst.push_back(m.r);
+    cl_reads_h[m.to] += cx->reads[m.r];
+    cluster_of_h[m.r] = m.to;
+    upd_e[m.from] = 1; upd_e[m.to] = 1;
+  }
+  if (slot0_changed)
+    for (auto &u : slot0_updates) CK(cudaMemcpyAsync(slot0.p + u.first, &u.second, 1, cudaMemcpyHostToDevice, s));
+  upload_cluster_arrays(false);
+  if (slot0_changed) CK(cudaStreamSynchronize(s));
+  return true;
+}
+
+void Run::p_update() {
+  upload_cluster_arrays(true);
+  launch_p_update(st, in, o->greedy != 0, o->detect_singletons != 0, s);
+  std::fill(upd_e.begin(), upd_e.end(), 0);
+  std::fill(chk_locks.begin(), chk_locks.end(), 0);
+}
+
+// b_bud (cluster.cpp:274-350).  Returns new cluster index or 0.
+int Run::bud() {
+  unsigned long long init[6] = {~0ull, 0ull, 0ull, ~0ull, 0ull, 0ull};
+  CK(cudaMemcpyAsync(ctr.p + CTR_PMIN, init, 6 * 8, cudaMemcpyHostToDevice, s));
+  launch_bud_scan(st, in, o->min_fold, o->min_hamming, o->min_abund, ties.p, ties_pr.p, tie_cap, s);
+  read_ctr();
+  unsigned long long nt = h_ctr.p[CTR_NTIE], ntp = h_ctr.p[CTR_NTIE_PR];
+  if (nt > tie_cap || ntp > tie_cap) {                         // pathological tie set: grow and rescan
+    tie_cap = (unsigned)std::max(nt, ntp) + 16;
+    ties.alloc(tie_cap * 3); ties_pr.alloc(tie_cap * 3); h_ties.alloc(tie_cap * 3); h_ties_pr.alloc(tie_cap * 3);
+    return bud();
+  }
+  if (nt) CK(cudaMemcpyAsync(h_ties.p, ties.p, nt * 4, cudaMemcpyDeviceToHost, s));
+  if (ntp) CK(cudaMemcpyAsync(h_ties_pr.p, ties_pr.p, ntp * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  auto pick = [&](const uint32_t *t, unsigned long long n) -> long {     // first in (cluster, slot) scan order
+    long best = -1;
+    for (unsigned long long k = 0; k < n; k++) {
+      uint32_t r = t[k];
+      if (best < 0 || cluster_of_h[r] < cluster_of_h[best] || (cluster_of_h[r] == cluster_of_h[best] && slot_of[r] < slot_of[best])) best = r;
+    }
+    return best;
+  };
+  // minraw starts as the centre of cluster 0 (p == 1 always: hamming 0 or singleton), cluster.cpp:279
+  const uint32_t c0 = cl_center_h[0];
+  auto bits2d = [](unsigned long long b) { double d; memcpy(&d, &b, 8); return d; };
+  long win = -1, win_pr = -1;
+  double pmin = 1.0, pmin_pr = 1.0;
+  if (nt) {
+    double pv = bits2d(h_ctr.p[CTR_PMIN]);
+    unsigned long long rm = h_ctr.p[CTR_RMAX];
+    if (pv < 1.0 || (pv == 1.0 && rm > cx->reads[c0])) { win = pick(h_ties.p, nt); pmin = pv; }
+  }
+  if (ntp) {
+    double pv = bits2d(h_ctr.p[CTR_PMIN_PR]);
+    unsigned long long rm = h_ctr.p[CTR_RMAX_PR];
+    if (pv < 1.0 || (pv == 1.0 && rm > cx->reads[c0])) { win_pr = pick(h_ties_pr.p, ntp); pmin_pr = pv; }
+  }
+  const double pA = pmin * (double)(unsigned)nraw, pP = pmin_pr;
+  long w = -1; char type = 0; double pv = 0;
+  if (pA < o->omegaA && win >= 0) { w = win; type = 'A'; pv = pA; }
+  else if (pP < o->omegaP && win_pr >= 0) { w = win_pr; type = 'P'; pv = pP; }
+  if (w < 0) return 0;
+  const uint32_t r = (uint32_t)w, from = cluster_of_h[r];
+  // fetch the winner's comparison (raw->comp)
+  double lam; uint32_t ham;
+  CK(cudaMemcpyAsync(&lam, comp_lambda.p + r, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&ham, comp_ham.p + r, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const double expected = lam * (double)cl_reads_h[from];
+  // bi_pop_raw(from, slot)
+  std::vector<uint32_t> &src = members[from];
+  const uint32_t sl = slot_of[r], last = src.back();
+  src[sl] = last; slot_of[last] = sl; src.pop_back();
+  cl_reads_h[from] -= cx->reads[r];
+  upd_e[from] = 1;
+  // b_add_bi + bi_add_raw + bi_assign_center
+  const uint32_t ni = (uint32_t)members.size();
+  members.emplace_back(1, r);
+  slot_of[r] = 0; cluster_of_h[r] = ni;
+  cl_reads_h.push_back(cx->reads[r]); cl_center_h.push_back(r);
+  upd_e.push_back(1); chk_locks.push_back(1);
+  Birth b; b.type = type; b.from = (type == 'A') ? from : from;  // 'P': uninitialised in the reference (cluster.cpp:334-339)
+  b.pval = pv; b.fold = (double)cx->reads[r] / expected; b.e = expected;
+  b.comp_i = from; b.comp_index = r; b.comp_lambda = lam; b.comp_ham = ham;
+  birth.push_back(b);
+  const uint8_t one = 1, zero = 0;
+  CK(cudaMemcpyAsync(cluster_of.p + r, &ni, 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(is_center.p + r, &one, 1, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(slot0.p + r, &one, 1, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(lock.p + r, &zero, 1, cudaMemcpyHostToDevice, s));       // bi_assign_center unlocks, cluster.cpp:377
+  upload_cluster_arrays(false);
+  CK(cudaStreamSynchronize(s));
+  return (int)ni;
+}
+
+template <typename T> T *dupv(const std::vector<T> &v) {
+  T *p = (T *)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
+  if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+  return p;
+}
+
+// Rmain.cpp:168-295: final subs, final p, output tables
+void Run::finish(dada2b_out *out) {
+  const uint32_t nclust = (uint32_t)members.size();
+  const int maxlen = in.maxlen;
+  upload_cluster_arrays(false);
+  launch_final_p(st, in, o->omegaC, s);
+  trans.alloc((size_t)16 * ncol); trans.zero(s);
+  cq_sum.alloc((size_t)nclust * maxlen); cq_cnt.alloc((size_t)nclust * maxlen); cq_sum.zero(s); cq_cnt.zero(s);
+  st.trans = trans.p; st.cq_sum = cq_sum.p; st.cq_cnt = cq_cnt.p;
+  {  // FinalSubsParallel: sub_new(centre, raw, use_kmers=false) for every raw
+    AlignArgs a = align_args(MODE_FINAL, P.band == 0 ? KIND_GAPLESS : KIND_NW);
+    a.jobs = nullptr; a.njobs_ptr = nullptr; a.njobs_fixed = nraw;
+    launch_align_jobs(MODE_FINAL, a, (unsigned long long)nraw);
+  }
+  // birth subs: sub_new(centre of birth_comp.i, centre i, use_kmers, cutoff 1.0)   Rmain.cpp:206-209
+  const uint32_t npair = nclust - 1;
+  std::vector<uint32_t> bns(npair, 0);
+  std::vector<uint16_t> bpos; std::vector<uint8_t> bnt0, bnt1, bq1;
+  const int bcap = maxlen;
+  if (npair) {
+    std::vector<uint32_t> pc(npair), pr(npair);
+    for (uint32_t i = 1; i < nclust; i++) { pc[i - 1] = cl_center_h[birth[i].comp_i]; pr[i - 1] = cl_center_h[i]; }
+    pair_centre.alloc(npair); pair_raw.alloc(npair);
+    CK(cudaMemcpyAsync(pair_centre.p, pc.data(), npair * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(pair_raw.p, pr.data(), npair * 4, cudaMemcpyHostToDevice, s));
+    b_nsubs.alloc(npair); b_lambda.alloc(npair); b_pos.alloc((size_t)npair * bcap); b_nt0.alloc((size_t)npair * bcap);
+    b_nt1.alloc((size_t)npair * bcap); b_q1.alloc((size_t)npair * bcap);
+    DBuf<uint32_t> nwl, gll; nwl.alloc(npair); gll.alloc(npair);
+    CK(cudaMemsetAsync(ctr.p + CTR_NW, 0, 2 * 8, s));
+    ClassifyArgs ca{};
+    ca.in = in; ca.P = P; ca.P.kdist_cutoff = 1.0; ca.mode = 1; ca.pair_centre = pair_centre.p; ca.pair_raw = pair_raw.p;
+    ca.nw_list = nwl.p; ca.gl_list = gll.p; ca.ctr = st.ctr; ca.kord_words = kord_words; ca.greedy = 0; ca.lock = st.lock;
+    // birth alignments are not counted in nalign/nshroud by the reference; restore the counters afterwards
+    read_ctr();
+    unsigned long long keepA = h_ctr.p[CTR_ALIGN], keepS = h_ctr.p[CTR_SHROUD];
+    launch_classify(ca, (int)npair, 256, classify_smem, s);
+    for (int kind : {KIND_NW, KIND_GAPLESS}) {
+      AlignArgs a = align_args(MODE_BIRTH, kind);
+      a.jobs = kind == KIND_NW ? nwl.p : gll.p;
+      a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
+      a.pair_centre = pair_centre.p; a.pair_raw = pair_raw.p;
+      a.b_nsubs = b_nsubs.p; a.b_lambda = b_lambda.p; a.b_pos = b_pos.p; a.b_nt0 = b_nt0.p; a.b_nt1 = b_nt1.p; a.b_q1 = b_q1.p;
+      a.b_cap = bcap; a.b_ops = nullptr; a.b_nops = nullptr; a.b_opcap = 0;
+      launch_align_jobs(MODE_BIRTH, a, npair);
+    }
+    CK(cudaMemcpyAsync(ctr.p + CTR_ALIGN, &keepA, 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctr.p + CTR_SHROUD, &keepS, 8, cudaMemcpyHostToDevice, s));
+    bpos.resize((size_t)npair * bcap); bnt0.resize((size_t)npair * bcap); bnt1.resize((size_t)npair * bcap); bq1.resize((size_t)npair * bcap);
+    CK(cudaMemcpyAsync(bns.data(), b_nsubs.p, npair * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(bpos.data(), b_pos.p, bpos.size() * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(bnt0.data(), b_nt0.p, bnt0.size(), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(bnt1.data(), b_nt1.p, bnt1.size(), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(bq1.data(), b_q1.p, bq1.size(), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  // post-hoc cluster p-values (error.cpp:99-119)
+  std::vector<double> tot_e(nclust, 0.0), cpval(nclust, 0.0);
+  {
+    std::vector<int> cc(nraw, -1);
+    for (uint32_t i = 0; i < nclust; i++) cc[cl_center_h[i]] = (int)i;
+    center_cluster.alloc(nraw);
+    CK(cudaMemcpyAsync(center_cluster.p, cc.data(), (size_t)nraw * 4, cudaMemcpyHostToDevice, s));
+    unsigned cap = std::max<unsigned>(4096, nclust * 8);
+    std::vector<uint32_t> tij; std::vector<double> tv; unsigned long long cnt = 0;
+    DBuf<unsigned long long> dcount; dcount.alloc(1);
+    for (;;) {
+      trip_ij.alloc((size_t)cap * 2); trip_v.alloc(cap); dcount.zero(s);
+      launch_posthoc(st, nraw, cs_count, center_cluster.p, trip_ij.p, trip_v.p, cap, dcount.p, s);
+      CK(cudaMemcpyAsync(&cnt, dcount.p, 8, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (cnt <= cap) break;
+      cap = (unsigned)cnt + 16;
+    }
+    tij.resize(cnt * 2); tv.resize(cnt);
+    if (cnt) {
+      CK(cudaMemcpyAsync(tij.data(), trip_ij.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(tv.data(), trip_v.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+    }
+    std::vector<size_t> ord(cnt);
+    for (size_t k = 0; k < cnt; k++) ord[k] = k;
+    std::sort(ord.begin(), ord.end(), [&](size_t x, size_t y) { return tij[2 * x] < tij[2 * y]; });   // ascending source cluster i
+    for (size_t k : ord) tot_e[tij[2 * k + 1]] += tv[k];
+    std::vector<int> rr(nclust), pp(nclust, 1);
+    for (uint32_t i = 0; i < nclust; i++) rr[i] = (int)cx->reads[cl_center_h[i]];
+    pa_reads.alloc(nclust); pa_prior.alloc(nclust); pa_E.alloc(nclust); pa_out.alloc(nclust);
+    CK(cudaMemcpyAsync(pa_reads.p, rr.data(), nclust * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(pa_prior.p, pp.data(), nclust * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(pa_E.p, tot_e.data(), nclust * 8, cudaMemcpyHostToDevice, s));
+    launch_calc_pA_vec(pa_reads.p, pa_E.p, pa_prior.p, pa_out.p, (int)nclust, s);
+    CK(cudaMemcpyAsync(cpval.data(), pa_out.p, nclust * 8, cudaMemcpyDeviceToHost, s));
+  }
+  // per-raw results
+  std::vector<double> hp(nraw); std::vector<uint8_t> hcorrect(nraw); std::vector<uint32_t> hns(nraw);
+  std::vector<int> htrans((size_t)16 * ncol); std::vector<unsigned long long> hsum((size_t)nclust * maxlen), hcnt((size_t)nclust * maxlen);
+  CK(cudaMemcpyAsync(hp.data(), p.p, (size_t)nraw * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hcorrect.data(), correct.p, nraw, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hns.data(), nsubs_final.p, (size_t)nraw * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(htrans.data(), trans.p, htrans.size() * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hsum.data(), cq_sum.p, hsum.size() * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hcnt.data(), cq_cnt.p, hcnt.size() * 8, cudaMemcpyDeviceToHost, s));
+  read_ctr();
+  check_dev_error();
+
+  out->nclust = nclust; out->nraw = nraw; out->maxlen = maxlen; out->Q = ncol;
+  out->n_align = (int64_t)h_ctr.p[CTR_ALIGN]; out->n_shroud = (int64_t)h_ctr.p[CTR_SHROUD];
+  out->n_nw = (int64_t)h_ctr.p[CTR_NWTOT]; out->n_gapless = (int64_t)h_ctr.p[CTR_GLTOT]; out->nw_cells = (int64_t)h_ctr.p[CTR_CELLS];
+  out->n_rounds = n_rounds; out->n_shuffles = n_shuffles;
+  // ---- $clustering (error.cpp:9-127)
+  std::string cseq; std::vector<int64_t> coff(1, 0);
+  std::vector<int32_t> ab(nclust, 0), n0(nclust, 0), n1(nclust, 0), nunq(nclust, 0), bfrom(nclust), bham(nclust);
+  std::vector<double> bpval(nclust), bfold(nclust), bqave(nclust);
+  for (uint32_t i = 0; i < nclust; i++) {
+    uint32_t max_reads = 0; long max_raw = -1;
+    for (uint32_t r : members[i]) if (cx->reads[r] > max_reads) { max_raw = r; max_reads = cx->reads[r]; }
+    if (max_raw >= 0) cseq.append(cx->seq_concat, (size_t)cx->seq_off[max_raw], (size_t)cx->len[max_raw]);
+    coff.push_back((int64_t)cseq.size());
+    for (uint32_t r : members[i]) if (hcorrect[r]) {
+      ab[i] += (int32_t)cx->reads[r]; nunq[i]++;
+      if (hns[r] == 0) n0[i] += (int32_t)cx->reads[r];
+      if (hns[r] == 1) n1[i] += (int32_t)cx->reads[r];
+    }
+    if (i == 0) { bpval[i] = na_real(); bfrom[i] = INT_MIN; bfold[i] = na_real(); bham[i] = INT_MIN; bqave[i] = na_real(); }
+    else {
+      bfrom[i] = (int32_t)birth[i].from + 1; bpval[i] = birth[i].pval; bfold[i] = birth[i].fold; bham[i] = (int32_t)birth[i].comp_ham;
+      double q_ave = 0.0; const uint32_t ns = bns[i - 1];
+      for (uint32_t k = 0; k < ns && k < (uint32_t)bcap; k++) q_ave += bq1[(size_t)(i - 1) * bcap + k];
+      q_ave = q_ave / ((double)ns);
+      bqave[i] = q_ave;
+    }
+  }
+  out->cl_seq_concat = (char *)malloc(cseq.size() + 1); memcpy(out->cl_seq_concat, cseq.data(), cseq.size()); out->cl_seq_concat[cseq.size()] = 0;
+  out->cl_seq_off = dupv(coff);
+  out->cl_abundance = dupv(ab); out->cl_n0 = dupv(n0); out->cl_n1 = dupv(n1); out->cl_nunq = dupv(nunq);
+  out->cl_pval = dupv(cpval); out->cl_birth_from = dupv(bfrom); out->cl_birth_pval = dupv(bpval); out->cl_birth_fold = dupv(bfold);
+  out->cl_birth_ham = dupv(bham); out->cl_birth_qave = dupv(bqave);
+  // ---- $birth_subs (error.cpp:261-300)
+  std::vector<int32_t> bs_pos, bs_clust; std::vector<char> bs_ref, bs_sub; std::vector<double> bs_qual;
+  for (uint32_t i = 1; i < nclust; i++)
+    for (uint32_t k = 0; k < bns[i - 1] && k < (uint32_t)bcap; k++) {
+      const size_t o2 = (size_t)(i - 1) * bcap + k;
+      bs_pos.push_back(bpos[o2] + 1); bs_ref.push_back("ACGT"[bnt0[o2]]); bs_sub.push_back("ACGT"[bnt1[o2]]);
+      bs_qual.push_back((double)bq1[o2]); bs_clust.push_back((int32_t)i + 1);
+    }
+  out->n_birth_subs = (int32_t)bs_pos.size();
+  out->bs_pos = dupv(bs_pos); out->bs_clust = dupv(bs_clust); out->bs_ref = dupv(bs_ref); out->bs_sub = dupv(bs_sub); out->bs_qual = dupv(bs_qual);
+  // ---- $subqual: device row-major [16][ncol] -> column-major 16 x ncol (error.cpp:131-172)
+  std::vector<int32_t> sq((size_t)16 * ncol);
+  for (int t = 0; t < 16; t++) for (int q = 0; q < ncol; q++) sq[t + 16 * (size_t)q] = htrans[(size_t)t * ncol + q];
+  out->subqual = dupv(sq); out->subqual_ncol = ncol;
+  // ---- $clusterquals (error.cpp:225-258)
+  std::vector<double> cq((size_t)maxlen * nclust);
+  for (uint32_t i = 0; i < nclust; i++) {
+    const int seqlen = cx->len[cl_center_h[i]];
+    for (int pos = 0; pos < maxlen; pos++) {
+      const size_t k = (size_t)i * maxlen + pos;
+      cq[pos + (size_t)maxlen * i] = pos < seqlen ? (double)hsum[k] / (double)(unsigned)hcnt[k] : na_real();
+    }
+  }
+  out->clusterquals = dupv(cq);
+  // ---- $map, $pval (Rmain.cpp:239-279)
+  std::vector<int32_t> map(nraw);
+  for (int r = 0; r < nraw; r++) map[r] = hcorrect[r] ? (int32_t)cluster_of_h[r] + 1 : INT_MIN;
+  out->map = dupv(map); out->pval = dupv(hp);
+}
+
+dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opts *o) {
+  const double t0 = now_ms();
+  CK(cudaSetDevice(cx->device));
+  if (Q < 1) throw Err{"Error matrix must have 16 rows."};
+  if (cx->bad_nt) throw Err{o->use_kmers ? "Unexpected nucleotide." : "Non-ACGT sequences in compute_lambda."};
+  if (o->use_quals && cx->maxq > Q - 1) throw Err{"Rounded quality exceeded range of err lookup table."};
+  Run R;
+  R.cx = cx; R.o = o; R.s = cx->stream; R.in = cx->in; R.nraw = cx->in.nraw; R.ncol = Q;
+  R.setup_params();
+  R.alloc_state();
+  {  // cluster.cpp:162-170: row-major copy of the error matrix
+    std::vector<double> e((size_t)16 * Q);
+    for (int r = 0; r < 16; r++) for (int c = 0; c < Q; c++) e[(size_t)r * Q + c] = err_cm[r + 16 * (size_t)c];
+    CK(cudaMemcpyAsync(R.err.p, e.data(), e.size() * 8, cudaMemcpyHostToDevice, R.s));
+    CK(cudaStreamSynchronize(R.s));
+  }
+  const int nraw = R.nraw;
+  // b_new / b_init (containers.cpp:78-137): one cluster holding every raw in index order
+  R.members.emplace_back(nraw);
+  for (int r = 0; r < nraw; r++) R.members[0][r] = r;
+  R.slot_of.resize(nraw); R.cluster_of_h.assign(nraw, 0);
+  for (int r = 0; r < nraw; r++) R.slot_of[r] = r;
+  uint32_t c0 = 0, mx = 0; bool found = false;
+  for (int r = 0; r < nraw; r++) if (cx->reads[r] > mx) { mx = cx->reads[r]; c0 = r; found = true; }   // bi_assign_center
+  if (!found) throw Err{"dada2b: all abundances are zero."};
+  R.cl_center_h.push_back(c0); R.cl_reads_h.push_back(cx->total_reads);
+  R.upd_e.push_back(1); R.chk_locks.push_back(1);
+  R.birth.emplace_back(); R.birth[0].e = cx->total_reads;
+  const uint8_t one = 1;
+  CK(cudaMemcpyAsync(R.is_center.p + c0, &one, 1, cudaMemcpyHostToDevice, R.s));
+  CK(cudaMemcpyAsync(R.slot0.p + 0, &one, 1, cudaMemcpyHostToDevice, R.s));
+  R.upload_cluster_arrays(true);
+  CK(cudaStreamSynchronize(R.s));
+  const double t1 = now_ms();
+  // run_dada (Rmain.cpp:297-336)
+  R.compare(0, 1.0);
+  R.p_update();
+  int max_clust = o->max_clust < 1 ? nraw : o->max_clust;
+  int newi;
+  while ((int)R.members.size() < max_clust && (newi = R.bud())) {
+    R.compare((uint32_t)newi, o->kdist_cutoff);
+    int nshuffle = 0; bool shuffled;
+    do { shuffled = R.shuffle_pass(); } while (shuffled && ++nshuffle < 10);   // MAX_SHUFFLE dada.h:30
+    R.p_update();
+    R.n_rounds++;
+  }
+  CK(cudaStreamSynchronize(R.s));
+  const double t2 = now_ms();
+  dada2b_out *out = (dada2b_out *)calloc(1, sizeof(dada2b_out));
+  try { R.finish(out); } catch (...) { dada2b_free(out); throw; }
+  const double t3 = now_ms();
+  out->ms_setup = t1 - t0; out->ms_loop = t2 - t1; out->ms_final = t3 - t2; out->ms_total = t3 - t0;
+  return out;
+}
+
+
+// ------------------------------- kernel-level test hooks -------------------------------
+static void do_test_pairs(dada2b_ctx *cx, int npairs, const uint32_t *centre, const uint32_t *raw, const double *err_cm,
+                          int Q, const dada2b_opts *o, int use_kmers, double kdist_cutoff, int32_t *kind, double *lambda,
+                          int32_t *nsubs, uint8_t *ops, int32_t *nops, int opcap, uint16_t *pos, uint8_t *nt0,
+                          uint8_t *nt1, uint8_t *q1, int subcap) {
+  CK(cudaSetDevice(cx->device));
+  if (cx->bad_nt) throw Err{"Unexpected nucleotide."};
+  Run R;
+  R.cx = cx; R.o = o; R.s = cx->stream; R.in = cx->in; R.nraw = cx->in.nraw; R.ncol = Q;
+  R.setup_params();
+  R.alloc_state();
+  std::vector<double> e((size_t)16 * Q);
+  for (int r = 0; r < 16; r++) for (int c = 0; c < Q; c++) e[(size_t)r * Q + c] = err_cm[r + 16 * (size_t)c];
+  CK(cudaMemcpyAsync(R.err.p, e.data(), e.size() * 8, cudaMemcpyHostToDevice, R.s));
+  cudaStream_t s = R.s;
+  R.pair_centre.alloc(npairs); R.pair_raw.alloc(npairs);
+  CK(cudaMemcpyAsync(R.pair_centre.p, centre, (size_t)npairs * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(R.pair_raw.p, raw, (size_t)npairs * 4, cudaMemcpyHostToDevice, s));
+  R.b_nsubs.alloc(npairs); R.b_nops.alloc(npairs); R.b_lambda.alloc(npairs); R.kind_out.alloc(npairs);
+  R.b_pos.alloc((size_t)npairs * subcap); R.b_nt0.alloc((size_t)npairs * subcap); R.b_nt1.alloc((size_t)npairs * subcap);
+  R.b_q1.alloc((size_t)npairs * subcap); R.b_ops.alloc((size_t)npairs * opcap);
+  R.b_nsubs.zero(s); R.b_nops.zero(s); R.b_lambda.zero(s); R.b_ops.zero(s); R.b_pos.zero(s); R.b_nt0.zero(s); R.b_nt1.zero(s); R.b_q1.zero(s);
+  DBuf<uint32_t> nwl, gll; nwl.alloc(npairs); gll.alloc(npairs);
+  ClassifyArgs ca{};
+  ca.in = R.in; ca.P = R.P; ca.P.use_kmers = use_kmers; ca.P.kdist_cutoff = kdist_cutoff; ca.mode = 1;
+  ca.pair_centre = R.pair_centre.p; ca.pair_raw = R.pair_raw.p; ca.nw_list = nwl.p; ca.gl_list = gll.p; ca.ctr = R.st.ctr;
+  ca.kord_words = R.kord_words; ca.kind_out = R.kind_out.p; ca.lock = R.st.lock;
+  launch_classify(ca, npairs, 256, R.classify_smem, s);
+  for (int kd : {KIND_NW, KIND_GAPLESS}) {
+    AlignArgs a = R.align_args(MODE_BIRTH, kd);
+    a.jobs = kd == KIND_NW ? nwl.p : gll.p;
+    a.njobs_ptr = R.st.ctr + (kd == KIND_NW ? CTR_NW : CTR_GL);
+    a.pair_centre = R.pair_centre.p; a.pair_raw = R.pair_raw.p;
+    a.b_nsubs = R.b_nsubs.p; a.b_lambda = R.b_lambda.p; a.b_pos = R.b_pos.p; a.b_nt0 = R.b_nt0.p; a.b_nt1 = R.b_nt1.p;
+    a.b_q1 = R.b_q1.p; a.b_cap = subcap; a.b_ops = R.b_ops.p; a.b_nops = R.b_nops.p; a.b_opcap = opcap;
+    R.launch_align_jobs(MODE_BIRTH, a, npairs);
+  }
+  std::vector<uint8_t> hk(npairs); std::vector<uint32_t> hns(npairs), hno(npairs);
+  CK(cudaMemcpyAsync(hk.data(), R.kind_out.p, npairs, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hns.data(), R.b_nsubs.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hno.data(), R.b_nops.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(lambda, R.b_lambda.p, (size_t)npairs * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ops, R.b_ops.p, (size_t)npairs * opcap, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(pos, R.b_pos.p, (size_t)npairs * subcap * 2, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(nt0, R.b_nt0.p, (size_t)npairs * subcap, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(nt1, R.b_nt1.p, (size_t)npairs * subcap, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(q1, R.b_q1.p, (size_t)npairs * subcap, cudaMemcpyDeviceToHost, s));
+  R.read_ctr();
+  R.check_dev_error();
+  for (int k = 0; k < npairs; k++) {
+    kind[k] = hk[k];
+    nsubs[k] = hk[k] == KIND_SHROUD ? -1 : (int32_t)hns[k];
+    nops[k] = (int32_t)hno[k];
+    if (hk[k] == KIND_SHROUD) lambda[k] = 0.0;             // compute_lambda of a NULL sub, pval.cpp:150-152
+  }
+}
+
+static void do_test_calc_pA(int n, const int32_t *reads, const double *E, const int32_t *prior, double *out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Err{"dada2b: no CUDA device available (this library has no CPU path)."};
+  DBuf<int> r, p; DBuf<double> e, o;
+  r.alloc(n); p.alloc(n); e.alloc(n); o.alloc(n);
+  CK(cudaMemcpy(r.p, reads, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p.p, prior, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e.p, E, (size_t)n * 8, cudaMemcpyHostToDevice));
+  launch_calc_pA_vec(r.p, e.p, p.p, o.p, n, 0);
+  CK(cudaMemcpy(out, o.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+}
+
+}  // namespace
+
+extern "C" {
+
+int dada2b_test_pairs(dada2b_ctx *ctx, int32_t npairs, const uint32_t *centre, const uint32_t *raw, const double *err,
+                      int32_t Q, const dada2b_opts *opts, int32_t use_kmers, double kdist_cutoff, int32_t *kind,
+                      double *lambda, int32_t *nsubs, uint8_t *ops, int32_t *nops, int32_t opcap, uint16_t *pos,
+                      uint8_t *nt0, uint8_t *nt1, uint8_t *q1, int32_t subcap, char errbuf[DADA2B_ERRLEN]) {
+  try { do_test_pairs(ctx, npairs, centre, raw, err, Q, opts, use_kmers, kdist_cutoff, kind, lambda, nsubs, ops, nops, opcap, pos, nt0, nt1, q1, subcap); return 0; }
+  catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
+  catch (std::exception &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.what()); return 2; }
+}
+int dada2b_test_calc_pA(int32_t n, const int32_t *reads, const double *E, const int32_t *prior, double *out,
+                        char errbuf[DADA2B_ERRLEN]) {
+  try { do_test_calc_pA(n, reads, E, prior, out); return 0; }
+  catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
+  catch (std::exception &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.what()); return 2; }
+}
+
+void dada2b_default_opts(dada2b_opts *o) {            // R/dada.R:1-26
+  memset(o, 0, sizeof *o);
+  o->match = 5; o->mismatch = -4; o->gap = -8; o->use_kmers = 1; o->kdist_cutoff = 0.42; o->band_size = 16;
+  o->omegaA = 1e-40; o->omegaP = 1e-4; o->omegaC = 1e-40; o->detect_singletons = 0; o->max_clust = 0;
+  o->min_fold = 1; o->min_hamming = 1; o->min_abund = 1; o->use_quals = 1; o->final_consensus = 0;
+  o->vectorized_alignment = 1; o->homo_gap = -8; o->multithread = 1; o->verbose = 0; o->SSE = 2; o->gapless = 1; o->greedy = 1;
+}
+
+int dada2b_upload(const dada2b_in *in, int32_t device, dada2b_ctx **ctx, char errbuf[DADA2B_ERRLEN]) {
+  *ctx = nullptr;
+  try { *ctx = do_upload(in, device); return 0; }
+  catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
+  catch (std::exception &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.what()); return 2; }
+}
+
+int dada2b_run_resident(dada2b_ctx *ctx, const double *err, int32_t Q, const dada2b_opts *opts, dada2b_out **out,
+                        char errbuf[DADA2B_ERRLEN]) {
+  *out = nullptr;
+  try { *out = do_run(ctx, err, Q, opts); return 0; }
+  catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
+  catch (std::exception &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.what()); return 2; }
+}
+
+void dada2b_ctx_free(dada2b_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int dada2b_run(const dada2b_in *in, const dada2b_opts *opts, dada2b_out **out, char errbuf[DADA2B_ERRLEN]) {
+  dada2b_ctx *cx = nullptr;
+  *out = nullptr;
+  int rc = dada2b_upload(in, 0, &cx, errbuf);
+  if (rc) return rc;
+  rc = dada2b_run_resident(cx, in->err, in->Q, opts, out, errbuf);
+  dada2b_ctx_free(cx);
+  return rc;
+}
+
+void dada2b_free(dada2b_out *o) {
+  if (!o) return;
+  free(o->cl_seq_concat); free(o->cl_seq_off); free(o->cl_abundance); free(o->cl_n0); free(o->cl_n1); free(o->cl_nunq);
+  free(o->cl_pval); free(o->cl_birth_from); free(o->cl_birth_pval); free(o->cl_birth_fold); free(o->cl_birth_ham);
+  free(o->cl_birth_qave); free(o->bs_pos); free(o->bs_ref); free(o->bs_sub); free(o->bs_qual); free(o->bs_clust);
+  free(o->subqual); free(o->clusterquals); free(o->map); free(o->pval); free(o);
+}
+
+}  // extern "C"

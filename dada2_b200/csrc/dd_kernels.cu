@@ -1,0 +1,586 @@
+// CUDA kernels of the B200-native dada() core (sm_100a).  Product code.
+//
+// Kernel                reference function(s) it replaces (under /root/reference/src)
+// k_classify            raw_align's k-mer screen + gapless test   nwalign_endsfree.cpp:10-55, kmers.cpp:13-150
+// k_align<LOOP>         sub_new + compute_lambda_ts + "selectively store"  nwalign_endsfree.cpp:76-216/220-396/539-672,
+//                       nwalign_vectorized.cpp:71-318, pval.cpp:144-197, cluster.cpp:90-204
+// k_align<FINAL>        FinalSubsParallel + transition / quality matrices   Rmain.cpp:179-236, error.cpp:131-172,225-258
+// k_align<BIRTH>        birth subs                                          Rmain.cpp:206-209, error.cpp:261-300
+// k_shuffle_*           b_shuffle2                                          cluster.cpp:210-266
+// k_p_update            b_p_update / get_pA / calc_pA                       pval.cpp:14-89
+// k_bud_*               b_bud's arg-min scan                                cluster.cpp:274-308
+// k_final_p             final p / correct flag                              Rmain.cpp:239-252
+//
+// Integer DP + scalar fp64: no tensor cores by construction.
+#include "dd_common.h"
+#include "dd_kernels.h"
+#include "ppois.cuh"
+#include <math_constants.h>
+
+namespace dd2 {
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << lane_id()) - 1u; }
+
+// 5-mer (10 bits, first base most significant like kmers.cpp:226) starting at base p of a packed row.
+__device__ __forceinline__ unsigned kmer_at(const uint32_t *row, int p) {
+  uint32_t w0 = row[p >> 4], w1 = row[(p + 4) >> 4];
+  uint32_t x = __funnelshift_r(w0, w1, 2 * (p & 15)) & 0x3FFu;   // base p in bits 1:0 ... base p+4 in bits 9:8
+  // reference order: kmer = 4*kmer + nt, first base most significant
+  return ((x & 3u) << 8) | (((x >> 2) & 3u) << 6) | (((x >> 4) & 3u) << 4) | (((x >> 6) & 3u) << 2) | ((x >> 8) & 3u);
+}
+__device__ __forceinline__ unsigned base_at(const uint32_t *row, int p) { return (row[p >> 4] >> (2 * (p & 15))) & 3u; }
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// =====================================================================================
+// k_classify : k-mer screen / gapless decision for (centre, raw) pairs; one warp per pair.
+//   mode 0: every block uses centre a.centre_idx; warps stride over raws [0, nraw)
+//   mode 1: block b handles the single pair (pair_centre[b], pair_raw[b])   (birth subs)
+// shared: centre 5-mer counts (1024 x u16 packed in 512 words), centre ordered 5-mers,
+//         per-warp 1024 x u16 scratch counts, per-warp packed raw row.
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
+  extern __shared__ uint32_t smem[];
+  const int nwarps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
+  const int SW = a.in.SW;
+  uint32_t *cen_cnt = smem;                                  // 512 words
+  uint16_t *cen_kord = (uint16_t *)(smem + 512);             // kord_words*2 entries
+  uint32_t *wtab = smem + 512 + a.kord_words + wid * 512;    // per warp
+  uint32_t *wseq = smem + 512 + a.kord_words + nwarps * 512 + wid * SW;
+  const AlnParams &P = a.P;
+
+  const uint32_t c = a.mode == 0 ? a.centre_idx : a.pair_centre[blockIdx.x];
+  const int len1 = a.in.len[c];
+  if (P.use_kmers) {
+    for (int x = threadIdx.x; x < 512; x += blockDim.x) cen_cnt[x] = 0;
+    for (int x = threadIdx.x; x < nwarps * 512; x += blockDim.x) smem[512 + a.kord_words + x] = 0;
+    __syncthreads();
+    const uint32_t *crow = a.in.seq2 + (size_t)c * SW;
+    for (int p = threadIdx.x; p + KMER <= len1; p += blockDim.x) {
+      unsigned km = kmer_at(crow, p);
+      cen_kord[p] = (uint16_t)km;
+      atomicAdd(&cen_cnt[km >> 1], 1u << (16 * (km & 1)));
+    }
+    __syncthreads();
+  }
+
+  const int gw = blockIdx.x * nwarps + wid, tw = gridDim.x * nwarps;
+  int r0 = a.mode == 0 ? gw : 0, rstep = a.mode == 0 ? tw : 1, rend = a.mode == 0 ? a.in.nraw : (wid == 0 ? 1 : 0);
+  for (int it = r0; it < rend; it += rstep) {
+    const uint32_t r = a.mode == 0 ? (uint32_t)it : a.pair_raw[blockIdx.x];
+    const uint32_t job = a.mode == 0 ? r : blockIdx.x;
+    if (a.mode == 0 && a.greedy && (a.in.reads[r] > a.centre_reads || a.lock[r])) continue;   // cluster.cpp:127-131
+    const int len2 = a.in.len[r];
+    int kind;
+    if (P.use_kmers) {
+      const uint32_t *rrow = a.in.seq2 + (size_t)r * SW;
+      for (int x = lane; x < SW; x += 32) wseq[x] = rrow[x];
+      __syncwarp();
+      const int minlen = min(len1, len2), nko = minlen - KMER + 1;
+      int ms = 0, om = 0;
+      for (int p = lane; p + KMER <= len2; p += 32) {
+        unsigned km = kmer_at(wseq, p);
+        unsigned sh = 16 * (km & 1);
+        unsigned old = atomicAdd(&wtab[km >> 1], 1u << sh);
+        unsigned rank = (old >> sh) & 0xFFFFu;
+        unsigned cc = (cen_cnt[km >> 1] >> sh) & 0xFFFFu;
+        ms += rank < cc;                     // sum_k min(c_raw[k], c_centre[k])   kmers.cpp:13-26
+        if (p < nko) om += (km == cen_kord[p]);  // ordered matches           kmers.cpp:102-116
+      }
+      ms = warp_sum(ms);
+      om = warp_sum(om);
+      __syncwarp();
+      for (int p = lane; p + KMER <= len2; p += 32) wtab[kmer_at(wseq, p) >> 1] = 0;
+      __syncwarp();
+      // kmers.cpp:24 / :91: dot = dotsum/(min(len)-k+1.), dist = 1-dot ; raw_align :51,:54
+      double denom = (double)(minlen - KMER) + 1.;
+      double kdist = 1. - ((double)(ms & 0xFFFF)) / denom;
+      bool ko_valid = P.gapless && !(P.sse == 0 && len1 != len2);
+      double kodist = ko_valid ? 1. - ((double)(om & 0xFFFF)) / denom : -1.0;
+      if (kdist > P.kdist_cutoff) kind = KIND_SHROUD;
+      else if (P.band == 0 || (P.gapless && kodist == kdist)) kind = KIND_GAPLESS;
+      else kind = KIND_NW;
+    } else {
+      kind = (P.band == 0) ? KIND_GAPLESS : KIND_NW;
+    }
+    if (lane == 0) {
+      atomicAdd(&a.ctr[CTR_ALIGN], 1ull);
+      if (kind == KIND_SHROUD) atomicAdd(&a.ctr[CTR_SHROUD], 1ull);
+      else if (kind == KIND_GAPLESS) { unsigned long long s = atomicAdd(&a.ctr[CTR_GL], 1ull); a.gl_list[s] = job; }
+      else { unsigned long long s = atomicAdd(&a.ctr[CTR_NW], 1ull); a.nw_list[s] = job; }
+      if (a.kind_out) a.kind_out[job] = (uint8_t)kind;
+    }
+  }
+}
+
+// =====================================================================================
+// Banded ends-free Needleman-Wunsch, one warp per pair, anti-diagonal wavefront.
+//   s1 = centre (rows i), s2 = raw (columns j); recurrence, tie order (up > left > diag),
+//   free end gaps on the last row/column and band geometry follow nwalign_endsfree.cpp:101-160
+//   (and :230-330 for homopolymer gap costs).  State: one live score per diagonal
+//   (delta = j - i) in shared memory; a step k = i + j updates the diagonals with the
+//   parity of k from their neighbours (k-1) and themselves (k-2).  2-bit move codes are
+//   written per step with two warp ballots.
+// =====================================================================================
+struct BandGeom { int lb, rb, W, nchunk; };
+
+__device__ __forceinline__ BandGeom band_geom(int len1, int len2, int band) {
+  int lband, rband;
+  if (band < 0) { lband = len1; rband = len2; }
+  else if (len2 > len1) { lband = band; rband = band + len2 - len1; }
+  else if (len1 > len2) { lband = band + len1 - len2; rband = band; }
+  else { lband = band; rband = band; }
+  BandGeom g;
+  g.lb = min(lband, len1);
+  g.rb = min(rband, len2);
+  g.W = g.lb + g.rb + 1;
+  g.nchunk = (((g.W + 1) >> 1) + 31) >> 5;
+  return g;
+}
+__device__ __forceinline__ int step_dlo(int k, int len1, const BandGeom &g) {
+  int dlo = max(max(-g.lb, -k), k - 2 * len1);
+  if ((dlo - k) & 1) dlo++;
+  return dlo;
+}
+
+// s1/s2: bytes, bits 1:0 = base, bit 2 = "inside a homopolymer run >= 3".  H: W+2 ints.
+// ptr: 2*nchunk words per step, (len1+len2+1) steps.  Returns number of ops; ops (1 diag, 2 gap in
+// centre row, 3 gap in raw row) are packed 2 bits each into opw in traceback (reverse) order.
+__device__ int nw_warp(const uint8_t *s1, int len1, const uint8_t *s2, int len2, const AlnParams &P, int *H,
+                       uint32_t *ptr, uint32_t *opw, unsigned long long *cells, int *err) {
+  const int lane = lane_id();
+  const BandGeom g = band_geom(len1, len2, P.band);
+  const int SENT = P.sentinel;
+  for (int x = lane; x < g.W + 2; x += 32) H[x] = SENT;
+  __syncwarp();
+  const int nsteps = len1 + len2;
+  unsigned long long ncell_tot = 0;
+  for (int k = 1; k <= nsteps; k++) {
+    const int dlo = step_dlo(k, len1, g);
+    const int dhi = min(min(g.rb, k), 2 * len2 - k);
+    const int ncell = dhi >= dlo ? ((dhi - dlo) >> 1) + 1 : 0;
+    uint32_t *row = ptr + (size_t)k * 2 * g.nchunk;
+    for (int m = 0; m * 32 < ncell; m++) {
+      const int cidx = m * 32 + lane;
+      const bool active = cidx < ncell;
+      int p = 0;
+      if (active) {
+        const int dl = dlo + 2 * cidx;
+        const int i = (k - dl) >> 1, j = (k + dl) >> 1;
+        int *h = H + dl + g.lb + 1;
+        int val;
+        if (i == 0) { val = 0; p = 2; }                 // nwalign_endsfree.cpp:97-101
+        else if (j == 0) { val = 0; p = 3; }            // :91-95
+        else {
+          const int c1 = s1[i - 1], c2 = s2[j - 1];
+          int left, up, diag;
+          if (i == len1) left = h[-1];                                   // :130-137 (homo :303-311)
+          else left = h[-1] + ((P.homo && (c2 & 4)) ? P.hgap : P.gap);
+          if (j == len2) up = h[1];                                      // :139-144 (homo :313-320)
+          else up = h[1] + ((P.homo && (c1 & 4)) ? P.hgap : P.gap);
+          diag = h[0] + (((c1 ^ c2) & 3) ? P.mismatch : P.match);
+          if (up >= diag && up >= left) { val = up; p = 3; }             // :147-156
+          else if (left >= diag) { val = left; p = 2; }
+          else { val = diag; p = 1; }
+          ncell_tot++;
+        }
+        h[0] = val;
+      }
+      const unsigned b0 = __ballot_sync(0xffffffffu, p & 1), b1 = __ballot_sync(0xffffffffu, p & 2);
+      if (lane == 0) { row[2 * m] = b0; row[2 * m + 1] = b1; }
+    }
+    __syncwarp();
+  }
+  // ---- traceback (warp-uniform), nwalign_endsfree.cpp:166-190 ----
+  int i = len1, j = len2, nops = 0;
+  uint32_t acc = 0;
+  while (i > 0 || j > 0) {
+    int p;
+    if (i == 0) p = 2;
+    else if (j == 0) p = 3;
+    else {
+      const int k = i + j, dl = j - i;
+      const int cidx = (dl - step_dlo(k, len1, g)) >> 1;
+      const uint32_t *row = ptr + (size_t)k * 2 * g.nchunk + 2 * (cidx >> 5);
+      const unsigned bit = cidx & 31;
+      p = ((row[0] >> bit) & 1u) | (((row[1] >> bit) & 1u) << 1);
+    }
+    if (p == 1) { i--; j--; }
+    else if (p == 2) { j--; }
+    else if (p == 3) { i--; }
+    else { *err = ERR_TRACE; break; }
+    acc |= (uint32_t)p << (2 * (nops & 15));
+    if ((nops & 15) == 15) { if (lane == 0) opw[nops >> 4] = acc; acc = 0; }
+    nops++;
+  }
+  if ((nops & 15) && lane == 0) opw[nops >> 4] = acc;
+  __syncwarp();
+  ncell_tot = warp_sum((int)ncell_tot);   // per-lane counts are small (< 2^31 per pair)
+  if (lane == 0 && cells) atomicAdd(cells, (unsigned long long)(unsigned)ncell_tot);
+  return nops;
+}
+
+// Unpack a 2-bit row into bytes; bit 2 flags "inside a homopolymer run of length >= 3"
+// (nwalign_endsfree.cpp:230-255).  Flag writes only touch bit 2, concurrent readers only use bits 1:0.
+__device__ void unpack_row(const uint32_t *grow, int len, uint8_t *dst, bool homo) {
+  const int lane = lane_id();
+  for (int p = lane; p < len; p += 32) dst[p] = (uint8_t)base_at(grow, p);
+  __syncwarp();
+  if (homo) {
+    for (int p = lane; p < len; p += 32) {
+      const int b = dst[p] & 3;
+      int L = 0, R = 0;
+      while (L < 2 && p - L - 1 >= 0 && (dst[p - L - 1] & 3) == b) L++;
+      while (R < 2 && p + R + 1 < len && (dst[p + R + 1] & 3) == b) R++;
+      if (L + R >= 2) dst[p] |= 4;
+    }
+    __syncwarp();
+  }
+}
+
+// =====================================================================================
+// k_align: alignment (NW or gapless) -> substitutions -> lambda, then mode-specific sink.
+// =====================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(128) k_align(AlignArgs a) {
+  extern __shared__ uint32_t smem[];
+  const int nwarps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
+  const AlnParams &P = a.P;
+  // ---- shared layout: [err 16*ncol doubles][trans ints (FINAL)] then per-warp regions ----
+  double *s_err = (double *)smem;
+  int *s_trans = (int *)(s_err + 16 * P.ncol);
+  uint32_t *wbase = (uint32_t *)(s_trans + (MODE == MODE_FINAL ? 16 * P.ncol : 0)) + (size_t)wid * a.warp_words;
+  uint8_t *s1 = (uint8_t *)wbase;
+  uint8_t *s2 = s1 + a.seq_bytes;
+  int *H = (int *)(wbase + 2 * (a.seq_bytes >> 2));
+  uint32_t *opw = (uint32_t *)(H + a.H_words);
+  uint32_t *ptr_s = opw + a.ops_words;
+  for (int x = threadIdx.x; x < 16 * P.ncol; x += blockDim.x) s_err[x] = a.st.err[x];
+  if (MODE == MODE_FINAL) for (int x = threadIdx.x; x < 16 * P.ncol; x += blockDim.x) s_trans[x] = 0;
+  __syncthreads();
+
+  const int gw = blockIdx.x * nwarps + wid, tw = gridDim.x * nwarps;
+  uint32_t *ptr = a.ptr_in_smem ? ptr_s : a.ptr_scratch + (size_t)gw * a.ptr_words;
+  const unsigned long long njobs = a.njobs_ptr ? *a.njobs_ptr : (unsigned long long)a.njobs_fixed;
+  int errflag = 0;
+
+  for (unsigned long long jb = gw; jb < njobs; jb += tw) {
+    uint32_t r, c, job = a.jobs ? a.jobs[jb] : (uint32_t)jb;
+    uint32_t cluster = 0;
+    int kind = a.kind;
+    if (MODE == MODE_LOOP) { r = job; c = a.centre_idx; }
+    else if (MODE == MODE_FINAL) { r = job; cluster = a.st.cluster_of[r]; c = a.st.cl_center[cluster]; }
+    else { r = a.pair_raw[job]; c = a.pair_centre[job]; }
+    const int len1 = a.in.len[c], len2 = a.in.len[r];
+    unpack_row(a.in.seq2 + (size_t)c * a.in.SW, len1, s1, P.homo && kind == KIND_NW);
+    unpack_row(a.in.seq2 + (size_t)r * a.in.SW, len2, s2, P.homo && kind == KIND_NW);
+    int nops;
+    if (kind == KIND_NW) {
+      nops = nw_warp(s1, len1, s2, len2, P, H, ptr, opw, &a.st.ctr[CTR_CELLS], &errflag);
+    } else {
+      nops = max(len1, len2);   // nwalign_gapless, nwalign_endsfree.cpp:539-555
+    }
+    // ---- forward pass over alignment columns: al2subs (:570-639) + compute_lambda_ts (pval.cpp:144-197)
+    const uint8_t *q2 = a.in.qual + (size_t)r * a.in.QS;
+    const int minlen = min(len1, len2);
+    double lambda = 1.0;
+    int nsubs = 0, i0b = 0, i1b = 0, qerr = 0;
+    const uint32_t rreads = a.in.reads[r];
+    const bool acc = (MODE == MODE_FINAL) && a.st.correct[r];
+    for (int cb = 0; cb < nops; cb += 32) {
+      const int col = cb + lane;
+      int op = 0;
+      if (col < nops) {
+        if (kind == KIND_NW) { const int e = nops - 1 - col; op = (opw[e >> 4] >> (2 * (e & 15))) & 3; }
+        else op = col < minlen ? 1 : (len1 > len2 ? 3 : 2);
+      }
+      const unsigned b0 = __ballot_sync(0xffffffffu, op == 1 || op == 3);   // consumes a centre base
+      const unsigned b1 = __ballot_sync(0xffffffffu, op == 1 || op == 2);   // consumes a raw base
+      const int i0 = i0b + __popc(b0 & lanemask_lt()), i1 = i1b + __popc(b1 & lanemask_lt());
+      double f = 1.0;
+      bool sub = false;
+      if (op == 1 || op == 2) {
+        const int nt1 = s2[i1] & 3;
+        const int qq = P.use_quals ? q2[i1] : 0;
+        if (qq > P.ncol - 1) qerr = 1;                                  // pval.cpp:169-171
+        int t = nt1 * 5;                                                // self transition, pval.cpp:160
+        if (op == 1) {
+          const int nt0 = s1[i0] & 3;
+          t = nt0 * 4 + nt1;                                            // pval.cpp:183-185
+          sub = nt0 != nt1;
+          if (MODE == MODE_FINAL && acc) {                              // error.cpp:150-165, :243-250
+            const int qa = q2[i1];
+            if (qa < P.ncol) atomicAdd(&s_trans[t * P.ncol + qa], (int)rreads);
+            atomicAdd(&a.st.cq_sum[(size_t)cluster * a.in.maxlen + i0], (unsigned long long)((unsigned)qa * rreads));
+            atomicAdd(&a.st.cq_cnt[(size_t)cluster * a.in.maxlen + i0], (unsigned long long)rreads);
+          }
+        }
+        f = s_err[t * P.ncol + min(qq, P.ncol - 1)];
+      }
+      if (MODE == MODE_BIRTH) {
+        const unsigned sb = __ballot_sync(0xffffffffu, sub);
+        if (sub) {
+          const int slot = nsubs + __popc(sb & lanemask_lt());
+          if (slot < a.b_cap) {
+            const size_t o = (size_t)job * a.b_cap + slot;
+            a.b_pos[o] = (uint16_t)i0; a.b_nt0[o] = s1[i0] & 3; a.b_nt1[o] = s2[i1] & 3; a.b_q1[o] = q2[i1];
+          }
+        }
+        if (a.b_ops && col < nops) a.b_ops[(size_t)job * a.b_opcap + col] = (uint8_t)op;
+      }
+      nsubs += __popc(__ballot_sync(0xffffffffu, sub));
+      // lambda: strictly sequential fp64 product in raw-position order (pval.cpp:190-193)
+      const int ncol_here = min(32, nops - cb);
+      for (int s = 0; s < ncol_here; s++) lambda = lambda * __shfl_sync(0xffffffffu, f, s);
+      i0b += __popc(b0); i1b += __popc(b1);
+    }
+    if (__any_sync(0xffffffffu, qerr)) errflag = ERR_QUAL;
+    if (lambda < 0 || lambda > 1) errflag = ERR_LAMBDA;                 // pval.cpp:195 / cluster.cpp:184
+    // ---- sinks ----
+    if (lane == 0) {
+      if (MODE == MODE_LOOP) {                                           // cluster.cpp:179-201
+        if (kind == KIND_NW) atomicAdd(&a.st.ctr[CTR_NWTOT], 1ull); else atomicAdd(&a.st.ctr[CTR_GLTOT], 1ull);
+        double emm = a.st.E_minmax[r];
+        if (lambda * (double)a.total_reads > emm) {
+          const double ec = lambda * (double)a.centre_reads;
+          if (ec > emm) a.st.E_minmax[r] = ec;
+          unsigned long long slot = a.cluster_i == 0 ? (unsigned long long)r : atomicAdd(&a.st.ctr[CTR_CS_COUNT], 1ull);
+          if (slot < a.st.cs_cap) {
+            a.st.cs_index[slot] = r; a.st.cs_i[slot] = a.cluster_i; a.st.cs_lambda[slot] = lambda; a.st.cs_ham[slot] = (uint32_t)nsubs;
+          }
+          if (a.cluster_i == 0 || r == c) { a.st.comp_lambda[r] = lambda; a.st.comp_ham[r] = (uint32_t)nsubs; }
+        }
+      } else if (MODE == MODE_FINAL) {
+        a.st.nsubs_final[r] = (uint32_t)nsubs;
+      } else {
+        a.b_nsubs[job] = (uint32_t)nsubs; a.b_lambda[job] = lambda; if (a.b_nops) a.b_nops[job] = (uint32_t)nops;
+      }
+    }
+    __syncwarp();
+  }
+  if (errflag && lane == 0) atomicMax(&a.st.ctr[CTR_ERR], (unsigned long long)errflag);
+  if (MODE == MODE_FINAL) {
+    __syncthreads();
+    for (int x = threadIdx.x; x < 16 * P.ncol; x += blockDim.x)
+      if (s_trans[x]) atomicAdd(&a.st.trans[x], s_trans[x]);
+  }
+}
+
+template __global__ void k_align<MODE_LOOP>(AlignArgs);
+template __global__ void k_align<MODE_FINAL>(AlignArgs);
+template __global__ void k_align<MODE_BIRTH>(AlignArgs);
+
+// =====================================================================================
+// b_shuffle2 (cluster.cpp:210-266) over the flat comparison store.
+//   pass A: emax[raw] = max_e (order-preserving u64 image of the non-negative double)
+//   pass B: best[raw] = lowest entry id attaining emax  (entries are appended cluster by
+//           cluster, so the lowest id is the lowest cluster index == strict '>' scan order)
+//   pass C: raws whose best cluster differs from their current one move (centres stay).
+// =====================================================================================
+__global__ void k_shuffle_init(DevState st, int nraw) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nraw) return;
+  double e = st.cs_lambda[r] * (double)st.cl_reads[0];    // cluster 0 holds every raw, in index order (:223-226)
+  st.emax_bits[r] = (unsigned long long)__double_as_longlong(e);
+  st.best_entry[r] = 0xFFFFFFFFu;
+}
+__global__ void k_shuffle_max(DevState st, int nraw) {
+  unsigned long long n = st.ctr[CTR_CS_COUNT];
+  unsigned long long x = (unsigned long long)nraw + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  double e = st.cs_lambda[x] * (double)st.cl_reads[st.cs_i[x]];
+  atomicMax(&st.emax_bits[st.cs_index[x]], (unsigned long long)__double_as_longlong(e));
+}
+__global__ void k_shuffle_arg(DevState st, int nraw) {
+  unsigned long long n = st.ctr[CTR_CS_COUNT];
+  unsigned long long x = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  double e = st.cs_lambda[x] * (double)st.cl_reads[st.cs_i[x]];
+  uint32_t r = st.cs_index[x];
+  if ((unsigned long long)__double_as_longlong(e) == st.emax_bits[r]) atomicMin(&st.best_entry[r], (uint32_t)x);
+}
+__global__ void k_shuffle_move(DevState st, int nraw, uint32_t *moves, unsigned move_cap) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nraw) return;
+  uint32_t be = st.best_entry[r];
+  uint32_t to = st.cs_i[be], from = st.cluster_of[r];
+  if (to != from && !st.is_center[r]) {
+    unsigned long long s = atomicAdd(&st.ctr[CTR_NMOVE], 1ull);
+    if (s < move_cap) { moves[2 * s] = (uint32_t)r; moves[2 * s + 1] = to; }
+    st.cluster_of[r] = to;
+    st.comp_lambda[r] = st.cs_lambda[be];
+    st.comp_ham[r] = st.cs_ham[be];
+  }
+}
+// =====================================================================================
+// b_p_update (pval.cpp:14-40): abundance p-value for raws of clusters flagged update_e; greedy
+// locking for clusters flagged check_locks.
+// =====================================================================================
+__global__ void k_p_update(DevState st, DevIn in, int greedy, int detect_singletons) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= in.nraw) return;
+  const uint32_t ci = st.cluster_of[r];
+  const uint32_t reads = in.reads[r];
+  const double lambda = st.comp_lambda[r];
+  if (st.cl_update_e[ci]) {                                            // get_pA pval.cpp:67-89
+    const bool prior = in.prior[r] != 0;
+    double pval;
+    if (reads == 1 && !prior && !detect_singletons) pval = 1.;
+    else if (st.comp_ham[r] == 0) pval = 1.;
+    else if (lambda == 0) pval = 0.;
+    else pval = calc_pA((int)reads, lambda * (double)st.cl_reads[ci], prior || detect_singletons);
+    st.p[r] = pval;
+  }
+  if (greedy && st.cl_check_locks[ci]) {                               // pval.cpp:29-38
+    const uint32_t cen = st.cl_center[ci];
+    const double E_reads_center = (double)in.reads[cen] * lambda;
+    if (E_reads_center > (double)reads) st.lock[r] = 1;
+    if ((uint32_t)r == cen) st.lock[r] = 1;
+  }
+}
+
+// =====================================================================================
+// b_bud scan (cluster.cpp:284-308): lexicographic minimum of (p asc, reads desc) over eligible
+// raws; every raw attaining it is returned so the host can apply the (cluster, slot) scan-order
+// tie-break exactly.  Same for the prior-carrying subset.
+// =====================================================================================
+__device__ __forceinline__ bool bud_eligible(const DevState &st, const DevIn &in, int r, double min_fold, int min_hamming,
+                                             int min_abund) {
+  if (st.slot0[r]) return false;                                       // r starts at 1 (:285)
+  const uint32_t reads = in.reads[r];
+  if ((int)reads < min_abund) return false;
+  if ((int)st.comp_ham[r] < min_hamming) return false;
+  if (!(min_fold <= 1 || ((double)reads) >= min_fold * st.comp_lambda[r] * (double)st.cl_reads[st.cluster_of[r]])) return false;
+  return true;
+}
+__global__ void k_bud_pmin(DevState st, DevIn in, double min_fold, int min_hamming, int min_abund) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long pb = ~0ull, pbp = ~0ull;
+  if (r < in.nraw && bud_eligible(st, in, r, min_fold, min_hamming, min_abund)) {
+    pb = (unsigned long long)__double_as_longlong(st.p[r]);
+    if (in.prior[r]) pbp = pb;
+  }
+  // warp-level min first, one atomic per warp
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, pb, o); pb = t < pb ? t : pb;
+    t = __shfl_xor_sync(0xffffffffu, pbp, o); pbp = t < pbp ? t : pbp;
+  }
+  if (lane_id() == 0) {
+    if (pb != ~0ull) atomicMin(&st.ctr[CTR_PMIN], pb);
+    if (pbp != ~0ull) atomicMin(&st.ctr[CTR_PMIN_PR], pbp);
+  }
+}
+__global__ void k_bud_rmax(DevState st, DevIn in, double min_fold, int min_hamming, int min_abund) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= in.nraw || !bud_eligible(st, in, r, min_fold, min_hamming, min_abund)) return;
+  const unsigned long long pb = (unsigned long long)__double_as_longlong(st.p[r]);
+  if (pb == st.ctr[CTR_PMIN]) atomicMax(&st.ctr[CTR_RMAX], (unsigned long long)in.reads[r]);
+  if (in.prior[r] && pb == st.ctr[CTR_PMIN_PR]) atomicMax(&st.ctr[CTR_RMAX_PR], (unsigned long long)in.reads[r]);
+}
+__global__ void k_bud_collect(DevState st, DevIn in, double min_fold, int min_hamming, int min_abund, uint32_t *ties,
+                              uint32_t *ties_pr, unsigned cap) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= in.nraw || !bud_eligible(st, in, r, min_fold, min_hamming, min_abund)) return;
+  const unsigned long long pb = (unsigned long long)__double_as_longlong(st.p[r]);
+  if (pb == st.ctr[CTR_PMIN] && (unsigned long long)in.reads[r] == st.ctr[CTR_RMAX]) {
+    unsigned long long s = atomicAdd(&st.ctr[CTR_NTIE], 1ull);
+    if (s < cap) ties[s] = (uint32_t)r;
+  }
+  if (in.prior[r] && pb == st.ctr[CTR_PMIN_PR] && (unsigned long long)in.reads[r] == st.ctr[CTR_RMAX_PR]) {
+    unsigned long long s = atomicAdd(&st.ctr[CTR_NTIE_PR], 1ull);
+    if (s < cap) ties_pr[s] = (uint32_t)r;
+  }
+}
+
+// Rmain.cpp:239-252: final within-cluster p and the correct flag.
+__global__ void k_final_p(DevState st, DevIn in, double omegaC) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= in.nraw) return;
+  const uint32_t ci = st.cluster_of[r];
+  double p;
+  uint8_t correct = 1;
+  if (st.cl_center[ci] == (uint32_t)r) p = 1.0;
+  else {
+    p = calc_pA((int)in.reads[r], st.comp_lambda[r] * (double)st.cl_reads[ci], true);
+    if (p < omegaC) correct = 0;
+  }
+  st.p[r] = p;
+  st.correct[r] = correct;
+}
+
+// error.cpp:99-119 post-hoc cluster p-value; one thread per cluster evaluates calc_pA(centre.reads, tot_e, true)
+__global__ void k_calc_pA_vec(const int *reads, const double *E, const int *prior, double *out, int n) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < n) out[x] = calc_pA(reads[x], E[x], prior[x] != 0);
+}
+
+// Post-hoc expected reads (error.cpp:106-116): every stored comparison whose raw is the centre of
+// another cluster j contributes lambda * reads_i to tot_e[j]; emit (i, j, value) triples, the host adds
+// them in ascending i like the reference's cluster-order loop.
+__global__ void k_posthoc(DevState st, unsigned long long n, const int *center_cluster, uint32_t *trip_ij, double *trip_v,
+                          unsigned cap, unsigned long long *count) {
+  unsigned long long x = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  const int j = center_cluster[st.cs_index[x]];
+  if (j < 0) return;
+  const uint32_t i = st.cs_i[x];
+  if ((int)i == j) return;
+  unsigned long long s = atomicAdd(count, 1ull);
+  if (s < cap) { trip_ij[2 * s] = i; trip_ij[2 * s + 1] = (uint32_t)j; trip_v[s] = st.cs_lambda[x] * (double)st.cl_reads[i]; }
+}
+
+// ------------------------------- launch wrappers --------------------------------------
+void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+  k_classify<<<grid, block, smem, s>>>(a);
+}
+cudaError_t align_set_smem(size_t bytes) {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_align<MODE_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes))) return e;
+  if ((e = cudaFuncSetAttribute(k_align<MODE_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes))) return e;
+  if ((e = cudaFuncSetAttribute(k_align<MODE_BIRTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes))) return e;
+  return cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+}
+void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+  if (mode == MODE_LOOP) k_align<MODE_LOOP><<<grid, block, smem, s>>>(a);
+  else if (mode == MODE_FINAL) k_align<MODE_FINAL><<<grid, block, smem, s>>>(a);
+  else k_align<MODE_BIRTH><<<grid, block, smem, s>>>(a);
+}
+void launch_shuffle_pass(const DevState &st, int nraw, unsigned long long n_entries, uint32_t *moves, unsigned move_cap,
+                         cudaStream_t s) {
+  const int B = 256;
+  k_shuffle_init<<<(nraw + B - 1) / B, B, 0, s>>>(st, nraw);
+  if (n_entries > (unsigned long long)nraw)
+    k_shuffle_max<<<(unsigned)((n_entries - nraw + B - 1) / B), B, 0, s>>>(st, nraw);
+  k_shuffle_arg<<<(unsigned)((n_entries + B - 1) / B), B, 0, s>>>(st, nraw);
+  k_shuffle_move<<<(nraw + B - 1) / B, B, 0, s>>>(st, nraw, moves, move_cap);
+}
+void launch_p_update(const DevState &st, const DevIn &in, int greedy, int detect_singletons, cudaStream_t s) {
+  k_p_update<<<(in.nraw + 127) / 128, 128, 0, s>>>(st, in, greedy, detect_singletons);
+}
+void launch_bud_scan(const DevState &st, const DevIn &in, double min_fold, int min_hamming, int min_abund, uint32_t *ties,
+                     uint32_t *ties_pr, unsigned cap, cudaStream_t s) {
+  const int B = 256, G = (in.nraw + B - 1) / B;
+  k_bud_pmin<<<G, B, 0, s>>>(st, in, min_fold, min_hamming, min_abund);
+  k_bud_rmax<<<G, B, 0, s>>>(st, in, min_fold, min_hamming, min_abund);
+  k_bud_collect<<<G, B, 0, s>>>(st, in, min_fold, min_hamming, min_abund, ties, ties_pr, cap);
+}
+void launch_final_p(const DevState &st, const DevIn &in, double omegaC, cudaStream_t s) {
+  k_final_p<<<(in.nraw + 127) / 128, 128, 0, s>>>(st, in, omegaC);
+}
+void launch_calc_pA_vec(const int *reads, const double *E, const int *prior, double *out, int n, cudaStream_t s) {
+  k_calc_pA_vec<<<(n + 127) / 128, 128, 0, s>>>(reads, E, prior, out, n);
+}
+void launch_posthoc(const DevState &st, int nraw, unsigned long long n_entries, const int *center_cluster, uint32_t *trip_ij,
+                    double *trip_v, unsigned cap, unsigned long long *count, cudaStream_t s) {
+  (void)nraw;
+  if (!n_entries) return;
+  k_posthoc<<<(unsigned)((n_entries + 255) / 256), 256, 0, s>>>(st, n_entries, center_cluster, trip_ij, trip_v, cap, count);
+}
+
+}  // namespace dd2

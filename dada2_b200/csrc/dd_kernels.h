@@ -1,0 +1,59 @@
+// Kernel argument blocks + launch wrappers (product code).
+#pragma once
+#include "dd_common.h"
+
+namespace dd2 {
+
+enum AlignMode : int { MODE_LOOP = 0, MODE_FINAL = 1, MODE_BIRTH = 2 };
+
+struct ClassifyArgs {
+  DevIn in;
+  AlnParams P;
+  int mode;                 // 0: centre_idx vs all raws; 1: block b = pair b
+  uint32_t centre_idx, centre_reads;
+  int greedy;
+  const uint8_t *lock;
+  const uint32_t *pair_centre, *pair_raw;
+  uint32_t *nw_list, *gl_list;
+  unsigned long long *ctr;
+  uint8_t *kind_out;
+  int kord_words;           // words reserved for the centre's ordered 5-mers
+};
+
+struct AlignArgs {
+  DevIn in;
+  AlnParams P;
+  DevState st;
+  const uint32_t *jobs;                 // job list (NULL => job = 0..njobs-1)
+  const unsigned long long *njobs_ptr;  // device-side count (NULL => njobs_fixed)
+  int njobs_fixed;
+  int kind;                             // KIND_NW or KIND_GAPLESS for every job of this launch
+  uint32_t centre_idx, centre_reads, cluster_i, total_reads;   // LOOP
+  const uint32_t *pair_centre, *pair_raw;                      // BIRTH
+  uint32_t *b_nsubs, *b_nops;
+  uint16_t *b_pos;
+  uint8_t *b_nt0, *b_nt1, *b_q1, *b_ops;
+  double *b_lambda;
+  int b_cap, b_opcap;
+  // per-warp shared-memory layout (32-bit words) and pointer-matrix placement
+  int warp_words, seq_bytes, H_words, ops_words;
+  int ptr_in_smem;
+  uint32_t *ptr_scratch;
+  unsigned long long ptr_words;         // words per warp in ptr_scratch
+};
+
+void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);
+void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s);
+cudaError_t align_set_smem(size_t bytes);
+
+void launch_shuffle_pass(const DevState &st, int nraw, unsigned long long n_entries_hint, uint32_t *moves,
+                         unsigned move_cap, cudaStream_t s);
+void launch_p_update(const DevState &st, const DevIn &in, int greedy, int detect_singletons, cudaStream_t s);
+void launch_bud_scan(const DevState &st, const DevIn &in, double min_fold, int min_hamming, int min_abund,
+                     uint32_t *ties, uint32_t *ties_pr, unsigned cap, cudaStream_t s);
+void launch_final_p(const DevState &st, const DevIn &in, double omegaC, cudaStream_t s);
+void launch_calc_pA_vec(const int *reads, const double *E, const int *prior, double *out, int n, cudaStream_t s);
+void launch_posthoc(const DevState &st, int nraw, unsigned long long n_entries, const int *center_cluster,
+                    uint32_t *trip_ij, double *trip_v, unsigned cap, unsigned long long *count, cudaStream_t s);
+
+}  // namespace dd2
