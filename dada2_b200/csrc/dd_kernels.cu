@@ -156,7 +156,7 @@ __device__ int nw_warp(const uint8_t *s1, int len1, const uint8_t *s2, int len2,
   const int lane = lane_id();
   const BandGeom g = band_geom(len1, len2, P.band);
   const int SENT = P.sentinel;
-  for (int x = lane; x < g.W + 2; x += 32) H[x] = SENT;
+  for (int x = lane; x < g.W + 2; x += 32) H[x] = (x == g.lb + 1) ? 0 : SENT;   // cell (0,0) = 0 on diagonal 0
   __syncwarp();
   const int nsteps = len1 + len2;
   unsigned long long ncell_tot = 0;
