@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py -- unique-reads/s through the dada() core (BASELINE.json metric) on N B200s.
+
+A "step" is one dada_uniques()-equivalent pass over one batch of synthetic dereplicated
+reads (BASELINE.json configs[1]: 1e5 synthetic 250 nt uniques, Zipf abundances, 100 true
+variants, Illumina-like qualities, tperr1 error matrix, selfConsist=FALSE, default options).
+
+  value  : uniques/s with the packed uniques already resident in HBM (Resident.run)
+  e2e    : uniques/s through the one-shot C-ABI call dada2b_run() on HOST buffers
+           (pack + H2D + loop + D2H of every output inside the timed region)
+  N > 1  : one process per GPU (torchrun); each rank denoises its own sample -- the
+           reference's per-sample loop (R/dada.R:266) -- no data-path collective, "weak".
+  --impl reference : the reference's own C++ (oracle/_ref, compiled unmodified from
+           /root/reference/src in the build container) on the host cores, same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUNIQ_DEFAULT = 100000
+
+
+def workload(n_uniques, seed):
+    from tools import synth
+    from tests import cases
+    seqs, ab, q, truth = synth.illumina(n_uniques, seed=seed)
+    return seqs, ab, q, cases.tperr1()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation, all host threads, same workload."""
+    if rank != 0:
+        return
+    from oracle import ref
+    ncores = os.cpu_count() or 1
+    ref.set_threads(ncores)
+    seqs, ab, q, err = workload(args.nuniques, 12345)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ref.dada_uniques(seqs, ab, None, err, q, multithread=True)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = args.nuniques * len(times) / total
+    line = {"impl": "reference", "metric": "unique-reads/sec through dada()", "value": val, "unit": "uniques/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 + f64",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: %d synthetic 250 nt uniques, 100 variants, tperr1, defaults" % args.nuniques},
+            "cpu_baseline": {"value": val, "unit": "uniques/s", "cores": ncores, "kind": "reference",
+                             "sample": "full workload, multithread=TRUE on %d threads (parallelFor shim over std::thread)" % ncores},
+            "e2e": {"value": val, "unit": "uniques/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nuniques", type=int, default=NUNIQ_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import dada2_b200
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    seqs, ab, q, err = workload(args.nuniques, 12345 + rank)
+    nraw = len(seqs)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    # ---------------- value: inputs resident in HBM ----------------
+    res = dada2_b200.Resident(seqs, ab, None, q, device=local_rank)
+    last = None
+    for _ in range(args.warmup):
+        last = res.run(err)
+        flush.zero_()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        last = res.run(err)
+        dev_ms += last["stats"]["ms_device"]
+    barrier()
+    t_val = time.perf_counter() - t0
+    st = last["stats"]
+
+    # ---------------- e2e: one-shot C-ABI call on host buffers ----------------
+    call = dada2_b200.PackedCall(seqs, ab, None, err, q)
+    for _ in range(max(1, args.warmup // 2)):
+        call.run(unpack=False)
+    barrier()
+    t0 = time.perf_counter()
+    est = None
+    for _ in range(args.steps):
+        flush.zero_()
+        r, _ms = call.run(unpack=False)
+        est = r["stats"]
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.finish()
+
+    tt = torch.tensor([t_val, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_val, t_e2e = float(tt[0]), float(tt[1])
+    value = world * nraw * args.steps / t_val
+    e2e = world * nraw * args.steps / t_e2e
+
+    if rank == 0:
+        L = len(seqs[0])
+        bytes_per_pair = (L + 3) // 4 + 16 + L                      # S + O + Q for an aligned pair
+        pairs = st["n_nw"] + st["n_final_nw"]
+        k_ms = st["ms_k_align_nw"] + st["ms_k_align_final"]
+        n_launch = st["n_k_align_nw"] + st["n_k_align_final"]
+        peak, peak_src = measured_peak_gbs()
+        achieved = (pairs * bytes_per_pair / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "k_align (banded NW + traceback + lambda; loop NW launches + final pass)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_pair": bytes_per_pair, "pairs_per_step": int(pairs),
+                    "kernel_ms_per_step": k_ms, "launches_per_step": int(n_launch),
+                    "avg_launch_ms": k_ms / max(1, n_launch),
+                    "nw_gcups": (st["nw_cells"] / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0,
+                    "kernel_share_of_device_time": k_ms / st["ms_device"] if st["ms_device"] else None,
+                    "note": "integer DP is issue-bound, not HBM-bound (DESIGN.md): frac is low by construction"}
+        cpu = None
+        parity = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import ref
+            from tests import cases
+            ncores = os.cpu_count() or 1
+            kind = "reference" if ref.available() else "port"
+            n_s = args.nuniques if ncores >= 8 else min(args.nuniques, 25000)
+            if n_s == args.nuniques:
+                s_seqs, s_ab, s_q = seqs, ab, q
+            else:
+                s_seqs, s_ab, s_q, _ = workload(n_s, 12345)
+            if kind == "reference":
+                ref.set_threads(ncores)
+                t0 = time.perf_counter()
+                cres = ref.dada_uniques(s_seqs, s_ab, None, err, s_q, multithread=True)
+                dt = time.perf_counter() - t0
+            else:
+                from oracle import port
+                ncores = 1
+                t0 = time.perf_counter()
+                cres = port.dada_uniques(s_seqs, s_ab, None, err, s_q)
+                dt = time.perf_counter() - t0
+            cpu = {"value": n_s / dt, "unit": "uniques/s", "cores": ncores, "kind": kind,
+                   "sample": "%d-unique %s of the step workload, one pass, %.1f s" % (n_s, "= all" if n_s == nraw else "subsample", dt)}
+            if n_s == nraw:
+                try:
+                    cases.assert_same(last, cres, rtol=1e-10, label="bench")
+                    parity = "outputs identical to the CPU reference on this workload (ints exact, fp64 <= 1e-10)"
+                except AssertionError as e:
+                    parity = "MISMATCH: %s" % e
+        line = {"metric": "unique-reads/sec through dada()", "value": value, "unit": "uniques/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_val / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 DP + f64 lambda/p-value",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE configs[1]: %d synthetic 250 nt uniques, 100 variants (Zipf), Illumina-like quals, "
+                                       "tperr1, dada() selfConsist=FALSE, default options" % nraw,
+                           "per_gpu": "one sample per GPU (reference's per-sample loop); no data-path collective",
+                           "l2": "256 MB buffer written between timed iterations (inputs 32 MB < 126 MB L2)",
+                           "nclust": len(last["clustering"]["sequence"]), "rounds": st["n_rounds"], "shuffles": st["n_shuffles"]},
+                "clocks": clocks,
+                "e2e": {"value": e2e, "unit": "uniques/s", "h2d_bytes_per_step": int(est["h2d_bytes"]),
+                        "d2h_bytes_per_step": int(est["d2h_bytes"]), "ms_per_step": 1e3 * t_e2e / args.steps},
+                "gpu_launches": int(st["gpu_launches"]) * args.steps,
+                "device_ms_per_step": dev_ms / args.steps,
+                "kernel_ms": {k: st[k] for k in ("ms_k_classify", "ms_k_align_nw", "ms_k_align_gl", "ms_k_align_final")},
+                "host_ms": {k: st[k] for k in ("ms_setup", "ms_loop", "ms_final", "ms_total")},
+                "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+        print(json.dumps(line))
+    res.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

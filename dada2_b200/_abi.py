@@ -40,9 +40,18 @@ class Out(C.Structure):
                 ("subqual", C.c_void_p), ("subqual_ncol", C.c_int32), ("clusterquals", C.c_void_p),
                 ("map", C.c_void_p), ("pval", C.c_void_p),
                 ("n_align", C.c_int64), ("n_shroud", C.c_int64), ("n_nw", C.c_int64), ("n_gapless", C.c_int64),
-                ("nw_cells", C.c_int64), ("n_rounds", C.c_int32), ("n_shuffles", C.c_int32),
-                ("ms_setup", C.c_double), ("ms_loop", C.c_double), ("ms_final", C.c_double),
-                ("ms_total", C.c_double), ("ms_kernel_compare", C.c_double)]
+                ("nw_cells", C.c_int64), ("n_final_nw", C.c_int64), ("n_rounds", C.c_int32), ("n_shuffles", C.c_int32),
+                ("gpu_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("ms_setup", C.c_double), ("ms_loop", C.c_double), ("ms_final", C.c_double), ("ms_total", C.c_double),
+                ("ms_device", C.c_double), ("ms_k_classify", C.c_double), ("ms_k_align_nw", C.c_double),
+                ("ms_k_align_gl", C.c_double), ("ms_k_align_final", C.c_double),
+                ("n_k_classify", C.c_int32), ("n_k_align_nw", C.c_int32), ("n_k_align_gl", C.c_int32),
+                ("n_k_align_final", C.c_int32)]
+
+STAT_FIELDS = ["n_align", "n_shroud", "n_nw", "n_gapless", "nw_cells", "n_final_nw", "n_rounds", "n_shuffles",
+               "gpu_launches", "h2d_bytes", "d2h_bytes", "ms_setup", "ms_loop", "ms_final", "ms_total", "ms_device",
+               "ms_k_classify", "ms_k_align_nw", "ms_k_align_gl", "ms_k_align_final", "n_k_classify", "n_k_align_nw",
+               "n_k_align_gl", "n_k_align_final"]
 
 
 # R/dada.R:1-26 defaults, in dada_uniques argument order (R/dada.R:340-352)
@@ -138,7 +147,5 @@ def unpack_out(o):
            "subqual": _arr(o.subqual, 16 * tc, np.int32).reshape((tc, 16)).T.copy(),
            "clusterquals": _arr(o.clusterquals, o.maxlen * nc, np.float64).reshape((nc, o.maxlen)).T.copy(),
            "map": _arr(o.map, nr, np.int32), "pval": _arr(o.pval, nr, np.float64),
-           "stats": {k: getattr(o, k) for k in ("n_align", "n_shroud", "n_nw", "n_gapless", "nw_cells", "n_rounds",
-                                                "n_shuffles", "ms_setup", "ms_loop", "ms_final", "ms_total",
-                                                "ms_kernel_compare")}}
+           "stats": {k: getattr(o, k) for k in STAT_FIELDS}}
     return res

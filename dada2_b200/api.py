@@ -166,6 +166,33 @@ def dada_uniques(seqs, abundances, priors, err, quals,
         L.dada2b_free(out)
 
 
+class PackedCall:
+    """Pre-marshalled one-shot call: `run()` is exactly one dada2b_run() C-ABI call on host buffers
+    (what the Rcpp shim of INTEGRATION.md does), so benchmarks can time the ABI without Python's
+    string joining."""
+
+    def __init__(self, seqs, abundances, priors, err, quals, **opts):
+        self.err = _check_err(err)
+        self.pin = _abi.PackedIn(seqs, abundances, priors, self.err, quals)
+        self.opts = _abi.make_opts(**_normalise_opts(dict(opts)))
+
+    def run(self, unpack=True):
+        import time
+        L = lib()
+        out = C.POINTER(_abi.Out)()
+        eb = C.create_string_buffer(_abi.ERRLEN)
+        t0 = time.perf_counter()
+        rc = L.dada2b_run(C.byref(self.pin.struct), C.byref(self.opts), C.byref(out), eb)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        if rc:
+            raise Dada2bError(eb.value.decode())
+        try:
+            res = _abi.unpack_out(out.contents) if unpack else {"stats": {k: getattr(out.contents, k) for k in _abi.STAT_FIELDS}}
+        finally:
+            L.dada2b_free(out)
+        return res, wall_ms
+
+
 def test_calc_pA(reads, E, prior):
     L = lib()
     reads = np.ascontiguousarray(reads, dtype=np.int32)

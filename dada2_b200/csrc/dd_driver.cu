@@ -79,6 +79,13 @@ struct dada2b_ctx {
   DBuf<uint8_t> d_qual, d_prior;
   DBuf<uint16_t> d_len;
   int num_sms = 148;
+  long long upload_h2d = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  cudaEvent_t get_event() {
+    if (ev_next == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+    return ev_pool[ev_next++];
+  }
 };
 
 // ------------------------------------------------------------------------------------
@@ -177,6 +184,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
   CK(cudaMemcpyAsync(cx->d_reads.p, cx->reads.data(), nraw * 4, cudaMemcpyHostToDevice, cx->stream));
   CK(cudaMemcpyAsync(cx->d_prior.p, cx->prior.data(), nraw, cudaMemcpyHostToDevice, cx->stream));
   CK(cudaStreamSynchronize(cx->stream));
+  cx->upload_h2d = (long long)nraw * d.SW * 4 + (long long)nraw * d.QS + (long long)nraw * 7;
   d.seq2 = cx->d_seq2.p; d.qual = cx->d_qual.p; d.len = cx->d_len.p; d.reads = cx->d_reads.p; d.prior = cx->d_prior.p;
   return cx.release();
 }
@@ -225,13 +233,25 @@ struct Run {
   int kord_words = 0;
   // stats
   int n_rounds = 0, n_shuffles = 0;
+  long long h2d_bytes = 0, d2h_bytes = 0, launches0 = 0;
+  struct Ev { cudaEvent_t a, b; int tag; };
+  std::vector<Ev> evs;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  enum { T_CLASSIFY = 0, T_NW, T_GL, T_FINAL, T_N };
+  template <typename F> void timed(int tag, F f) {
+    Ev e{cx->get_event(), cx->get_event(), tag};
+    cudaEventRecord(e.a, s); f(); cudaEventRecord(e.b, s);
+    evs.push_back(e);
+  }
+  void h2d(void *d, const void *h, size_t n) { h2d_bytes += (long long)n; h2d(d, h, n); }
+  void d2h(void *h, const void *d, size_t n) { d2h_bytes += (long long)n; d2h(h, d, n); }
 
   void setup_params();
   void alloc_state();
   void ensure_cluster_cap(size_t n);
   void ensure_cs_cap(unsigned long long need);
   void upload_cluster_arrays(bool flags);
-  void read_ctr() { CK(cudaMemcpyAsync(h_ctr.p, ctr.p, CTR_N * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
+  void read_ctr() { d2h(h_ctr.p, ctr.p, CTR_N * 8); CK(cudaStreamSynchronize(s)); }
   void check_dev_error();
   void compare(uint32_t i, double kdist_cutoff);
   bool shuffle_pass();
@@ -324,7 +344,7 @@ void Run::alloc_state() {
   lock.zero(s); is_center.zero(s); slot0.zero(s); correct.zero(s); p.zero(s); comp_lambda.zero(s); comp_ham.zero(s);
   cluster_of.zero(s); ctr.zero(s);
   std::vector<double> em(n, -999.0);                               // containers.cpp:39
-  CK(cudaMemcpyAsync(E_minmax.p, em.data(), n * 8, cudaMemcpyHostToDevice, s));
+  h2d(E_minmax.p, em.data(), n * 8);
   CK(cudaStreamSynchronize(s));
   st.lock = lock.p; st.is_center = is_center.p; st.slot0 = slot0.p; st.correct = correct.p;
   st.E_minmax = E_minmax.p; st.p = p.p; st.comp_lambda = comp_lambda.p; st.comp_ham = comp_ham.p; st.cluster_of = cluster_of.p;
@@ -370,17 +390,17 @@ void Run::compare(uint32_t i, double kdist_cutoff) {
   ca.greedy = o->greedy != 0; ca.lock = st.lock; ca.nw_list = st.nw_list; ca.gl_list = st.gl_list; ca.ctr = st.ctr;
   ca.kind_out = nullptr; ca.kord_words = kord_words;
   int cgrid = std::min((nraw + 7) / 8, cx->num_sms * 4);
-  launch_classify(ca, cgrid, 256, classify_smem, s);
+  timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   for (int kind : {KIND_NW, KIND_GAPLESS}) {
     AlignArgs a = align_args(MODE_LOOP, kind);
     a.jobs = kind == KIND_NW ? st.nw_list : st.gl_list;
     a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
     a.centre_idx = c; a.centre_reads = cx->reads[c]; a.cluster_i = i; a.total_reads = cx->total_reads;
-    launch_align_jobs(MODE_LOOP, a, (unsigned long long)nraw);
+    timed(kind == KIND_NW ? T_NW : T_GL, [&]() { launch_align_jobs(MODE_LOOP, a, (unsigned long long)nraw); });
   }
   if (i == 0) {
     unsigned long long n = nraw;
-    CK(cudaMemcpyAsync(ctr.p + CTR_CS_COUNT, &n, 8, cudaMemcpyHostToDevice, s));
+    h2d(ctr.p + CTR_CS_COUNT, &n, 8);
     CK(cudaStreamSynchronize(s));
   }
   read_ctr();
@@ -392,11 +412,11 @@ void Run::compare(uint32_t i, double kdist_cutoff) {
 void Run::upload_cluster_arrays(bool flags) {
   const size_t nc = members.size();
   ensure_cluster_cap(nc);
-  CK(cudaMemcpyAsync(cl_reads.p, cl_reads_h.data(), nc * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(cl_center.p, cl_center_h.data(), nc * 4, cudaMemcpyHostToDevice, s));
+  h2d(cl_reads.p, cl_reads_h.data(), nc * 4);
+  h2d(cl_center.p, cl_center_h.data(), nc * 4);
   if (flags) {
-    CK(cudaMemcpyAsync(cl_update_e.p, upd_e.data(), nc, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(cl_check_locks.p, chk_locks.data(), nc, cudaMemcpyHostToDevice, s));
+    h2d(cl_update_e.p, upd_e.data(), nc);
+    h2d(cl_check_locks.p, chk_locks.data(), nc);
   }
 }
 
@@ -409,7 +429,7 @@ bool Run::shuffle_pass() {
   const unsigned long long nm = h_ctr.p[CTR_NMOVE];
   n_shuffles++;
   if (nm == 0) return false;
-  CK(cudaMemcpyAsync(h_moves.p, moves.p, nm * 8, cudaMemcpyDeviceToHost, s));
+  d2h(h_moves.p, moves.p, nm * 8);
   CK(cudaStreamSynchronize(s));
   struct Mv { uint32_t from, slot, r, to; };
   std::vector<Mv> mv(nm);
@@ -435,7 +455,7 @@ bool Run::shuffle_pass() {
     upd_e[m.from] = 1; upd_e[m.to] = 1;
   }
   if (slot0_changed)
-    for (auto &u : slot0_updates) CK(cudaMemcpyAsync(slot0.p + u.first, &u.second, 1, cudaMemcpyHostToDevice, s));
+    for (auto &u : slot0_updates) h2d(slot0.p + u.first, &u.second, 1);
   upload_cluster_arrays(false);
   if (slot0_changed) CK(cudaStreamSynchronize(s));
   return true;
@@ -451,7 +471,7 @@ void Run::p_update() {
 // b_bud (cluster.cpp:274-350).  Returns new cluster index or 0.
 int Run::bud() {
   unsigned long long init[6] = {~0ull, 0ull, 0ull, ~0ull, 0ull, 0ull};
-  CK(cudaMemcpyAsync(ctr.p + CTR_PMIN, init, 6 * 8, cudaMemcpyHostToDevice, s));
+  h2d(ctr.p + CTR_PMIN, init, 6 * 8);
   launch_bud_scan(st, in, o->min_fold, o->min_hamming, o->min_abund, ties.p, ties_pr.p, tie_cap, s);
   read_ctr();
   unsigned long long nt = h_ctr.p[CTR_NTIE], ntp = h_ctr.p[CTR_NTIE_PR];
@@ -460,8 +480,8 @@ int Run::bud() {
     ties.alloc(tie_cap * 3); ties_pr.alloc(tie_cap * 3); h_ties.alloc(tie_cap * 3); h_ties_pr.alloc(tie_cap * 3);
     return bud();
   }
-  if (nt) CK(cudaMemcpyAsync(h_ties.p, ties.p, nt * 4, cudaMemcpyDeviceToHost, s));
-  if (ntp) CK(cudaMemcpyAsync(h_ties_pr.p, ties_pr.p, ntp * 4, cudaMemcpyDeviceToHost, s));
+  if (nt) d2h(h_ties.p, ties.p, nt * 4);
+  if (ntp) d2h(h_ties_pr.p, ties_pr.p, ntp * 4);
   CK(cudaStreamSynchronize(s));
   auto pick = [&](const uint32_t *t, unsigned long long n) -> long {     // first in (cluster, slot) scan order
     long best = -1;
@@ -494,8 +514,8 @@ int Run::bud() {
   const uint32_t r = (uint32_t)w, from = cluster_of_h[r];
   // fetch the winner's comparison (raw->comp)
   double lam; uint32_t ham;
-  CK(cudaMemcpyAsync(&lam, comp_lambda.p + r, 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&ham, comp_ham.p + r, 4, cudaMemcpyDeviceToHost, s));
+  d2h(&lam, comp_lambda.p + r, 8);
+  d2h(&ham, comp_ham.p + r, 4);
   CK(cudaStreamSynchronize(s));
   const double expected = lam * (double)cl_reads_h[from];
   // bi_pop_raw(from, slot)
@@ -515,10 +535,10 @@ int Run::bud() {
   b.comp_i = from; b.comp_index = r; b.comp_lambda = lam; b.comp_ham = ham;
   birth.push_back(b);
   const uint8_t one = 1, zero = 0;
-  CK(cudaMemcpyAsync(cluster_of.p + r, &ni, 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(is_center.p + r, &one, 1, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(slot0.p + r, &one, 1, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(lock.p + r, &zero, 1, cudaMemcpyHostToDevice, s));       // bi_assign_center unlocks, cluster.cpp:377
+  h2d(cluster_of.p + r, &ni, 4);
+  h2d(is_center.p + r, &one, 1);
+  h2d(slot0.p + r, &one, 1);
+  h2d(lock.p + r, &zero, 1);       // bi_assign_center unlocks, cluster.cpp:377
   upload_cluster_arrays(false);
   CK(cudaStreamSynchronize(s));
   return (int)ni;
@@ -542,7 +562,7 @@ void Run::finish(dada2b_out *out) {
   {  // FinalSubsParallel: sub_new(centre, raw, use_kmers=false) for every raw
     AlignArgs a = align_args(MODE_FINAL, P.band == 0 ? KIND_GAPLESS : KIND_NW);
     a.jobs = nullptr; a.njobs_ptr = nullptr; a.njobs_fixed = nraw;
-    launch_align_jobs(MODE_FINAL, a, (unsigned long long)nraw);
+    timed(T_FINAL, [&]() { launch_align_jobs(MODE_FINAL, a, (unsigned long long)nraw); });
   }
   // birth subs: sub_new(centre of birth_comp.i, centre i, use_kmers, cutoff 1.0)   Rmain.cpp:206-209
   const uint32_t npair = nclust - 1;
@@ -553,8 +573,8 @@ void Run::finish(dada2b_out *out) {
     std::vector<uint32_t> pc(npair), pr(npair);
     for (uint32_t i = 1; i < nclust; i++) { pc[i - 1] = cl_center_h[birth[i].comp_i]; pr[i - 1] = cl_center_h[i]; }
     pair_centre.alloc(npair); pair_raw.alloc(npair);
-    CK(cudaMemcpyAsync(pair_centre.p, pc.data(), npair * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(pair_raw.p, pr.data(), npair * 4, cudaMemcpyHostToDevice, s));
+    h2d(pair_centre.p, pc.data(), npair * 4);
+    h2d(pair_raw.p, pr.data(), npair * 4);
     b_nsubs.alloc(npair); b_lambda.alloc(npair); b_pos.alloc((size_t)npair * bcap); b_nt0.alloc((size_t)npair * bcap);
     b_nt1.alloc((size_t)npair * bcap); b_q1.alloc((size_t)npair * bcap);
     DBuf<uint32_t> nwl, gll; nwl.alloc(npair); gll.alloc(npair);
@@ -575,14 +595,14 @@ void Run::finish(dada2b_out *out) {
       a.b_cap = bcap; a.b_ops = nullptr; a.b_nops = nullptr; a.b_opcap = 0;
       launch_align_jobs(MODE_BIRTH, a, npair);
     }
-    CK(cudaMemcpyAsync(ctr.p + CTR_ALIGN, &keepA, 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctr.p + CTR_SHROUD, &keepS, 8, cudaMemcpyHostToDevice, s));
+    h2d(ctr.p + CTR_ALIGN, &keepA, 8);
+    h2d(ctr.p + CTR_SHROUD, &keepS, 8);
     bpos.resize((size_t)npair * bcap); bnt0.resize((size_t)npair * bcap); bnt1.resize((size_t)npair * bcap); bq1.resize((size_t)npair * bcap);
-    CK(cudaMemcpyAsync(bns.data(), b_nsubs.p, npair * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(bpos.data(), b_pos.p, bpos.size() * 2, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(bnt0.data(), b_nt0.p, bnt0.size(), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(bnt1.data(), b_nt1.p, bnt1.size(), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(bq1.data(), b_q1.p, bq1.size(), cudaMemcpyDeviceToHost, s));
+    d2h(bns.data(), b_nsubs.p, npair * 4);
+    d2h(bpos.data(), b_pos.p, bpos.size() * 2);
+    d2h(bnt0.data(), b_nt0.p, bnt0.size());
+    d2h(bnt1.data(), b_nt1.p, bnt1.size());
+    d2h(bq1.data(), b_q1.p, bq1.size());
     CK(cudaStreamSynchronize(s));
   }
   // post-hoc cluster p-values (error.cpp:99-119)
@@ -591,22 +611,22 @@ void Run::finish(dada2b_out *out) {
     std::vector<int> cc(nraw, -1);
     for (uint32_t i = 0; i < nclust; i++) cc[cl_center_h[i]] = (int)i;
     center_cluster.alloc(nraw);
-    CK(cudaMemcpyAsync(center_cluster.p, cc.data(), (size_t)nraw * 4, cudaMemcpyHostToDevice, s));
+    h2d(center_cluster.p, cc.data(), (size_t)nraw * 4);
     unsigned cap = std::max<unsigned>(4096, nclust * 8);
     std::vector<uint32_t> tij; std::vector<double> tv; unsigned long long cnt = 0;
     DBuf<unsigned long long> dcount; dcount.alloc(1);
     for (;;) {
       trip_ij.alloc((size_t)cap * 2); trip_v.alloc(cap); dcount.zero(s);
       launch_posthoc(st, nraw, cs_count, center_cluster.p, trip_ij.p, trip_v.p, cap, dcount.p, s);
-      CK(cudaMemcpyAsync(&cnt, dcount.p, 8, cudaMemcpyDeviceToHost, s));
+      d2h(&cnt, dcount.p, 8);
       CK(cudaStreamSynchronize(s));
       if (cnt <= cap) break;
       cap = (unsigned)cnt + 16;
     }
     tij.resize(cnt * 2); tv.resize(cnt);
     if (cnt) {
-      CK(cudaMemcpyAsync(tij.data(), trip_ij.p, cnt * 8, cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(tv.data(), trip_v.p, cnt * 8, cudaMemcpyDeviceToHost, s));
+      d2h(tij.data(), trip_ij.p, cnt * 8);
+      d2h(tv.data(), trip_v.p, cnt * 8);
       CK(cudaStreamSynchronize(s));
     }
     std::vector<size_t> ord(cnt);
@@ -616,21 +636,21 @@ void Run::finish(dada2b_out *out) {
     std::vector<int> rr(nclust), pp(nclust, 1);
     for (uint32_t i = 0; i < nclust; i++) rr[i] = (int)cx->reads[cl_center_h[i]];
     pa_reads.alloc(nclust); pa_prior.alloc(nclust); pa_E.alloc(nclust); pa_out.alloc(nclust);
-    CK(cudaMemcpyAsync(pa_reads.p, rr.data(), nclust * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(pa_prior.p, pp.data(), nclust * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(pa_E.p, tot_e.data(), nclust * 8, cudaMemcpyHostToDevice, s));
+    h2d(pa_reads.p, rr.data(), nclust * 4);
+    h2d(pa_prior.p, pp.data(), nclust * 4);
+    h2d(pa_E.p, tot_e.data(), nclust * 8);
     launch_calc_pA_vec(pa_reads.p, pa_E.p, pa_prior.p, pa_out.p, (int)nclust, s);
-    CK(cudaMemcpyAsync(cpval.data(), pa_out.p, nclust * 8, cudaMemcpyDeviceToHost, s));
+    d2h(cpval.data(), pa_out.p, nclust * 8);
   }
   // per-raw results
   std::vector<double> hp(nraw); std::vector<uint8_t> hcorrect(nraw); std::vector<uint32_t> hns(nraw);
   std::vector<int> htrans((size_t)16 * ncol); std::vector<unsigned long long> hsum((size_t)nclust * maxlen), hcnt((size_t)nclust * maxlen);
-  CK(cudaMemcpyAsync(hp.data(), p.p, (size_t)nraw * 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(hcorrect.data(), correct.p, nraw, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(hns.data(), nsubs_final.p, (size_t)nraw * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(htrans.data(), trans.p, htrans.size() * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(hsum.data(), cq_sum.p, hsum.size() * 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(hcnt.data(), cq_cnt.p, hcnt.size() * 8, cudaMemcpyDeviceToHost, s));
+  d2h(hp.data(), p.p, (size_t)nraw * 8);
+  d2h(hcorrect.data(), correct.p, nraw);
+  d2h(hns.data(), nsubs_final.p, (size_t)nraw * 4);
+  d2h(htrans.data(), trans.p, htrans.size() * 4);
+  d2h(hsum.data(), cq_sum.p, hsum.size() * 8);
+  d2h(hcnt.data(), cq_cnt.p, hcnt.size() * 8);
   read_ctr();
   check_dev_error();
 
@@ -694,6 +714,19 @@ void Run::finish(dada2b_out *out) {
   std::vector<int32_t> map(nraw);
   for (int r = 0; r < nraw; r++) map[r] = hcorrect[r] ? (int32_t)cluster_of_h[r] + 1 : INT_MIN;
   out->map = dupv(map); out->pval = dupv(hp);
+  // ---- timing / traffic diagnostics
+  CK(cudaEventRecord(ev_end, s));
+  CK(cudaEventSynchronize(ev_end));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+  out->ms_device = ms;
+  double sum[T_N] = {0, 0, 0, 0}; int cnt[T_N] = {0, 0, 0, 0};
+  for (const Ev &e : evs) { float t = 0; if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) { sum[e.tag] += t; cnt[e.tag]++; } }
+  out->ms_k_classify = sum[T_CLASSIFY]; out->ms_k_align_nw = sum[T_NW]; out->ms_k_align_gl = sum[T_GL]; out->ms_k_align_final = sum[T_FINAL];
+  out->n_k_classify = cnt[T_CLASSIFY]; out->n_k_align_nw = cnt[T_NW]; out->n_k_align_gl = cnt[T_GL]; out->n_k_align_final = cnt[T_FINAL];
+  out->n_final_nw = (P.band == 0) ? 0 : nraw;
+  out->gpu_launches = launches_count() - launches0;
+  out->h2d_bytes = h2d_bytes; out->d2h_bytes = d2h_bytes;
 }
 
 dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opts *o) {
@@ -704,12 +737,16 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
   if (o->use_quals && cx->maxq > Q - 1) throw Err{"Rounded quality exceeded range of err lookup table."};
   Run R;
   R.cx = cx; R.o = o; R.s = cx->stream; R.in = cx->in; R.nraw = cx->in.nraw; R.ncol = Q;
+  cx->ev_next = 0;
+  R.launches0 = launches_count();
+  R.ev_begin = cx->get_event(); R.ev_end = cx->get_event();
   R.setup_params();
   R.alloc_state();
+  CK(cudaEventRecord(R.ev_begin, R.s));
   {  // cluster.cpp:162-170: row-major copy of the error matrix
     std::vector<double> e((size_t)16 * Q);
     for (int r = 0; r < 16; r++) for (int c = 0; c < Q; c++) e[(size_t)r * Q + c] = err_cm[r + 16 * (size_t)c];
-    CK(cudaMemcpyAsync(R.err.p, e.data(), e.size() * 8, cudaMemcpyHostToDevice, R.s));
+    R.h2d(R.err.p, e.data(), e.size() * 8);
     CK(cudaStreamSynchronize(R.s));
   }
   const int nraw = R.nraw;
@@ -725,8 +762,8 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
   R.upd_e.push_back(1); R.chk_locks.push_back(1);
   R.birth.emplace_back(); R.birth[0].e = cx->total_reads;
   const uint8_t one = 1;
-  CK(cudaMemcpyAsync(R.is_center.p + c0, &one, 1, cudaMemcpyHostToDevice, R.s));
-  CK(cudaMemcpyAsync(R.slot0.p + 0, &one, 1, cudaMemcpyHostToDevice, R.s));
+  R.h2d(R.is_center.p + c0, &one, 1);
+  R.h2d(R.slot0.p + 0, &one, 1);
   R.upload_cluster_arrays(true);
   CK(cudaStreamSynchronize(R.s));
   const double t1 = now_ms();
@@ -765,11 +802,11 @@ static void do_test_pairs(dada2b_ctx *cx, int npairs, const uint32_t *centre, co
   R.alloc_state();
   std::vector<double> e((size_t)16 * Q);
   for (int r = 0; r < 16; r++) for (int c = 0; c < Q; c++) e[(size_t)r * Q + c] = err_cm[r + 16 * (size_t)c];
-  CK(cudaMemcpyAsync(R.err.p, e.data(), e.size() * 8, cudaMemcpyHostToDevice, R.s));
+  R.h2d(R.err.p, e.data(), e.size() * 8);
   cudaStream_t s = R.s;
   R.pair_centre.alloc(npairs); R.pair_raw.alloc(npairs);
-  CK(cudaMemcpyAsync(R.pair_centre.p, centre, (size_t)npairs * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(R.pair_raw.p, raw, (size_t)npairs * 4, cudaMemcpyHostToDevice, s));
+  R.h2d(R.pair_centre.p, centre, (size_t)npairs * 4);
+  R.h2d(R.pair_raw.p, raw, (size_t)npairs * 4);
   R.b_nsubs.alloc(npairs); R.b_nops.alloc(npairs); R.b_lambda.alloc(npairs); R.kind_out.alloc(npairs);
   R.b_pos.alloc((size_t)npairs * subcap); R.b_nt0.alloc((size_t)npairs * subcap); R.b_nt1.alloc((size_t)npairs * subcap);
   R.b_q1.alloc((size_t)npairs * subcap); R.b_ops.alloc((size_t)npairs * opcap);
@@ -790,15 +827,15 @@ static void do_test_pairs(dada2b_ctx *cx, int npairs, const uint32_t *centre, co
     R.launch_align_jobs(MODE_BIRTH, a, npairs);
   }
   std::vector<uint8_t> hk(npairs); std::vector<uint32_t> hns(npairs), hno(npairs);
-  CK(cudaMemcpyAsync(hk.data(), R.kind_out.p, npairs, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(hns.data(), R.b_nsubs.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(hno.data(), R.b_nops.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(lambda, R.b_lambda.p, (size_t)npairs * 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(ops, R.b_ops.p, (size_t)npairs * opcap, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(pos, R.b_pos.p, (size_t)npairs * subcap * 2, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(nt0, R.b_nt0.p, (size_t)npairs * subcap, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(nt1, R.b_nt1.p, (size_t)npairs * subcap, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(q1, R.b_q1.p, (size_t)npairs * subcap, cudaMemcpyDeviceToHost, s));
+  R.d2h(hk.data(), R.kind_out.p, npairs);
+  R.d2h(hns.data(), R.b_nsubs.p, (size_t)npairs * 4);
+  R.d2h(hno.data(), R.b_nops.p, (size_t)npairs * 4);
+  R.d2h(lambda, R.b_lambda.p, (size_t)npairs * 8);
+  R.d2h(ops, R.b_ops.p, (size_t)npairs * opcap);
+  R.d2h(pos, R.b_pos.p, (size_t)npairs * subcap * 2);
+  R.d2h(nt0, R.b_nt0.p, (size_t)npairs * subcap);
+  R.d2h(nt1, R.b_nt1.p, (size_t)npairs * subcap);
+  R.d2h(q1, R.b_q1.p, (size_t)npairs * subcap);
   R.read_ctr();
   R.check_dev_error();
   for (int k = 0; k < npairs; k++) {
@@ -867,6 +904,7 @@ void dada2b_ctx_free(dada2b_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -876,6 +914,7 @@ int dada2b_run(const dada2b_in *in, const dada2b_opts *opts, dada2b_out **out, c
   int rc = dada2b_upload(in, 0, &cx, errbuf);
   if (rc) return rc;
   rc = dada2b_run_resident(cx, in->err, in->Q, opts, out, errbuf);
+  if (!rc && *out) (*out)->h2d_bytes += cx->upload_h2d;
   dada2b_ctx_free(cx);
   return rc;
 }

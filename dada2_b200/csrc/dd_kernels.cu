@@ -536,7 +536,11 @@ __global__ void k_posthoc(DevState st, unsigned long long n, const int *center_c
 }
 
 // ------------------------------- launch wrappers --------------------------------------
+static long long g_launches = 0;
+long long launches_count() { return g_launches; }
+#define COUNT_LAUNCH(n) (g_launches += (n))
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+  COUNT_LAUNCH(1);
   k_classify<<<grid, block, smem, s>>>(a);
 }
 cudaError_t align_set_smem(size_t bytes) {
@@ -547,6 +551,7 @@ cudaError_t align_set_smem(size_t bytes) {
   return cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+  COUNT_LAUNCH(1);
   if (mode == MODE_LOOP) k_align<MODE_LOOP><<<grid, block, smem, s>>>(a);
   else if (mode == MODE_FINAL) k_align<MODE_FINAL><<<grid, block, smem, s>>>(a);
   else k_align<MODE_BIRTH><<<grid, block, smem, s>>>(a);
@@ -554,6 +559,7 @@ void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem
 void launch_shuffle_pass(const DevState &st, int nraw, unsigned long long n_entries, uint32_t *moves, unsigned move_cap,
                          cudaStream_t s) {
   const int B = 256;
+  COUNT_LAUNCH(3 + (n_entries > (unsigned long long)nraw ? 1 : 0));
   k_shuffle_init<<<(nraw + B - 1) / B, B, 0, s>>>(st, nraw);
   if (n_entries > (unsigned long long)nraw)
     k_shuffle_max<<<(unsigned)((n_entries - nraw + B - 1) / B), B, 0, s>>>(st, nraw);
@@ -561,25 +567,30 @@ void launch_shuffle_pass(const DevState &st, int nraw, unsigned long long n_entr
   k_shuffle_move<<<(nraw + B - 1) / B, B, 0, s>>>(st, nraw, moves, move_cap);
 }
 void launch_p_update(const DevState &st, const DevIn &in, int greedy, int detect_singletons, cudaStream_t s) {
+  COUNT_LAUNCH(1);
   k_p_update<<<(in.nraw + 127) / 128, 128, 0, s>>>(st, in, greedy, detect_singletons);
 }
 void launch_bud_scan(const DevState &st, const DevIn &in, double min_fold, int min_hamming, int min_abund, uint32_t *ties,
                      uint32_t *ties_pr, unsigned cap, cudaStream_t s) {
   const int B = 256, G = (in.nraw + B - 1) / B;
+  COUNT_LAUNCH(3);
   k_bud_pmin<<<G, B, 0, s>>>(st, in, min_fold, min_hamming, min_abund);
   k_bud_rmax<<<G, B, 0, s>>>(st, in, min_fold, min_hamming, min_abund);
   k_bud_collect<<<G, B, 0, s>>>(st, in, min_fold, min_hamming, min_abund, ties, ties_pr, cap);
 }
 void launch_final_p(const DevState &st, const DevIn &in, double omegaC, cudaStream_t s) {
+  COUNT_LAUNCH(1);
   k_final_p<<<(in.nraw + 127) / 128, 128, 0, s>>>(st, in, omegaC);
 }
 void launch_calc_pA_vec(const int *reads, const double *E, const int *prior, double *out, int n, cudaStream_t s) {
+  COUNT_LAUNCH(1);
   k_calc_pA_vec<<<(n + 127) / 128, 128, 0, s>>>(reads, E, prior, out, n);
 }
 void launch_posthoc(const DevState &st, int nraw, unsigned long long n_entries, const int *center_cluster, uint32_t *trip_ij,
                     double *trip_v, unsigned cap, unsigned long long *count, cudaStream_t s) {
   (void)nraw;
   if (!n_entries) return;
+  COUNT_LAUNCH(1);
   k_posthoc<<<(unsigned)((n_entries + 255) / 256), 256, 0, s>>>(st, n_entries, center_cluster, trip_ij, trip_v, cap, count);
 }
 

@@ -42,6 +42,7 @@ struct AlignArgs {
   unsigned long long ptr_words;         // words per warp in ptr_scratch
 };
 
+long long launches_count();
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 cudaError_t align_set_smem(size_t bytes);

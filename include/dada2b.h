@@ -88,10 +88,18 @@ typedef struct {
   /* $map (1-based cluster or NA), $pval */
   int32_t *map;
   double *pval;
-  /* diagnostics (not part of the R list): verbose counters of Rmain.cpp:333 and timings */
-  int64_t n_align, n_shroud, n_nw, n_gapless, nw_cells;
+  /* diagnostics (not part of the R list): counters of Rmain.cpp:333 and timings */
+  int64_t n_align, n_shroud;        /* loop: pairs screened / rejected by the k-mer screen      */
+  int64_t n_nw, n_gapless;          /* loop: pairs aligned by NW / by the gapless shortcut      */
+  int64_t nw_cells;                 /* DP cells filled (loop + final pass)                      */
+  int64_t n_final_nw;               /* final pass: alignments (one per unique)                  */
   int32_t n_rounds, n_shuffles;
-  double ms_setup, ms_loop, ms_final, ms_total, ms_kernel_compare;
+  int64_t gpu_launches;             /* kernels launched by this call                            */
+  int64_t h2d_bytes, d2h_bytes;     /* bytes copied host->device / device->host by this call    */
+  double ms_setup, ms_loop, ms_final, ms_total;   /* host wall clock                            */
+  double ms_device;                 /* CUDA-event time, first to last device operation          */
+  double ms_k_classify, ms_k_align_nw, ms_k_align_gl, ms_k_align_final;  /* CUDA-event sums per kernel family */
+  int32_t n_k_classify, n_k_align_nw, n_k_align_gl, n_k_align_final;     /* launches in each sum              */
 } dada2b_out;
 
 /* One-shot: host buffers in, host buffers out (what the Rcpp shim calls). */
