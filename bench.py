@@ -128,7 +128,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nuniques", type=int, default=NUNIQ_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=1500, help="dump stacks and exit after this many seconds")
     args = ap.parse_args()
+    import faulthandler
+    faulthandler.dump_traceback_later(args.watchdog, exit=True)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

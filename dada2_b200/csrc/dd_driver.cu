@@ -30,6 +30,7 @@ namespace {
 struct Err { std::string msg; };
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw Err{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x}; } while (0)
 
+#define DBG(...) do { if (getenv("DADA2B_SYNCDEBUG")) { fprintf(stderr, "[dada2b] " __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 double na_real() { union { double d; uint64_t u; } v; v.u = 0x7FF00000000007A2ULL; return v.d; }
 
@@ -93,6 +94,7 @@ struct dada2b_ctx {
 // ------------------------------------------------------------------------------------
 static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
   const unsigned nraw = in->nraw;
+  DBG("upload: nraw=%u", nraw);
   if (in->nraw <= 0) throw Err{"Zero input sequences."};
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -103,6 +105,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   cx->num_sms = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
+  DBG("upload: device ready, %d SMs", cx->num_sms);
   unsigned maxlen = 0, minlen = 9999;
   cx->len.resize(nraw);
   for (unsigned i = 0; i < nraw; i++) {
@@ -174,6 +177,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
     for (auto &x : th) x.join();
     (void)slot;
   }
+  DBG("upload: packed on host");
   for (int v : tmaxq) cx->maxq = std::max(cx->maxq, v);
   for (int v : tbad) cx->bad_nt |= (v != 0);
   cx->d_seq2.alloc((size_t)nraw * d.SW); cx->d_qual.alloc((size_t)nraw * d.QS);
@@ -184,6 +188,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
   CK(cudaMemcpyAsync(cx->d_reads.p, cx->reads.data(), nraw * 4, cudaMemcpyHostToDevice, cx->stream));
   CK(cudaMemcpyAsync(cx->d_prior.p, cx->prior.data(), nraw, cudaMemcpyHostToDevice, cx->stream));
   CK(cudaStreamSynchronize(cx->stream));
+  DBG("upload: H2D done");
   cx->upload_h2d = (long long)nraw * d.SW * 4 + (long long)nraw * d.QS + (long long)nraw * 7;
   d.seq2 = cx->d_seq2.p; d.qual = cx->d_qual.p; d.len = cx->d_len.p; d.reads = cx->d_reads.p; d.prior = cx->d_prior.p;
   return cx.release();
@@ -243,8 +248,8 @@ struct Run {
     cudaEventRecord(e.a, s); f(); cudaEventRecord(e.b, s);
     evs.push_back(e);
   }
-  void h2d(void *d, const void *h, size_t n) { h2d_bytes += (long long)n; h2d(d, h, n); }
-  void d2h(void *h, const void *d, size_t n) { d2h_bytes += (long long)n; d2h(h, d, n); }
+  void h2d(void *d, const void *h, size_t n) { h2d_bytes += (long long)n; CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+  void d2h(void *h, const void *d, size_t n) { d2h_bytes += (long long)n; CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
 
   void setup_params();
   void alloc_state();
@@ -337,22 +342,31 @@ void Run::alloc_state() {
   lock.alloc(n); is_center.alloc(n); slot0.alloc(n); correct.alloc(n);
   E_minmax.alloc(n); p.alloc(n); comp_lambda.alloc(n); comp_ham.alloc(n); cluster_of.alloc(n);
   emax_bits.alloc(n); best_entry.alloc(n); nw_list.alloc(n); gl_list.alloc(n); nsubs_final.alloc(n);
+  DBG("alloc: device arrays done");
   ctr.alloc(CTR_N); h_ctr.alloc(CTR_N);
+  DBG("alloc: ctr done");
   move_cap = (unsigned)n; moves.alloc(2 * n); h_moves.alloc(2 * n);
+  DBG("alloc: moves done");
   ties.alloc(tie_cap * 3); ties_pr.alloc(tie_cap * 3); h_ties.alloc(tie_cap * 3); h_ties_pr.alloc(tie_cap * 3);
   err.alloc((size_t)16 * ncol);
+  DBG("alloc: ties done");
   lock.zero(s); is_center.zero(s); slot0.zero(s); correct.zero(s); p.zero(s); comp_lambda.zero(s); comp_ham.zero(s);
   cluster_of.zero(s); ctr.zero(s);
   std::vector<double> em(n, -999.0);                               // containers.cpp:39
+  DBG("alloc: memsets queued");
   h2d(E_minmax.p, em.data(), n * 8);
+  DBG("alloc: h2d queued");
   CK(cudaStreamSynchronize(s));
+  DBG("alloc: synced");
   st.lock = lock.p; st.is_center = is_center.p; st.slot0 = slot0.p; st.correct = correct.p;
   st.E_minmax = E_minmax.p; st.p = p.p; st.comp_lambda = comp_lambda.p; st.comp_ham = comp_ham.p; st.cluster_of = cluster_of.p;
   st.emax_bits = emax_bits.p; st.best_entry = best_entry.p; st.nw_list = nw_list.p; st.gl_list = gl_list.p;
   st.ctr = ctr.p; st.err = err.p; st.nsubs_final = nsubs_final.p;
   st.cs_cap = 0;
   ensure_cs_cap(2ull * n + 1024);
+  DBG("alloc: cs cap done");
   ensure_cluster_cap(256);
+  DBG("alloc: cluster cap done");
   if (!ptr_in_smem) {
     ptr_scratch.alloc((size_t)ptr_words * align_grid * 4);
   }
@@ -390,13 +404,17 @@ void Run::compare(uint32_t i, double kdist_cutoff) {
   ca.greedy = o->greedy != 0; ca.lock = st.lock; ca.nw_list = st.nw_list; ca.gl_list = st.gl_list; ca.ctr = st.ctr;
   ca.kind_out = nullptr; ca.kord_words = kord_words;
   int cgrid = std::min((nraw + 7) / 8, cx->num_sms * 4);
+  const bool sdbg = getenv("DADA2B_SYNCDEBUG") != nullptr;
+  if (sdbg) { CK(cudaStreamSynchronize(s)); fprintf(stderr, "[dada2b] compare(%u): launching classify grid=%d smem=%zu\n", i, cgrid, classify_smem); }
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
+  if (sdbg) { CK(cudaStreamSynchronize(s)); read_ctr(); fprintf(stderr, "[dada2b] classify done: nw=%llu gl=%llu align=%llu shroud=%llu\n", h_ctr.p[CTR_NW], h_ctr.p[CTR_GL], h_ctr.p[CTR_ALIGN], h_ctr.p[CTR_SHROUD]); }
   for (int kind : {KIND_NW, KIND_GAPLESS}) {
     AlignArgs a = align_args(MODE_LOOP, kind);
     a.jobs = kind == KIND_NW ? st.nw_list : st.gl_list;
     a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
     a.centre_idx = c; a.centre_reads = cx->reads[c]; a.cluster_i = i; a.total_reads = cx->total_reads;
     timed(kind == KIND_NW ? T_NW : T_GL, [&]() { launch_align_jobs(MODE_LOOP, a, (unsigned long long)nraw); });
+    if (sdbg) { CK(cudaStreamSynchronize(s)); fprintf(stderr, "[dada2b] align kind=%d done\n", kind); }
   }
   if (i == 0) {
     unsigned long long n = nraw;
@@ -737,11 +755,14 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
   if (o->use_quals && cx->maxq > Q - 1) throw Err{"Rounded quality exceeded range of err lookup table."};
   Run R;
   R.cx = cx; R.o = o; R.s = cx->stream; R.in = cx->in; R.nraw = cx->in.nraw; R.ncol = Q;
+  DBG("run: begin");
   cx->ev_next = 0;
   R.launches0 = launches_count();
   R.ev_begin = cx->get_event(); R.ev_end = cx->get_event();
   R.setup_params();
+  DBG("run: params set");
   R.alloc_state();
+  if (getenv("DADA2B_SYNCDEBUG")) fprintf(stderr, "[dada2b] state allocated; warp_words=%d ptr_in_smem=%d align_smem=%zu grid=%d\n", R.warp_words, R.ptr_in_smem, R.align_smem, R.align_grid);
   CK(cudaEventRecord(R.ev_begin, R.s));
   {  // cluster.cpp:162-170: row-major copy of the error matrix
     std::vector<double> e((size_t)16 * Q);
@@ -772,13 +793,20 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
   R.p_update();
   int max_clust = o->max_clust < 1 ? nraw : o->max_clust;
   int newi;
+  const bool dbg = o->verbose || getenv("DADA2B_VERBOSE");
+  if (dbg) fprintf(stderr, "[dada2b] round 0 done: %.2f ms, cs=%llu\n", now_ms() - t1, R.cs_count);
   while ((int)R.members.size() < max_clust && (newi = R.bud())) {
+    const double tr = now_ms();
     R.compare((uint32_t)newi, o->kdist_cutoff);
+    const double tc = now_ms();
     int nshuffle = 0; bool shuffled;
     do { shuffled = R.shuffle_pass(); } while (shuffled && ++nshuffle < 10);   // MAX_SHUFFLE dada.h:30
     R.p_update();
     R.n_rounds++;
+    if (dbg) fprintf(stderr, "[dada2b] C%d seed=%u: compare %.3f ms, shuffle+p %.3f ms (%d passes), cs=%llu nw=%llu gl=%llu\n", newi,
+                     R.cl_center_h[newi], tc - tr, now_ms() - tc, nshuffle + 1, R.cs_count, R.h_ctr.p[CTR_NW], R.h_ctr.p[CTR_GL]);
   }
+  if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters\n", (int)R.members.size());
   CK(cudaStreamSynchronize(R.s));
   const double t2 = now_ms();
   dada2b_out *out = (dada2b_out *)calloc(1, sizeof(dada2b_out));
