@@ -67,7 +67,7 @@ enum Ctr : int {
   CTR_CS_COUNT = 0,   // entries in the comparison store
   CTR_NW, CTR_GL,     // job list lengths
   CTR_ALIGN, CTR_SHROUD, CTR_NWTOT, CTR_GLTOT, CTR_CELLS,
-  CTR_NMOVE, CTR_ERR, CTR_PMIN, CTR_RMAX, CTR_NTIE, CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR,
+  CTR_NMOVE, CTR_ERR, CTR_FB, CTR_PMIN, CTR_RMAX, CTR_NTIE, CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR,
   CTR_N
 };
 

@@ -224,6 +224,9 @@ struct Run {
   PBuf<unsigned long long> h_ctr;
   PBuf<uint32_t> h_moves, h_ties, h_ties_pr;
   unsigned move_cap = 0, tie_cap = 4096;
+  DBuf<uint32_t> fb_list;
+  int fwd_slots = 0;
+  unsigned long long est_active = 0;
   size_t cl_cap = 0;
   unsigned long long cs_count = 0;
   // host membership (Bi::raw with slot order) and cluster records
@@ -284,6 +287,7 @@ void Run::setup_params() {
   if (P.band < 0) { lbmax = rbmax = maxlen; }
   else { lbmax = rbmax = std::min(P.band + (maxlen - minlen), maxlen); }
   const int Wmax = lbmax + rbmax + 1;
+  fwd_slots = ((lbmax + 1) & ~1) + rbmax + 1;   // band slots of dd_nwfwd.cu for the widest pair
   const int nchunk = (((Wmax + 1) >> 1) + 31) >> 5;
   seq_bytes = (maxlen + 15) & ~15;
   H_words = (Wmax + 2 + 3) & ~3;
@@ -345,7 +349,7 @@ void Run::alloc_state() {
   DBG("alloc: device arrays done");
   ctr.alloc(CTR_N); h_ctr.alloc(CTR_N);
   DBG("alloc: ctr done");
-  move_cap = (unsigned)n; moves.alloc(2 * n); h_moves.alloc(2 * n);
+  move_cap = (unsigned)n; moves.alloc(2 * n); h_moves.alloc(2 * n); fb_list.alloc(n);
   DBG("alloc: moves done");
   ties.alloc(tie_cap * 3); ties_pr.alloc(tie_cap * 3); h_ties.alloc(tie_cap * 3); h_ties_pr.alloc(tie_cap * 3);
   err.alloc((size_t)16 * ncol);
@@ -398,6 +402,7 @@ void Run::launch_align_jobs(int mode, AlignArgs &a, unsigned long long upper) {
 void Run::compare(uint32_t i, double kdist_cutoff) {
   const uint32_t c = cl_center_h[i];
   ensure_cs_cap(cs_count + (unsigned long long)nraw + 1024);
+  if (i == 0) est_active = nraw;
   CK(cudaMemsetAsync(ctr.p + CTR_NW, 0, 2 * 8, s));
   ClassifyArgs ca{};
   ca.in = in; ca.P = P; ca.P.kdist_cutoff = kdist_cutoff; ca.mode = 0; ca.centre_idx = c; ca.centre_reads = cx->reads[c];
@@ -408,10 +413,20 @@ void Run::compare(uint32_t i, double kdist_cutoff) {
   if (sdbg) { CK(cudaStreamSynchronize(s)); fprintf(stderr, "[dada2b] compare(%u): launching classify grid=%d smem=%zu\n", i, cgrid, classify_smem); }
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   if (sdbg) { CK(cudaStreamSynchronize(s)); read_ctr(); fprintf(stderr, "[dada2b] classify done: nw=%llu gl=%llu align=%llu shroud=%llu\n", h_ctr.p[CTR_NW], h_ctr.p[CTR_GL], h_ctr.p[CTR_ALIGN], h_ctr.p[CTR_SHROUD]); }
+  bool fwd_done = false;
+  if (!P.homo && P.band >= 0 && !getenv("DADA2B_NO_NWFWD")) {       // register-resident forward-carry NW (dd_nwfwd.cu)
+    FwdArgs f{};
+    f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
+    f.centre_idx = c; f.centre_reads = cx->reads[c]; f.cluster_i = i; f.total_reads = cx->total_reads;
+    f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes;
+    CK(cudaMemsetAsync(ctr.p + CTR_FB, 0, 8, s));
+    timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, est_active, cx->num_sms, s); });
+  }
   for (int kind : {KIND_NW, KIND_GAPLESS}) {
     AlignArgs a = align_args(MODE_LOOP, kind);
     a.jobs = kind == KIND_NW ? st.nw_list : st.gl_list;
-    a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
+    if (kind == KIND_NW && fwd_done) { a.jobs = fb_list.p; a.njobs_ptr = st.ctr + CTR_FB; }
+    else a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
     a.centre_idx = c; a.centre_reads = cx->reads[c]; a.cluster_i = i; a.total_reads = cx->total_reads;
     timed(kind == KIND_NW ? T_NW : T_GL, [&]() { launch_align_jobs(MODE_LOOP, a, (unsigned long long)nraw); });
     if (sdbg) { CK(cudaStreamSynchronize(s)); fprintf(stderr, "[dada2b] align kind=%d done\n", kind); }
@@ -424,6 +439,7 @@ void Run::compare(uint32_t i, double kdist_cutoff) {
   read_ctr();
   check_dev_error();
   cs_count = h_ctr.p[CTR_CS_COUNT];
+  est_active = std::max<unsigned long long>(1024, 2 * h_ctr.p[CTR_NW]);   // sizing hint for the next round's grid
   if (cs_count > st.cs_cap) throw Err{"dada2b: comparison store overflow"};
 }
 

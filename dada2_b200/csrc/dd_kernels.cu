@@ -252,6 +252,10 @@ __global__ void __launch_bounds__(128) k_align(AlignArgs a) {
   const int nwarps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
   const AlnParams &P = a.P;
   // ---- shared layout: [err 16*ncol doubles][trans ints (FINAL)] then per-warp regions ----
+  {
+    const unsigned long long nj = a.njobs_ptr ? *a.njobs_ptr : (unsigned long long)a.njobs_fixed;
+    if ((unsigned long long)blockIdx.x * nwarps >= nj) return;            // idle block: skip the prologue
+  }
   double *s_err = (double *)smem;
   int *s_trans = (int *)(s_err + 16 * P.ncol);
   uint32_t *wbase = (uint32_t *)(s_trans + (MODE == MODE_FINAL ? 16 * P.ncol : 0)) + (size_t)wid * a.warp_words;
@@ -538,6 +542,7 @@ __global__ void k_posthoc(DevState st, unsigned long long n, const int *center_c
 // ------------------------------- launch wrappers --------------------------------------
 static long long g_launches = 0;
 long long launches_count() { return g_launches; }
+void count_launch(int n) { g_launches += n; }
 #define COUNT_LAUNCH(n) (g_launches += (n))
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
   COUNT_LAUNCH(1);

@@ -43,6 +43,19 @@ struct AlignArgs {
 };
 
 long long launches_count();
+struct FwdArgs {
+  DevIn in;
+  AlnParams P;
+  DevState st;
+  const uint32_t *jobs;                 // raw indices to align against centre_idx
+  const unsigned long long *njobs_ptr;  // device-side count
+  uint32_t centre_idx, centre_reads, cluster_i, total_reads;
+  uint32_t *fb_list;                    // pairs that do not fit the register band -> k_align
+  unsigned long long *fb_count;
+  int seq_bytes;
+};
+bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s);
+void count_launch(int n);
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 cudaError_t align_set_smem(size_t bytes);

@@ -1,0 +1,255 @@
+// k_nwfwd<G, ND>: register-resident banded ends-free NW for the LOOP comparisons (b_compare),
+// G lanes per (centre, raw) pair, ND diagonals per lane.  Product code (sm_100a).
+//
+// Replaces, for pairs that need a real alignment inside the divisive loop,
+//   nwalign_vectorized2 / nwalign_endsfree   (/root/reference/src/nwalign_vectorized.cpp:71-318,
+//                                             nwalign_endsfree.cpp:76-216)
+//   al2subs + compute_lambda_ts              (nwalign_endsfree.cpp:570-639, pval.cpp:144-197)
+//   the "selectively store" step             (cluster.cpp:179-201)
+// The loop only consumes (lambda, nsubs) of each alignment, so no move matrix is stored and
+// nothing is traced back: every DP cell carries, next to its score, the lambda product and the
+// substitution count of the unique path the reference's traceback would follow to that cell
+// (predecessor chosen with the reference's precedence up > left > diag).  lambda is multiplied
+// along that path in raw-position order, i.e. in the exact order of pval.cpp:190-193, so it is
+// bit-identical to trace-then-multiply.  The final pass (which needs per-position pairs) and
+// anything this kernel cannot hold in registers go through k_align (dd_kernels.cu).
+//
+// Layout: anti-diagonal wavefront.  Band index dd = (j - i) + LB with LB = lb rounded up to even;
+// lane gl of a group owns dd in [gl*ND, gl*ND + ND).  Step k = i + j updates the dd of parity k&1
+// from neighbours of the other parity (step k-1) and itself (step k-2): ND/2 independent cells
+// per lane per step, one neighbour exchange by warp shuffle.  The centre's bases stream up the
+// lanes and the raw's bases/qualities stream down, one shuffle each per step (systolic).
+#include "dd_common.h"
+#include "dd_kernels.h"
+#include <math_constants.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+namespace dd2 {
+
+template <int G, int ND>
+__global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
+  constexpr int NSL = ND / 2;             // cells per lane per step
+  constexpr int PPW = 32 / G;             // pairs per warp
+  static_assert(ND % 2 == 0 && NSL <= 16, "base windows are one 32-bit register each");
+  extern __shared__ uint32_t smem[];
+  const AlnParams &P = a.P;
+  const int ncol = P.ncol;
+  double *s_err = (double *)smem;                       // 16*ncol + 1 (last = 1.0)
+  uint8_t *s_cen = (uint8_t *)(s_err + 16 * ncol + 2);  // centre bases
+  const int nwarps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane / G, gl = lane % G;
+  uint8_t *s_raw = s_cen + a.seq_bytes + (size_t)(wid * PPW + gid) * 2 * a.seq_bytes;   // bases then quals
+  uint8_t *s_q = s_raw + a.seq_bytes;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gid * G));
+  (void)gmask;
+
+  const unsigned long long njobs = *a.njobs_ptr;
+  if ((unsigned long long)blockIdx.x * nwarps * PPW >= njobs) return;      // whole block idle (grid is sized for the worst case)
+  const uint32_t c = a.centre_idx;
+  const int len1 = a.in.len[c];
+  for (int x = threadIdx.x; x < 16 * ncol; x += blockDim.x) s_err[x] = a.st.err[x];
+  if (threadIdx.x == 0) s_err[16 * ncol] = 1.0;
+  {
+    const uint32_t *crow = a.in.seq2 + (size_t)c * a.in.SW;
+    for (int p = threadIdx.x; p < len1; p += blockDim.x) s_cen[p] = (uint8_t)((crow[p >> 4] >> (2 * (p & 15))) & 3u);
+  }
+  __syncthreads();
+  const int ONE_IDX = 16 * ncol;
+  const int SENT = P.sentinel, match = P.match, mismatch = P.mismatch, gap = P.gap;
+  int errflag = 0;
+
+  for (unsigned long long base = (unsigned long long)(blockIdx.x * nwarps + wid) * PPW; base < njobs;
+       base += (unsigned long long)gridDim.x * nwarps * PPW) {
+    const unsigned long long jb = base + gid;
+    bool act = jb < njobs;
+    const uint32_t r = act ? a.jobs[jb] : 0;
+    const int len2 = act ? a.in.len[r] : 1;
+    // ---- stage raw bases + qualities (group-cooperative) ----
+    if (act) {
+      const uint32_t *rrow = a.in.seq2 + (size_t)r * a.in.SW;
+      const uint8_t *qrow = a.in.qual + (size_t)r * a.in.QS;
+      for (int p = gl; p < len2; p += G) {
+        s_raw[p] = (uint8_t)((rrow[p >> 4] >> (2 * (p & 15))) & 3u);
+        int q = P.use_quals ? qrow[p] : 0;
+        if (q > ncol - 1) { errflag = ERR_QUAL; q = ncol - 1; }             // pval.cpp:169-171
+        s_q[p] = (uint8_t)q;
+      }
+    }
+    __syncwarp();
+    // ---- band geometry (nwalign_endsfree.cpp:101-111) ----
+    int lband, rband;
+    if (len2 > len1) { lband = P.band; rband = P.band + len2 - len1; }
+    else if (len1 > len2) { lband = P.band + len1 - len2; rband = P.band; }
+    else { lband = P.band; rband = P.band; }
+    const int lb = min(lband, len1), rb = min(rband, len2);
+    const int LB = (lb + 1) & ~1;
+    const int lo = LB - lb, hi = LB + rb;          // in-band dd range [lo, hi]
+    if (act && (P.band < 0 || hi >= G * ND)) {     // does not fit this instantiation: hand over to k_align
+      if (gl == 0) { unsigned long long s = atomicAdd(a.fb_count, 1ull); a.fb_list[s] = r; }
+      act = false;
+    }
+    const int tlo = lo - gl * ND, thi = hi - gl * ND;   // in-band local t range for this lane
+    const int D = gl * ND - LB;                          // delta of local t = 0 (even)
+    const int nsteps = act ? len1 + len2 : 0;
+    int maxsteps = nsteps;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) maxsteps = max(maxsteps, __shfl_xor_sync(0xffffffffu, maxsteps, o));
+
+    int H[ND], NSUB[ND];
+    double LAM[ND];
+#pragma unroll
+    for (int t = 0; t < ND; t++) { H[t] = SENT; NSUB[t] = 0; LAM[t] = 1.0; }
+    // windows for step k = 0: I = -D/2, J = D/2 ; slot c: s1[I-1-c], s2[J-1+c]
+    int I = -(D / 2), J = D / 2;      // D even; exact
+    uint32_t A = 0, B = 0;
+#pragma unroll
+    for (int cc = 0; cc < NSL; cc++) {
+      const int i1 = I - 1 - cc, j1 = J - 1 + cc;
+      const uint32_t b1 = (i1 >= 0 && i1 < len1) ? s_cen[i1] : 0u;
+      const uint32_t b2 = (act && j1 >= 0 && j1 < len2) ? s_raw[j1] : 0u;
+      A |= b1 << (2 * cc); B |= b2 << (2 * cc);
+    }
+
+    for (int kk = 0; kk <= maxsteps; kk += 2) {
+#pragma unroll
+      for (int PAR = 0; PAR < 2; PAR++) {
+        const int k = kk + PAR;
+        // ---- neighbour exchange ----
+        int Hn, Nn; double Ln;
+        if (PAR == 0) {           // left neighbour of local t=0 is lane gl-1's t=ND-1
+          Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G);
+          Nn = __shfl_up_sync(0xffffffffu, NSUB[ND - 1], 1, G);
+          Ln = __shfl_up_sync(0xffffffffu, LAM[ND - 1], 1, G);
+          if (gl == 0) { Hn = SENT; Nn = 0; Ln = 1.0; }
+        } else {                  // up neighbour of local t=ND-1 is lane gl+1's t=0
+          Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G);
+          Nn = __shfl_down_sync(0xffffffffu, NSUB[0], 1, G);
+          Ln = __shfl_down_sync(0xffffffffu, LAM[0], 1, G);
+          if (gl == G - 1) { Hn = SENT; Nn = 0; Ln = 1.0; }
+        }
+        const uint32_t X = A ^ B;
+        const int Jp = J + PAR;
+        int Hnew[NSL], Nnew[NSL]; double Lnew[NSL];
+#pragma unroll
+        for (int cc = 0; cc < NSL; cc++) {
+          const int t = 2 * cc + PAR;
+          const int i = I - cc, j = Jp + cc;
+          const int hl = (PAR == 0 && cc == 0) ? Hn : H[t - 1 < 0 ? 0 : t - 1];
+          const int nl = (PAR == 0 && cc == 0) ? Nn : NSUB[t - 1 < 0 ? 0 : t - 1];
+          const double ll = (PAR == 0 && cc == 0) ? Ln : LAM[t - 1 < 0 ? 0 : t - 1];
+          const int hu = (PAR == 1 && cc == NSL - 1) ? Hn : H[t + 1 >= ND ? ND - 1 : t + 1];
+          const int nu = (PAR == 1 && cc == NSL - 1) ? Nn : NSUB[t + 1 >= ND ? ND - 1 : t + 1];
+          const double lu = (PAR == 1 && cc == NSL - 1) ? Ln : LAM[t + 1 >= ND ? ND - 1 : t + 1];
+          const int nt1 = (A >> (2 * cc)) & 3, nt2 = (B >> (2 * cc)) & 3;
+          const int q = s_q[min(max(j - 1, 0), a.seq_bytes - 1)];   // quality of raw base j-1
+          const bool eq = ((X >> (2 * cc)) & 3u) == 0u;
+          const bool valid = (t >= tlo) && (t <= thi) && i >= 0 && j >= 0 && i <= len1 && j <= len2 && k <= nsteps;
+          // scores (nwalign_endsfree.cpp:128-156)
+          const int left = hl + ((i == len1) ? 0 : gap);
+          const int up = hu + ((j == len2) ? 0 : gap);
+          const int diag = H[t] + (eq ? match : mismatch);
+          const int m = max(max(left, up), diag);
+          int pmove = (up == m) ? 3 : ((left == m) ? 2 : 1);
+          int val = m;
+          if (i == 0) { val = 0; pmove = (j == 0) ? 0 : 2; }      // top row: ends-free, p=2  (:97-101)
+          else if (j == 0) { val = 0; pmove = 0; }                  // left column: p=3, no raw base consumed
+          // lambda / nsubs along the chosen predecessor (al2subs + compute_lambda_ts)
+          const int trans = (pmove == 1) ? (4 * nt1 + nt2) : (5 * nt2);
+          const int idx = (pmove == 1 || pmove == 2) ? trans * ncol + q : ONE_IDX;
+          const double f = s_err[idx];
+          double lp = (pmove == 3) ? lu : ((pmove == 2) ? ll : LAM[t]);
+          int np = (pmove == 3) ? nu : ((pmove == 2) ? nl : NSUB[t]);
+          if (pmove == 0) { lp = 1.0; np = 0; }
+          if (pmove == 1 && !eq) np++;
+          Hnew[cc] = valid ? val : H[t];
+          Nnew[cc] = valid ? np : NSUB[t];
+          Lnew[cc] = valid ? lp * f : LAM[t];
+        }
+#pragma unroll
+        for (int cc = 0; cc < NSL; cc++) { H[2 * cc + PAR] = Hnew[cc]; NSUB[2 * cc + PAR] = Nnew[cc]; LAM[2 * cc + PAR] = Lnew[cc]; }
+        // ---- advance the sequence windows ----
+        if (PAR == 0) {           // even -> odd: raw window moves one base (J -> J+1)
+          uint32_t nbB = __shfl_down_sync(0xffffffffu, B, 1, G);
+          uint32_t newb = nbB & 3u;
+          if (gl == G - 1) {
+            const int jn = J + NSL - 1;
+            const bool ok = act && jn >= 0 && jn < len2;
+            newb = ok ? s_raw[jn] : 0u;
+          }
+          B = (B >> 2) | (newb << (2 * (NSL - 1)));
+        } else {                  // odd -> even: centre window moves one base (I -> I+1), J -> J+1 completes
+          uint32_t nbA = __shfl_up_sync(0xffffffffu, A, 1, G);
+          uint32_t newa = (nbA >> (2 * (NSL - 1))) & 3u;
+          if (gl == 0) { const int in = I; newa = (in >= 0 && in < len1) ? s_cen[in] : 0u; }
+          A = ((A << 2) | newa) & (NSL == 16 ? 0xffffffffu : ((1u << (2 * NSL)) - 1u));
+          I += 1; J += 1;
+        }
+      }
+    }
+    // ---- result: cell (len1, len2) on dd = len2 - len1 + LB ----
+    const int ddf = len2 - len1 + LB;
+    const int tf = ddf - gl * ND;
+    double lam = 0.0; int ns = 0;
+#pragma unroll
+    for (int t = 0; t < ND; t++) if (t == tf) { lam = LAM[t]; ns = NSUB[t]; }
+    if (act && tf >= 0 && tf < ND) {
+      if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;                 // pval.cpp:195
+      atomicAdd(&a.st.ctr[CTR_NWTOT], 1ull);
+      const double emm = a.st.E_minmax[r];                                          // cluster.cpp:192-200
+      if (lam * (double)a.total_reads > emm) {
+        const double ec = lam * (double)a.centre_reads;
+        if (ec > emm) a.st.E_minmax[r] = ec;
+        const unsigned long long slot = a.cluster_i == 0 ? (unsigned long long)r : atomicAdd(&a.st.ctr[CTR_CS_COUNT], 1ull);
+        if (slot < a.st.cs_cap) {
+          a.st.cs_index[slot] = r; a.st.cs_i[slot] = a.cluster_i; a.st.cs_lambda[slot] = lam; a.st.cs_ham[slot] = (uint32_t)ns;
+        }
+        if (a.cluster_i == 0 || r == c) { a.st.comp_lambda[r] = lam; a.st.comp_ham[r] = (uint32_t)ns; }
+      }
+    }
+    __syncwarp();
+  }
+  if (errflag) atomicMax(&a.st.ctr[CTR_ERR], (unsigned long long)errflag);
+}
+
+template <int G, int ND> static void launch_one(const FwdArgs &a, int grid, size_t smem, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_nwfwd<G, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+  k_nwfwd<G, ND><<<grid, 128, smem, s>>>(a);
+}
+
+// Picks the instantiation: smallest G*ND >= needed band slots, preferring few lanes per pair for
+// large batches (throughput) and many lanes for small batches (latency).
+bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s) {
+  extern void count_launch(int);
+  int G, ND;
+  const bool big = njobs_hint > (unsigned long long)num_sms * 512;
+  const char *force = getenv("DADA2B_NWFWD");          // tuning override, e.g. "8x6"
+  int fg = 0, fnd = 0;
+  if (force && sscanf(force, "%dx%d", &fg, &fnd) == 2) { G = fg; ND = fnd; }
+  else if (slots_needed <= 40) { G = big ? 4 : 8; ND = big ? 10 : 6; }
+  else if (slots_needed <= 48) { G = 8; ND = 6; }
+  else if (slots_needed <= 64) { G = 8; ND = 8; }
+  else if (slots_needed <= 128) { G = 16; ND = 8; }
+  else if (slots_needed <= 256) { G = 32; ND = 8; }
+  else return false;
+  if (G * ND < slots_needed) return false;
+  const int PPW = 32 / G;
+  const size_t smem = (size_t)(16 * a.P.ncol + 2) * 8 + a.seq_bytes + (size_t)4 * PPW * 2 * a.seq_bytes;
+  if (smem > 160 * 1024) return false;
+  unsigned long long warps = (njobs_upper + PPW - 1) / PPW;
+  int grid = (int)std::min<unsigned long long>((warps + 3) / 4, (unsigned long long)num_sms * 16);
+  if (grid < 1) grid = 1;
+  count_launch(1);
+  if (G == 4 && ND == 10) launch_one<4, 10>(a, grid, smem, s);
+  else if (G == 8 && ND == 6) launch_one<8, 6>(a, grid, smem, s);
+  else if (G == 16 && ND == 4) launch_one<16, 4>(a, grid, smem, s);
+  else if (G == 8 && ND == 8) launch_one<8, 8>(a, grid, smem, s);
+  else if (G == 16 && ND == 8) launch_one<16, 8>(a, grid, smem, s);
+  else if (G == 32 && ND == 8) launch_one<32, 8>(a, grid, smem, s);
+  else return false;
+  return true;
+}
+
+}  // namespace dd2
