@@ -35,6 +35,28 @@ struct AlnParams {
   int ncol;           // columns of err
 };
 
+enum Ctr : int {
+  CTR_CS_COUNT = 0,   // entries in the comparison store
+  CTR_NW, CTR_GL,     // job list lengths
+  CTR_ALIGN, CTR_SHROUD, CTR_NWTOT, CTR_GLTOT, CTR_CELLS,
+  CTR_NMOVE, CTR_ERR, CTR_FB, CTR_PMIN, CTR_RMAX, CTR_NTIE, CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR,
+  CTR_N
+};
+
+constexpr int TIE_MAX = 64;      // tie candidates reported per round without a second copy
+constexpr int MAX_PASS = 10;     // MAX_SHUFFLE, /root/reference/src/dada.h:30
+
+// Written by the device into mapped pinned host memory once per round; read by the host after a
+// single stream synchronisation (no per-step D2H copies).
+struct RoundReport {
+  unsigned long long ctr[CTR_N];
+  uint32_t pinfo[MAX_PASS + 2];   // pinfo[p+1] = moves recorded up to and including shuffle pass p
+  uint32_t converged;             // last launched pass moved nothing
+  uint32_t pad;
+  uint32_t tie_r[TIE_MAX], tie_ham[TIE_MAX], tiep_r[TIE_MAX], tiep_ham[TIE_MAX];
+  double tie_lam[TIE_MAX], tiep_lam[TIE_MAX];
+};
+
 // Mutable per-run state.
 struct DevState {
   // per raw
@@ -46,7 +68,7 @@ struct DevState {
   double *cs_lambda;
   unsigned long long cs_cap;
   // per cluster
-  uint32_t *cl_reads, *cl_center;
+  uint32_t *cl_reads, *cl_reads_next, *cl_center;
   uint8_t *cl_update_e, *cl_check_locks;
   // shuffle scratch (per raw)
   unsigned long long *emax_bits;
@@ -57,19 +79,18 @@ struct DevState {
   unsigned long long *ctr;
   // error matrix, row-major 16 x ncol (cluster.cpp:162-170)
   double *err;
+  // per-round control block (device) + host-mapped report / move list
+  uint32_t *pinfo;                  // [MAX_PASS + 2]
+  uint32_t *moves;                  // mapped pinned host memory: (raw, to) pairs
+  unsigned move_cap;
+  RoundReport *report;              // mapped pinned host memory
   // final-pass accumulators
   int *trans;                       // [16][ncol] row-major
   unsigned long long *cq_sum, *cq_cnt;  // [nclust][maxlen]
   uint32_t *nsubs_final;            // per raw
 };
 
-enum Ctr : int {
-  CTR_CS_COUNT = 0,   // entries in the comparison store
-  CTR_NW, CTR_GL,     // job list lengths
-  CTR_ALIGN, CTR_SHROUD, CTR_NWTOT, CTR_GLTOT, CTR_CELLS,
-  CTR_NMOVE, CTR_ERR, CTR_FB, CTR_PMIN, CTR_RMAX, CTR_NTIE, CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR,
-  CTR_N
-};
+
 
 enum ErrCode : int { ERR_NONE = 0, ERR_LAMBDA = 1, ERR_QUAL = 2, ERR_TRACE = 3 };
 

@@ -30,21 +30,31 @@ namespace {
 struct Err { std::string msg; };
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw Err{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x}; } while (0)
 
+#define TDBG(msg) do { if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] t=%.3f ms %s\n", now_ms() - g_t0, msg); } while (0)
 #define DBG(...) do { if (getenv("DADA2B_SYNCDEBUG")) { fprintf(stderr, "[dada2b] " __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static double g_t0 = 0;
 double na_real() { union { double d; uint64_t u; } v; v.u = 0x7FF00000000007A2ULL; return v.d; }
 
-template <typename T> struct DBuf {   // device buffer
-  T *p = nullptr; size_t n = 0;
-  void alloc(size_t count) { free(); n = count; if (count) CK(cudaMalloc(&p, count * sizeof(T))); }
-  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+template <typename T> struct DBuf {   // device buffer (grow-only: reused across runs of a context)
+  T *p = nullptr; size_t n = 0, cap = 0;
+  void alloc(size_t count) {
+    if (count <= cap && p) { n = count; return; }
+    free(); n = cap = count;
+    if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; n = cap = 0; }
   void zero(cudaStream_t s) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   ~DBuf() { free(); }
 };
-template <typename T> struct PBuf {   // pinned host buffer
-  T *p = nullptr; size_t n = 0;
-  void alloc(size_t count) { free(); n = count; if (count) CK(cudaMallocHost(&p, count * sizeof(T))); }
-  void free() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+template <typename T> struct PBuf {   // pinned host buffer (grow-only)
+  T *p = nullptr; size_t n = 0, cap = 0;
+  void alloc(size_t count) {
+    if (count <= cap && p) { n = count; return; }
+    free(); n = cap = count;
+    if (count) CK(cudaMallocHost(&p, count * sizeof(T)));
+  }
+  void free() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
   ~PBuf() { free(); }
 };
 
@@ -63,7 +73,9 @@ template <typename F> void parallel_for(size_t n, F f) {
 
 }  // namespace
 
+namespace { struct Run; void delete_run(Run *); }
 struct dada2b_ctx {
+  Run *run = nullptr;             // per-run device state, kept across runs (grow-only buffers)
   int device = 0;
   cudaStream_t stream = nullptr;
   DevIn in{};
@@ -79,6 +91,8 @@ struct dada2b_ctx {
   DBuf<uint32_t> d_seq2, d_reads;
   DBuf<uint8_t> d_qual, d_prior;
   DBuf<uint16_t> d_len;
+  PBuf<uint32_t> st_seq;          // pinned staging for the packed upload
+  PBuf<uint8_t> st_qual;
   int num_sms = 148;
   long long upload_h2d = 0;
   std::vector<cudaEvent_t> ev_pool;
@@ -92,19 +106,26 @@ struct dada2b_ctx {
 // ------------------------------------------------------------------------------------
 // upload: validation of Rmain.cpp:52-78, raw_new (containers.cpp:19-43) and packing
 // ------------------------------------------------------------------------------------
-static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
+static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse = nullptr) {
   const unsigned nraw = in->nraw;
+  const double tu0 = now_ms();
   DBG("upload: nraw=%u", nraw);
   if (in->nraw <= 0) throw Err{"Zero input sequences."};
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     throw Err{"dada2b: no CUDA device available (this library has no CPU path)."};
   CK(cudaSetDevice(device));
-  std::unique_ptr<dada2b_ctx> cx(new dada2b_ctx());
-  cx->device = device;
-  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
-  cx->num_sms = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
+  std::unique_ptr<dada2b_ctx> fresh;
+  dada2b_ctx *cx = reuse;
+  if (!cx) {
+    fresh.reset(new dada2b_ctx());
+    cx = fresh.get();
+    cx->device = device;
+    int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    cx->num_sms = sms;
+    CK(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
+  }
+  cx->maxq = 0; cx->bad_nt = false;
   DBG("upload: device ready, %d SMs", cx->num_sms);
   unsigned maxlen = 0, minlen = 9999;
   cx->len.resize(nraw);
@@ -138,8 +159,9 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
   }
   cx->total_reads = tot;
   // pack on the host into pinned staging, then one H2D per array
-  PBuf<uint32_t> h_seq; h_seq.alloc((size_t)nraw * d.SW);
-  PBuf<uint8_t> h_qual; h_qual.alloc((size_t)nraw * d.QS);
+  const double tu1 = now_ms();
+  PBuf<uint32_t> &h_seq = cx->st_seq; h_seq.alloc((size_t)nraw * d.SW);
+  PBuf<uint8_t> &h_qual = cx->st_qual; h_qual.alloc((size_t)nraw * d.QS);
   std::vector<int> tmaxq(64, 0), tbad(64, 0);
   const char *sc = cx->seq_concat.data();
   const double *qd = in->quals;
@@ -147,7 +169,8 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
   unsigned slot = 0;
   std::vector<std::pair<size_t, size_t>> ranges;
   {
-    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (nraw < 20000) nt = std::min(nt, 4u);
     size_t chunk = (nraw + nt - 1) / nt;
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nt; t++) {
@@ -168,7 +191,13 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
           }
           uint8_t *q = h_qual.p + r * QS;
           const double *src = qd + (size_t)ML * r;
-          for (int p = 0; p < L; p++) { uint8_t v = (uint8_t)round(src[p]); q[p] = v; if (v > mq) mq = v; }   // containers.cpp:34
+          for (int p = 0; p < L; p++) {                                   // (uint8_t) round(qual[i]), containers.cpp:34
+            const double x = src[p];
+            int rv = (int)(x + 0.5);                                      // == round(x) for x >= 0 except when x+0.5 rounds up
+            if ((double)rv - x > 0.5) rv--;
+            if (!(x >= 0)) rv = (int)round(x);
+            const uint8_t v = (uint8_t)rv; q[p] = v; if (v > mq) mq = v;
+          }
           for (int p = L; p < QS; p++) q[p] = 0;
         }
         tmaxq[t] = mq; tbad[t] = bad;
@@ -177,6 +206,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
     for (auto &x : th) x.join();
     (void)slot;
   }
+  const double tu2 = now_ms();
   DBG("upload: packed on host");
   for (int v : tmaxq) cx->maxq = std::max(cx->maxq, v);
   for (int v : tbad) cx->bad_nt |= (v != 0);
@@ -188,10 +218,12 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device) {
   CK(cudaMemcpyAsync(cx->d_reads.p, cx->reads.data(), nraw * 4, cudaMemcpyHostToDevice, cx->stream));
   CK(cudaMemcpyAsync(cx->d_prior.p, cx->prior.data(), nraw, cudaMemcpyHostToDevice, cx->stream));
   CK(cudaStreamSynchronize(cx->stream));
+  if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] upload: validate+copy %.2f ms, pack %.2f ms, alloc+H2D %.2f ms\n", tu1 - tu0, tu2 - tu1, now_ms() - tu2);
   DBG("upload: H2D done");
   cx->upload_h2d = (long long)nraw * d.SW * 4 + (long long)nraw * d.QS + (long long)nraw * 7;
   d.seq2 = cx->d_seq2.p; d.qual = cx->d_qual.p; d.len = cx->d_len.p; d.reads = cx->d_reads.p; d.prior = cx->d_prior.p;
-  return cx.release();
+  if (fresh) fresh.release();
+  return cx;
 }
 
 // ------------------------------------------------------------------------------------
@@ -222,7 +254,16 @@ struct Run {
   DBuf<unsigned long long> emax_bits, ctr, cq_sum, cq_cnt;
   DBuf<int> trans, center_cluster, pa_reads, pa_prior;
   PBuf<unsigned long long> h_ctr;
-  PBuf<uint32_t> h_moves, h_ties, h_ties_pr;
+  PBuf<uint32_t> h_ties, h_ties_pr;
+  DBuf<uint32_t> cl_reads_next, pinfo;
+  DBuf<RoundReport> d_report;
+  DBuf<uint32_t> d_moves;
+  PBuf<RoundReport> h_report_buf;
+  PBuf<uint32_t> h_moves_buf;
+  RoundReport *h_report = nullptr;       // pinned host copy, refreshed once per round
+  uint32_t *h_moves = nullptr;
+  static constexpr unsigned MOVES_EAGER = 8192;   // moves copied back with the report; more => one extra copy
+  int NP = 3;                            // shuffle passes launched speculatively per round
   unsigned move_cap = 0, tie_cap = 4096;
   DBuf<uint32_t> fb_list;
   int fwd_slots = 0;
@@ -232,7 +273,6 @@ struct Run {
   // host membership (Bi::raw with slot order) and cluster records
   std::vector<std::vector<uint32_t>> members;
   std::vector<uint32_t> slot_of, cluster_of_h, cl_center_h, cl_reads_h;
-  std::vector<uint8_t> upd_e, chk_locks;
   std::vector<Birth> birth;
   // align launch geometry
   int warp_words = 0, seq_bytes = 0, H_words = 0, ops_words = 0, ptr_in_smem = 0, align_grid = 0;
@@ -254,21 +294,32 @@ struct Run {
   void h2d(void *d, const void *h, size_t n) { h2d_bytes += (long long)n; CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
   void d2h(void *h, const void *d, size_t n) { d2h_bytes += (long long)n; CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
 
+  void reset_host();
   void setup_params();
   void alloc_state();
   void ensure_cluster_cap(size_t n);
   void ensure_cs_cap(unsigned long long need);
-  void upload_cluster_arrays(bool flags);
   void read_ctr() { d2h(h_ctr.p, ctr.p, CTR_N * 8); CK(cudaStreamSynchronize(s)); }
   void check_dev_error();
-  void compare(uint32_t i, double kdist_cutoff);
-  bool shuffle_pass();
-  void p_update();
-  int bud();
+  void launch_compare(uint32_t i, double kdist_cutoff);
+  void launch_round_tail(int first_pass, int npass);
+  void launch_shuffle_only(int pass);
+  void launch_round_tail_noshuffle();
+  void sync_report();
+  int replay_moves(int first_pass, int last_pass);
+  int decide_bud(uint32_t *r_out, uint32_t *from_out);
+  struct Pending { int apply = 0; uint32_t r = 0, from = 0, newi = 0, reads = 0; } pending;
   void finish(dada2b_out *out);
   AlignArgs align_args(int mode, int kind);
   void launch_align_jobs(int mode, AlignArgs &a, unsigned long long upper);
 };
+
+void Run::reset_host() {
+  members.clear(); slot_of.clear(); cluster_of_h.clear(); cl_center_h.clear(); cl_reads_h.clear(); birth.clear(); evs.clear();
+  n_rounds = n_shuffles = 0; h2d_bytes = d2h_bytes = 0; cs_count = 0; est_active = 0; pending = Pending();
+  st = DevState{};
+}
+void delete_run(Run *r) { delete r; }
 
 void Run::setup_params() {
   const dada2b_opts &op = *o;
@@ -308,22 +359,35 @@ void Run::setup_params() {
 
 void Run::ensure_cluster_cap(size_t n) {
   if (n <= cl_cap) return;
-  size_t nc = std::max<size_t>(256, cl_cap * 2);
+  size_t nc = std::max<size_t>(1024, cl_cap * 2);
   while (nc < n) nc *= 2;
-  DBuf<uint32_t> r2, c2; DBuf<uint8_t> u2, k2;
-  r2.alloc(nc); c2.alloc(nc); u2.alloc(nc); k2.alloc(nc);
-  r2.zero(s); c2.zero(s); u2.zero(s); k2.zero(s);
+  DBuf<uint32_t> r2, rn2, c2; DBuf<uint8_t> u2, k2;
+  r2.alloc(nc); rn2.alloc(nc); c2.alloc(nc); u2.alloc(nc); k2.alloc(nc);
+  r2.zero(s); rn2.zero(s); c2.zero(s); u2.zero(s); k2.zero(s);
+  if (cl_cap) {
+    CK(cudaMemcpyAsync(r2.p, cl_reads.p, cl_cap * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(rn2.p, cl_reads_next.p, cl_cap * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(c2.p, cl_center.p, cl_cap * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(u2.p, cl_update_e.p, cl_cap, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(k2.p, cl_check_locks.p, cl_cap, cudaMemcpyDeviceToDevice, s));
+  }
+  CK(cudaStreamSynchronize(s));
   std::swap(cl_reads.p, r2.p); std::swap(cl_reads.n, r2.n);
+  std::swap(cl_reads_next.p, rn2.p); std::swap(cl_reads_next.n, rn2.n);
   std::swap(cl_center.p, c2.p); std::swap(cl_center.n, c2.n);
   std::swap(cl_update_e.p, u2.p); std::swap(cl_update_e.n, u2.n);
   std::swap(cl_check_locks.p, k2.p); std::swap(cl_check_locks.n, k2.n);
   cl_cap = nc;
-  st.cl_reads = cl_reads.p; st.cl_center = cl_center.p; st.cl_update_e = cl_update_e.p; st.cl_check_locks = cl_check_locks.p;
-  CK(cudaStreamSynchronize(s));
+  st.cl_reads = cl_reads.p; st.cl_reads_next = cl_reads_next.p; st.cl_center = cl_center.p;
+  st.cl_update_e = cl_update_e.p; st.cl_check_locks = cl_check_locks.p;
 }
 
 void Run::ensure_cs_cap(unsigned long long need) {
   if (need <= st.cs_cap) return;
+  if (cs_index.p && need <= cs_index.cap) {   // buffers kept from an earlier run of this context
+    st.cs_index = cs_index.p; st.cs_i = cs_i.p; st.cs_ham = cs_ham.p; st.cs_lambda = cs_lambda.p; st.cs_cap = cs_index.cap;
+    return;
+  }
   unsigned long long nc = std::max<unsigned long long>(need, st.cs_cap * 2);
   DBuf<uint32_t> a, b, c; DBuf<double> l;
   a.alloc(nc); b.alloc(nc); c.alloc(nc); l.alloc(nc);
@@ -346,31 +410,44 @@ void Run::alloc_state() {
   lock.alloc(n); is_center.alloc(n); slot0.alloc(n); correct.alloc(n);
   E_minmax.alloc(n); p.alloc(n); comp_lambda.alloc(n); comp_ham.alloc(n); cluster_of.alloc(n);
   emax_bits.alloc(n); best_entry.alloc(n); nw_list.alloc(n); gl_list.alloc(n); nsubs_final.alloc(n);
-  DBG("alloc: device arrays done");
+  TDBG("alloc: device arrays");
   ctr.alloc(CTR_N); h_ctr.alloc(CTR_N);
   DBG("alloc: ctr done");
-  move_cap = (unsigned)n; moves.alloc(2 * n); h_moves.alloc(2 * n); fb_list.alloc(n);
+  move_cap = (unsigned)(4 * n + 1024); fb_list.alloc(n);
+  pinfo.alloc(MAX_PASS + 2); pinfo.zero(s);
+  d_report.alloc(1); d_moves.alloc((size_t)move_cap * 2);
+  h_report_buf.alloc(1); h_moves_buf.alloc((size_t)move_cap * 2);
+  h_report = h_report_buf.p; h_moves = h_moves_buf.p;
+  memset(h_report, 0, sizeof(RoundReport));
   DBG("alloc: moves done");
   ties.alloc(tie_cap * 3); ties_pr.alloc(tie_cap * 3); h_ties.alloc(tie_cap * 3); h_ties_pr.alloc(tie_cap * 3);
   err.alloc((size_t)16 * ncol);
   DBG("alloc: ties done");
   lock.zero(s); is_center.zero(s); slot0.zero(s); correct.zero(s); p.zero(s); comp_lambda.zero(s); comp_ham.zero(s);
   cluster_of.zero(s); ctr.zero(s);
-  std::vector<double> em(n, -999.0);                               // containers.cpp:39
-  DBG("alloc: memsets queued");
-  h2d(E_minmax.p, em.data(), n * 8);
-  DBG("alloc: h2d queued");
+  launch_fill_f64(E_minmax.p, -999.0, n, s);                      // containers.cpp:39
+  TDBG("alloc: memsets queued");
   CK(cudaStreamSynchronize(s));
-  DBG("alloc: synced");
+  TDBG("alloc: synced");
   st.lock = lock.p; st.is_center = is_center.p; st.slot0 = slot0.p; st.correct = correct.p;
   st.E_minmax = E_minmax.p; st.p = p.p; st.comp_lambda = comp_lambda.p; st.comp_ham = comp_ham.p; st.cluster_of = cluster_of.p;
   st.emax_bits = emax_bits.p; st.best_entry = best_entry.p; st.nw_list = nw_list.p; st.gl_list = gl_list.p;
   st.ctr = ctr.p; st.err = err.p; st.nsubs_final = nsubs_final.p;
+  st.pinfo = pinfo.p; st.move_cap = move_cap;
+  st.report = d_report.p; st.moves = d_moves.p;
+  emax_bits.zero(s);                                               // shuffle scratch starts clean
+  CK(cudaMemsetAsync(best_entry.p, 0xFF, n * 4, s));
+  { unsigned long long nn = n; h2d(ctr.p + CTR_CS_COUNT, &nn, 8); }  // cluster 0 owns entries [0, nraw)
+  CK(cudaStreamSynchronize(s));
   st.cs_cap = 0;
   ensure_cs_cap(2ull * n + 1024);
-  DBG("alloc: cs cap done");
-  ensure_cluster_cap(256);
-  DBG("alloc: cluster cap done");
+  TDBG("alloc: cs cap");
+  ensure_cluster_cap(1024);
+  st.cl_reads = cl_reads.p; st.cl_reads_next = cl_reads_next.p; st.cl_center = cl_center.p;
+  st.cl_update_e = cl_update_e.p; st.cl_check_locks = cl_check_locks.p;
+  cl_reads.zero(s); cl_reads_next.zero(s); cl_center.zero(s); cl_update_e.zero(s); cl_check_locks.zero(s);
+  CK(cudaStreamSynchronize(s));
+  TDBG("alloc: cluster cap");
   if (!ptr_in_smem) {
     ptr_scratch.alloc((size_t)ptr_words * align_grid * 4);
   }
@@ -398,29 +475,27 @@ void Run::launch_align_jobs(int mode, AlignArgs &a, unsigned long long upper) {
   launch_align(mode, a, grid, 128, align_smem, s);
 }
 
-// b_compare_parallel (cluster.cpp:152-204) for seed cluster i
-void Run::compare(uint32_t i, double kdist_cutoff) {
+// One round on the device, no host round trip inside:
+//   [apply previous bud] -> b_compare_parallel (cluster.cpp:152-204) -> NP x b_shuffle2 -> b_p_update -> b_bud scan -> report
+void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   const uint32_t c = cl_center_h[i];
-  ensure_cs_cap(cs_count + (unsigned long long)nraw + 1024);
-  if (i == 0) est_active = nraw;
-  CK(cudaMemsetAsync(ctr.p + CTR_NW, 0, 2 * 8, s));
+  ensure_cs_cap(cs_count + 2ull * (unsigned long long)nraw + 1024);
+  ensure_cluster_cap(members.size() + 2);
+  launch_round_begin(st, pending.apply, pending.r, pending.from, pending.newi, pending.reads, s);
+  pending.apply = 0;
   ClassifyArgs ca{};
   ca.in = in; ca.P = P; ca.P.kdist_cutoff = kdist_cutoff; ca.mode = 0; ca.centre_idx = c; ca.centre_reads = cx->reads[c];
   ca.greedy = o->greedy != 0; ca.lock = st.lock; ca.nw_list = st.nw_list; ca.gl_list = st.gl_list; ca.ctr = st.ctr;
   ca.kind_out = nullptr; ca.kord_words = kord_words;
   int cgrid = std::min((nraw + 7) / 8, cx->num_sms * 4);
-  const bool sdbg = getenv("DADA2B_SYNCDEBUG") != nullptr;
-  if (sdbg) { CK(cudaStreamSynchronize(s)); fprintf(stderr, "[dada2b] compare(%u): launching classify grid=%d smem=%zu\n", i, cgrid, classify_smem); }
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
-  if (sdbg) { CK(cudaStreamSynchronize(s)); read_ctr(); fprintf(stderr, "[dada2b] classify done: nw=%llu gl=%llu align=%llu shroud=%llu\n", h_ctr.p[CTR_NW], h_ctr.p[CTR_GL], h_ctr.p[CTR_ALIGN], h_ctr.p[CTR_SHROUD]); }
   bool fwd_done = false;
   if (!P.homo && P.band >= 0 && !getenv("DADA2B_NO_NWFWD")) {       // register-resident forward-carry NW (dd_nwfwd.cu)
     FwdArgs f{};
     f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
     f.centre_idx = c; f.centre_reads = cx->reads[c]; f.cluster_i = i; f.total_reads = cx->total_reads;
     f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes;
-    CK(cudaMemsetAsync(ctr.p + CTR_FB, 0, 8, s));
-    timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, est_active, cx->num_sms, s); });
+    timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, i == 0 ? (unsigned long long)nraw : est_active, cx->num_sms, s); });
   }
   for (int kind : {KIND_NW, KIND_GAPLESS}) {
     AlignArgs a = align_args(MODE_LOOP, kind);
@@ -429,116 +504,124 @@ void Run::compare(uint32_t i, double kdist_cutoff) {
     else a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
     a.centre_idx = c; a.centre_reads = cx->reads[c]; a.cluster_i = i; a.total_reads = cx->total_reads;
     timed(kind == KIND_NW ? T_NW : T_GL, [&]() { launch_align_jobs(MODE_LOOP, a, (unsigned long long)nraw); });
-    if (sdbg) { CK(cudaStreamSynchronize(s)); fprintf(stderr, "[dada2b] align kind=%d done\n", kind); }
   }
-  if (i == 0) {
-    unsigned long long n = nraw;
-    h2d(ctr.p + CTR_CS_COUNT, &n, 8);
+}
+
+// shuffle passes [first_pass, first_pass + npass) then p-update, bud scan and the report
+void Run::launch_round_tail(int first_pass, int npass) {
+  const int nclust = (int)members.size();
+  const unsigned long long upper = cs_count + (unsigned long long)nraw;
+  for (int p = first_pass; p < first_pass + npass; p++) launch_shuffle_pass(st, in, upper, nclust, p, s);
+  const int last = first_pass + npass - 1;          // -1 => no shuffling this round (initial cluster)
+  launch_p_update(st, in, o->greedy != 0, o->detect_singletons != 0, last, s);
+  BudParams bp{o->min_fold, o->min_hamming, o->min_abund};
+  launch_bud_scan(st, in, bp, nclust, last, s);
+  launch_report(st, last, s);
+}
+
+void Run::launch_shuffle_only(int pass) {
+  launch_shuffle_pass(st, in, cs_count + (unsigned long long)nraw, (int)members.size(), pass, s);
+  launch_report(st, pass, s);
+}
+void Run::launch_round_tail_noshuffle() {
+  launch_p_update(st, in, o->greedy != 0, o->detect_singletons != 0, -1, s);
+  BudParams bp{o->min_fold, o->min_hamming, o->min_abund};
+  launch_bud_scan(st, in, bp, (int)members.size(), -1, s);
+  launch_report(st, -1, s);
+}
+
+void Run::sync_report() {
+  d2h(h_report, d_report.p, sizeof(RoundReport));
+  const unsigned eager = std::min<unsigned>(MOVES_EAGER, move_cap);
+  d2h(h_moves, d_moves.p, (size_t)eager * 8);
+  CK(cudaStreamSynchronize(s));
+  if (h_report->ctr[CTR_NMOVE] > eager && h_report->ctr[CTR_NMOVE] <= move_cap) {
+    d2h(h_moves + 2 * (size_t)eager, d_moves.p + 2 * (size_t)eager, (size_t)(h_report->ctr[CTR_NMOVE] - eager) * 8);
     CK(cudaStreamSynchronize(s));
   }
-  read_ctr();
+  memcpy(h_ctr.p, h_report->ctr, sizeof(unsigned long long) * CTR_N);
   check_dev_error();
-  cs_count = h_ctr.p[CTR_CS_COUNT];
-  est_active = std::max<unsigned long long>(1024, 2 * h_ctr.p[CTR_NW]);   // sizing hint for the next round's grid
+  cs_count = h_report->ctr[CTR_CS_COUNT];
+  est_active = std::max<unsigned long long>(1024, 2 * h_report->ctr[CTR_NW]);
   if (cs_count > st.cs_cap) throw Err{"dada2b: comparison store overflow"};
+  if (h_report->ctr[CTR_NMOVE] > move_cap) throw Err{"dada2b: move list overflow"};
 }
 
-void Run::upload_cluster_arrays(bool flags) {
-  const size_t nc = members.size();
-  ensure_cluster_cap(nc);
-  h2d(cl_reads.p, cl_reads_h.data(), nc * 4);
-  h2d(cl_center.p, cl_center_h.data(), nc * 4);
-  if (flags) {
-    h2d(cl_update_e.p, upd_e.data(), nc);
-    h2d(cl_check_locks.p, chk_locks.data(), nc);
+// b_shuffle2's container updates (cluster.cpp:242-260) replayed on the host member arrays in the
+// reference's order: clusters ascending, slots descending, swap-with-last pops, appends.
+// Returns the number of passes that actually ran.
+int Run::replay_moves(int first_pass, int last_pass) {
+  int ran = 0;
+  for (int p = first_pass; p <= last_pass; p++) {
+    if (p > first_pass && h_report->pinfo[p] == h_report->pinfo[p - 1]) break;   // skipped on the device (previous pass moved nothing)
+    ran++; n_shuffles++;
+    const uint32_t b = h_report->pinfo[p], e = h_report->pinfo[p + 1];
+    if (e == b) continue;
+    struct Mv { uint32_t from, slot, r, to; };
+    std::vector<Mv> mv(e - b);
+    for (uint32_t k = b; k < e; k++) {
+      const uint32_t r = h_moves[2 * (size_t)k], to = h_moves[2 * (size_t)k + 1];
+      mv[k - b] = Mv{cluster_of_h[r], slot_of[r], r, to};
+    }
+    std::sort(mv.begin(), mv.end(), [](const Mv &a, const Mv &b2) { return a.from != b2.from ? a.from < b2.from : a.slot > b2.slot; });
+    for (const Mv &m : mv) {
+      std::vector<uint32_t> &src = members[m.from];
+      const uint32_t sl = slot_of[m.r];
+      const uint32_t last = src.back();                          // bi_pop_raw: slot <- last
+      src[sl] = last; slot_of[last] = sl; src.pop_back();
+      if (sl == 0) {                                             // only possible when slot 0 is not the centre (unsorted input)
+        const uint8_t z = 0, one = 1;
+        h2d(slot0.p + m.r, &z, 1);
+        if (last != m.r) h2d(slot0.p + last, &one, 1);
+      }
+      cl_reads_h[m.from] -= cx->reads[m.r];
+      std::vector<uint32_t> &dst = members[m.to];                // bi_add_raw: append
+      slot_of[m.r] = (uint32_t)dst.size(); dst.push_back(m.r);
+      cl_reads_h[m.to] += cx->reads[m.r];
+      cluster_of_h[m.r] = m.to;
+    }
   }
+  return ran;
 }
 
-// b_shuffle2 (cluster.cpp:210-266): device finds each raw's best cluster, host replays the moves on the
-// member arrays in the reference's order (clusters ascending, slots descending, swap-with-last pops).
-bool Run::shuffle_pass() {
-  CK(cudaMemsetAsync(ctr.p + CTR_NMOVE, 0, 8, s));
-  launch_shuffle_pass(st, nraw, cs_count, moves.p, move_cap, s);
-  read_ctr();
-  const unsigned long long nm = h_ctr.p[CTR_NMOVE];
-  n_shuffles++;
-  if (nm == 0) return false;
-  d2h(h_moves.p, moves.p, nm * 8);
-  CK(cudaStreamSynchronize(s));
-  struct Mv { uint32_t from, slot, r, to; };
-  std::vector<Mv> mv(nm);
-  for (unsigned long long k = 0; k < nm; k++) {
-    uint32_t r = h_moves.p[2 * k], to = h_moves.p[2 * k + 1];
-    mv[k] = Mv{cluster_of_h[r], slot_of[r], r, to};
+// b_bud (cluster.cpp:274-350) decision from the device scan.  Returns the new cluster index or 0.
+int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
+  const RoundReport &R = *h_report;
+  unsigned long long nt = R.ctr[CTR_NTIE], ntp = R.ctr[CTR_NTIE_PR];
+  std::vector<uint32_t> big, bigp;
+  const uint32_t *tr = R.tie_r, *trp = R.tiep_r;
+  if (nt > TIE_MAX || ntp > TIE_MAX) {                          // pathological tie set: fetch all of it
+    const unsigned cap = (unsigned)std::max(nt, ntp);
+    DBuf<uint32_t> d1, d2; d1.alloc(cap); d2.alloc(cap);
+    unsigned long long z[2] = {0ull, 0ull};
+    h2d(ctr.p + CTR_NTIE, &z[0], 8); h2d(ctr.p + CTR_NTIE_PR, &z[1], 8);
+    BudParams bp{o->min_fold, o->min_hamming, o->min_abund};
+    launch_bud_collect_big(st, in, bp, d1.p, d2.p, cap, s);
+    big.resize(nt); bigp.resize(ntp);
+    if (nt) d2h(big.data(), d1.p, nt * 4);
+    if (ntp) d2h(bigp.data(), d2.p, ntp * 4);
+    CK(cudaStreamSynchronize(s));
+    tr = big.data(); trp = bigp.data();
   }
-  std::sort(mv.begin(), mv.end(), [](const Mv &a, const Mv &b) { return a.from != b.from ? a.from < b.from : a.slot > b.slot; });
-  bool slot0_changed = false;
-  std::vector<std::pair<uint32_t, uint8_t>> slot0_updates;
-  for (const Mv &m : mv) {
-    std::vector<uint32_t> &src = members[m.from];
-    const uint32_t sl = slot_of[m.r];                          // still valid: pops only disturb higher slots' tail
-    const uint32_t last = src.back();                          // bi_pop_raw: slot <- last
-    src[sl] = last; slot_of[last] = sl; src.pop_back();
-    if (sl == 0) { slot0_updates.push_back({m.r, 0}); if (last != m.r) slot0_updates.push_back({last, 1}); slot0_changed = true; }
-    cl_reads_h[m.from] -= cx->reads[m.r];
-    std::vector<uint32_t> &dst = members[m.to];                // bi_add_raw: append
-    if (dst.empty()) { slot0_updates.push_back({m.r, 1}); slot0_changed = true; }
-    slot_of[m.r] = (uint32_t)dst.size(); dst.push_back(m.r);
-    cl_reads_h[m.to] += cx->reads[m.r];
-    cluster_of_h[m.r] = m.to;
-    upd_e[m.from] = 1; upd_e[m.to] = 1;
-  }
-  if (slot0_changed)
-    for (auto &u : slot0_updates) h2d(slot0.p + u.first, &u.second, 1);
-  upload_cluster_arrays(false);
-  if (slot0_changed) CK(cudaStreamSynchronize(s));
-  return true;
-}
-
-void Run::p_update() {
-  upload_cluster_arrays(true);
-  launch_p_update(st, in, o->greedy != 0, o->detect_singletons != 0, s);
-  std::fill(upd_e.begin(), upd_e.end(), 0);
-  std::fill(chk_locks.begin(), chk_locks.end(), 0);
-}
-
-// b_bud (cluster.cpp:274-350).  Returns new cluster index or 0.
-int Run::bud() {
-  unsigned long long init[6] = {~0ull, 0ull, 0ull, ~0ull, 0ull, 0ull};
-  h2d(ctr.p + CTR_PMIN, init, 6 * 8);
-  launch_bud_scan(st, in, o->min_fold, o->min_hamming, o->min_abund, ties.p, ties_pr.p, tie_cap, s);
-  read_ctr();
-  unsigned long long nt = h_ctr.p[CTR_NTIE], ntp = h_ctr.p[CTR_NTIE_PR];
-  if (nt > tie_cap || ntp > tie_cap) {                         // pathological tie set: grow and rescan
-    tie_cap = (unsigned)std::max(nt, ntp) + 16;
-    ties.alloc(tie_cap * 3); ties_pr.alloc(tie_cap * 3); h_ties.alloc(tie_cap * 3); h_ties_pr.alloc(tie_cap * 3);
-    return bud();
-  }
-  if (nt) d2h(h_ties.p, ties.p, nt * 4);
-  if (ntp) d2h(h_ties_pr.p, ties_pr.p, ntp * 4);
-  CK(cudaStreamSynchronize(s));
   auto pick = [&](const uint32_t *t, unsigned long long n) -> long {     // first in (cluster, slot) scan order
     long best = -1;
     for (unsigned long long k = 0; k < n; k++) {
-      uint32_t r = t[k];
+      const uint32_t r = t[k];
       if (best < 0 || cluster_of_h[r] < cluster_of_h[best] || (cluster_of_h[r] == cluster_of_h[best] && slot_of[r] < slot_of[best])) best = r;
     }
     return best;
   };
-  // minraw starts as the centre of cluster 0 (p == 1 always: hamming 0 or singleton), cluster.cpp:279
-  const uint32_t c0 = cl_center_h[0];
+  const uint32_t c0 = cl_center_h[0];     // minraw starts as the centre of cluster 0 (p == 1), cluster.cpp:279
   auto bits2d = [](unsigned long long b) { double d; memcpy(&d, &b, 8); return d; };
   long win = -1, win_pr = -1;
   double pmin = 1.0, pmin_pr = 1.0;
   if (nt) {
-    double pv = bits2d(h_ctr.p[CTR_PMIN]);
-    unsigned long long rm = h_ctr.p[CTR_RMAX];
-    if (pv < 1.0 || (pv == 1.0 && rm > cx->reads[c0])) { win = pick(h_ties.p, nt); pmin = pv; }
+    const double pv = bits2d(R.ctr[CTR_PMIN]);
+    if (pv < 1.0 || (pv == 1.0 && R.ctr[CTR_RMAX] > cx->reads[c0])) { win = pick(tr, nt); pmin = pv; }
   }
   if (ntp) {
-    double pv = bits2d(h_ctr.p[CTR_PMIN_PR]);
-    unsigned long long rm = h_ctr.p[CTR_RMAX_PR];
-    if (pv < 1.0 || (pv == 1.0 && rm > cx->reads[c0])) { win_pr = pick(h_ties_pr.p, ntp); pmin_pr = pv; }
+    const double pv = bits2d(R.ctr[CTR_PMIN_PR]);
+    if (pv < 1.0 || (pv == 1.0 && R.ctr[CTR_RMAX_PR] > cx->reads[c0])) { win_pr = pick(trp, ntp); pmin_pr = pv; }
   }
   const double pA = pmin * (double)(unsigned)nraw, pP = pmin_pr;
   long w = -1; char type = 0; double pv = 0;
@@ -546,35 +629,31 @@ int Run::bud() {
   else if (pP < o->omegaP && win_pr >= 0) { w = win_pr; type = 'P'; pv = pP; }
   if (w < 0) return 0;
   const uint32_t r = (uint32_t)w, from = cluster_of_h[r];
-  // fetch the winner's comparison (raw->comp)
-  double lam; uint32_t ham;
-  d2h(&lam, comp_lambda.p + r, 8);
-  d2h(&ham, comp_ham.p + r, 4);
-  CK(cudaStreamSynchronize(s));
+  // the winner's comparison (raw->comp)
+  double lam = 0; uint32_t ham = 0; bool have = false;
+  for (unsigned long long k = 0; k < std::min<unsigned long long>(nt, TIE_MAX) && !have; k++)
+    if (R.tie_r[k] == r && type == 'A') { lam = R.tie_lam[k]; ham = R.tie_ham[k]; have = true; }
+  for (unsigned long long k = 0; k < std::min<unsigned long long>(ntp, TIE_MAX) && !have; k++)
+    if (R.tiep_r[k] == r && type == 'P') { lam = R.tiep_lam[k]; ham = R.tiep_ham[k]; have = true; }
+  if (!have) {
+    d2h(&lam, comp_lambda.p + r, 8); d2h(&ham, comp_ham.p + r, 4);
+    CK(cudaStreamSynchronize(s));
+  }
   const double expected = lam * (double)cl_reads_h[from];
-  // bi_pop_raw(from, slot)
-  std::vector<uint32_t> &src = members[from];
+  std::vector<uint32_t> &src = members[from];                   // bi_pop_raw(from, slot)
   const uint32_t sl = slot_of[r], last = src.back();
   src[sl] = last; slot_of[last] = sl; src.pop_back();
   cl_reads_h[from] -= cx->reads[r];
-  upd_e[from] = 1;
-  // b_add_bi + bi_add_raw + bi_assign_center
-  const uint32_t ni = (uint32_t)members.size();
+  const uint32_t ni = (uint32_t)members.size();                 // b_add_bi + bi_add_raw + bi_assign_center
   members.emplace_back(1, r);
   slot_of[r] = 0; cluster_of_h[r] = ni;
   cl_reads_h.push_back(cx->reads[r]); cl_center_h.push_back(r);
-  upd_e.push_back(1); chk_locks.push_back(1);
-  Birth b; b.type = type; b.from = (type == 'A') ? from : from;  // 'P': uninitialised in the reference (cluster.cpp:334-339)
+  Birth b; b.type = type; b.from = from;                        // 'P': uninitialised in the reference (cluster.cpp:334-339)
   b.pval = pv; b.fold = (double)cx->reads[r] / expected; b.e = expected;
   b.comp_i = from; b.comp_index = r; b.comp_lambda = lam; b.comp_ham = ham;
   birth.push_back(b);
-  const uint8_t one = 1, zero = 0;
-  h2d(cluster_of.p + r, &ni, 4);
-  h2d(is_center.p + r, &one, 1);
-  h2d(slot0.p + r, &one, 1);
-  h2d(lock.p + r, &zero, 1);       // bi_assign_center unlocks, cluster.cpp:377
-  upload_cluster_arrays(false);
-  CK(cudaStreamSynchronize(s));
+  pending.apply = 1; pending.r = r; pending.from = from; pending.newi = ni; pending.reads = cx->reads[r];
+  *r_out = r; *from_out = from;
   return (int)ni;
 }
 
@@ -588,7 +667,7 @@ template <typename T> T *dupv(const std::vector<T> &v) {
 void Run::finish(dada2b_out *out) {
   const uint32_t nclust = (uint32_t)members.size();
   const int maxlen = in.maxlen;
-  upload_cluster_arrays(false);
+  if (pending.apply) { launch_round_begin(st, 1, pending.r, pending.from, pending.newi, pending.reads, s); pending.apply = 0; }
   launch_final_p(st, in, o->omegaC, s);
   trans.alloc((size_t)16 * ncol); trans.zero(s);
   cq_sum.alloc((size_t)nclust * maxlen); cq_cnt.alloc((size_t)nclust * maxlen); cq_sum.zero(s); cq_cnt.zero(s);
@@ -642,10 +721,9 @@ void Run::finish(dada2b_out *out) {
   // post-hoc cluster p-values (error.cpp:99-119)
   std::vector<double> tot_e(nclust, 0.0), cpval(nclust, 0.0);
   {
-    std::vector<int> cc(nraw, -1);
-    for (uint32_t i = 0; i < nclust; i++) cc[cl_center_h[i]] = (int)i;
     center_cluster.alloc(nraw);
-    h2d(center_cluster.p, cc.data(), (size_t)nraw * 4);
+    CK(cudaMemsetAsync(center_cluster.p, 0xFF, (size_t)nraw * 4, s));     // -1 everywhere
+    launch_center_cluster(center_cluster.p, st.cl_center, (int)nclust, s);
     unsigned cap = std::max<unsigned>(4096, nclust * 8);
     std::vector<uint32_t> tij; std::vector<double> tv; unsigned long long cnt = 0;
     DBuf<unsigned long long> dcount; dcount.alloc(1);
@@ -765,19 +843,24 @@ void Run::finish(dada2b_out *out) {
 
 dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opts *o) {
   const double t0 = now_ms();
+  g_t0 = t0;
   CK(cudaSetDevice(cx->device));
   if (Q < 1) throw Err{"Error matrix must have 16 rows."};
   if (cx->bad_nt) throw Err{o->use_kmers ? "Unexpected nucleotide." : "Non-ACGT sequences in compute_lambda."};
   if (o->use_quals && cx->maxq > Q - 1) throw Err{"Rounded quality exceeded range of err lookup table."};
-  Run R;
+  if (!cx->run) cx->run = new Run();
+  Run &R = *cx->run;
+  R.reset_host();
   R.cx = cx; R.o = o; R.s = cx->stream; R.in = cx->in; R.nraw = cx->in.nraw; R.ncol = Q;
   DBG("run: begin");
   cx->ev_next = 0;
   R.launches0 = launches_count();
   R.ev_begin = cx->get_event(); R.ev_end = cx->get_event();
+  TDBG("begin");
   R.setup_params();
-  DBG("run: params set");
+  TDBG("params set");
   R.alloc_state();
+  TDBG("state allocated");
   if (getenv("DADA2B_SYNCDEBUG")) fprintf(stderr, "[dada2b] state allocated; warp_words=%d ptr_in_smem=%d align_smem=%zu grid=%d\n", R.warp_words, R.ptr_in_smem, R.align_smem, R.align_grid);
   CK(cudaEventRecord(R.ev_begin, R.s));
   {  // cluster.cpp:162-170: row-major copy of the error matrix
@@ -796,31 +879,49 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
   for (int r = 0; r < nraw; r++) if (cx->reads[r] > mx) { mx = cx->reads[r]; c0 = r; found = true; }   // bi_assign_center
   if (!found) throw Err{"dada2b: all abundances are zero."};
   R.cl_center_h.push_back(c0); R.cl_reads_h.push_back(cx->total_reads);
-  R.upd_e.push_back(1); R.chk_locks.push_back(1);
   R.birth.emplace_back(); R.birth[0].e = cx->total_reads;
-  const uint8_t one = 1;
-  R.h2d(R.is_center.p + c0, &one, 1);
-  R.h2d(R.slot0.p + 0, &one, 1);
-  R.upload_cluster_arrays(true);
-  CK(cudaStreamSynchronize(R.s));
+  {
+    const uint8_t one = 1;
+    R.h2d(R.is_center.p + c0, &one, 1);
+    R.h2d(R.slot0.p + 0, &one, 1);
+    R.h2d(R.cl_reads.p, &cx->total_reads, 4); R.h2d(R.cl_reads_next.p, &cx->total_reads, 4);
+    R.h2d(R.cl_center.p, &c0, 4);
+    R.h2d(R.cl_update_e.p, &one, 1); R.h2d(R.cl_check_locks.p, &one, 1);
+    CK(cudaStreamSynchronize(R.s));
+  }
+  TDBG("cluster 0 initialised");
   const double t1 = now_ms();
-  // run_dada (Rmain.cpp:297-336)
-  R.compare(0, 1.0);
-  R.p_update();
-  int max_clust = o->max_clust < 1 ? nraw : o->max_clust;
-  int newi;
   const bool dbg = o->verbose || getenv("DADA2B_VERBOSE");
+  // run_dada (Rmain.cpp:297-336)
+  R.launch_compare(0, 1.0);
+  R.launch_round_tail(0, 0);                 // initial cluster: b_p_update + first b_bud scan
+  R.sync_report();
   if (dbg) fprintf(stderr, "[dada2b] round 0 done: %.2f ms, cs=%llu\n", now_ms() - t1, R.cs_count);
-  while ((int)R.members.size() < max_clust && (newi = R.bud())) {
+  const int max_clust = o->max_clust < 1 ? nraw : o->max_clust;
+  uint32_t wr = 0, wfrom = 0;
+  int newi;
+  while ((int)R.members.size() < max_clust && (newi = R.decide_bud(&wr, &wfrom))) {
     const double tr = now_ms();
-    R.compare((uint32_t)newi, o->kdist_cutoff);
-    const double tc = now_ms();
-    int nshuffle = 0; bool shuffled;
-    do { shuffled = R.shuffle_pass(); } while (shuffled && ++nshuffle < 10);   // MAX_SHUFFLE dada.h:30
-    R.p_update();
+    R.launch_compare((uint32_t)newi, o->kdist_cutoff);
+    R.launch_round_tail(0, R.NP);
+    R.sync_report();
+    int last = R.NP - 1;
+    int ran = R.replay_moves(0, last);
+    if (!R.h_report->converged) {            // rare: more than NP passes needed (MAX_SHUFFLE = 10, dada.h:30)
+      while (last + 1 < MAX_PASS) {
+        last++;
+        R.launch_shuffle_only(last);
+        R.sync_report();
+        ran += R.replay_moves(last, last);
+        if (R.h_report->converged) break;
+      }
+      R.launch_round_tail_noshuffle();       // p-update + bud scan skipped themselves on the device: run them now
+      R.sync_report();
+    }
     R.n_rounds++;
-    if (dbg) fprintf(stderr, "[dada2b] C%d seed=%u: compare %.3f ms, shuffle+p %.3f ms (%d passes), cs=%llu nw=%llu gl=%llu\n", newi,
-                     R.cl_center_h[newi], tc - tr, now_ms() - tc, nshuffle + 1, R.cs_count, R.h_ctr.p[CTR_NW], R.h_ctr.p[CTR_GL]);
+    if (dbg) fprintf(stderr, "[dada2b] C%d seed=%u: round %.3f ms (%d passes), cs=%llu nw=%llu gl=%llu moves=%llu\n", newi,
+                     R.cl_center_h[newi], now_ms() - tr, ran, R.cs_count, R.h_report->ctr[CTR_NW], R.h_report->ctr[CTR_GL],
+                     R.h_report->ctr[CTR_NMOVE]);
   }
   if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters\n", (int)R.members.size());
   CK(cudaStreamSynchronize(R.s));
@@ -949,17 +1050,24 @@ void dada2b_ctx_free(dada2b_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  delete_run(ctx->run);
   delete ctx;
 }
 
+// One-shot call.  The device/pinned workspace of the previous call on this thread is kept and reused
+// (grow-only), like a caching allocator: repeated dada_uniques() calls -- the per-sample loop of
+// R/dada.R:266 -- do not pay cudaMalloc/cudaMallocHost again.
 int dada2b_run(const dada2b_in *in, const dada2b_opts *opts, dada2b_out **out, char errbuf[DADA2B_ERRLEN]) {
-  dada2b_ctx *cx = nullptr;
+  static thread_local dada2b_ctx *ws = nullptr;
   *out = nullptr;
-  int rc = dada2b_upload(in, 0, &cx, errbuf);
-  if (rc) return rc;
-  rc = dada2b_run_resident(cx, in->err, in->Q, opts, out, errbuf);
-  if (!rc && *out) (*out)->h2d_bytes += cx->upload_h2d;
-  dada2b_ctx_free(cx);
+  try {
+    int dev = 0;
+    if (ws) dev = ws->device;
+    ws = do_upload(in, dev, ws);
+  } catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
+  catch (std::exception &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.what()); return 2; }
+  int rc = dada2b_run_resident(ws, in->err, in->Q, opts, out, errbuf);
+  if (!rc && *out) (*out)->h2d_bytes += ws->upload_h2d;
   return rc;
 }
 

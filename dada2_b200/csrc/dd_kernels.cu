@@ -379,129 +379,6 @@ template __global__ void k_align<MODE_LOOP>(AlignArgs);
 template __global__ void k_align<MODE_FINAL>(AlignArgs);
 template __global__ void k_align<MODE_BIRTH>(AlignArgs);
 
-// =====================================================================================
-// b_shuffle2 (cluster.cpp:210-266) over the flat comparison store.
-//   pass A: emax[raw] = max_e (order-preserving u64 image of the non-negative double)
-//   pass B: best[raw] = lowest entry id attaining emax  (entries are appended cluster by
-//           cluster, so the lowest id is the lowest cluster index == strict '>' scan order)
-//   pass C: raws whose best cluster differs from their current one move (centres stay).
-// =====================================================================================
-__global__ void k_shuffle_init(DevState st, int nraw) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= nraw) return;
-  double e = st.cs_lambda[r] * (double)st.cl_reads[0];    // cluster 0 holds every raw, in index order (:223-226)
-  st.emax_bits[r] = (unsigned long long)__double_as_longlong(e);
-  st.best_entry[r] = 0xFFFFFFFFu;
-}
-__global__ void k_shuffle_max(DevState st, int nraw) {
-  unsigned long long n = st.ctr[CTR_CS_COUNT];
-  unsigned long long x = (unsigned long long)nraw + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (x >= n) return;
-  double e = st.cs_lambda[x] * (double)st.cl_reads[st.cs_i[x]];
-  atomicMax(&st.emax_bits[st.cs_index[x]], (unsigned long long)__double_as_longlong(e));
-}
-__global__ void k_shuffle_arg(DevState st, int nraw) {
-  unsigned long long n = st.ctr[CTR_CS_COUNT];
-  unsigned long long x = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  if (x >= n) return;
-  double e = st.cs_lambda[x] * (double)st.cl_reads[st.cs_i[x]];
-  uint32_t r = st.cs_index[x];
-  if ((unsigned long long)__double_as_longlong(e) == st.emax_bits[r]) atomicMin(&st.best_entry[r], (uint32_t)x);
-}
-__global__ void k_shuffle_move(DevState st, int nraw, uint32_t *moves, unsigned move_cap) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= nraw) return;
-  uint32_t be = st.best_entry[r];
-  uint32_t to = st.cs_i[be], from = st.cluster_of[r];
-  if (to != from && !st.is_center[r]) {
-    unsigned long long s = atomicAdd(&st.ctr[CTR_NMOVE], 1ull);
-    if (s < move_cap) { moves[2 * s] = (uint32_t)r; moves[2 * s + 1] = to; }
-    st.cluster_of[r] = to;
-    st.comp_lambda[r] = st.cs_lambda[be];
-    st.comp_ham[r] = st.cs_ham[be];
-  }
-}
-// =====================================================================================
-// b_p_update (pval.cpp:14-40): abundance p-value for raws of clusters flagged update_e; greedy
-// locking for clusters flagged check_locks.
-// =====================================================================================
-__global__ void k_p_update(DevState st, DevIn in, int greedy, int detect_singletons) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= in.nraw) return;
-  const uint32_t ci = st.cluster_of[r];
-  const uint32_t reads = in.reads[r];
-  const double lambda = st.comp_lambda[r];
-  if (st.cl_update_e[ci]) {                                            // get_pA pval.cpp:67-89
-    const bool prior = in.prior[r] != 0;
-    double pval;
-    if (reads == 1 && !prior && !detect_singletons) pval = 1.;
-    else if (st.comp_ham[r] == 0) pval = 1.;
-    else if (lambda == 0) pval = 0.;
-    else pval = calc_pA((int)reads, lambda * (double)st.cl_reads[ci], prior || detect_singletons);
-    st.p[r] = pval;
-  }
-  if (greedy && st.cl_check_locks[ci]) {                               // pval.cpp:29-38
-    const uint32_t cen = st.cl_center[ci];
-    const double E_reads_center = (double)in.reads[cen] * lambda;
-    if (E_reads_center > (double)reads) st.lock[r] = 1;
-    if ((uint32_t)r == cen) st.lock[r] = 1;
-  }
-}
-
-// =====================================================================================
-// b_bud scan (cluster.cpp:284-308): lexicographic minimum of (p asc, reads desc) over eligible
-// raws; every raw attaining it is returned so the host can apply the (cluster, slot) scan-order
-// tie-break exactly.  Same for the prior-carrying subset.
-// =====================================================================================
-__device__ __forceinline__ bool bud_eligible(const DevState &st, const DevIn &in, int r, double min_fold, int min_hamming,
-                                             int min_abund) {
-  if (st.slot0[r]) return false;                                       // r starts at 1 (:285)
-  const uint32_t reads = in.reads[r];
-  if ((int)reads < min_abund) return false;
-  if ((int)st.comp_ham[r] < min_hamming) return false;
-  if (!(min_fold <= 1 || ((double)reads) >= min_fold * st.comp_lambda[r] * (double)st.cl_reads[st.cluster_of[r]])) return false;
-  return true;
-}
-__global__ void k_bud_pmin(DevState st, DevIn in, double min_fold, int min_hamming, int min_abund) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long pb = ~0ull, pbp = ~0ull;
-  if (r < in.nraw && bud_eligible(st, in, r, min_fold, min_hamming, min_abund)) {
-    pb = (unsigned long long)__double_as_longlong(st.p[r]);
-    if (in.prior[r]) pbp = pb;
-  }
-  // warp-level min first, one atomic per warp
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    unsigned long long t = __shfl_xor_sync(0xffffffffu, pb, o); pb = t < pb ? t : pb;
-    t = __shfl_xor_sync(0xffffffffu, pbp, o); pbp = t < pbp ? t : pbp;
-  }
-  if (lane_id() == 0) {
-    if (pb != ~0ull) atomicMin(&st.ctr[CTR_PMIN], pb);
-    if (pbp != ~0ull) atomicMin(&st.ctr[CTR_PMIN_PR], pbp);
-  }
-}
-__global__ void k_bud_rmax(DevState st, DevIn in, double min_fold, int min_hamming, int min_abund) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= in.nraw || !bud_eligible(st, in, r, min_fold, min_hamming, min_abund)) return;
-  const unsigned long long pb = (unsigned long long)__double_as_longlong(st.p[r]);
-  if (pb == st.ctr[CTR_PMIN]) atomicMax(&st.ctr[CTR_RMAX], (unsigned long long)in.reads[r]);
-  if (in.prior[r] && pb == st.ctr[CTR_PMIN_PR]) atomicMax(&st.ctr[CTR_RMAX_PR], (unsigned long long)in.reads[r]);
-}
-__global__ void k_bud_collect(DevState st, DevIn in, double min_fold, int min_hamming, int min_abund, uint32_t *ties,
-                              uint32_t *ties_pr, unsigned cap) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= in.nraw || !bud_eligible(st, in, r, min_fold, min_hamming, min_abund)) return;
-  const unsigned long long pb = (unsigned long long)__double_as_longlong(st.p[r]);
-  if (pb == st.ctr[CTR_PMIN] && (unsigned long long)in.reads[r] == st.ctr[CTR_RMAX]) {
-    unsigned long long s = atomicAdd(&st.ctr[CTR_NTIE], 1ull);
-    if (s < cap) ties[s] = (uint32_t)r;
-  }
-  if (in.prior[r] && pb == st.ctr[CTR_PMIN_PR] && (unsigned long long)in.reads[r] == st.ctr[CTR_RMAX_PR]) {
-    unsigned long long s = atomicAdd(&st.ctr[CTR_NTIE_PR], 1ull);
-    if (s < cap) ties_pr[s] = (uint32_t)r;
-  }
-}
-
 // Rmain.cpp:239-252: final within-cluster p and the correct flag.
 __global__ void k_final_p(DevState st, DevIn in, double omegaC) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -560,28 +437,6 @@ void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem
   if (mode == MODE_LOOP) k_align<MODE_LOOP><<<grid, block, smem, s>>>(a);
   else if (mode == MODE_FINAL) k_align<MODE_FINAL><<<grid, block, smem, s>>>(a);
   else k_align<MODE_BIRTH><<<grid, block, smem, s>>>(a);
-}
-void launch_shuffle_pass(const DevState &st, int nraw, unsigned long long n_entries, uint32_t *moves, unsigned move_cap,
-                         cudaStream_t s) {
-  const int B = 256;
-  COUNT_LAUNCH(3 + (n_entries > (unsigned long long)nraw ? 1 : 0));
-  k_shuffle_init<<<(nraw + B - 1) / B, B, 0, s>>>(st, nraw);
-  if (n_entries > (unsigned long long)nraw)
-    k_shuffle_max<<<(unsigned)((n_entries - nraw + B - 1) / B), B, 0, s>>>(st, nraw);
-  k_shuffle_arg<<<(unsigned)((n_entries + B - 1) / B), B, 0, s>>>(st, nraw);
-  k_shuffle_move<<<(nraw + B - 1) / B, B, 0, s>>>(st, nraw, moves, move_cap);
-}
-void launch_p_update(const DevState &st, const DevIn &in, int greedy, int detect_singletons, cudaStream_t s) {
-  COUNT_LAUNCH(1);
-  k_p_update<<<(in.nraw + 127) / 128, 128, 0, s>>>(st, in, greedy, detect_singletons);
-}
-void launch_bud_scan(const DevState &st, const DevIn &in, double min_fold, int min_hamming, int min_abund, uint32_t *ties,
-                     uint32_t *ties_pr, unsigned cap, cudaStream_t s) {
-  const int B = 256, G = (in.nraw + B - 1) / B;
-  COUNT_LAUNCH(3);
-  k_bud_pmin<<<G, B, 0, s>>>(st, in, min_fold, min_hamming, min_abund);
-  k_bud_rmax<<<G, B, 0, s>>>(st, in, min_fold, min_hamming, min_abund);
-  k_bud_collect<<<G, B, 0, s>>>(st, in, min_fold, min_hamming, min_abund, ties, ties_pr, cap);
 }
 void launch_final_p(const DevState &st, const DevIn &in, double omegaC, cudaStream_t s) {
   COUNT_LAUNCH(1);

@@ -1,6 +1,7 @@
 // Kernel argument blocks + launch wrappers (product code).
 #pragma once
 #include "dd_common.h"
+#include <algorithm>
 
 namespace dd2 {
 
@@ -60,11 +61,16 @@ void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cu
 void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 cudaError_t align_set_smem(size_t bytes);
 
-void launch_shuffle_pass(const DevState &st, int nraw, unsigned long long n_entries_hint, uint32_t *moves,
-                         unsigned move_cap, cudaStream_t s);
-void launch_p_update(const DevState &st, const DevIn &in, int greedy, int detect_singletons, cudaStream_t s);
-void launch_bud_scan(const DevState &st, const DevIn &in, double min_fold, int min_hamming, int min_abund,
-                     uint32_t *ties, uint32_t *ties_pr, unsigned cap, cudaStream_t s);
+// per-round control kernels (dd_round.cu)
+struct BudParams { double min_fold; int min_hamming, min_abund; };
+void launch_round_begin(const DevState &st, int apply, uint32_t r, uint32_t from, uint32_t newi, uint32_t reads_r, cudaStream_t s);
+void launch_shuffle_pass(const DevState &st, const DevIn &in, unsigned long long n_entries_upper, int nclust, int pass, cudaStream_t s);
+void launch_p_update(const DevState &st, const DevIn &in, int greedy, int detect_singletons, int last_pass, cudaStream_t s);
+void launch_bud_scan(const DevState &st, const DevIn &in, const BudParams &bp, int nclust, int last_pass, cudaStream_t s);
+void launch_report(const DevState &st, int last_pass, cudaStream_t s);
+void launch_fill_f64(double *p, double v, size_t n, cudaStream_t s);
+void launch_center_cluster(int *cc, const uint32_t *cl_center, int nclust, cudaStream_t s);
+void launch_bud_collect_big(const DevState &st, const DevIn &in, const BudParams &bp, uint32_t *ties, uint32_t *ties_pr, unsigned cap, cudaStream_t s);
 void launch_final_p(const DevState &st, const DevIn &in, double omegaC, cudaStream_t s);
 void launch_calc_pA_vec(const int *reads, const double *E, const int *prior, double *out, int n, cudaStream_t s);
 void launch_posthoc(const DevState &st, int nraw, unsigned long long n_entries, const int *center_cluster,
