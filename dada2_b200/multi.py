@@ -1,0 +1,34 @@
+"""Multi-GPU host logic: one process per GPU (torch.distributed), samples of a run distributed over
+ranks -- the reference's own per-sample loop (R/dada.R:266-365) made data-parallel.  No collective is
+on the data path; results are gathered once at the end (gather_object).  Works with the `gloo` backend
+on CPU for the logic tests (the per-sample runner is injectable)."""
+from __future__ import annotations
+
+
+def shard_samples(n_samples: int, rank: int, world: int):
+    """Round-robin assignment (sample i -> rank i % world): balances the abundance-sorted sample lists
+    dada() usually sees without any communication."""
+    return list(range(rank, n_samples, world))
+
+
+def dada_samples(samples, err, runner=None, group=None, **opts):
+    """samples: list of (seqs, abundances, priors, quals).  Every rank passes the same list; rank r runs
+    its shard with `runner` (default: dada2_b200.dada_uniques on this rank's GPU) and rank 0 returns the
+    full list of per-sample results in input order (other ranks return None)."""
+    import torch.distributed as dist
+    if runner is None:
+        from .api import dada_uniques as runner
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    mine = shard_samples(len(samples), rank, world)
+    local = {i: runner(samples[i][0], samples[i][1], samples[i][2], err, samples[i][3], **opts) for i in mine}
+    if world == 1:
+        return [local[i] for i in range(len(samples))]
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(local, gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    merged = {}
+    for part in gathered:
+        merged.update(part)
+    return [merged[i] for i in range(len(samples))]
