@@ -495,6 +495,10 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
     f.centre_idx = c; f.centre_reads = cx->reads[c]; f.cluster_i = i; f.total_reads = cx->total_reads;
     f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes;
+    {  // the fast path replaces the reference's sentinel by a larger penalty: only valid while no real score can come near it
+      const long worst = 2L * in.maxlen * std::max(std::max(std::abs(P.mismatch), std::abs(P.gap)), std::abs(P.match));
+      f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
+    }
     timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, i == 0 ? (unsigned long long)nraw : est_active, cx->num_sms, s); });
   }
   for (int kind : {KIND_NW, KIND_GAPLESS}) {

@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
 
   const uint32_t c = a.mode == 0 ? a.centre_idx : a.pair_centre[blockIdx.x];
   const int len1 = a.in.len[c];
+  __shared__ uint32_t cen_bits_s[32];      // presence bitmap of the centre's 5-mers (1024 bits)
+  uint32_t cen_bits = 0;                   // lane l keeps word l
   if (P.use_kmers) {
+    if (threadIdx.x < 32) cen_bits_s[threadIdx.x] = 0;
     for (int x = threadIdx.x; x < 512; x += blockDim.x) cen_cnt[x] = 0;
     for (int x = threadIdx.x; x < nwarps * 512; x += blockDim.x) smem[512 + a.kord_words + x] = 0;
     __syncthreads();
@@ -65,8 +68,10 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
       unsigned km = kmer_at(crow, p);
       cen_kord[p] = (uint16_t)km;
       atomicAdd(&cen_cnt[km >> 1], 1u << (16 * (km & 1)));
+      atomicOr(&cen_bits_s[km >> 5], 1u << (km & 31));
     }
     __syncthreads();
+    cen_bits = cen_bits_s[lane];
   }
 
   const int gw = blockIdx.x * nwarps + wid, tw = gridDim.x * nwarps;
@@ -82,6 +87,26 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
       for (int x = lane; x < SW; x += 32) wseq[x] = rrow[x];
       __syncwarp();
       const int minlen = min(len1, len2), nko = minlen - KMER + 1;
+      const double denom = (double)(minlen - KMER) + 1.;
+      // Tier 1 (no atomics): U = #raw 5-mers present in the centre >= sum_k min(c_raw, c_centre).  kdist is
+      // monotone in that sum, so 1 - U/denom > cutoff proves the pair is shrouded exactly (raw_align :51).
+      {
+        int U = 0;
+        for (int p0 = 0; p0 + KMER <= len2; p0 += 32) {
+          const int p = p0 + lane;
+          const bool ok = p + KMER <= len2;
+          const unsigned km = ok ? kmer_at(wseq, p) : 0u;
+          const uint32_t w = __shfl_sync(0xffffffffu, cen_bits, km >> 5);
+          U += ok ? (int)((w >> (km & 31)) & 1u) : 0;
+        }
+        U = warp_sum(U);
+        const double kd_lb = 1. - ((double)(U & 0xFFFF)) / denom;
+        if (kd_lb > P.kdist_cutoff) {
+          if (lane == 0) { atomicAdd(&a.ctr[CTR_ALIGN], 1ull); atomicAdd(&a.ctr[CTR_SHROUD], 1ull); if (a.kind_out) a.kind_out[job] = (uint8_t)KIND_SHROUD; }
+          __syncwarp();
+          continue;
+        }
+      }
       int ms = 0, om = 0;
       for (int p = lane; p + KMER <= len2; p += 32) {
         unsigned km = kmer_at(wseq, p);
@@ -98,7 +123,6 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
       for (int p = lane; p + KMER <= len2; p += 32) wtab[kmer_at(wseq, p) >> 1] = 0;
       __syncwarp();
       // kmers.cpp:24 / :91: dot = dotsum/(min(len)-k+1.), dist = 1-dot ; raw_align :51,:54
-      double denom = (double)(minlen - KMER) + 1.;
       double kdist = 1. - ((double)(ms & 0xFFFF)) / denom;
       bool ko_valid = P.gapless && !(P.sse == 0 && len1 != len2);
       double kodist = ko_valid ? 1. - ((double)(om & 0xFFFF)) / denom : -1.0;

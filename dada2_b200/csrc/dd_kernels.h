@@ -54,6 +54,7 @@ struct FwdArgs {
   uint32_t *fb_list;                    // pairs that do not fit the register band -> k_align
   unsigned long long *fb_count;
   int seq_bytes;
+  int fast_ok;                          // interior fast path allowed (scores cannot approach the sentinel)
 };
 bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s);
 void count_launch(int n);

@@ -40,8 +40,10 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
   uint8_t *s_cen = (uint8_t *)(s_err + 16 * ncol + 2);  // centre bases
   const int nwarps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane / G, gl = lane % G;
-  uint8_t *s_raw = s_cen + a.seq_bytes + (size_t)(wid * PPW + gid) * 2 * a.seq_bytes;   // bases then quals
-  uint8_t *s_q = s_raw + a.seq_bytes;
+  // per pair: raw bases [seq_bytes] then b2[pos] = nt*ncol + qual as u16 with PAD zeroed entries on both sides
+  constexpr int PAD = 64;
+  uint8_t *s_raw = s_cen + a.seq_bytes + (size_t)(wid * PPW + gid) * (3 * a.seq_bytes + 4 * PAD);
+  uint16_t *s_b2 = (uint16_t *)(s_raw + a.seq_bytes) + PAD;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gid * G));
   (void)gmask;
 
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
     for (int p = threadIdx.x; p < len1; p += blockDim.x) s_cen[p] = (uint8_t)((crow[p >> 4] >> (2 * (p & 15))) & 3u);
   }
   __syncthreads();
-  const int ONE_IDX = 16 * ncol;
+  const int ONE_IDX = 16 * ncol, ncol4 = 4 * ncol;
   const int SENT = P.sentinel, match = P.match, mismatch = P.mismatch, gap = P.gap;
   int errflag = 0;
 
@@ -65,17 +67,21 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
     const unsigned long long jb = base + gid;
     bool act = jb < njobs;
     const uint32_t r = act ? a.jobs[jb] : 0;
-    const int len2 = act ? a.in.len[r] : 1;
+    const int len2 = act ? a.in.len[r] : len1;     // idle groups run a benign geometry (their lanes still execute)
     // ---- stage raw bases + qualities (group-cooperative) ----
     if (act) {
       const uint32_t *rrow = a.in.seq2 + (size_t)r * a.in.SW;
       const uint8_t *qrow = a.in.qual + (size_t)r * a.in.QS;
       for (int p = gl; p < len2; p += G) {
-        s_raw[p] = (uint8_t)((rrow[p >> 4] >> (2 * (p & 15))) & 3u);
+        const uint32_t b = (rrow[p >> 4] >> (2 * (p & 15))) & 3u;
+        s_raw[p] = (uint8_t)b;
         int q = P.use_quals ? qrow[p] : 0;
         if (q > ncol - 1) { errflag = ERR_QUAL; q = ncol - 1; }             // pval.cpp:169-171
-        s_q[p] = (uint8_t)q;
+        s_b2[p] = (uint16_t)(b * ncol + q);
       }
+      for (int p = gl; p < PAD; p += G) { s_b2[-1 - p] = 0; s_b2[len2 + p] = 0; }
+    } else {   // idle group: its lanes still execute the DP; keep their table indices in range
+      for (int p = gl; p < a.seq_bytes + 2 * PAD; p += G) s_b2[p - PAD] = 0;
     }
     __syncwarp();
     // ---- band geometry (nwalign_endsfree.cpp:101-111) ----
@@ -112,7 +118,80 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
       A |= b1 << (2 * cc); B |= b2 << (2 * cc);
     }
 
+    // Interior steps (no boundary cell, no free end gap, every pair still running) take a branch-free path;
+    // out-of-band slots are kept far below any real score by an additive penalty instead of a mask.
+    int kf_lo = act ? max(lb, rb) + 2 : 0, kf_hi = act ? min(2 * len1 - lb, 2 * len2 - rb) - 1 : 0x3fffffff;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      kf_lo = max(kf_lo, __shfl_xor_sync(0xffffffffu, kf_lo, o));
+      kf_hi = min(kf_hi, __shfl_xor_sync(0xffffffffu, kf_hi, o));
+    }
+    if (!a.fast_ok) kf_hi = -1;
+    constexpr int BIGPEN = 1 << 20;
+    int PEN[ND];
+#pragma unroll
+    for (int t = 0; t < ND; t++) PEN[t] = (t >= tlo && t <= thi) ? 0 : -BIGPEN;
+
     for (int kk = 0; kk <= maxsteps; kk += 2) {
+      if (kk >= kf_lo && kk + 1 <= kf_hi) {
+#pragma unroll
+        for (int PAR = 0; PAR < 2; PAR++) {
+          int Hn, Nn; double Ln;
+          if (PAR == 0) {
+            Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G);
+            Nn = __shfl_up_sync(0xffffffffu, NSUB[ND - 1], 1, G);
+            Ln = __shfl_up_sync(0xffffffffu, LAM[ND - 1], 1, G);
+            if (gl == 0) Hn = -BIGPEN;
+          } else {
+            Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G);
+            Nn = __shfl_down_sync(0xffffffffu, NSUB[0], 1, G);
+            Ln = __shfl_down_sync(0xffffffffu, LAM[0], 1, G);
+            if (gl == G - 1) Hn = -BIGPEN;
+          }
+          const uint32_t X = A ^ B;
+          const uint16_t *b2p = s_b2 + (J + PAR - 1);
+          int Hnew[NSL], Nnew[NSL]; double Lnew[NSL];
+#pragma unroll
+          for (int cc = 0; cc < NSL; cc++) {
+            const int t = 2 * cc + PAR;
+            const int hl = (PAR == 0 && cc == 0) ? Hn : H[t - 1 < 0 ? 0 : t - 1];
+            const int nl = (PAR == 0 && cc == 0) ? Nn : NSUB[t - 1 < 0 ? 0 : t - 1];
+            const double ll = (PAR == 0 && cc == 0) ? Ln : LAM[t - 1 < 0 ? 0 : t - 1];
+            const int hu = (PAR == 1 && cc == NSL - 1) ? Hn : H[t + 1 >= ND ? ND - 1 : t + 1];
+            const int nu = (PAR == 1 && cc == NSL - 1) ? Nn : NSUB[t + 1 >= ND ? ND - 1 : t + 1];
+            const double lu = (PAR == 1 && cc == NSL - 1) ? Ln : LAM[t + 1 >= ND ? ND - 1 : t + 1];
+            const uint32_t nt1 = (A >> (2 * cc)) & 3u, nt2 = (B >> (2 * cc)) & 3u;
+            const bool eq = ((X >> (2 * cc)) & 3u) == 0u;
+            const int left = hl + gap, up = hu + gap, diag = H[t] + (eq ? match : mismatch);
+            const int m = __vimax3_s32(left, up, diag);
+            const bool isU = up == m;                      // precedence up > left > diag (nwalign_endsfree.cpp:147-156)
+            const bool isL = (left == m) && !isU;
+            const int b2 = b2p[cc];
+            const int idx = isU ? ONE_IDX : b2 + (int)(isL ? nt2 : nt1) * ncol4;
+            const double f = s_err[idx];
+            const double lp = isU ? lu : (isL ? ll : LAM[t]);
+            const int np = isU ? nu : (isL ? nl : NSUB[t] + (eq ? 0 : 1));
+            Hnew[cc] = m + PEN[t];
+            Nnew[cc] = np;
+            Lnew[cc] = lp * f;
+          }
+#pragma unroll
+          for (int cc = 0; cc < NSL; cc++) { H[2 * cc + PAR] = Hnew[cc]; NSUB[2 * cc + PAR] = Nnew[cc]; LAM[2 * cc + PAR] = Lnew[cc]; }
+          if (PAR == 0) {
+            uint32_t nbB = __shfl_down_sync(0xffffffffu, B, 1, G);
+            uint32_t newb = nbB & 3u;
+            if (gl == G - 1) { const int jn = J + NSL - 1; newb = (jn >= 0 && jn < len2) ? s_raw[jn] : 0u; }
+            B = (B >> 2) | (newb << (2 * (NSL - 1)));
+          } else {
+            uint32_t nbA = __shfl_up_sync(0xffffffffu, A, 1, G);
+            uint32_t newa = (nbA >> (2 * (NSL - 1))) & 3u;
+            if (gl == 0) newa = (I >= 0 && I < len1) ? s_cen[I] : 0u;
+            A = ((A << 2) | newa) & (NSL == 16 ? 0xffffffffu : ((1u << (2 * NSL)) - 1u));
+            I += 1; J += 1;
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int PAR = 0; PAR < 2; PAR++) {
         const int k = kk + PAR;
@@ -143,7 +222,7 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
           const int nu = (PAR == 1 && cc == NSL - 1) ? Nn : NSUB[t + 1 >= ND ? ND - 1 : t + 1];
           const double lu = (PAR == 1 && cc == NSL - 1) ? Ln : LAM[t + 1 >= ND ? ND - 1 : t + 1];
           const int nt1 = (A >> (2 * cc)) & 3, nt2 = (B >> (2 * cc)) & 3;
-          const int q = s_q[min(max(j - 1, 0), a.seq_bytes - 1)];   // quality of raw base j-1
+          const int b2 = s_b2[min(max(j - 1, -PAD), len2 + PAD - 1)];   // nt2*ncol + quality of raw base j-1
           const bool eq = ((X >> (2 * cc)) & 3u) == 0u;
           const bool valid = (t >= tlo) && (t <= thi) && i >= 0 && j >= 0 && i <= len1 && j <= len2 && k <= nsteps;
           // scores (nwalign_endsfree.cpp:128-156)
@@ -156,8 +235,8 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
           if (i == 0) { val = 0; pmove = (j == 0) ? 0 : 2; }      // top row: ends-free, p=2  (:97-101)
           else if (j == 0) { val = 0; pmove = 0; }                  // left column: p=3, no raw base consumed
           // lambda / nsubs along the chosen predecessor (al2subs + compute_lambda_ts)
-          const int trans = (pmove == 1) ? (4 * nt1 + nt2) : (5 * nt2);
-          const int idx = (pmove == 1 || pmove == 2) ? trans * ncol + q : ONE_IDX;
+          // err row 4*nt0+nt1 (diag) or 5*nt1 (raw base vs gap), column q:  b2 + {nt0 | nt1} * 4*ncol
+          const int idx = (pmove == 1 || pmove == 2) ? b2 + ((pmove == 1) ? nt1 : nt2) * ncol4 : ONE_IDX;
           const double f = s_err[idx];
           double lp = (pmove == 3) ? lu : ((pmove == 2) ? ll : LAM[t]);
           int np = (pmove == 3) ? nu : ((pmove == 2) ? nl : NSUB[t]);
@@ -236,7 +315,7 @@ bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_u
   else return false;
   if (G * ND < slots_needed) return false;
   const int PPW = 32 / G;
-  const size_t smem = (size_t)(16 * a.P.ncol + 2) * 8 + a.seq_bytes + (size_t)4 * PPW * 2 * a.seq_bytes;
+  const size_t smem = (size_t)(16 * a.P.ncol + 2) * 8 + a.seq_bytes + (size_t)4 * PPW * (3 * a.seq_bytes + 4 * 64);
   if (smem > 160 * 1024) return false;
   unsigned long long warps = (njobs_upper + PPW - 1) / PPW;
   int grid = (int)std::min<unsigned long long>((warps + 3) / 4, (unsigned long long)num_sms * 16);
