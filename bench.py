@@ -167,9 +167,14 @@ def main():
     barrier()
     t0 = time.perf_counter()
     dev_ms = 0.0
+    step_ms, step_host = [], []
     for _ in range(args.steps):
         flush.zero_()
+        torch.cuda.synchronize()
+        ts = time.perf_counter()
         last = res.run(err)
+        step_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
+        step_host.append([round(last["stats"][k], 2) for k in ("ms_setup", "ms_loop", "ms_final")])
         dev_ms += last["stats"]["ms_device"]
     barrier()
     t_val = time.perf_counter() - t0
@@ -182,9 +187,12 @@ def main():
     barrier()
     t0 = time.perf_counter()
     est = None
+    e2e_ms = []
     for _ in range(args.steps):
         flush.zero_()
+        torch.cuda.synchronize()
         r, _ms = call.run(unpack=False)
+        e2e_ms.append(round(_ms, 2))
         est = r["stats"]
     barrier()
     t_e2e = time.perf_counter() - t0
@@ -258,6 +266,7 @@ def main():
                         "d2h_bytes_per_step": int(est["d2h_bytes"]), "ms_per_step": 1e3 * t_e2e / args.steps},
                 "gpu_launches": int(st["gpu_launches"]) * args.steps,
                 "device_ms_per_step": dev_ms / args.steps,
+                "step_ms": step_ms, "step_host_ms": step_host, "e2e_step_ms": e2e_ms,
                 "kernel_ms": {k: st[k] for k in ("ms_k_classify", "ms_k_align_nw", "ms_k_align_gl", "ms_k_align_final")},
                 "host_ms": {k: st[k] for k in ("ms_setup", "ms_loop", "ms_final", "ms_total")},
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity}

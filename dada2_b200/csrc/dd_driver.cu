@@ -281,6 +281,8 @@ struct Run {
   int kord_words = 0;
   // stats
   int n_rounds = 0, n_shuffles = 0;
+  unsigned long long tot_nw = 0, tot_gl = 0;
+  bool count_round = false;
   long long h2d_bytes = 0, d2h_bytes = 0, launches0 = 0;
   struct Ev { cudaEvent_t a, b; int tag; };
   std::vector<Ev> evs;
@@ -316,7 +318,7 @@ struct Run {
 
 void Run::reset_host() {
   members.clear(); slot_of.clear(); cluster_of_h.clear(); cl_center_h.clear(); cl_reads_h.clear(); birth.clear(); evs.clear();
-  n_rounds = n_shuffles = 0; h2d_bytes = d2h_bytes = 0; cs_count = 0; est_active = 0; pending = Pending();
+  n_rounds = n_shuffles = 0; tot_nw = tot_gl = 0; count_round = false; h2d_bytes = d2h_bytes = 0; cs_count = 0; est_active = 0; pending = Pending();
   st = DevState{};
 }
 void delete_run(Run *r) { delete r; }
@@ -483,6 +485,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   ensure_cluster_cap(members.size() + 2);
   launch_round_begin(st, pending.apply, pending.r, pending.from, pending.newi, pending.reads, s);
   pending.apply = 0;
+  count_round = true;
   ClassifyArgs ca{};
   ca.in = in; ca.P = P; ca.P.kdist_cutoff = kdist_cutoff; ca.mode = 0; ca.centre_idx = c; ca.centre_reads = cx->reads[c];
   ca.greedy = o->greedy != 0; ca.lock = st.lock; ca.nw_list = st.nw_list; ca.gl_list = st.gl_list; ca.ctr = st.ctr;
@@ -546,6 +549,7 @@ void Run::sync_report() {
   memcpy(h_ctr.p, h_report->ctr, sizeof(unsigned long long) * CTR_N);
   check_dev_error();
   cs_count = h_report->ctr[CTR_CS_COUNT];
+  if (count_round) { tot_nw += h_report->ctr[CTR_NW]; tot_gl += h_report->ctr[CTR_GL]; count_round = false; }
   est_active = std::max<unsigned long long>(1024, 2 * h_report->ctr[CTR_NW]);
   if (cs_count > st.cs_cap) throw Err{"dada2b: comparison store overflow"};
   if (h_report->ctr[CTR_NMOVE] > move_cap) throw Err{"dada2b: move list overflow"};
@@ -772,7 +776,7 @@ void Run::finish(dada2b_out *out) {
 
   out->nclust = nclust; out->nraw = nraw; out->maxlen = maxlen; out->Q = ncol;
   out->n_align = (int64_t)h_ctr.p[CTR_ALIGN]; out->n_shroud = (int64_t)h_ctr.p[CTR_SHROUD];
-  out->n_nw = (int64_t)h_ctr.p[CTR_NWTOT]; out->n_gapless = (int64_t)h_ctr.p[CTR_GLTOT]; out->nw_cells = (int64_t)h_ctr.p[CTR_CELLS];
+  out->n_nw = (int64_t)tot_nw; out->n_gapless = (int64_t)tot_gl; out->nw_cells = (int64_t)h_ctr.p[CTR_CELLS];
   out->n_rounds = n_rounds; out->n_shuffles = n_shuffles;
   // ---- $clustering (error.cpp:9-127)
   std::string cseq; std::vector<int64_t> coff(1, 0);

@@ -24,10 +24,11 @@ __device__ __forceinline__ unsigned lanemask_lt() { return (1u << lane_id()) - 1
 
 // 5-mer (10 bits, first base most significant like kmers.cpp:226) starting at base p of a packed row.
 __device__ __forceinline__ unsigned kmer_at(const uint32_t *row, int p) {
+  // 10-bit label of the 5-mer starting at base p.  The reference labels 5-mers with the first base most
+  // significant (kmers.cpp:226); counts, min-sums and position-wise equality are invariant under any
+  // bijective relabelling, so the raw bit order of the packed row is used as is.
   uint32_t w0 = row[p >> 4], w1 = row[(p + 4) >> 4];
-  uint32_t x = __funnelshift_r(w0, w1, 2 * (p & 15)) & 0x3FFu;   // base p in bits 1:0 ... base p+4 in bits 9:8
-  // reference order: kmer = 4*kmer + nt, first base most significant
-  return ((x & 3u) << 8) | (((x >> 2) & 3u) << 6) | (((x >> 4) & 3u) << 4) | (((x >> 6) & 3u) << 2) | ((x >> 8) & 3u);
+  return __funnelshift_r(w0, w1, 2 * (p & 15)) & 0x3FFu;
 }
 __device__ __forceinline__ unsigned base_at(const uint32_t *row, int p) { return (row[p >> 4] >> (2 * (p & 15))) & 3u; }
 
@@ -76,6 +77,19 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
 
   const int gw = blockIdx.x * nwarps + wid, tw = gridDim.x * nwarps;
   int r0 = a.mode == 0 ? gw : 0, rstep = a.mode == 0 ? tw : 1, rend = a.mode == 0 ? a.in.nraw : (wid == 0 ? 1 : 0);
+  // Job ids are staged per warp (one register slot per lane) and flushed 32 at a time with a single
+  // atomic reservation; the diagnostic counters are accumulated per warp.  (One same-address global
+  // atomic per pair costs more than the screen itself.)
+  uint32_t st_nw = 0, st_gl = 0;      // lane l holds staged entry l
+  int n_nw = 0, n_gl = 0, c_align = 0, c_shroud = 0;
+  auto flush = [&](uint32_t *list, unsigned long long *counter, uint32_t &stage, int &n) {
+    if (n == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < n) list[base + lane] = stage;
+    n = 0;
+  };
   for (int it = r0; it < rend; it += rstep) {
     const uint32_t r = a.mode == 0 ? (uint32_t)it : a.pair_raw[blockIdx.x];
     const uint32_t job = a.mode == 0 ? r : blockIdx.x;
@@ -102,8 +116,8 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
         U = warp_sum(U);
         const double kd_lb = 1. - ((double)(U & 0xFFFF)) / denom;
         if (kd_lb > P.kdist_cutoff) {
-          if (lane == 0) { atomicAdd(&a.ctr[CTR_ALIGN], 1ull); atomicAdd(&a.ctr[CTR_SHROUD], 1ull); if (a.kind_out) a.kind_out[job] = (uint8_t)KIND_SHROUD; }
-          __syncwarp();
+          c_align++; c_shroud++;
+          if (lane == 0 && a.kind_out) a.kind_out[job] = (uint8_t)KIND_SHROUD;
           continue;
         }
       }
@@ -132,14 +146,15 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
     } else {
       kind = (P.band == 0) ? KIND_GAPLESS : KIND_NW;
     }
-    if (lane == 0) {
-      atomicAdd(&a.ctr[CTR_ALIGN], 1ull);
-      if (kind == KIND_SHROUD) atomicAdd(&a.ctr[CTR_SHROUD], 1ull);
-      else if (kind == KIND_GAPLESS) { unsigned long long s = atomicAdd(&a.ctr[CTR_GL], 1ull); a.gl_list[s] = job; }
-      else { unsigned long long s = atomicAdd(&a.ctr[CTR_NW], 1ull); a.nw_list[s] = job; }
-      if (a.kind_out) a.kind_out[job] = (uint8_t)kind;
-    }
+    c_align++;
+    if (kind == KIND_SHROUD) c_shroud++;
+    else if (kind == KIND_GAPLESS) { if (lane == n_gl) st_gl = job; if (++n_gl == 32) flush(a.gl_list, &a.ctr[CTR_GL], st_gl, n_gl); }
+    else { if (lane == n_nw) st_nw = job; if (++n_nw == 32) flush(a.nw_list, &a.ctr[CTR_NW], st_nw, n_nw); }
+    if (lane == 0 && a.kind_out) a.kind_out[job] = (uint8_t)kind;
   }
+  flush(a.gl_list, &a.ctr[CTR_GL], st_gl, n_gl);
+  flush(a.nw_list, &a.ctr[CTR_NW], st_nw, n_nw);
+  if (lane == 0 && c_align) { atomicAdd(&a.ctr[CTR_ALIGN], (unsigned long long)c_align); if (c_shroud) atomicAdd(&a.ctr[CTR_SHROUD], (unsigned long long)c_shroud); }
 }
 
 // =====================================================================================
@@ -244,8 +259,7 @@ __device__ int nw_warp(const uint8_t *s1, int len1, const uint8_t *s2, int len2,
   }
   if ((nops & 15) && lane == 0) opw[nops >> 4] = acc;
   __syncwarp();
-  ncell_tot = warp_sum((int)ncell_tot);   // per-lane counts are small (< 2^31 per pair)
-  if (lane == 0 && cells) atomicAdd(cells, (unsigned long long)(unsigned)ncell_tot);
+  if (cells) *cells += ncell_tot;         // per-lane running total, reduced once per warp by the caller
   return nops;
 }
 
@@ -296,6 +310,7 @@ __global__ void __launch_bounds__(128) k_align(AlignArgs a) {
   uint32_t *ptr = a.ptr_in_smem ? ptr_s : a.ptr_scratch + (size_t)gw * a.ptr_words;
   const unsigned long long njobs = a.njobs_ptr ? *a.njobs_ptr : (unsigned long long)a.njobs_fixed;
   int errflag = 0;
+  unsigned long long cells_lane = 0;
 
   for (unsigned long long jb = gw; jb < njobs; jb += tw) {
     uint32_t r, c, job = a.jobs ? a.jobs[jb] : (uint32_t)jb;
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(128) k_align(AlignArgs a) {
     unpack_row(a.in.seq2 + (size_t)r * a.in.SW, len2, s2, P.homo && kind == KIND_NW);
     int nops;
     if (kind == KIND_NW) {
-      nops = nw_warp(s1, len1, s2, len2, P, H, ptr, opw, &a.st.ctr[CTR_CELLS], &errflag);
+      nops = nw_warp(s1, len1, s2, len2, P, H, ptr, opw, &cells_lane, &errflag);
     } else {
       nops = max(len1, len2);   // nwalign_gapless, nwalign_endsfree.cpp:539-555
     }
@@ -372,7 +387,6 @@ __global__ void __launch_bounds__(128) k_align(AlignArgs a) {
     // ---- sinks ----
     if (lane == 0) {
       if (MODE == MODE_LOOP) {                                           // cluster.cpp:179-201
-        if (kind == KIND_NW) atomicAdd(&a.st.ctr[CTR_NWTOT], 1ull); else atomicAdd(&a.st.ctr[CTR_GLTOT], 1ull);
         double emm = a.st.E_minmax[r];
         if (lambda * (double)a.total_reads > emm) {
           const double ec = lambda * (double)a.centre_reads;
@@ -392,6 +406,12 @@ __global__ void __launch_bounds__(128) k_align(AlignArgs a) {
     __syncwarp();
   }
   if (errflag && lane == 0) atomicMax(&a.st.ctr[CTR_ERR], (unsigned long long)errflag);
+  {
+    unsigned cl = (unsigned)cells_lane;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cl += __shfl_xor_sync(0xffffffffu, cl, o);
+    if (lane == 0 && cl) atomicAdd(&a.st.ctr[CTR_CELLS], (unsigned long long)cl);
+  }
   if (MODE == MODE_FINAL) {
     __syncthreads();
     for (int x = threadIdx.x; x < 16 * P.ncol; x += blockDim.x)

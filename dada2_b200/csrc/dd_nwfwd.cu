@@ -275,7 +275,6 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
     for (int t = 0; t < ND; t++) if (t == tf) { lam = LAM[t]; ns = NSUB[t]; }
     if (act && tf >= 0 && tf < ND) {
       if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;                 // pval.cpp:195
-      atomicAdd(&a.st.ctr[CTR_NWTOT], 1ull);
       const double emm = a.st.E_minmax[r];                                          // cluster.cpp:192-200
       if (lam * (double)a.total_reads > emm) {
         const double ec = lam * (double)a.centre_reads;
