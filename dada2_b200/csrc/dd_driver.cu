@@ -93,6 +93,7 @@ struct dada2b_ctx {
   DBuf<uint16_t> d_len;
   PBuf<uint32_t> st_seq;          // pinned staging for the packed upload
   PBuf<uint8_t> st_qual;
+  PBuf<uint8_t> st_meta;          // len (u16) | reads (u32) | prior (u8), pinned
   int num_sms = 148;
   long long upload_h2d = 0;
   std::vector<cudaEvent_t> ev_pool;
@@ -214,9 +215,16 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   cx->d_len.alloc(nraw); cx->d_reads.alloc(nraw); cx->d_prior.alloc(nraw);
   CK(cudaMemcpyAsync(cx->d_seq2.p, h_seq.p, (size_t)nraw * d.SW * 4, cudaMemcpyHostToDevice, cx->stream));
   CK(cudaMemcpyAsync(cx->d_qual.p, h_qual.p, (size_t)nraw * d.QS, cudaMemcpyHostToDevice, cx->stream));
-  CK(cudaMemcpyAsync(cx->d_len.p, cx->len.data(), nraw * 2, cudaMemcpyHostToDevice, cx->stream));
-  CK(cudaMemcpyAsync(cx->d_reads.p, cx->reads.data(), nraw * 4, cudaMemcpyHostToDevice, cx->stream));
-  CK(cudaMemcpyAsync(cx->d_prior.p, cx->prior.data(), nraw, cudaMemcpyHostToDevice, cx->stream));
+  {
+    cx->st_meta.alloc((size_t)nraw * 8);
+    uint8_t *m = cx->st_meta.p;
+    memcpy(m, cx->reads.data(), (size_t)nraw * 4);
+    memcpy(m + (size_t)nraw * 4, cx->len.data(), (size_t)nraw * 2);
+    memcpy(m + (size_t)nraw * 6, cx->prior.data(), nraw);
+    CK(cudaMemcpyAsync(cx->d_reads.p, m, (size_t)nraw * 4, cudaMemcpyHostToDevice, cx->stream));
+    CK(cudaMemcpyAsync(cx->d_len.p, m + (size_t)nraw * 4, (size_t)nraw * 2, cudaMemcpyHostToDevice, cx->stream));
+    CK(cudaMemcpyAsync(cx->d_prior.p, m + (size_t)nraw * 6, nraw, cudaMemcpyHostToDevice, cx->stream));
+  }
   CK(cudaStreamSynchronize(cx->stream));
   if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] upload: validate+copy %.2f ms, pack %.2f ms, alloc+H2D %.2f ms\n", tu1 - tu0, tu2 - tu1, now_ms() - tu2);
   DBG("upload: H2D done");
@@ -293,15 +301,50 @@ struct Run {
     cudaEventRecord(e.a, s); f(); cudaEventRecord(e.b, s);
     evs.push_back(e);
   }
-  void h2d(void *d, const void *h, size_t n) { h2d_bytes += (long long)n; CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
-  void d2h(void *h, const void *d, size_t n) { d2h_bytes += (long long)n; CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
+  // All host<->device copies go through a pinned arena: cudaMemcpyAsync on pageable memory is staged by the
+  // driver and was observed to stall for 10-1000 ms at a time on a loaded host.
+  PBuf<uint8_t> arena;
+  size_t arena_off = 0;
+  struct PendingD2H { void *dst; const void *src; size_t n; };
+  std::vector<PendingD2H> pend;
+  void sync() {
+    CK(cudaStreamSynchronize(s));
+    for (const PendingD2H &q : pend) memcpy(q.dst, q.src, q.n);
+    pend.clear();
+    arena_off = 0;
+  }
+  uint8_t *arena_get(size_t n) {
+    n = (n + 63) & ~(size_t)63;
+    if (arena_off + n > arena.cap) {
+      sync();                                   // every copy staged so far has completed: the arena can be reused
+      if (n > arena.cap) arena.alloc(std::max<size_t>(n, 2 * arena.cap));
+    }
+    uint8_t *q = arena.p + arena_off;
+    arena_off += n;
+    return q;
+  }
+  void h2d(void *d, const void *h, size_t n) {
+    if (!n) return;
+    h2d_bytes += (long long)n;
+    uint8_t *q = arena_get(n);
+    memcpy(q, h, n);
+    CK(cudaMemcpyAsync(d, q, n, cudaMemcpyHostToDevice, s));
+  }
+  void d2h(void *h, const void *d, size_t n) {
+    if (!n) return;
+    d2h_bytes += (long long)n;
+    uint8_t *q = arena_get(n);
+    CK(cudaMemcpyAsync(q, d, n, cudaMemcpyDeviceToHost, s));
+    pend.push_back(PendingD2H{h, q, n});
+  }
+  void d2h_pinned(void *h, const void *d, size_t n) { d2h_bytes += (long long)n; CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
 
   void reset_host();
   void setup_params();
   void alloc_state();
   void ensure_cluster_cap(size_t n);
   void ensure_cs_cap(unsigned long long need);
-  void read_ctr() { d2h(h_ctr.p, ctr.p, CTR_N * 8); CK(cudaStreamSynchronize(s)); }
+  void read_ctr() { d2h_pinned(h_ctr.p, ctr.p, CTR_N * 8); sync(); }
   void check_dev_error();
   void launch_compare(uint32_t i, double kdist_cutoff);
   void launch_round_tail(int first_pass, int npass);
@@ -373,7 +416,7 @@ void Run::ensure_cluster_cap(size_t n) {
     CK(cudaMemcpyAsync(u2.p, cl_update_e.p, cl_cap, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(k2.p, cl_check_locks.p, cl_cap, cudaMemcpyDeviceToDevice, s));
   }
-  CK(cudaStreamSynchronize(s));
+  sync();
   std::swap(cl_reads.p, r2.p); std::swap(cl_reads.n, r2.n);
   std::swap(cl_reads_next.p, rn2.p); std::swap(cl_reads_next.n, rn2.n);
   std::swap(cl_center.p, c2.p); std::swap(cl_center.n, c2.n);
@@ -399,7 +442,7 @@ void Run::ensure_cs_cap(unsigned long long need) {
     CK(cudaMemcpyAsync(c.p, cs_ham.p, cs_count * 4, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(l.p, cs_lambda.p, cs_count * 8, cudaMemcpyDeviceToDevice, s));
   }
-  CK(cudaStreamSynchronize(s));
+  sync();
   std::swap(cs_index.p, a.p); std::swap(cs_index.n, a.n);
   std::swap(cs_i.p, b.p); std::swap(cs_i.n, b.n);
   std::swap(cs_ham.p, c.p); std::swap(cs_ham.n, c.n);
@@ -409,6 +452,8 @@ void Run::ensure_cs_cap(unsigned long long need) {
 
 void Run::alloc_state() {
   const size_t n = nraw;
+  arena.alloc(std::max<size_t>(8u << 20, n * 40));
+  arena_off = 0; pend.clear();
   lock.alloc(n); is_center.alloc(n); slot0.alloc(n); correct.alloc(n);
   E_minmax.alloc(n); p.alloc(n); comp_lambda.alloc(n); comp_ham.alloc(n); cluster_of.alloc(n);
   emax_bits.alloc(n); best_entry.alloc(n); nw_list.alloc(n); gl_list.alloc(n); nsubs_final.alloc(n);
@@ -429,7 +474,7 @@ void Run::alloc_state() {
   cluster_of.zero(s); ctr.zero(s);
   launch_fill_f64(E_minmax.p, -999.0, n, s);                      // containers.cpp:39
   TDBG("alloc: memsets queued");
-  CK(cudaStreamSynchronize(s));
+  sync();
   TDBG("alloc: synced");
   st.lock = lock.p; st.is_center = is_center.p; st.slot0 = slot0.p; st.correct = correct.p;
   st.E_minmax = E_minmax.p; st.p = p.p; st.comp_lambda = comp_lambda.p; st.comp_ham = comp_ham.p; st.cluster_of = cluster_of.p;
@@ -440,7 +485,7 @@ void Run::alloc_state() {
   emax_bits.zero(s);                                               // shuffle scratch starts clean
   CK(cudaMemsetAsync(best_entry.p, 0xFF, n * 4, s));
   { unsigned long long nn = n; h2d(ctr.p + CTR_CS_COUNT, &nn, 8); }  // cluster 0 owns entries [0, nraw)
-  CK(cudaStreamSynchronize(s));
+  sync();
   st.cs_cap = 0;
   ensure_cs_cap(2ull * n + 1024);
   TDBG("alloc: cs cap");
@@ -448,7 +493,7 @@ void Run::alloc_state() {
   st.cl_reads = cl_reads.p; st.cl_reads_next = cl_reads_next.p; st.cl_center = cl_center.p;
   st.cl_update_e = cl_update_e.p; st.cl_check_locks = cl_check_locks.p;
   cl_reads.zero(s); cl_reads_next.zero(s); cl_center.zero(s); cl_update_e.zero(s); cl_check_locks.zero(s);
-  CK(cudaStreamSynchronize(s));
+  sync();
   TDBG("alloc: cluster cap");
   if (!ptr_in_smem) {
     ptr_scratch.alloc((size_t)ptr_words * align_grid * 4);
@@ -538,13 +583,13 @@ void Run::launch_round_tail_noshuffle() {
 }
 
 void Run::sync_report() {
-  d2h(h_report, d_report.p, sizeof(RoundReport));
+  d2h_pinned(h_report, d_report.p, sizeof(RoundReport));
   const unsigned eager = std::min<unsigned>(MOVES_EAGER, move_cap);
-  d2h(h_moves, d_moves.p, (size_t)eager * 8);
-  CK(cudaStreamSynchronize(s));
+  d2h_pinned(h_moves, d_moves.p, (size_t)eager * 8);
+  sync();
   if (h_report->ctr[CTR_NMOVE] > eager && h_report->ctr[CTR_NMOVE] <= move_cap) {
-    d2h(h_moves + 2 * (size_t)eager, d_moves.p + 2 * (size_t)eager, (size_t)(h_report->ctr[CTR_NMOVE] - eager) * 8);
-    CK(cudaStreamSynchronize(s));
+    d2h_pinned(h_moves + 2 * (size_t)eager, d_moves.p + 2 * (size_t)eager, (size_t)(h_report->ctr[CTR_NMOVE] - eager) * 8);
+    sync();
   }
   memcpy(h_ctr.p, h_report->ctr, sizeof(unsigned long long) * CTR_N);
   check_dev_error();
@@ -608,7 +653,7 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
     big.resize(nt); bigp.resize(ntp);
     if (nt) d2h(big.data(), d1.p, nt * 4);
     if (ntp) d2h(bigp.data(), d2.p, ntp * 4);
-    CK(cudaStreamSynchronize(s));
+    sync();
     tr = big.data(); trp = bigp.data();
   }
   auto pick = [&](const uint32_t *t, unsigned long long n) -> long {     // first in (cluster, slot) scan order
@@ -645,7 +690,7 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
     if (R.tiep_r[k] == r && type == 'P') { lam = R.tiep_lam[k]; ham = R.tiep_ham[k]; have = true; }
   if (!have) {
     d2h(&lam, comp_lambda.p + r, 8); d2h(&ham, comp_ham.p + r, 4);
-    CK(cudaStreamSynchronize(s));
+    sync();
   }
   const double expected = lam * (double)cl_reads_h[from];
   std::vector<uint32_t> &src = members[from];                   // bi_pop_raw(from, slot)
@@ -724,7 +769,7 @@ void Run::finish(dada2b_out *out) {
     d2h(bnt0.data(), b_nt0.p, bnt0.size());
     d2h(bnt1.data(), b_nt1.p, bnt1.size());
     d2h(bq1.data(), b_q1.p, bq1.size());
-    CK(cudaStreamSynchronize(s));
+    sync();
   }
   // post-hoc cluster p-values (error.cpp:99-119)
   std::vector<double> tot_e(nclust, 0.0), cpval(nclust, 0.0);
@@ -739,7 +784,7 @@ void Run::finish(dada2b_out *out) {
       trip_ij.alloc((size_t)cap * 2); trip_v.alloc(cap); dcount.zero(s);
       launch_posthoc(st, nraw, cs_count, center_cluster.p, trip_ij.p, trip_v.p, cap, dcount.p, s);
       d2h(&cnt, dcount.p, 8);
-      CK(cudaStreamSynchronize(s));
+      sync();
       if (cnt <= cap) break;
       cap = (unsigned)cnt + 16;
     }
@@ -747,7 +792,7 @@ void Run::finish(dada2b_out *out) {
     if (cnt) {
       d2h(tij.data(), trip_ij.p, cnt * 8);
       d2h(tv.data(), trip_v.p, cnt * 8);
-      CK(cudaStreamSynchronize(s));
+      sync();
     }
     std::vector<size_t> ord(cnt);
     for (size_t k = 0; k < cnt; k++) ord[k] = k;
@@ -875,7 +920,7 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
     std::vector<double> e((size_t)16 * Q);
     for (int r = 0; r < 16; r++) for (int c = 0; c < Q; c++) e[(size_t)r * Q + c] = err_cm[r + 16 * (size_t)c];
     R.h2d(R.err.p, e.data(), e.size() * 8);
-    CK(cudaStreamSynchronize(R.s));
+    R.sync();
   }
   const int nraw = R.nraw;
   // b_new / b_init (containers.cpp:78-137): one cluster holding every raw in index order
@@ -895,7 +940,7 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
     R.h2d(R.cl_reads.p, &cx->total_reads, 4); R.h2d(R.cl_reads_next.p, &cx->total_reads, 4);
     R.h2d(R.cl_center.p, &c0, 4);
     R.h2d(R.cl_update_e.p, &one, 1); R.h2d(R.cl_check_locks.p, &one, 1);
-    CK(cudaStreamSynchronize(R.s));
+    R.sync();
   }
   TDBG("cluster 0 initialised");
   const double t1 = now_ms();
@@ -932,7 +977,7 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
                      R.h_report->ctr[CTR_NMOVE]);
   }
   if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters\n", (int)R.members.size());
-  CK(cudaStreamSynchronize(R.s));
+  R.sync();
   const double t2 = now_ms();
   dada2b_out *out = (dada2b_out *)calloc(1, sizeof(dada2b_out));
   try { R.finish(out); } catch (...) { dada2b_free(out); throw; }
