@@ -542,9 +542,9 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     FwdArgs f{};
     f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
     f.centre_idx = c; f.centre_reads = cx->reads[c]; f.cluster_i = i; f.total_reads = cx->total_reads;
-    f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes;
+    f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes; f.mode = 0;
     {  // the fast path replaces the reference's sentinel by a larger penalty: only valid while no real score can come near it
-      const long worst = 2L * in.maxlen * std::max(std::max(std::abs(P.mismatch), std::abs(P.gap)), std::abs(P.match));
+      const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::abs(P.gap) + 16;
       f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
     }
     timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, i == 0 ? (unsigned long long)nraw : est_active, cx->num_sms, s); });
@@ -726,9 +726,35 @@ void Run::finish(dada2b_out *out) {
   cq_sum.alloc((size_t)nclust * maxlen); cq_cnt.alloc((size_t)nclust * maxlen); cq_sum.zero(s); cq_cnt.zero(s);
   st.trans = trans.p; st.cq_sum = cq_sum.p; st.cq_cnt = cq_cnt.p;
   {  // FinalSubsParallel: sub_new(centre, raw, use_kmers=false) for every raw
-    AlignArgs a = align_args(MODE_FINAL, P.band == 0 ? KIND_GAPLESS : KIND_NW);
-    a.jobs = nullptr; a.njobs_ptr = nullptr; a.njobs_fixed = nraw;
-    timed(T_FINAL, [&]() { launch_align_jobs(MODE_FINAL, a, (unsigned long long)nraw); });
+    bool split = false;
+    if (P.band > 0 && !P.homo && !getenv("DADA2B_NO_NWFWD")) {
+      // 1) forward-carry NW of every raw against its own centre: nsubs + "is the optimal path the pure diagonal?"
+      FwdArgs f{};
+      unsigned long long nn = (unsigned long long)nraw;
+      h2d(ctr.p + CTR_FB, &nn, 8);                       // job count lives in CTR_FB for this launch
+      { unsigned long long z[2] = {0ull, 0ull}; h2d(ctr.p + CTR_NW, z, 16); }
+      f.in = in; f.P = P; f.st = st; f.jobs = nullptr; f.njobs_ptr = st.ctr + CTR_FB;
+      f.seq_bytes = seq_bytes; f.mode = 1;
+      f.gl_out = st.gl_list; f.nw_out = st.nw_list; f.gl_count = st.ctr + CTR_GL; f.nw_count = st.ctr + CTR_NW;
+      f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_NMOVE;   // (scratch counter; pairs that do not fit -> traceback list below)
+      { unsigned long long z = 0; h2d(ctr.p + CTR_NMOVE, &z, 8); }
+      const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::abs(P.gap) + 16;
+      f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
+      timed(T_FINAL, [&]() { split = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, (unsigned long long)nraw, cx->num_sms, s); });
+    }
+    if (split) {
+      // 2) gapless column list for the pure-diagonal pairs, 3) traceback kernel for the rest (+ pairs that did not fit)
+      for (int pass = 0; pass < 3; pass++) {
+        AlignArgs a = align_args(MODE_FINAL, pass == 0 ? KIND_GAPLESS : KIND_NW);
+        a.jobs = pass == 0 ? st.gl_list : (pass == 1 ? st.nw_list : fb_list.p);
+        a.njobs_ptr = st.ctr + (pass == 0 ? CTR_GL : (pass == 1 ? CTR_NW : CTR_NMOVE));
+        timed(T_FINAL, [&]() { launch_align_jobs(MODE_FINAL, a, (unsigned long long)nraw); });
+      }
+    } else {
+      AlignArgs a = align_args(MODE_FINAL, P.band == 0 ? KIND_GAPLESS : KIND_NW);
+      a.jobs = nullptr; a.njobs_ptr = nullptr; a.njobs_fixed = nraw;
+      timed(T_FINAL, [&]() { launch_align_jobs(MODE_FINAL, a, (unsigned long long)nraw); });
+    }
   }
   // birth subs: sub_new(centre of birth_comp.i, centre i, use_kmers, cutoff 1.0)   Rmain.cpp:206-209
   const uint32_t npair = nclust - 1;

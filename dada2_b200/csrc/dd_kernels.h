@@ -55,6 +55,9 @@ struct FwdArgs {
   unsigned long long *fb_count;
   int seq_bytes;
   int fast_ok;                          // interior fast path allowed (scores cannot approach the sentinel)
+  int mode;                             // 0 = LOOP (one centre, store rule), 1 = FINAL (own centre per raw, nsubs + path class)
+  uint32_t *gl_out, *nw_out;            // FINAL: raws whose final alignment is gapless / needs a traceback
+  unsigned long long *gl_count, *nw_count;
 };
 bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s);
 void count_launch(int n);

@@ -28,6 +28,15 @@
 
 namespace dd2 {
 
+// DP cells of a banded alignment: sum_i [min(len2, i + rband) - max(1, i - lband) + 1], closed form.
+__device__ __forceinline__ long long band_cells(int n, int m, int l, int r) {
+  const long long k = min(max(m - r, 0), n);
+  const long long A = k * (k + 1) / 2 + k * r + (long long)(n - k) * m;
+  const long long k2 = min(max(l + 1, 0), n);
+  const long long B = k2 + ((long long)n * (n + 1) / 2 - k2 * (k2 + 1) / 2) - (long long)l * (n - k2);
+  return A - B + n;
+}
+
 template <int G, int ND>
 __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
   constexpr int NSL = ND / 2;             // cells per lane per step
@@ -37,37 +46,49 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
   const AlnParams &P = a.P;
   const int ncol = P.ncol;
   double *s_err = (double *)smem;                       // 16*ncol + 1 (last = 1.0)
-  uint8_t *s_cen = (uint8_t *)(s_err + 16 * ncol + 2);  // centre bases
+  uint8_t *s_cen_shared = (uint8_t *)(s_err + 16 * ncol + 2);  // centre bases (LOOP: one centre per launch)
   const int nwarps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane / G, gl = lane % G;
   // per pair: raw bases [seq_bytes] then b2[pos] = nt*ncol + qual as u16 with PAD zeroed entries on both sides
   constexpr int PAD = 64;
-  uint8_t *s_raw = s_cen + a.seq_bytes + (size_t)(wid * PPW + gid) * (3 * a.seq_bytes + 4 * PAD);
+  uint8_t *s_grp = s_cen_shared + a.seq_bytes + (size_t)(wid * PPW + gid) * (4 * a.seq_bytes + 4 * PAD);
+  uint8_t *s_cen_own = s_grp;                            // FINAL: each pair has its own centre
+  uint8_t *s_raw = s_grp + a.seq_bytes;
   uint16_t *s_b2 = (uint16_t *)(s_raw + a.seq_bytes) + PAD;
+  const bool final_mode = a.mode == 1;
+  const uint8_t *s_cen = final_mode ? s_cen_own : s_cen_shared;
+  constexpr int GAPFLAG = 1 << 30;                       // carried in the nsubs word: the path contains a gap move
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gid * G));
   (void)gmask;
 
   const unsigned long long njobs = *a.njobs_ptr;
   if ((unsigned long long)blockIdx.x * nwarps * PPW >= njobs) return;      // whole block idle (grid is sized for the worst case)
-  const uint32_t c = a.centre_idx;
-  const int len1 = a.in.len[c];
+  const int len1_shared = final_mode ? 0 : a.in.len[a.centre_idx];
   for (int x = threadIdx.x; x < 16 * ncol; x += blockDim.x) s_err[x] = a.st.err[x];
   if (threadIdx.x == 0) s_err[16 * ncol] = 1.0;
-  {
-    const uint32_t *crow = a.in.seq2 + (size_t)c * a.in.SW;
-    for (int p = threadIdx.x; p < len1; p += blockDim.x) s_cen[p] = (uint8_t)((crow[p >> 4] >> (2 * (p & 15))) & 3u);
+  if (!final_mode) {
+    const uint32_t *crow = a.in.seq2 + (size_t)a.centre_idx * a.in.SW;
+    for (int p = threadIdx.x; p < len1_shared; p += blockDim.x) s_cen_shared[p] = (uint8_t)((crow[p >> 4] >> (2 * (p & 15))) & 3u);
   }
   __syncthreads();
   const int ONE_IDX = 16 * ncol, ncol4 = 4 * ncol;
   const int SENT = P.sentinel, match = P.match, mismatch = P.mismatch, gap = P.gap;
   int errflag = 0;
+  long long cells_lane = 0;
 
   for (unsigned long long base = (unsigned long long)(blockIdx.x * nwarps + wid) * PPW; base < njobs;
        base += (unsigned long long)gridDim.x * nwarps * PPW) {
     const unsigned long long jb = base + gid;
     bool act = jb < njobs;
-    const uint32_t r = act ? a.jobs[jb] : 0;
+    const uint32_t r = act ? (a.jobs ? a.jobs[jb] : (uint32_t)jb) : 0;
+    uint32_t c = a.centre_idx, cluster = 0;
+    if (final_mode && act) { cluster = a.st.cluster_of[r]; c = a.st.cl_center[cluster]; }
+    const int len1 = final_mode ? (act ? (int)a.in.len[c] : 16) : len1_shared;
     const int len2 = act ? a.in.len[r] : len1;     // idle groups run a benign geometry (their lanes still execute)
+    if (final_mode && act) {
+      const uint32_t *crow = a.in.seq2 + (size_t)c * a.in.SW;
+      for (int p = gl; p < len1; p += G) s_cen_own[p] = (uint8_t)((crow[p >> 4] >> (2 * (p & 15))) & 3u);
+    }
     // ---- stage raw bases + qualities (group-cooperative) ----
     if (act) {
       const uint32_t *rrow = a.in.seq2 + (size_t)r * a.in.SW;
@@ -170,7 +191,7 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
             const int idx = isU ? ONE_IDX : b2 + (int)(isL ? nt2 : nt1) * ncol4;
             const double f = s_err[idx];
             const double lp = isU ? lu : (isL ? ll : LAM[t]);
-            const int np = isU ? nu : (isL ? nl : NSUB[t] + (eq ? 0 : 1));
+            const int np = isU ? (nu | GAPFLAG) : (isL ? (nl | GAPFLAG) : NSUB[t] + (eq ? 0 : 1));
             Hnew[cc] = m + PEN[t];
             Nnew[cc] = np;
             Lnew[cc] = lp * f;
@@ -240,8 +261,9 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
           const double f = s_err[idx];
           double lp = (pmove == 3) ? lu : ((pmove == 2) ? ll : LAM[t]);
           int np = (pmove == 3) ? nu : ((pmove == 2) ? nl : NSUB[t]);
-          if (pmove == 0) { lp = 1.0; np = 0; }
+          if (pmove == 0) { lp = 1.0; np = (i > 0) ? GAPFLAG : 0; }     // left column = leading gap in the raw row
           if (pmove == 1 && !eq) np++;
+          if (pmove == 2 || pmove == 3) np |= GAPFLAG;
           Hnew[cc] = valid ? val : H[t];
           Nnew[cc] = valid ? np : NSUB[t];
           Lnew[cc] = valid ? lp * f : LAM[t];
@@ -273,7 +295,22 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
     double lam = 0.0; int ns = 0;
 #pragma unroll
     for (int t = 0; t < ND; t++) if (t == tf) { lam = LAM[t]; ns = NSUB[t]; }
-    if (act && tf >= 0 && tf < ND) {
+    const bool owner = act && tf >= 0 && tf < ND;
+    if (owner) cells_lane += band_cells(len1, len2, lband, rband);
+    if (final_mode) {
+      // FinalSubsParallel (Rmain.cpp:179-236): nsubs of the final alignment; pairs whose optimal path is the pure
+      // diagonal get the trivial (gapless) column list, the rest go to the traceback kernel.
+      const bool pure = owner && !(ns & GAPFLAG);
+      const bool gapped = owner && (ns & GAPFLAG);
+      if (owner) a.st.nsubs_final[r] = (uint32_t)(ns & (GAPFLAG - 1));
+      const unsigned mp = __ballot_sync(0xffffffffu, pure), mg = __ballot_sync(0xffffffffu, gapped);
+      unsigned long long bp = 0, bg = 0;
+      if (lane == 0) { if (mp) bp = atomicAdd(a.gl_count, (unsigned long long)__popc(mp)); if (mg) bg = atomicAdd(a.nw_count, (unsigned long long)__popc(mg)); }
+      bp = __shfl_sync(0xffffffffu, bp, 0); bg = __shfl_sync(0xffffffffu, bg, 0);
+      if (pure) a.gl_out[bp + __popc(mp & ((1u << lane) - 1u))] = r;
+      if (gapped) a.nw_out[bg + __popc(mg & ((1u << lane) - 1u))] = r;
+    } else if (owner) {
+      ns &= (GAPFLAG - 1);
       if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;                 // pval.cpp:195
       const double emm = a.st.E_minmax[r];                                          // cluster.cpp:192-200
       if (lam * (double)a.total_reads > emm) {
@@ -289,6 +326,9 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
     __syncwarp();
   }
   if (errflag) atomicMax(&a.st.ctr[CTR_ERR], (unsigned long long)errflag);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) cells_lane += __shfl_xor_sync(0xffffffffu, cells_lane, o);
+  if (lane == 0 && cells_lane) atomicAdd(&a.st.ctr[CTR_CELLS], (unsigned long long)cells_lane);
 }
 
 template <int G, int ND> static void launch_one(const FwdArgs &a, int grid, size_t smem, cudaStream_t s) {
@@ -314,7 +354,7 @@ bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_u
   else return false;
   if (G * ND < slots_needed) return false;
   const int PPW = 32 / G;
-  const size_t smem = (size_t)(16 * a.P.ncol + 2) * 8 + a.seq_bytes + (size_t)4 * PPW * (3 * a.seq_bytes + 4 * 64);
+  const size_t smem = (size_t)(16 * a.P.ncol + 2) * 8 + a.seq_bytes + (size_t)4 * PPW * (4 * a.seq_bytes + 4 * 64);
   if (smem > 160 * 1024) return false;
   unsigned long long warps = (njobs_upper + PPW - 1) / PPW;
   int grid = (int)std::min<unsigned long long>((warps + 3) / 4, (unsigned long long)num_sms * 16);
