@@ -41,7 +41,7 @@ class ClockSampler(threading.Thread):
     `nvidia-smi -lms` child was observed to stall the stream synchronisations of this latency-bound loop
     for hundreds of ms at a time).  Falls back to one nvidia-smi query per second."""
 
-    def __init__(self, index, period=0.25):
+    def __init__(self, index, period=0.5):
         super().__init__(daemon=True)
         self.index = index
         self.period = period
@@ -49,6 +49,8 @@ class ClockSampler(threading.Thread):
         self.stop_flag = False
 
     def run(self):
+        if os.environ.get("DADA2B_BENCH_NOCLOCKS"):
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -177,7 +179,7 @@ def main():
         last = res.run(err)
         flush.zero_()
     t_wait = time.time()
-    while not sampler.rows and time.time() - t_wait < 10:
+    while not sampler.rows and time.time() - t_wait < (0 if os.environ.get("DADA2B_BENCH_NOCLOCKS") else 10):
         time.sleep(0.05)
     sampler.rows.clear()
     barrier()
@@ -224,19 +226,28 @@ def main():
     if rank == 0:
         L = len(seqs[0])
         bytes_per_pair = (L + 3) // 4 + 16 + L                      # S + O + Q for an aligned pair
-        pairs = st["n_nw"] + st["n_final_nw"]
-        k_ms = st["ms_k_align_nw"] + st["ms_k_align_final"]
-        n_launch = st["n_k_align_nw"] + st["n_k_align_final"]
+        pairs = st["n_nw"]                                         # loop alignments (k_nwfwd + its fallback)
+        k_ms = st["ms_k_align_nw"]
+        n_launch = st["n_rounds"] + 1                              # one k_nwfwd launch per compare round
         peak, peak_src = measured_peak_gbs()
         achieved = (pairs * bytes_per_pair / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "k_align (banded NW + traceback + lambda; loop NW launches + final pass)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_pair": bytes_per_pair, "pairs_per_step": int(pairs),
-                    "kernel_ms_per_step": k_ms, "launches_per_step": int(n_launch),
-                    "avg_launch_ms": k_ms / max(1, n_launch),
-                    "nw_gcups": (st["nw_cells"] / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0,
+        prof = {}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_final_k_nwfwd_metrics.json")))
+        except Exception:
+            pass
+        traffic = prof.get("dram_bytes_per_pair")
+        roofline = {"bound": "hbm", "kernel": "k_nwfwd (loop banded NW with forward-carried lambda; CUDA-event sum over its launches)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": (traffic * pairs / n_launch) if traffic else None,
+                    "traffic_note": "ncu dram read+write bytes per aligned pair x average pairs per launch (profiles/r1_final_k_nwfwd_full.txt)",
+                    "peak_source": peak_src, "algorithmic_bytes_per_pair": bytes_per_pair,
+                    "algorithmic_bytes_per_launch": bytes_per_pair * pairs / n_launch, "pairs_per_step": int(pairs),
+                    "kernel_ms_per_step": k_ms, "launches_per_step": int(n_launch), "avg_launch_ms": k_ms / max(1, n_launch),
+                    "nw_gcups": (pairs * (L * 33 - 16 * 17) / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0,
                     "kernel_share_of_device_time": k_ms / st["ms_device"] if st["ms_device"] else None,
-                    "note": "integer DP is issue-bound, not HBM-bound (DESIGN.md): frac is low by construction"}
+                    "issue_bound_evidence": prof.get("large_round"),
+                    "note": "integer DP is ALU-issue bound, not HBM-bound (DESIGN.md 4.2): the HBM fraction is low by construction"}
         cpu = None
         parity = None
         if world == 1 and not args.no_cpu_baseline:
