@@ -36,6 +36,8 @@ def lib():
         L.dada2b_run_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, P(_abi.Opts), P(P(_abi.Out)), C.c_char_p]
         L.dada2b_ctx_free.argtypes = [C.c_void_p]
         L.dada2b_default_opts.argtypes = [P(_abi.Opts)]
+        L.dada2b_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
+        L.dada2b_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p]
         L.dada2b_test_calc_pA.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
         L.dada2b_test_pairs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                         P(_abi.Opts), C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -76,6 +78,14 @@ class Resident:
         if rc:
             raise Dada2bError(eb.value.decode())
         self._pin = None  # host buffers are copied by the library
+
+    def comm_init(self, rank, world, unique_id):
+        """Join a sharded multi-GPU run (one process per GPU): raw r is aligned by rank r % world, one NCCL
+        all-gather per split round.  `unique_id` comes from nccl_unique_id() on rank 0."""
+        eb = C.create_string_buffer(_abi.ERRLEN)
+        rc = lib().dada2b_comm_init(self._ctx, int(rank), int(world), bytes(unique_id), eb)
+        if rc:
+            raise Dada2bError(eb.value.decode())
 
     def run(self, err, **opts):
         L = lib()
@@ -164,6 +174,14 @@ def dada_uniques(seqs, abundances, priors, err, quals,
         return _abi.unpack_out(out.contents)
     finally:
         L.dada2b_free(out)
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    eb = C.create_string_buffer(_abi.ERRLEN)
+    if lib().dada2b_nccl_unique_id(buf, eb):
+        raise Dada2bError(eb.value.decode())
+    return buf.raw
 
 
 class PackedCall:

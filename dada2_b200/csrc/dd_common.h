@@ -39,7 +39,7 @@ enum Ctr : int {
   CTR_CS_COUNT = 0,   // entries in the comparison store
   CTR_NW, CTR_GL,     // job list lengths
   CTR_ALIGN, CTR_SHROUD, CTR_NWTOT, CTR_GLTOT, CTR_CELLS,
-  CTR_NMOVE, CTR_ERR, CTR_FB, CTR_PMIN, CTR_RMAX, CTR_NTIE, CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR,
+  CTR_NMOVE, CTR_ERR, CTR_FB, CTR_NE, CTR_PMIN, CTR_RMAX, CTR_NTIE, CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR,
   CTR_N
 };
 
@@ -56,6 +56,10 @@ struct RoundReport {
   uint32_t tie_r[TIE_MAX], tie_ham[TIE_MAX], tiep_r[TIE_MAX], tiep_ham[TIE_MAX];
   double tie_lam[TIE_MAX], tiep_lam[TIE_MAX];
 };
+
+// A stored comparison produced by this rank in the current round (sharded runs): exchanged with one
+// all-gather per round, then appended to every rank's comparison store in rank-major order.
+struct NewEntry { uint32_t index, ham; double lambda; };
 
 // Mutable per-run state.
 struct DevState {
@@ -79,6 +83,9 @@ struct DevState {
   unsigned long long *ctr;
   // error matrix, row-major 16 x ncol (cluster.cpp:162-170)
   double *err;
+  // sharded runs (one process per GPU): raw r is owned by rank r % shard_world
+  int shard_rank, shard_world;
+  NewEntry *ne_local;               // this rank's new stored comparisons of the round (count in ctr[CTR_NE])
   // per-round control block (device) + host-mapped report / move list
   uint32_t *pinfo;                  // [MAX_PASS + 2]
   uint32_t *moves;                  // mapped pinned host memory: (raw, to) pairs

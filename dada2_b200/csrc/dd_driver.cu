@@ -9,6 +9,8 @@
 #include "../../include/dada2b.h"
 #include "../../include/dada2b_test.h"
 #include <memory>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "dd_common.h"
 #include "dd_kernels.h"
 
@@ -73,8 +75,38 @@ template <typename F> void parallel_for(size_t n, F f) {
 
 }  // namespace
 
-namespace { struct Run; void delete_run(Run *); }
+namespace {
+struct Run; void delete_run(Run *);
+// NCCL is resolved at run time from the process (torch's bundled libnccl.so.2 when present): single-GPU use has no
+// NCCL dependency at all.
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string &why) {
+    if (h) return true;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { why = "dada2b: cannot load libnccl.so.2"; return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllGather || !AllReduce || !CommDestroy) { why = "dada2b: libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+}  // namespace
+#define NC(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) throw Err{std::string("NCCL error: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?") + " at " #x}; } while (0)
 struct dada2b_ctx {
+  ncclComm_t comm = nullptr;      // sharded runs
+  int rank = 0, world = 1;
   Run *run = nullptr;             // per-run device state, kept across runs (grow-only buffers)
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -264,6 +296,10 @@ struct Run {
   PBuf<unsigned long long> h_ctr;
   PBuf<uint32_t> h_ties, h_ties_pr;
   DBuf<uint32_t> cl_reads_next, pinfo;
+  DBuf<NewEntry> ne_local, ne_all;       // sharded runs: staged / all-gathered new comparisons
+  DBuf<unsigned long long> d_counts;
+  PBuf<unsigned long long> h_counts;
+  unsigned shard_cap = 0;
   DBuf<RoundReport> d_report;
   DBuf<uint32_t> d_moves;
   PBuf<RoundReport> h_report_buf;
@@ -481,6 +517,12 @@ void Run::alloc_state() {
   st.emax_bits = emax_bits.p; st.best_entry = best_entry.p; st.nw_list = nw_list.p; st.gl_list = gl_list.p;
   st.ctr = ctr.p; st.err = err.p; st.nsubs_final = nsubs_final.p;
   st.pinfo = pinfo.p; st.move_cap = move_cap;
+  st.shard_rank = cx->rank; st.shard_world = cx->world; st.ne_local = nullptr;
+  if (cx->world > 1) {
+    shard_cap = (unsigned)((n + cx->world - 1) / cx->world + 32);
+    ne_local.alloc(shard_cap); ne_all.alloc((size_t)shard_cap * cx->world); d_counts.alloc(cx->world); h_counts.alloc(cx->world);
+    st.ne_local = ne_local.p;
+  }
   st.report = d_report.p; st.moves = d_moves.p;
   emax_bits.zero(s);                                               // shuffle scratch starts clean
   CK(cudaMemsetAsync(best_entry.p, 0xFF, n * 4, s));
@@ -509,7 +551,7 @@ void Run::check_dev_error() {
 
 AlignArgs Run::align_args(int mode, int kind) {
   AlignArgs a{};
-  a.in = in; a.P = P; a.st = st; a.kind = kind;
+  a.in = in; a.P = P; a.st = st; a.kind = kind; a.job_mul = 1; a.job_add = 0;
   a.warp_words = warp_words; a.seq_bytes = seq_bytes; a.H_words = H_words; a.ops_words = ops_words;
   a.ptr_in_smem = ptr_in_smem; a.ptr_scratch = ptr_scratch.p; a.ptr_words = ptr_words;
   (void)mode;
@@ -534,7 +576,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   ClassifyArgs ca{};
   ca.in = in; ca.P = P; ca.P.kdist_cutoff = kdist_cutoff; ca.mode = 0; ca.centre_idx = c; ca.centre_reads = cx->reads[c];
   ca.greedy = o->greedy != 0; ca.lock = st.lock; ca.nw_list = st.nw_list; ca.gl_list = st.gl_list; ca.ctr = st.ctr;
-  ca.kind_out = nullptr; ca.kord_words = kord_words;
+  ca.kind_out = nullptr; ca.kord_words = kord_words; ca.shard_rank = cx->rank; ca.shard_world = cx->world;
   int cgrid = std::min((nraw + 7) / 8, cx->num_sms * 4);
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   bool fwd_done = false;
@@ -542,7 +584,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     FwdArgs f{};
     f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
     f.centre_idx = c; f.centre_reads = cx->reads[c]; f.cluster_i = i; f.total_reads = cx->total_reads;
-    f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes; f.mode = 0;
+    f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes; f.mode = 0; f.job_mul = 1; f.job_add = 0;
     {  // the fast path replaces the reference's sentinel by a larger penalty: only valid while no real score can come near it
       const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::abs(P.gap) + 16;
       f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
@@ -556,6 +598,20 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     else a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
     a.centre_idx = c; a.centre_reads = cx->reads[c]; a.cluster_i = i; a.total_reads = cx->total_reads;
     timed(kind == KIND_NW ? T_NW : T_GL, [&]() { launch_align_jobs(MODE_LOOP, a, (unsigned long long)nraw); });
+  }
+  if (cx->world > 1) {
+    // The one collective of a split round: all-gather of the new stored comparisons (count first, then the
+    // payload padded to the largest count), appended on every rank in rank-major order.
+    NC(g_nccl.AllGather(ctr.p + CTR_NE, d_counts.p, 1, ncclUint64, cx->comm, s));
+    d2h_pinned(h_counts.p, d_counts.p, (size_t)cx->world * 8);
+    sync();
+    unsigned long long maxc = 0;
+    for (int q = 0; q < cx->world; q++) maxc = std::max(maxc, h_counts.p[q]);
+    if (maxc > shard_cap) throw Err{"dada2b: shard staging overflow"};
+    if (maxc) {
+      NC(g_nccl.AllGather(ne_local.p, ne_all.p, (size_t)maxc * sizeof(NewEntry), ncclChar, cx->comm, s));
+      launch_cs_append(st, ne_all.p, d_counts.p, (unsigned)maxc, i, c, s);
+    }
   }
 }
 
@@ -725,16 +781,18 @@ void Run::finish(dada2b_out *out) {
   trans.alloc((size_t)16 * ncol); trans.zero(s);
   cq_sum.alloc((size_t)nclust * maxlen); cq_cnt.alloc((size_t)nclust * maxlen); cq_sum.zero(s); cq_cnt.zero(s);
   st.trans = trans.p; st.cq_sum = cq_sum.p; st.cq_cnt = cq_cnt.p;
+  const int n_owned = (nraw - cx->rank + cx->world - 1) / cx->world;     // raws aligned by this rank in the final pass
+  if (cx->world > 1) nsubs_final.zero(s);
   {  // FinalSubsParallel: sub_new(centre, raw, use_kmers=false) for every raw
     bool split = false;
     if (P.band > 0 && !P.homo && !getenv("DADA2B_NO_NWFWD")) {
       // 1) forward-carry NW of every raw against its own centre: nsubs + "is the optimal path the pure diagonal?"
       FwdArgs f{};
-      unsigned long long nn = (unsigned long long)nraw;
+      unsigned long long nn = (unsigned long long)n_owned;
       h2d(ctr.p + CTR_FB, &nn, 8);                       // job count lives in CTR_FB for this launch
       { unsigned long long z[2] = {0ull, 0ull}; h2d(ctr.p + CTR_NW, z, 16); }
       f.in = in; f.P = P; f.st = st; f.jobs = nullptr; f.njobs_ptr = st.ctr + CTR_FB;
-      f.seq_bytes = seq_bytes; f.mode = 1;
+      f.seq_bytes = seq_bytes; f.mode = 1; f.job_mul = cx->world; f.job_add = cx->rank;
       f.gl_out = st.gl_list; f.nw_out = st.nw_list; f.gl_count = st.ctr + CTR_GL; f.nw_count = st.ctr + CTR_NW;
       f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_NMOVE;   // (scratch counter; pairs that do not fit -> traceback list below)
       { unsigned long long z = 0; h2d(ctr.p + CTR_NMOVE, &z, 8); }
@@ -752,9 +810,15 @@ void Run::finish(dada2b_out *out) {
       }
     } else {
       AlignArgs a = align_args(MODE_FINAL, P.band == 0 ? KIND_GAPLESS : KIND_NW);
-      a.jobs = nullptr; a.njobs_ptr = nullptr; a.njobs_fixed = nraw;
+      a.jobs = nullptr; a.njobs_ptr = nullptr; a.njobs_fixed = n_owned; a.job_mul = cx->world; a.job_add = cx->rank;
       timed(T_FINAL, [&]() { launch_align_jobs(MODE_FINAL, a, (unsigned long long)nraw); });
     }
+  }
+  if (cx->world > 1) {   // every rank tallied its own raws: integer sums are exact and order-independent
+    NC(g_nccl.AllReduce(trans.p, trans.p, (size_t)16 * ncol, ncclInt32, ncclSum, cx->comm, s));
+    NC(g_nccl.AllReduce(cq_sum.p, cq_sum.p, (size_t)nclust * maxlen, ncclUint64, ncclSum, cx->comm, s));
+    NC(g_nccl.AllReduce(cq_cnt.p, cq_cnt.p, (size_t)nclust * maxlen, ncclUint64, ncclSum, cx->comm, s));
+    NC(g_nccl.AllReduce(nsubs_final.p, nsubs_final.p, (size_t)nraw, ncclUint32, ncclSum, cx->comm, s));
   }
   // birth subs: sub_new(centre of birth_comp.i, centre i, use_kmers, cutoff 1.0)   Rmain.cpp:206-209
   const uint32_t npair = nclust - 1;
@@ -774,6 +838,7 @@ void Run::finish(dada2b_out *out) {
     ClassifyArgs ca{};
     ca.in = in; ca.P = P; ca.P.kdist_cutoff = 1.0; ca.mode = 1; ca.pair_centre = pair_centre.p; ca.pair_raw = pair_raw.p;
     ca.nw_list = nwl.p; ca.gl_list = gll.p; ca.ctr = st.ctr; ca.kord_words = kord_words; ca.greedy = 0; ca.lock = st.lock;
+    ca.shard_rank = 0; ca.shard_world = 1;
     // birth alignments are not counted in nalign/nshroud by the reference; restore the counters afterwards
     read_ctr();
     unsigned long long keepA = h_ctr.p[CTR_ALIGN], keepS = h_ctr.p[CTR_SHROUD];
@@ -1039,7 +1104,7 @@ static void do_test_pairs(dada2b_ctx *cx, int npairs, const uint32_t *centre, co
   ClassifyArgs ca{};
   ca.in = R.in; ca.P = R.P; ca.P.use_kmers = use_kmers; ca.P.kdist_cutoff = kdist_cutoff; ca.mode = 1;
   ca.pair_centre = R.pair_centre.p; ca.pair_raw = R.pair_raw.p; ca.nw_list = nwl.p; ca.gl_list = gll.p; ca.ctr = R.st.ctr;
-  ca.kord_words = R.kord_words; ca.kind_out = R.kind_out.p; ca.lock = R.st.lock;
+  ca.kord_words = R.kord_words; ca.kind_out = R.kind_out.p; ca.lock = R.st.lock; ca.shard_rank = 0; ca.shard_world = 1;
   launch_classify(ca, npairs, 256, R.classify_smem, s);
   for (int kd : {KIND_NW, KIND_GAPLESS}) {
     AlignArgs a = R.align_args(MODE_BIRTH, kd);
@@ -1109,6 +1174,34 @@ void dada2b_default_opts(dada2b_opts *o) {            // R/dada.R:1-26
   o->vectorized_alignment = 1; o->homo_gap = -8; o->multithread = 1; o->verbose = 0; o->SSE = 2; o->gapless = 1; o->greedy = 1;
 }
 
+int dada2b_nccl_unique_id(char id[DADA2B_NCCL_ID_BYTES], char errbuf[DADA2B_ERRLEN]) {
+  try {
+    std::string why;
+    if (!g_nccl.load(why)) throw Err{why};
+    static_assert(sizeof(ncclUniqueId) <= DADA2B_NCCL_ID_BYTES, "id buffer");
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memset(id, 0, DADA2B_NCCL_ID_BYTES);
+    memcpy(id, &u, sizeof u);
+    return 0;
+  } catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
+}
+
+int dada2b_comm_init(dada2b_ctx *ctx, int32_t rank, int32_t world, const char id[DADA2B_NCCL_ID_BYTES], char errbuf[DADA2B_ERRLEN]) {
+  try {
+    if (world < 1 || rank < 0 || rank >= world) throw Err{"dada2b: bad rank/world"};
+    if (world == 1) { ctx->rank = 0; ctx->world = 1; return 0; }
+    std::string why;
+    if (!g_nccl.load(why)) throw Err{why};
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    NC(g_nccl.CommInitRank(&ctx->comm, world, u, rank));
+    ctx->rank = rank; ctx->world = world;
+    return 0;
+  } catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
+}
+
 int dada2b_upload(const dada2b_in *in, int32_t device, dada2b_ctx **ctx, char errbuf[DADA2B_ERRLEN]) {
   *ctx = nullptr;
   try { *ctx = do_upload(in, device); return 0; }
@@ -1130,6 +1223,7 @@ void dada2b_ctx_free(dada2b_ctx *ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete_run(ctx->run);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   delete ctx;
 }
 

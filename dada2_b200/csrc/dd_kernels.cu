@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
   for (int it = r0; it < rend; it += rstep) {
     const uint32_t r = a.mode == 0 ? (uint32_t)it : a.pair_raw[blockIdx.x];
     const uint32_t job = a.mode == 0 ? r : blockIdx.x;
+    if (a.mode == 0 && a.shard_world > 1 && (int)(r % (uint32_t)a.shard_world) != a.shard_rank) continue;   // not this rank's raw
     if (a.mode == 0 && a.greedy && (a.in.reads[r] > a.centre_reads || a.lock[r])) continue;   // cluster.cpp:127-131
     const int len2 = a.in.len[r];
     int kind;
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(128) k_align(AlignArgs a) {
   unsigned long long cells_lane = 0;
 
   for (unsigned long long jb = gw; jb < njobs; jb += tw) {
-    uint32_t r, c, job = a.jobs ? a.jobs[jb] : (uint32_t)jb;
+    uint32_t r, c, job = a.jobs ? a.jobs[jb] : (uint32_t)jb * (uint32_t)a.job_mul + (uint32_t)a.job_add;
     uint32_t cluster = 0;
     int kind = a.kind;
     if (MODE == MODE_LOOP) { r = job; c = a.centre_idx; }
@@ -391,11 +392,16 @@ __global__ void __launch_bounds__(128) k_align(AlignArgs a) {
         if (lambda * (double)a.total_reads > emm) {
           const double ec = lambda * (double)a.centre_reads;
           if (ec > emm) a.st.E_minmax[r] = ec;
-          unsigned long long slot = a.cluster_i == 0 ? (unsigned long long)r : atomicAdd(&a.st.ctr[CTR_CS_COUNT], 1ull);
-          if (slot < a.st.cs_cap) {
-            a.st.cs_index[slot] = r; a.st.cs_i[slot] = a.cluster_i; a.st.cs_lambda[slot] = lambda; a.st.cs_ham[slot] = (uint32_t)nsubs;
+          if (a.st.shard_world > 1) {          // sharded: stage, exchange with one all-gather, append on every rank
+            const unsigned long long slot = atomicAdd(&a.st.ctr[CTR_NE], 1ull);
+            a.st.ne_local[slot] = NewEntry{r, (uint32_t)nsubs, lambda};
+          } else {
+            unsigned long long slot = a.cluster_i == 0 ? (unsigned long long)r : atomicAdd(&a.st.ctr[CTR_CS_COUNT], 1ull);
+            if (slot < a.st.cs_cap) {
+              a.st.cs_index[slot] = r; a.st.cs_i[slot] = a.cluster_i; a.st.cs_lambda[slot] = lambda; a.st.cs_ham[slot] = (uint32_t)nsubs;
+            }
+            if (a.cluster_i == 0 || r == c) { a.st.comp_lambda[r] = lambda; a.st.comp_ham[r] = (uint32_t)nsubs; }
           }
-          if (a.cluster_i == 0 || r == c) { a.st.comp_lambda[r] = lambda; a.st.comp_ham[r] = (uint32_t)nsubs; }
         }
       } else if (MODE == MODE_FINAL) {
         a.st.nsubs_final[r] = (uint32_t)nsubs;

@@ -19,6 +19,7 @@ struct ClassifyArgs {
   unsigned long long *ctr;
   uint8_t *kind_out;
   int kord_words;           // words reserved for the centre's ordered 5-mers
+  int shard_rank, shard_world;
 };
 
 struct AlignArgs {
@@ -28,6 +29,7 @@ struct AlignArgs {
   const uint32_t *jobs;                 // job list (NULL => job = 0..njobs-1)
   const unsigned long long *njobs_ptr;  // device-side count (NULL => njobs_fixed)
   int njobs_fixed;
+  int job_mul, job_add;                 // jobs == NULL: raw index = job * job_mul + job_add (owned raws of a sharded run)
   int kind;                             // KIND_NW or KIND_GAPLESS for every job of this launch
   uint32_t centre_idx, centre_reads, cluster_i, total_reads;   // LOOP
   const uint32_t *pair_centre, *pair_raw;                      // BIRTH
@@ -55,6 +57,7 @@ struct FwdArgs {
   unsigned long long *fb_count;
   int seq_bytes;
   int fast_ok;                          // interior fast path allowed (scores cannot approach the sentinel)
+  int job_mul, job_add;                 // jobs == NULL: raw index = job * job_mul + job_add
   int mode;                             // 0 = LOOP (one centre, store rule), 1 = FINAL (own centre per raw, nsubs + path class)
   uint32_t *gl_out, *nw_out;            // FINAL: raws whose final alignment is gapless / needs a traceback
   unsigned long long *gl_count, *nw_count;
@@ -72,6 +75,7 @@ void launch_shuffle_pass(const DevState &st, const DevIn &in, unsigned long long
 void launch_p_update(const DevState &st, const DevIn &in, int greedy, int detect_singletons, int last_pass, cudaStream_t s);
 void launch_bud_scan(const DevState &st, const DevIn &in, const BudParams &bp, int nclust, int last_pass, cudaStream_t s);
 void launch_report(const DevState &st, int last_pass, cudaStream_t s);
+void launch_cs_append(const DevState &st, const NewEntry *all, const unsigned long long *counts, unsigned cap, uint32_t cluster_i, uint32_t centre, cudaStream_t s);
 void launch_fill_f64(double *p, double v, size_t n, cudaStream_t s);
 void launch_center_cluster(int *cc, const uint32_t *cl_center, int nclust, cudaStream_t s);
 void launch_bud_collect_big(const DevState &st, const DevIn &in, const BudParams &bp, uint32_t *ties, uint32_t *ties_pr, unsigned cap, cudaStream_t s);

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
        base += (unsigned long long)gridDim.x * nwarps * PPW) {
     const unsigned long long jb = base + gid;
     bool act = jb < njobs;
-    const uint32_t r = act ? (a.jobs ? a.jobs[jb] : (uint32_t)jb) : 0;
+    const uint32_t r = act ? (a.jobs ? a.jobs[jb] : (uint32_t)jb * (uint32_t)a.job_mul + (uint32_t)a.job_add) : 0;
     uint32_t c = a.centre_idx, cluster = 0;
     if (final_mode && act) { cluster = a.st.cluster_of[r]; c = a.st.cl_center[cluster]; }
     const int len1 = final_mode ? (act ? (int)a.in.len[c] : 16) : len1_shared;
@@ -316,11 +316,16 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
       if (lam * (double)a.total_reads > emm) {
         const double ec = lam * (double)a.centre_reads;
         if (ec > emm) a.st.E_minmax[r] = ec;
-        const unsigned long long slot = a.cluster_i == 0 ? (unsigned long long)r : atomicAdd(&a.st.ctr[CTR_CS_COUNT], 1ull);
-        if (slot < a.st.cs_cap) {
-          a.st.cs_index[slot] = r; a.st.cs_i[slot] = a.cluster_i; a.st.cs_lambda[slot] = lam; a.st.cs_ham[slot] = (uint32_t)ns;
+        if (a.st.shard_world > 1) {
+          const unsigned long long slot = atomicAdd(&a.st.ctr[CTR_NE], 1ull);
+          a.st.ne_local[slot] = NewEntry{r, (uint32_t)ns, lam};
+        } else {
+          const unsigned long long slot = a.cluster_i == 0 ? (unsigned long long)r : atomicAdd(&a.st.ctr[CTR_CS_COUNT], 1ull);
+          if (slot < a.st.cs_cap) {
+            a.st.cs_index[slot] = r; a.st.cs_i[slot] = a.cluster_i; a.st.cs_lambda[slot] = lam; a.st.cs_ham[slot] = (uint32_t)ns;
+          }
+          if (a.cluster_i == 0 || r == c) { a.st.comp_lambda[r] = lam; a.st.comp_ham[r] = (uint32_t)ns; }
         }
-        if (a.cluster_i == 0 || r == c) { a.st.comp_lambda[r] = lam; a.st.comp_ham[r] = (uint32_t)ns; }
       }
     }
     __syncwarp();

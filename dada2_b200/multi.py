@@ -32,3 +32,20 @@ def dada_samples(samples, err, runner=None, group=None, **opts):
     for part in gathered:
         merged.update(part)
     return [merged[i] for i in range(len(samples))]
+
+
+def sharded_resident(seqs, abundances, priors, quals, device=None, group=None):
+    """One sample sharded over all ranks of `group` (every rank passes the same uniques): returns a
+    Resident whose run() aligns raw r on rank r % world and exchanges the new stored comparisons with one
+    NCCL all-gather per split round (dada2b_comm_init).  Every rank gets the complete result."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+        device = torch.cuda.current_device()
+    res = api.Resident(seqs, abundances, priors, quals, device=device)
+    box = [api.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    res.comm_init(rank, world, box[0])
+    return res

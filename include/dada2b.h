@@ -115,6 +115,17 @@ int dada2b_run_resident(dada2b_ctx *ctx, const double *err, int32_t Q, const dad
                         dada2b_out **out, char errbuf[DADA2B_ERRLEN]);
 void dada2b_ctx_free(dada2b_ctx *ctx);
 
+/* Sharded multi-GPU runs (one process per GPU).  Every rank uploads the same uniques and calls
+ * dada2b_run_resident() with the same arguments; raw r is aligned by rank r % world, the new stored
+ * comparisons of a round are exchanged with ONE NCCL all-gather per split round, everything else
+ * (shuffle, p-values, bud decision) is replicated deterministically, the final tallies are all-reduced.
+ * Every rank returns the complete result.  The NCCL unique id is created on rank 0 and distributed by the
+ * caller (e.g. torch.distributed broadcast). */
+#define DADA2B_NCCL_ID_BYTES 128
+int dada2b_nccl_unique_id(char id[DADA2B_NCCL_ID_BYTES], char errbuf[DADA2B_ERRLEN]);
+int dada2b_comm_init(dada2b_ctx *ctx, int32_t rank, int32_t world, const char id[DADA2B_NCCL_ID_BYTES],
+                     char errbuf[DADA2B_ERRLEN]);
+
 /* Defaults of R/dada.R:1-26 (dada_opts) as passed at R/dada.R:335-352. */
 void dada2b_default_opts(dada2b_opts *opts);
 
