@@ -142,6 +142,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nuniques", type=int, default=NUNIQ_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
+                    help="N>1: shard ONE sample of N x nuniques uniques over the ranks (NCCL all-gather per split round; weak scaling) "
+                         "or run one independent sample per rank (no collective)")
     ap.add_argument("--watchdog", type=int, default=1500, help="dump stacks and exit after this many seconds")
     args = ap.parse_args()
     import faulthandler
@@ -166,12 +169,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    seqs, ab, q, err = workload(args.nuniques, 12345 + rank)
+    shard = world > 1 and args.mode == "shard"
+    if shard:
+        seqs, ab, q, err = workload(args.nuniques * world, 12345)       # same sample on every rank
+    else:
+        seqs, ab, q, err = workload(args.nuniques, 12345 + rank)
     nraw = len(seqs)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     # ---------------- value: inputs resident in HBM ----------------
-    res = dada2_b200.Resident(seqs, ab, None, q, device=local_rank)
+    if shard:
+        from dada2_b200 import multi
+        res = multi.sharded_resident(seqs, ab, None, q, device=local_rank)
+    else:
+        res = dada2_b200.Resident(seqs, ab, None, q, device=local_rank)
     last = None
     sampler = ClockSampler(local_rank)
     sampler.start()                      # nvidia-smi's start-up takes ~1 s of driver calls: keep it out of the timed region
@@ -198,30 +209,53 @@ def main():
     t_val = time.perf_counter() - t0
     st = last["stats"]
 
-    # ---------------- e2e: one-shot C-ABI call on host buffers ----------------
-    call = dada2_b200.PackedCall(seqs, ab, None, err, q)
-    for _ in range(max(1, args.warmup // 2)):
-        call.run(unpack=False)
-    barrier()
-    t0 = time.perf_counter()
-    est = None
+    # ---------------- e2e: host buffers in, host buffers out, through the C-ABI ----------------
     e2e_ms = []
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        r, _ms = call.run(unpack=False)
-        e2e_ms.append(round(_ms, 2))
-        est = r["stats"]
-    barrier()
-    t_e2e = time.perf_counter() - t0
+    est = None
+    if shard:
+        from dada2_b200 import _abi
+        pin = _abi.PackedIn(seqs, ab, None, None, q)
+        ecm = np.asfortranarray(np.asarray(err, dtype=np.float64))
+        ostruct = _abi.make_opts(homo_gap=-8)
+        for _ in range(max(1, args.warmup // 2)):
+            res.reupload(pin); res.run_raw(ecm, ecm.shape[1], ostruct)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ts = time.perf_counter()
+            res.reupload(pin)                                   # dada2b_reupload: pack + H2D of this rank's copy
+            est = res.run_raw(ecm, ecm.shape[1], ostruct)       # dada2b_run_resident: loop + D2H of every output
+            e2e_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        L0 = len(seqs[0])
+        est = dict(est)
+        est["h2d_bytes"] += nraw * ((((L0 + 15) // 16 + 3) & ~3) * 4 + ((L0 + 15) & ~15) + 7)   # packed upload of dada2b_reupload
+    else:
+        call = dada2_b200.PackedCall(seqs, ab, None, err, q)
+        for _ in range(max(1, args.warmup // 2)):
+            call.run(unpack=False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            r, _ms = call.run(unpack=False)
+            e2e_ms.append(round(_ms, 2))
+            est = r["stats"]
+        barrier()
+        t_e2e = time.perf_counter() - t0
     clocks = sampler.finish()
 
     tt = torch.tensor([t_val, t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_val, t_e2e = float(tt[0]), float(tt[1])
-    value = world * nraw * args.steps / t_val
-    e2e = world * nraw * args.steps / t_e2e
+    units = nraw if shard else world * nraw          # uniques denoised per step by the whole job
+    value = units * args.steps / t_val
+    e2e = units * args.steps / t_e2e
 
     if rank == 0:
         L = len(seqs[0])
@@ -283,9 +317,11 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_val / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 DP + f64 lambda/p-value",
                 "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: %d synthetic 250 nt uniques, 100 variants (Zipf), Illumina-like quals, "
-                                       "tperr1, dada() selfConsist=FALSE, default options" % nraw,
-                           "per_gpu": "one sample per GPU (reference's per-sample loop); no data-path collective",
+                "config": {"workload": "BASELINE configs[1]: %d synthetic 250 nt uniques per GPU (%d in total), 100 variants (Zipf), Illumina-like quals, "
+                                       "tperr1, dada() selfConsist=FALSE, default options" % (args.nuniques, units),
+                           "per_gpu": ("ONE sample of %d uniques sharded over %d GPUs: raw r aligned on rank r %% N, one NCCL all-gather of "
+                                       "new stored comparisons per split round, final tallies all-reduced" % (nraw, world)) if shard else
+                                      "one sample per GPU (reference's per-sample loop); no data-path collective",
                            "l2": "256 MB buffer written between timed iterations (inputs 32 MB < 126 MB L2)",
                            "nclust": len(last["clustering"]["sequence"]), "rounds": st["n_rounds"], "shuffles": st["n_shuffles"]},
                 "clocks": clocks,

@@ -35,6 +35,7 @@ def lib():
         L.dada2b_upload.argtypes = [P(_abi.In), C.c_int32, P(C.c_void_p), C.c_char_p]
         L.dada2b_run_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, P(_abi.Opts), P(P(_abi.Out)), C.c_char_p]
         L.dada2b_ctx_free.argtypes = [C.c_void_p]
+        L.dada2b_reupload.argtypes = [C.c_void_p, P(_abi.In), C.c_char_p]
         L.dada2b_default_opts.argtypes = [P(_abi.Opts)]
         L.dada2b_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
         L.dada2b_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p]
@@ -78,6 +79,26 @@ class Resident:
         if rc:
             raise Dada2bError(eb.value.decode())
         self._pin = None  # host buffers are copied by the library
+
+    def reupload(self, packed_in):
+        """Replace this context's uniques from host buffers (`_abi.PackedIn`); keeps buffers and communicator."""
+        eb = C.create_string_buffer(_abi.ERRLEN)
+        rc = lib().dada2b_reupload(self._ctx, C.byref(packed_in.struct), eb)
+        if rc:
+            raise Dada2bError(eb.value.decode())
+
+    def run_raw(self, ecm, Q, opts_struct):
+        """run() without Python-side marshalling of the result (stats only) -- for timing."""
+        L = lib()
+        out = C.POINTER(_abi.Out)()
+        eb = C.create_string_buffer(_abi.ERRLEN)
+        rc = L.dada2b_run_resident(self._ctx, ecm.ctypes.data, int(Q), C.byref(opts_struct), C.byref(out), eb)
+        if rc:
+            raise Dada2bError(eb.value.decode())
+        try:
+            return {k: getattr(out.contents, k) for k in _abi.STAT_FIELDS}
+        finally:
+            L.dada2b_free(out)
 
     def comm_init(self, rank, world, unique_id):
         """Join a sharded multi-GPU run (one process per GPU): raw r is aligned by rank r % world, one NCCL

@@ -577,7 +577,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   ca.in = in; ca.P = P; ca.P.kdist_cutoff = kdist_cutoff; ca.mode = 0; ca.centre_idx = c; ca.centre_reads = cx->reads[c];
   ca.greedy = o->greedy != 0; ca.lock = st.lock; ca.nw_list = st.nw_list; ca.gl_list = st.gl_list; ca.ctr = st.ctr;
   ca.kind_out = nullptr; ca.kord_words = kord_words; ca.shard_rank = cx->rank; ca.shard_world = cx->world;
-  int cgrid = std::min((nraw + 7) / 8, cx->num_sms * 4);
+  int cgrid = std::min((nraw / cx->world + 8) / 8, cx->num_sms * 4);
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   bool fwd_done = false;
   if (!P.homo && P.band >= 0 && !getenv("DADA2B_NO_NWFWD")) {       // register-resident forward-carry NW (dd_nwfwd.cu)
@@ -1205,6 +1205,12 @@ int dada2b_comm_init(dada2b_ctx *ctx, int32_t rank, int32_t world, const char id
 int dada2b_upload(const dada2b_in *in, int32_t device, dada2b_ctx **ctx, char errbuf[DADA2B_ERRLEN]) {
   *ctx = nullptr;
   try { *ctx = do_upload(in, device); return 0; }
+  catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
+  catch (std::exception &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.what()); return 2; }
+}
+
+int dada2b_reupload(dada2b_ctx *ctx, const dada2b_in *in, char errbuf[DADA2B_ERRLEN]) {
+  try { do_upload(in, ctx->device, ctx); return 0; }
   catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
   catch (std::exception &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.what()); return 2; }
 }

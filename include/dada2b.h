@@ -114,6 +114,8 @@ int dada2b_upload(const dada2b_in *in, int32_t device, dada2b_ctx **ctx, char er
 int dada2b_run_resident(dada2b_ctx *ctx, const double *err, int32_t Q, const dada2b_opts *opts,
                         dada2b_out **out, char errbuf[DADA2B_ERRLEN]);
 void dada2b_ctx_free(dada2b_ctx *ctx);
+/* Replace the uniques held by an existing context (keeps its buffers, stream and NCCL communicator). */
+int dada2b_reupload(dada2b_ctx *ctx, const dada2b_in *in, char errbuf[DADA2B_ERRLEN]);
 
 /* Sharded multi-GPU runs (one process per GPU).  Every rank uploads the same uniques and calls
  * dada2b_run_resident() with the same arguments; raw r is aligned by rank r % world, the new stored
