@@ -289,12 +289,11 @@ struct Run {
   DBuf<uint8_t> lock, is_center, slot0, correct, cl_update_e, cl_check_locks, b_nt0, b_nt1, b_q1, b_ops, kind_out;
   DBuf<double> E_minmax, p, comp_lambda, cs_lambda, err, b_lambda, trip_v, pa_E, pa_out;
   DBuf<uint32_t> comp_ham, cluster_of, cs_index, cs_i, cs_ham, cl_reads, cl_center, best_entry, nw_list, gl_list,
-      moves, ties, ties_pr, nsubs_final, ptr_scratch, pair_centre, pair_raw, b_nsubs, b_nops, trip_ij;
+      nsubs_final, ptr_scratch, pair_centre, pair_raw, b_nsubs, b_nops, trip_ij;
   DBuf<uint16_t> b_pos;
   DBuf<unsigned long long> emax_bits, ctr, cq_sum, cq_cnt;
   DBuf<int> trans, center_cluster, pa_reads, pa_prior;
   PBuf<unsigned long long> h_ctr;
-  PBuf<uint32_t> h_ties, h_ties_pr;
   DBuf<uint32_t> cl_reads_next, pinfo;
   DBuf<NewEntry> ne_local, ne_all;       // sharded runs: staged / all-gathered new comparisons
   DBuf<unsigned long long> d_counts;
@@ -308,7 +307,7 @@ struct Run {
   uint32_t *h_moves = nullptr;
   static constexpr unsigned MOVES_EAGER = 8192;   // moves copied back with the report; more => one extra copy
   int NP = 3;                            // shuffle passes launched speculatively per round
-  unsigned move_cap = 0, tie_cap = 4096;
+  unsigned move_cap = 0;
   DBuf<uint32_t> fb_list;
   int fwd_slots = 0;
   unsigned long long est_active = 0;
@@ -502,10 +501,7 @@ void Run::alloc_state() {
   h_report_buf.alloc(1); h_moves_buf.alloc((size_t)move_cap * 2);
   h_report = h_report_buf.p; h_moves = h_moves_buf.p;
   memset(h_report, 0, sizeof(RoundReport));
-  DBG("alloc: moves done");
-  ties.alloc(tie_cap * 3); ties_pr.alloc(tie_cap * 3); h_ties.alloc(tie_cap * 3); h_ties_pr.alloc(tie_cap * 3);
   err.alloc((size_t)16 * ncol);
-  DBG("alloc: ties done");
   lock.zero(s); is_center.zero(s); slot0.zero(s); correct.zero(s); p.zero(s); comp_lambda.zero(s); comp_ham.zero(s);
   cluster_of.zero(s); ctr.zero(s);
   launch_fill_f64(E_minmax.p, -999.0, n, s);                      // containers.cpp:39
