@@ -99,6 +99,8 @@ struct DevState {
 
 
 
+constexpr int CTR_SURV = CTR_NWTOT;   // survivor count of the two-phase bound pass (slot otherwise unused by kernels)
+
 enum ErrCode : int { ERR_NONE = 0, ERR_LAMBDA = 1, ERR_QUAL = 2, ERR_TRACE = 3 };
 
 }  // namespace dd2

@@ -308,7 +308,9 @@ struct Run {
   static constexpr unsigned MOVES_EAGER = 8192;   // moves copied back with the report; more => one extra copy
   int NP = 3;                            // shuffle passes launched speculatively per round
   unsigned move_cap = 0;
-  DBuf<uint32_t> fb_list;
+  DBuf<uint32_t> fb_list, surv_list;
+  DBuf<double> raw_S, raw_rho;           // two-phase loop NW (experimental, DADA2B_TWOPHASE=1): per-raw bound factors
+  bool two_phase = false;
   int fwd_slots = 0;
   unsigned long long est_active = 0;
   size_t cl_cap = 0;
@@ -496,6 +498,8 @@ void Run::alloc_state() {
   ctr.alloc(CTR_N); h_ctr.alloc(CTR_N);
   DBG("alloc: ctr done");
   move_cap = (unsigned)(4 * n + 1024); fb_list.alloc(n);
+  two_phase = getenv("DADA2B_TWOPHASE") != nullptr;      // off by default: not yet validated on hardware
+  if (two_phase) { surv_list.alloc(n); raw_S.alloc(n); raw_rho.alloc(n); }
   pinfo.alloc(MAX_PASS + 2); pinfo.zero(s);
   d_report.alloc(1); d_moves.alloc((size_t)move_cap * 2);
   h_report_buf.alloc(1); h_moves_buf.alloc((size_t)move_cap * 2);
@@ -584,6 +588,15 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     {  // the fast path replaces the reference's sentinel by a larger penalty: only valid while no real score can come near it
       const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::abs(P.gap) + 16;
       f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
+    }
+    if (two_phase && i > 0) {
+      // pass 1: scores + substitution counts only; lambda <= S_r * rho_r^nsubs decides which pairs can pass the store rule
+      FwdArgs fbnd = f;
+      fbnd.raw_S = raw_S.p; fbnd.raw_rho = raw_rho.p; fbnd.surv_list = surv_list.p; fbnd.surv_count = st.ctr + CTR_SURV;
+      CK(cudaMemsetAsync(ctr.p + CTR_SURV, 0, 8, s));
+      timed(T_NW, [&]() { fwd_done = launch_nwfwd(fbnd, fwd_slots, (unsigned long long)nraw, est_active, cx->num_sms, s, true); });
+      // pass 2: the exact forward-carry kernel on the survivors
+      if (fwd_done) { f.jobs = surv_list.p; f.njobs_ptr = st.ctr + CTR_SURV; }
     }
     timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, i == 0 ? (unsigned long long)nraw : est_active, cx->num_sms, s); });
   }
@@ -1007,6 +1020,7 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
     std::vector<double> e((size_t)16 * Q);
     for (int r = 0; r < 16; r++) for (int c = 0; c < Q; c++) e[(size_t)r * Q + c] = err_cm[r + 16 * (size_t)c];
     R.h2d(R.err.p, e.data(), e.size() * 8);
+    if (R.two_phase) launch_raw_bounds(R.in, R.err.p, Q, o->use_quals != 0, R.raw_S.p, R.raw_rho.p, R.s);
     R.sync();
   }
   const int nraw = R.nraw;

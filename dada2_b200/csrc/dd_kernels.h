@@ -61,8 +61,14 @@ struct FwdArgs {
   int mode;                             // 0 = LOOP (one centre, store rule), 1 = FINAL (own centre per raw, nsubs + path class)
   uint32_t *gl_out, *nw_out;            // FINAL: raws whose final alignment is gapless / needs a traceback
   unsigned long long *gl_count, *nw_count;
+  // two-phase loop NW (bound pass): per-raw bound factors and the survivor list
+  const double *raw_S, *raw_rho;
+  uint32_t *surv_list;
+  unsigned long long *surv_count;
 };
-bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s);
+bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s,
+                  bool bound_only = false);
+void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, cudaStream_t s);
 void count_launch(int n);
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s);

@@ -37,7 +37,9 @@ __device__ __forceinline__ long long band_cells(int n, int m, int l, int r) {
   return A - B + n;
 }
 
-template <int G, int ND>
+// WL = carry lambda (the exact kernel).  WL = false is the bound pass of the two-phase scheme: scores and
+// substitution counts only; pairs that provably fail the store rule are dropped, the rest are listed for the exact kernel.
+template <int G, int ND, bool WL>
 __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
   constexpr int NSL = ND / 2;             // cells per lane per step
   constexpr int PPW = 32 / G;             // pairs per warp
@@ -158,15 +160,16 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
 #pragma unroll
         for (int PAR = 0; PAR < 2; PAR++) {
           int Hn, Nn; double Ln;
+          if (!WL) Ln = 1.0;
           if (PAR == 0) {
             Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G);
             Nn = __shfl_up_sync(0xffffffffu, NSUB[ND - 1], 1, G);
-            Ln = __shfl_up_sync(0xffffffffu, LAM[ND - 1], 1, G);
+            if (WL) Ln = __shfl_up_sync(0xffffffffu, LAM[ND - 1], 1, G);
             if (gl == 0) Hn = -BIGPEN;
           } else {
             Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G);
             Nn = __shfl_down_sync(0xffffffffu, NSUB[0], 1, G);
-            Ln = __shfl_down_sync(0xffffffffu, LAM[0], 1, G);
+            if (WL) Ln = __shfl_down_sync(0xffffffffu, LAM[0], 1, G);
             if (gl == G - 1) Hn = -BIGPEN;
           }
           const uint32_t X = A ^ B;
@@ -187,14 +190,14 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
             const int m = __vimax3_s32(left, up, diag);
             const bool isU = up == m;                      // precedence up > left > diag (nwalign_endsfree.cpp:147-156)
             const bool isL = (left == m) && !isU;
-            const int b2 = b2p[cc];
+            const int b2 = WL ? b2p[cc] : 0;
             const int idx = isU ? ONE_IDX : b2 + (int)(isL ? nt2 : nt1) * ncol4;
-            const double f = s_err[idx];
+            const double f = WL ? s_err[idx] : 1.0;
             const double lp = isU ? lu : (isL ? ll : LAM[t]);
             const int np = isU ? (nu | GAPFLAG) : (isL ? (nl | GAPFLAG) : NSUB[t] + (eq ? 0 : 1));
             Hnew[cc] = m + PEN[t];
             Nnew[cc] = np;
-            Lnew[cc] = lp * f;
+            Lnew[cc] = WL ? lp * f : 1.0;
           }
 #pragma unroll
           for (int cc = 0; cc < NSL; cc++) { H[2 * cc + PAR] = Hnew[cc]; NSUB[2 * cc + PAR] = Nnew[cc]; LAM[2 * cc + PAR] = Lnew[cc]; }
@@ -218,15 +221,16 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
         const int k = kk + PAR;
         // ---- neighbour exchange ----
         int Hn, Nn; double Ln;
+        if (!WL) Ln = 1.0;
         if (PAR == 0) {           // left neighbour of local t=0 is lane gl-1's t=ND-1
           Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G);
           Nn = __shfl_up_sync(0xffffffffu, NSUB[ND - 1], 1, G);
-          Ln = __shfl_up_sync(0xffffffffu, LAM[ND - 1], 1, G);
+          if (WL) Ln = __shfl_up_sync(0xffffffffu, LAM[ND - 1], 1, G);
           if (gl == 0) { Hn = SENT; Nn = 0; Ln = 1.0; }
         } else {                  // up neighbour of local t=ND-1 is lane gl+1's t=0
           Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G);
           Nn = __shfl_down_sync(0xffffffffu, NSUB[0], 1, G);
-          Ln = __shfl_down_sync(0xffffffffu, LAM[0], 1, G);
+          if (WL) Ln = __shfl_down_sync(0xffffffffu, LAM[0], 1, G);
           if (gl == G - 1) { Hn = SENT; Nn = 0; Ln = 1.0; }
         }
         const uint32_t X = A ^ B;
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
           // lambda / nsubs along the chosen predecessor (al2subs + compute_lambda_ts)
           // err row 4*nt0+nt1 (diag) or 5*nt1 (raw base vs gap), column q:  b2 + {nt0 | nt1} * 4*ncol
           const int idx = (pmove == 1 || pmove == 2) ? b2 + ((pmove == 1) ? nt1 : nt2) * ncol4 : ONE_IDX;
-          const double f = s_err[idx];
+          const double f = WL ? s_err[idx] : 1.0;
           double lp = (pmove == 3) ? lu : ((pmove == 2) ? ll : LAM[t]);
           int np = (pmove == 3) ? nu : ((pmove == 2) ? nl : NSUB[t]);
           if (pmove == 0) { lp = 1.0; np = (i > 0) ? GAPFLAG : 0; }     // left column = leading gap in the raw row
@@ -309,6 +313,20 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
       bp = __shfl_sync(0xffffffffu, bp, 0); bg = __shfl_sync(0xffffffffu, bg, 0);
       if (pure) a.gl_out[bp + __popc(mp & ((1u << lane) - 1u))] = r;
       if (gapped) a.nw_out[bg + __popc(mg & ((1u << lane) - 1u))] = r;
+    } else if (!WL) {
+      // bound pass: lambda <= S_r * rho_r^nsubs for ANY alignment with nsubs substitutions (S_r = product of the raw's
+      // self-transition factors, rho_r = largest substitution/self ratio at the raw's own (base, quality) positions), so
+      // bound * total_reads <= E_minmax proves the comparison fails cluster.cpp:192 and can never matter again.
+      bool survive = false;
+      if (owner) {
+        const double bound = a.raw_S[r] * pow(a.raw_rho[r], (double)(ns & (GAPFLAG - 1))) * (double)a.total_reads * (1.0 + 1e-9);
+        survive = !(bound <= a.st.E_minmax[r]) || bound < 1e-280;     // near underflow the fp product is not a safe bound: keep
+      }
+      const unsigned ms = __ballot_sync(0xffffffffu, survive);
+      unsigned long long bs = 0;
+      if (lane == 0 && ms) bs = atomicAdd(a.surv_count, (unsigned long long)__popc(ms));
+      bs = __shfl_sync(0xffffffffu, bs, 0);
+      if (survive) a.surv_list[bs + __popc(ms & ((1u << lane) - 1u))] = r;
     } else if (owner) {
       ns &= (GAPFLAG - 1);
       if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;                 // pval.cpp:195
@@ -336,15 +354,20 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
   if (lane == 0 && cells_lane) atomicAdd(&a.st.ctr[CTR_CELLS], (unsigned long long)cells_lane);
 }
 
-template <int G, int ND> static void launch_one(const FwdArgs &a, int grid, size_t smem, cudaStream_t s) {
+template <int G, int ND, bool WL> static void launch_one(const FwdArgs &a, int grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_nwfwd<G, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
-  k_nwfwd<G, ND><<<grid, 128, smem, s>>>(a);
+  if (!attr_set) { cudaFuncSetAttribute(k_nwfwd<G, ND, WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+  k_nwfwd<G, ND, WL><<<grid, 128, smem, s>>>(a);
+}
+template <int G, int ND> static void launch_wl(const FwdArgs &a, bool bound_only, int grid, size_t smem, cudaStream_t s) {
+  if (bound_only) launch_one<G, ND, false>(a, grid, smem, s);
+  else launch_one<G, ND, true>(a, grid, smem, s);
 }
 
 // Picks the instantiation: smallest G*ND >= needed band slots, preferring few lanes per pair for
 // large batches (throughput) and many lanes for small batches (latency).
-bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s) {
+bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s,
+                  bool bound_only) {
   extern void count_launch(int);
   int G, ND;
   const bool big = njobs_hint > (unsigned long long)num_sms * 512;
@@ -365,12 +388,12 @@ bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_u
   int grid = (int)std::min<unsigned long long>((warps + 3) / 4, (unsigned long long)num_sms * 16);
   if (grid < 1) grid = 1;
   count_launch(1);
-  if (G == 4 && ND == 10) launch_one<4, 10>(a, grid, smem, s);
-  else if (G == 8 && ND == 6) launch_one<8, 6>(a, grid, smem, s);
-  else if (G == 16 && ND == 4) launch_one<16, 4>(a, grid, smem, s);
-  else if (G == 8 && ND == 8) launch_one<8, 8>(a, grid, smem, s);
-  else if (G == 16 && ND == 8) launch_one<16, 8>(a, grid, smem, s);
-  else if (G == 32 && ND == 8) launch_one<32, 8>(a, grid, smem, s);
+  if (G == 4 && ND == 10) launch_wl<4, 10>(a, bound_only, grid, smem, s);
+  else if (G == 8 && ND == 6) launch_wl<8, 6>(a, bound_only, grid, smem, s);
+  else if (G == 16 && ND == 4) launch_wl<16, 4>(a, bound_only, grid, smem, s);
+  else if (G == 8 && ND == 8) launch_wl<8, 8>(a, bound_only, grid, smem, s);
+  else if (G == 16 && ND == 8) launch_wl<16, 8>(a, bound_only, grid, smem, s);
+  else if (G == 32 && ND == 8) launch_wl<32, 8>(a, bound_only, grid, smem, s);
   else return false;
   return true;
 }

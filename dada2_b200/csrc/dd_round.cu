@@ -208,6 +208,25 @@ __global__ void k_cs_append_commit(DevState st, const unsigned long long *counts
   }
 }
 
+// Two-phase loop NW: per-raw bound factors.  S_r = product over the raw's positions of its self-transition factor
+// err[5*nt][q]; rho_r = max over positions and nt0 != nt of err[4*nt0+nt][q] / err[5*nt][q].
+__global__ void k_raw_bounds(DevIn in, const double *err, int ncol, int use_quals, double *S, double *rho) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= in.nraw) return;
+  const uint32_t *row = in.seq2 + (size_t)r * in.SW;
+  const uint8_t *q = in.qual + (size_t)r * in.QS;
+  double s = 1.0, rh = 0.0;
+  const int L = in.len[r];
+  for (int p = 0; p < L; p++) {
+    const int b = (row[p >> 4] >> (2 * (p & 15))) & 3;
+    const int qq = use_quals ? min((int)q[p], ncol - 1) : 0;
+    const double self = err[(5 * b) * ncol + qq];
+    s *= self;
+    for (int a0 = 0; a0 < 4; a0++) if (a0 != b) rh = fmax(rh, err[(4 * a0 + b) * ncol + qq] / self);
+  }
+  S[r] = s; rho[r] = rh;
+}
+
 __global__ void k_fill_f64(double *p, double v, size_t n) {
   for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) p[x] = v;
 }
@@ -217,6 +236,10 @@ __global__ void k_center_cluster(int *cc, const uint32_t *cl_center, int nclust)
 }
 
 // ------------------------------- launch wrappers --------------------------------------
+void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, cudaStream_t s) {
+  count_launch(1);
+  k_raw_bounds<<<(in.nraw + 127) / 128, 128, 0, s>>>(in, err_rowmajor, ncol, use_quals, S, rho);
+}
 void launch_fill_f64(double *p, double v, size_t n, cudaStream_t s) {
   count_launch(1);
   k_fill_f64<<<(unsigned)std::min<size_t>((n + 255) / 256, 2048), 256, 0, s>>>(p, v, n);

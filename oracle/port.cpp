@@ -320,17 +320,24 @@ void bi_assign_center(Bi &bi, std::vector<Raw> &raws) {               // cluster
 }
 
 // ---- cluster.cpp:152-204 b_compare_parallel (== :13-88 b_compare where that is defined)
+static FILE *g_trace = nullptr;   // optional: PORT_TRACE=<file> dumps one record per real alignment (analysis tooling)
 void b_compare(B &b, unsigned i, const Params &P, double kdist_cutoff, const double *err, unsigned ncol) {
   const Raw &center = b.raw[b.bi[i].center];
   for (unsigned index = 0; index < b.raw.size(); index++) {
     Raw &raw = b.raw[index];
     Cmp comp{i, index, 0.0, (uint32_t)-1};
     if (!(P.greedy && raw.reads > center.reads) && !(P.greedy && raw.lock)) {
-      Sub sub = sub_new(center, raw, P, P.use_kmers, kdist_cutoff);
+      int kind = 0;
+      Sub sub = sub_new(center, raw, P, P.use_kmers, kdist_cutoff, &kind);
       b.nalign++;
       if (sub.null) b.nshroud++;
       comp.lambda = compute_lambda(raw, sub, ncol, err, P.use_quals);
       if (!sub.null) comp.hamming = sub.nsubs;
+      if (g_trace && kind == 2) {
+        struct { uint32_t i, index, nsubs, stored; double lambda, emm, breads; } rec{i, index, sub.nsubs,
+            (uint32_t)(comp.lambda * b.reads > raw.E_minmax), comp.lambda, raw.E_minmax, (double)b.reads};
+        fwrite(&rec, sizeof rec, 1, g_trace);
+      }
     }
     double lambda = comp.lambda;
     if (index == (unsigned)b.bi[i].center) b.bi[i].self = lambda;
@@ -440,6 +447,8 @@ template <typename T> T *dup(const std::vector<T> &v) {
 
 // ---- Rmain.cpp:30-295 dada_uniques --------------------------------------------------
 dada2b_out *run(const dada2b_in *in, const dada2b_opts *o) {
+  if (const char *tp = getenv("PORT_TRACE")) g_trace = fopen(tp, "wb");
+  struct TraceCloser { ~TraceCloser() { if (g_trace) { fclose(g_trace); g_trace = nullptr; } } } trace_closer;
   unsigned nraw = in->nraw;
   if (nraw == 0) throw Stop("Zero input sequences.");
   unsigned maxlen = 0, minlen = SEQLEN;
