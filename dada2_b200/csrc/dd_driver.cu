@@ -594,11 +594,11 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       FwdArgs fbnd = f;
       fbnd.raw_S = raw_S.p; fbnd.raw_rho = raw_rho.p; fbnd.surv_list = surv_list.p; fbnd.surv_count = st.ctr + CTR_SURV;
       CK(cudaMemsetAsync(ctr.p + CTR_SURV, 0, 8, s));
-      timed(T_NW, [&]() { fwd_done = launch_nwfwd(fbnd, fwd_slots, (unsigned long long)nraw, est_active, cx->num_sms, s, true); });
+      timed(T_NW, [&]() { fwd_done = launch_nwfwd_sel(fbnd, fwd_slots, (unsigned long long)nraw, est_active, cx->num_sms, s, true); });
       // pass 2: the exact forward-carry kernel on the survivors
       if (fwd_done) { f.jobs = surv_list.p; f.njobs_ptr = st.ctr + CTR_SURV; }
     }
-    timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, i == 0 ? (unsigned long long)nraw : est_active, cx->num_sms, s); });
+    timed(T_NW, [&]() { fwd_done = launch_nwfwd_sel(f, fwd_slots, (unsigned long long)nraw, i == 0 ? (unsigned long long)nraw : est_active, cx->num_sms, s); });
   }
   for (int kind : {KIND_NW, KIND_GAPLESS}) {
     AlignArgs a = align_args(MODE_LOOP, kind);
@@ -807,7 +807,7 @@ void Run::finish(dada2b_out *out) {
       { unsigned long long z = 0; h2d(ctr.p + CTR_NMOVE, &z, 8); }
       const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::abs(P.gap) + 16;
       f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
-      timed(T_FINAL, [&]() { split = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, (unsigned long long)nraw, cx->num_sms, s); });
+      timed(T_FINAL, [&]() { split = launch_nwfwd_sel(f, fwd_slots, (unsigned long long)nraw, (unsigned long long)nraw, cx->num_sms, s); });
     }
     if (split) {
       // 2) gapless column list for the pure-diagonal pairs, 3) traceback kernel for the rest (+ pairs that did not fit)

@@ -2,6 +2,7 @@
 #pragma once
 #include "dd_common.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace dd2 {
 
@@ -68,6 +69,15 @@ struct FwdArgs {
 };
 bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s,
                   bool bound_only = false);
+// dd_nwfwd2.cu: restructured variant of the same kernel (EXPERIMENTAL, DADA2B_NWFWD_V2=1; checked on the host SIMT
+// emulator of tests/emu, not yet on hardware).
+bool launch_nwfwd2(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s,
+                   bool bound_only = false);
+inline bool launch_nwfwd_sel(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms,
+                             cudaStream_t s, bool bound_only = false) {
+  return getenv("DADA2B_NWFWD_V2") ? launch_nwfwd2(a, slots_needed, njobs_upper, njobs_hint, num_sms, s, bound_only)
+                                   : launch_nwfwd(a, slots_needed, njobs_upper, njobs_hint, num_sms, s, bound_only);
+}
 void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, cudaStream_t s);
 void count_launch(int n);
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);

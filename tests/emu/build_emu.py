@@ -1,0 +1,89 @@
+"""Builds tests/emu/_build/libdada2b_emu.so: the CUDA sources of dada2_b200/csrc compiled for the host SIMT emulator.
+
+TEST INFRASTRUCTURE ONLY (see cuda_emu.h).  The .cu files are not modified: a textual pass turns
+    kern<<<grid, block, smem, stream>>>(args);   ->  cuemu::launch("kern", [=]() { kern(args); }, grid, block, smem, stream);
+    extern __shared__ T name[];                  ->  T *name = (T *)cuemu::dyn_smem();
+into tests/emu/_build/*.cpp, which g++ compiles against cuda_emu.h (-ffp-contract=off mirrors nvcc's -fmad=false).
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "dada2_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libdada2b_emu.so")
+
+_LAUNCH = re.compile(r"([A-Za-z_][\w:]*(?:<[^<>;()]*>)?)\s*<<<(.+?)>>>\s*\((.*)\)\s*;")
+_DYN = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w:]+(?:\s+\w+)*?)\s+(\w+)\s*\[\s*\]\s*;")
+
+
+def transform(text):
+    out = []
+    for line in text.splitlines():
+        if "<<<" in line:
+            new = _LAUNCH.sub(lambda m: f"cuemu::launch(\"{m.group(1)}\", [=]() {{ {m.group(1)}({m.group(3)}); }}, {m.group(2)});", line)
+            if new == line:
+                raise RuntimeError("build_emu: cannot rewrite launch: " + line.strip())
+            line = new
+        elif "extern __shared__" in line:
+            new = _DYN.sub(lambda m: f"{m.group(1)} *{m.group(2)} = ({m.group(1)} *)cuemu::dyn_smem();", line)
+            if new == line:
+                raise RuntimeError("build_emu: cannot rewrite dynamic shared memory: " + line.strip())
+            line = new
+        out.append(line)
+    return "\n".join(out) + "\n"
+
+
+def sources():
+    sys.path.insert(0, ROOT)
+    from dada2_b200.build import SOURCES
+    return list(SOURCES)
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "build_emu.py")]
+    deps += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, extra_sources=(), lib=LIB, opt="-O1"):
+    if not force and not needs_build() and not extra_sources:
+        return lib
+    os.makedirs(OUT, exist_ok=True)
+    cxx = os.environ.get("CXX", "g++")
+    flags = [opt, "-g1", "-std=c++17", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-strict-aliasing", "-w", "-DDADA2B_EMU=1",
+             "-I", os.path.join(HERE, "stub"), "-I", CSRC, "-include", os.path.join(HERE, "cuda_emu.h")]
+    procs, objs = [], []
+    for src in list(sources()) + list(extra_sources):
+        path = src if os.path.isabs(src) else os.path.join(CSRC, src)
+        cpp = os.path.join(OUT, os.path.basename(src).replace(".cu", ".emu.cpp"))
+        with open(path) as f:
+            body = transform(f.read())
+        # keep relative includes of the original directory working
+        with open(cpp, "w") as f:
+            f.write(f'#line 1 "{path}"\n' + body)
+        obj = cpp.replace(".cpp", ".o")
+        cmd = [cxx] + flags + ["-I", os.path.dirname(path), "-c", cpp, "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    obj = os.path.join(OUT, "cuda_emu.o")
+    cmd = [cxx, "-O2", "-g1", "-std=c++17", "-fPIC", "-c", os.path.join(HERE, "cuda_emu.cpp"), "-o", obj]
+    procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    objs.append(obj)
+    for cmd, p in procs:
+        out = p.communicate()[0].decode()
+        if p.returncode:
+            sys.stderr.write(out[-6000:])
+            raise RuntimeError("emulator build failed: " + " ".join(cmd))
+    subprocess.check_call([cxx, "-shared", "-o", lib] + objs + ["-ldl", "-pthread"])
+    return lib
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

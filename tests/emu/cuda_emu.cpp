@@ -1,0 +1,220 @@
+// Fiber scheduler behind cuda_emu.h (x86-64 SysV only) -- test infrastructure, see the header.
+#include "cuda_emu.h"
+#include <sys/mman.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#if !defined(__x86_64__)
+#error "cuda_emu: the fiber switch is written for x86-64"
+#endif
+
+// void cuemu_switch(void **save_sp, void *load_sp): saves the callee-saved registers on the current stack, stores the
+// stack pointer, loads another stack and restores its callee-saved registers.
+extern "C" void cuemu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl cuemu_switch
+.type cuemu_switch,@function
+cuemu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size cuemu_switch,.-cuemu_switch
+)");
+
+namespace cuemu {
+thread_local uint3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
+thread_local int t_lane;
+
+namespace {
+constexpr size_t STACK_BYTES = 256 * 1024;
+constexpr int MAX_THREADS = 1024;
+constexpr size_t SMEM_BYTES = 232448;     // 227 KB
+
+struct Warp {
+  uint64_t slot[2][32];
+  uint32_t valid[2];
+  int kind[2];
+  int gen, arrived, live;
+};
+struct Fiber {
+  void *sp;
+  bool done;
+  uint3 tid;
+  int lane;
+  Warp *warp;
+  const volatile int *wait_ptr;    // non-null while parked on a barrier generation
+  int wait_val;
+};
+struct BlockRt {
+  std::vector<Fiber> fibers;
+  std::vector<Warp> warps;
+  int bgen, barrived, blive;
+  void *main_sp;
+  Fiber *cur;
+  void (*tramp)(void *);
+  void *closure;
+  unsigned long long progress;
+};
+thread_local BlockRt R;
+thread_local unsigned char *t_smem = nullptr;
+thread_local char *t_stacks = nullptr;
+
+void park(const volatile int *gen_ptr, int gen) {
+  Fiber *f = R.cur;
+  f->wait_ptr = gen_ptr;
+  f->wait_val = gen;
+  while (*gen_ptr == gen) cuemu_switch(&f->sp, R.main_sp);
+  f->wait_ptr = nullptr;
+}
+
+[[noreturn]] void fiber_main() {
+  R.tramp(R.closure);
+  Fiber *f = R.cur;
+  f->done = true;
+  R.progress++;
+  Warp &w = *f->warp;
+  w.live--;
+  if (w.arrived > 0 && w.arrived == w.live) { w.arrived = 0; w.gen++; }        // the rest of the warp was waiting for us
+  R.blive--;
+  if (R.barrived > 0 && R.barrived == R.blive) { R.barrived = 0; R.bgen++; }
+  for (;;) cuemu_switch(&f->sp, R.main_sp);
+}
+}  // namespace
+
+const uint64_t *warp_publish(uint64_t v, uint32_t *valid, int kind) {
+  Fiber *f = R.cur;
+  Warp &w = *f->warp;
+  const int g = w.gen, b = g & 1;
+  if (w.arrived == 0) { w.valid[b] = 0; w.kind[b] = kind; }
+  else if (w.kind[b] != kind) {
+    std::fprintf(stderr, "cuda_emu: divergent warp collective (kind %d vs %d) in block %u thread %u\n", w.kind[b], kind, t_blockIdx.x, f->tid.x);
+    std::abort();
+  }
+  w.slot[b][f->lane] = v;
+  w.valid[b] |= 1u << f->lane;
+  R.progress++;
+  if (++w.arrived == w.live) { w.arrived = 0; w.gen++; }
+  else park(&w.gen, g);
+  *valid = w.valid[b];
+  return w.slot[b];
+}
+
+void block_barrier() {
+  const int g = R.bgen;
+  R.progress++;
+  if (++R.barrived == R.blive) { R.barrived = 0; R.bgen++; }
+  else park(&R.bgen, g);
+}
+
+unsigned char *dyn_smem() { return t_smem; }
+
+namespace {
+std::mutex g_count_mu;
+std::map<std::string, long> g_counts;
+}  // namespace
+void note_launch(const char *kernel) {
+  std::lock_guard<std::mutex> lk(g_count_mu);
+  g_counts[kernel]++;
+}
+
+void *dev_alloc(size_t bytes) {
+  if (!bytes) return nullptr;
+  const size_t n = (bytes + 255) / 256 * 256;
+  void *p = std::aligned_alloc(256, n);
+  if (p) std::memset(p, 0xCD, n);
+  return p;
+}
+void dev_free(void *p) { std::free(p); }
+
+int num_sms() {
+  const char *e = std::getenv("CUEMU_SMS");
+  const int n = e ? std::atoi(e) : 2;
+  return n > 0 ? n : 2;
+}
+
+void launch_impl(dim3 grid, dim3 block, size_t smem, void (*tramp)(void *), void *closure) {
+  const int nthreads = (int)(block.x * block.y * block.z);
+  if (nthreads <= 0 || nthreads > MAX_THREADS || smem > SMEM_BYTES) {
+    std::fprintf(stderr, "cuda_emu: bad launch configuration (%d threads, %zu bytes of shared memory)\n", nthreads, smem);
+    std::abort();
+  }
+  if (R.cur) { std::fprintf(stderr, "cuda_emu: nested launch\n"); std::abort(); }
+  if (!t_smem) t_smem = (unsigned char *)std::aligned_alloc(1024, (SMEM_BYTES + 1023) / 1024 * 1024);
+  if (!t_stacks) {
+    t_stacks = (char *)mmap(nullptr, STACK_BYTES * MAX_THREADS, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (t_stacks == (char *)MAP_FAILED) { std::perror("cuda_emu: mmap"); std::abort(); }
+  }
+  const int nwarps = (nthreads + 31) / 32;
+  R.fibers.resize(nthreads);
+  R.warps.resize(nwarps);
+  R.tramp = tramp;
+  R.closure = closure;
+  t_blockDim = {block.x, block.y, block.z};
+  t_gridDim = {grid.x, grid.y, grid.z};
+  for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+      for (unsigned bx = 0; bx < grid.x; bx++) {
+        t_blockIdx = {bx, by, bz};
+        std::memset(t_smem, 0xCD, smem);
+        for (int w = 0; w < nwarps; w++) { R.warps[w].gen = 0; R.warps[w].arrived = 0; R.warps[w].live = std::min(32, nthreads - 32 * w); }
+        R.bgen = 0; R.barrived = 0; R.blive = nthreads; R.progress = 0;
+        for (int t = 0; t < nthreads; t++) {
+          Fiber &f = R.fibers[t];
+          f.done = false;
+          f.tid = {(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+          f.lane = t & 31;
+          f.warp = &R.warps[t >> 5];
+          f.wait_ptr = nullptr;
+          void **sp = (void **)(t_stacks + STACK_BYTES * (size_t)(t + 1));
+          *--sp = nullptr;                    // fake return address: keeps the stack 16-byte aligned as after a call
+          *--sp = (void *)&fiber_main;
+          for (int i = 0; i < 6; i++) *--sp = nullptr;
+          f.sp = sp;
+        }
+        while (R.blive > 0) {
+          const unsigned long long before = R.progress;
+          for (int t = 0; t < nthreads; t++) {
+            Fiber &f = R.fibers[t];
+            if (f.done || (f.wait_ptr && *f.wait_ptr == f.wait_val)) continue;
+            R.cur = &f;
+            t_threadIdx = f.tid;
+            t_lane = f.lane;
+            cuemu_switch(&R.main_sp, f.sp);
+          }
+          if (R.progress == before && R.blive > 0) {
+            std::fprintf(stderr, "cuda_emu: deadlock in block (%u,%u,%u): threads wait on a barrier the others never reach\n", bx, by, bz);
+            std::abort();
+          }
+        }
+        R.cur = nullptr;
+      }
+}
+}  // namespace cuemu
+
+// Launch counters for the tests: how often kernels whose name starts with `prefix` were launched since the last reset.
+extern "C" long cuemu_launches(const char *prefix) {
+  std::lock_guard<std::mutex> lk(cuemu::g_count_mu);
+  long n = 0;
+  const std::string p(prefix ? prefix : "");
+  for (auto &kv : cuemu::g_counts) if (kv.first.compare(0, p.size(), p) == 0) n += kv.second;
+  return n;
+}
+extern "C" void cuemu_reset_launches() {
+  std::lock_guard<std::mutex> lk(cuemu::g_count_mu);
+  cuemu::g_counts.clear();
+}
