@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY (see cuda_emu.h).  The .cu files are not modified: a textual pass turns
     kern<<<grid, block, smem, stream>>>(args);   ->  cuemu::launch("kern", [=]() { kern(args); }, grid, block, smem, stream);
     extern __shared__ T name[];                  ->  T *name = (T *)cuemu::dyn_smem();
-into tests/emu/_build/*.cpp, which g++ compiles against cuda_emu.h (-ffp-contract=off mirrors nvcc's -fmad=false).
+and points the driver's dlopen of libnccl at the emulator's in-process stand-in (ranks = threads), into
+tests/emu/_build/*.cpp, which g++ compiles against cuda_emu.h (-ffp-contract=off mirrors nvcc's -fmad=false).
 """
 import os
 import re
@@ -33,6 +34,8 @@ def transform(text):
             if new == line:
                 raise RuntimeError("build_emu: cannot rewrite dynamic shared memory: " + line.strip())
             line = new
+        if "dlopen(name" in line:          # NCCL is resolved with dlopen: point it at the emulator's in-process stand-in
+            line = line.replace("dlopen(name", "dlopen(cuemu_self_path()")
         out.append(line)
     return "\n".join(out) + "\n"
 

@@ -1,6 +1,8 @@
 // Fiber scheduler behind cuda_emu.h (x86-64 SysV only) -- test infrastructure, see the header.
 #include "cuda_emu.h"
 #include <sys/mman.h>
+#include <condition_variable>
+#include <dlfcn.h>
 #include <map>
 #include <mutex>
 #include <string>
@@ -218,3 +220,91 @@ extern "C" void cuemu_reset_launches() {
   std::lock_guard<std::mutex> lk(cuemu::g_count_mu);
   cuemu::g_counts.clear();
 }
+
+// ---- in-process stand-in for NCCL: the ranks of a sharded run are OS threads of one test process ----
+// build_emu.py points the driver's dlopen("libnccl.so.2") at this library, so the sharded code path (comm init, the
+// per-round all-gather, the final all-reduces) runs unchanged.  Collectives rendezvous on a condition variable.
+namespace {
+struct FakeComm {
+  std::mutex mu;
+  std::condition_variable cv;
+  int world = 0, joined = 0, arrived = 0, left = 0;
+  unsigned long long gen = 0;
+  std::vector<const void *> src;
+  std::vector<void *> dst;
+};
+struct FakeRank { FakeComm *c; int rank; };
+std::mutex g_comm_mu;
+std::map<std::string, FakeComm *> g_comms;
+unsigned long long g_next_id = 1;
+
+// Runs `work` (on the last arriving rank, with every rank's buffers visible) between two rendezvous.
+template <class W> void rendezvous(FakeRank *r, const void *send, void *recv, W work) {
+  FakeComm &c = *r->c;
+  std::unique_lock<std::mutex> lk(c.mu);
+  c.src[r->rank] = send;
+  c.dst[r->rank] = recv;
+  const unsigned long long g = c.gen;
+  if (++c.arrived == c.world) { work(c); c.arrived = 0; c.gen++; c.cv.notify_all(); }
+  else c.cv.wait(lk, [&] { return c.gen != g; });
+}
+size_t dtype_bytes(int dt) { return dt <= 1 ? 1 : dt <= 3 ? 4 : dt <= 5 ? 8 : dt == 6 ? 2 : dt == 7 ? 4 : 8; }
+}  // namespace
+
+extern "C" const char *cuemu_self_path() {
+  static std::string path;
+  Dl_info info;
+  if (path.empty() && dladdr((void *)&cuemu_self_path, &info) && info.dli_fname) path = info.dli_fname;
+  return path.c_str();
+}
+extern "C" int ncclGetUniqueId(char *id128) {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  std::memset(id128, 0, 128);
+  std::snprintf(id128, 128, "cuemu-%llu", g_next_id++);
+  return 0;
+}
+struct FakeId { char internal[128]; };
+extern "C" int ncclCommInitRank(void **comm, int world, FakeId id, int rank) {
+  FakeComm *c;
+  {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    FakeComm *&slot = g_comms[std::string(id.internal)];
+    if (!slot) { slot = new FakeComm(); slot->world = world; slot->src.resize(world); slot->dst.resize(world); }
+    c = slot;
+  }
+  if (c->world != world || rank < 0 || rank >= world) return 5;
+  *comm = new FakeRank{c, rank};
+  std::unique_lock<std::mutex> lk(c->mu);
+  c->joined++;
+  c->cv.notify_all();
+  c->cv.wait(lk, [&] { return c->joined >= c->world; });       // like NCCL: returns once every rank has joined
+  return 0;
+}
+extern "C" int ncclAllGather(const void *send, void *recv, size_t count, int dtype, void *comm, void *) {
+  const size_t bytes = count * dtype_bytes(dtype);
+  rendezvous((FakeRank *)comm, send, recv, [&](FakeComm &c) {
+    std::vector<unsigned char> tmp(bytes * c.world);
+    for (int r = 0; r < c.world; r++) std::memcpy(tmp.data() + bytes * r, c.src[r], bytes);     // staged: send may alias recv
+    for (int r = 0; r < c.world; r++) std::memcpy(c.dst[r], tmp.data(), tmp.size());
+  });
+  return 0;
+}
+extern "C" int ncclAllReduce(const void *send, void *recv, size_t count, int dtype, int op, void *comm, void *) {
+  if (op != 0) return 4;                                          // only ncclSum is used
+  rendezvous((FakeRank *)comm, send, recv, [&](FakeComm &c) {
+    const size_t eb = dtype_bytes(dtype);
+    std::vector<unsigned char> acc(count * eb, 0);
+    for (int r = 0; r < c.world; r++)
+      for (size_t i = 0; i < count; i++) {
+        if (dtype == 2 || dtype == 3) ((uint32_t *)acc.data())[i] += ((const uint32_t *)c.src[r])[i];
+        else if (dtype == 4 || dtype == 5) ((uint64_t *)acc.data())[i] += ((const uint64_t *)c.src[r])[i];
+        else if (dtype == 8) ((double *)acc.data())[i] += ((const double *)c.src[r])[i];
+        else if (dtype <= 1) acc[i] += ((const unsigned char *)c.src[r])[i];
+        else std::abort();
+      }
+    for (int r = 0; r < c.world; r++) std::memcpy(c.dst[r], acc.data(), acc.size());
+  });
+  return 0;
+}
+extern "C" int ncclCommDestroy(void *comm) { delete (FakeRank *)comm; return 0; }
+extern "C" const char *ncclGetErrorString(int) { return "cuda_emu fake NCCL error"; }

@@ -48,6 +48,7 @@ enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaStreamNonBlocking = 1 };
 
+extern "C" const char *cuemu_self_path();
 namespace cuemu {
 extern thread_local uint3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 extern thread_local int t_lane;

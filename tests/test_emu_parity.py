@@ -89,3 +89,58 @@ def test_emu_e2e_twophase(emu, monkeypatch, name):
     """The two-phase loop NW (exact lambda bound first, DADA2B_TWOPHASE=1) gives the reference's results."""
     monkeypatch.setenv("DADA2B_TWOPHASE", "1")
     _gpu_tests().test_e2e_matches_reference_golden(name)
+
+
+def test_emu_long_reads_band32_homopolymer(emu):
+    """BASELINE config 5 flavour at toy size: ~1.5 kb uniques, band 32, 94 quality columns; the homopolymer-gap scalar
+    path (nwalign_endsfree.cpp:220-396) and the vectorized path with ragged lengths."""
+    from oracle import port
+    from tools import synth
+    import dada2_b200
+    seqs, ab, q = synth.pacbio(60, L=1500, nvar=4, seed=5)
+    err = synth.extend_err(cases.tperr1(), 94)
+    for opts in (dict(band_size=32, vectorized_alignment=False, homo_gap=-1), dict(band_size=32)):
+        o = dict(opts)
+        o.setdefault("homo_gap", -8)
+        got = dada2_b200.dada_uniques(seqs, ab, None, err, q, **opts)
+        want = port.dada_uniques(seqs, ab, None, err, q, **o)
+        cases.assert_same(got, want, rtol=1e-10, label=str(opts))
+
+
+@pytest.mark.parametrize("world,name", [(2, "syn800_default"), (3, "syn700_ragged"), (8, "syn800_priors")])
+def test_emu_sharded_ranks(emu, world, name):
+    """The sharded multi-GPU path (raw r aligned by rank r % world, one all-gather per split round, final all-reduces)
+    with the ranks as threads and the emulator's in-process NCCL stand-in: every rank returns the reference's result."""
+    import threading
+
+    import numpy as np
+
+    import dada2_b200.api as api
+    from tests.test_oracle import load_golden
+    seqs, ab, pri, err, q, opts = cases.build_case(name)
+    want = load_golden(name)
+    uid = api.nccl_unique_id()
+    results = [None] * world
+
+    def rank_main(r):
+        try:
+            res = api.Resident(seqs, ab, pri, q)
+            res.comm_init(r, world, uid)
+            results[r] = res.run(err, **opts)
+            res.close()
+        except Exception as e:      # surfaced below, on the main thread
+            results[r] = e
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    pb = None
+    if pri is not None:
+        pb = np.zeros(len(want["clustering"]["sequence"]), dtype=bool)
+        pb[1:] = want["clustering"]["birth_pval"][1:] >= opts.get("omegaA", 1e-40)
+    for r in range(world):
+        if isinstance(results[r], Exception):
+            raise results[r]
+        cases.assert_same(results[r], want, rtol=1e-10, prior_born=pb, label=f"{name} rank {r}/{world}")
