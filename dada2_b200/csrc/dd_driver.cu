@@ -311,6 +311,14 @@ struct Run {
   DBuf<uint32_t> fb_list, surv_list;
   DBuf<double> raw_S, raw_rho;           // two-phase loop NW (experimental, DADA2B_TWOPHASE=1): per-raw bound factors
   bool two_phase = false;
+  // fused round tail (experimental, DADA2B_FUSED_TAIL=1; dd_round2.cu)
+  bool fused_tail = false;
+  TailState ts{};
+  DBuf<uint32_t> t_head, t_prev, t_nmove, t_bt, t_btp;
+  DBuf<int> t_delta;
+  DBuf<unsigned> t_done;
+  DBuf<BlkBest> t_blk;
+  void tail_sync_caps();
   int fwd_slots = 0;
   unsigned long long est_active = 0;
   size_t cl_cap = 0;
@@ -439,6 +447,20 @@ void Run::setup_params() {
   if (classify_smem > 100 * 1024) throw Err{"dada2b: sequences too long for the k-mer screen kernel."};
 }
 
+// Keeps the fused tail's per-entry / per-cluster arrays as large as the comparison store and the cluster arrays.
+void Run::tail_sync_caps() {
+  if (!fused_tail) return;
+  if (t_prev.n < st.cs_cap) {
+    DBuf<uint32_t> np;
+    np.alloc(st.cs_cap);
+    if (cs_count && t_prev.p) CK(cudaMemcpyAsync(np.p, t_prev.p, cs_count * 4, cudaMemcpyDeviceToDevice, s));
+    sync();
+    std::swap(t_prev.p, np.p); std::swap(t_prev.n, np.n); std::swap(t_prev.cap, np.cap);
+  }
+  if (t_delta.n < (size_t)MAX_PASS * cl_cap) { t_delta.alloc((size_t)MAX_PASS * cl_cap); t_delta.zero(s); }   // cleared every round by k_tail_link
+  ts.cs_prev = t_prev.p; ts.delta = t_delta.p; ts.cl_cap = (uint32_t)cl_cap;
+}
+
 void Run::ensure_cluster_cap(size_t n) {
   if (n <= cl_cap) return;
   size_t nc = std::max<size_t>(1024, cl_cap * 2);
@@ -500,6 +522,14 @@ void Run::alloc_state() {
   move_cap = (unsigned)(4 * n + 1024); fb_list.alloc(n);
   two_phase = getenv("DADA2B_TWOPHASE") != nullptr;      // off by default: not yet validated on hardware
   if (two_phase) { surv_list.alloc(n); raw_S.alloc(n); raw_rho.alloc(n); }
+  if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
+  fused_tail = getenv("DADA2B_FUSED_TAIL") != nullptr;   // off by default: not yet validated on hardware
+  if (fused_tail) {
+    const size_t g = (size_t)tail_grid(nraw);
+    t_head.alloc(n); t_nmove.alloc(MAX_PASS); t_done.alloc(1); t_blk.alloc(g); t_bt.alloc(g * TIE_MAX); t_btp.alloc(g * TIE_MAX);
+    t_nmove.zero(s); t_done.zero(s);
+    ts.head = t_head.p; ts.nmove_pass = t_nmove.p; ts.done = t_done.p; ts.blk = t_blk.p; ts.blk_ties = t_bt.p; ts.blk_ties_pr = t_btp.p;
+  }
   pinfo.alloc(MAX_PASS + 2); pinfo.zero(s);
   d_report.alloc(1); d_moves.alloc((size_t)move_cap * 2);
   h_report_buf.alloc(1); h_moves_buf.alloc((size_t)move_cap * 2);
@@ -570,6 +600,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   const uint32_t c = cl_center_h[i];
   ensure_cs_cap(cs_count + 2ull * (unsigned long long)nraw + 1024);
   ensure_cluster_cap(members.size() + 2);
+  tail_sync_caps();
   launch_round_begin(st, pending.apply, pending.r, pending.from, pending.newi, pending.reads, s);
   pending.apply = 0;
   count_round = true;
@@ -622,12 +653,19 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       launch_cs_append(st, ne_all.p, d_counts.p, (unsigned)maxc, i, c, s);
     }
   }
+  if (fused_tail) launch_tail_link(st, ts, cs_count, i, nraw, (int)members.size(), s);
 }
 
 // shuffle passes [first_pass, first_pass + npass) then p-update, bud scan and the report
 void Run::launch_round_tail(int first_pass, int npass) {
   const int nclust = (int)members.size();
   const unsigned long long upper = cs_count + (unsigned long long)nraw;
+  if (fused_tail && first_pass == 0 && tail_fits(nclust)) {
+    for (int p = 0; p < npass; p++) launch_tail_pass(st, in, ts, p, nclust, s);
+    BudParams bp{o->min_fold, o->min_hamming, o->min_abund};
+    launch_tail_final(st, in, ts, bp, o->greedy != 0, o->detect_singletons != 0, npass - 1, nclust, s);
+    return;
+  }
   for (int p = first_pass; p < first_pass + npass; p++) launch_shuffle_pass(st, in, upper, nclust, p, s);
   const int last = first_pass + npass - 1;          // -1 => no shuffling this round (initial cluster)
   launch_p_update(st, in, o->greedy != 0, o->detect_singletons != 0, last, s);

@@ -84,6 +84,26 @@ void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cu
 void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 cudaError_t align_set_smem(size_t bytes);
 
+// fused round tail (dd_round2.cu; EXPERIMENTAL, DADA2B_FUSED_TAIL=1)
+struct BlkBest { unsigned long long pb, pbp; uint32_t rd, rdp, n, np; };
+struct TailState {
+  uint32_t *head;          // [nraw] newest stored comparison of the raw
+  uint32_t *cs_prev;       // [cs_cap] the same raw's previous stored comparison (lower cluster index); chain ends at the cluster-0 entry
+  int *delta;              // [MAX_PASS][cl_cap] net change of each cluster's reads made by shuffle pass k of the current round
+  uint32_t cl_cap;
+  uint32_t *nmove_pass;    // [MAX_PASS] moves made by pass k of the current round
+  unsigned *done;          // block tickets of k_tail_final
+  BlkBest *blk;            // [grid of k_tail_final] per-block bud minima
+  uint32_t *blk_ties, *blk_ties_pr;   // [grid][TIE_MAX] their tie candidates
+};
+struct BudParams;
+bool tail_fits(int nclust);
+int tail_grid(int nraw);
+void launch_tail_link(const DevState &st, const TailState &ts, unsigned long long base, uint32_t cluster_i, int nraw, int nclust, cudaStream_t s);
+void launch_tail_pass(const DevState &st, const DevIn &in, const TailState &ts, int pass, int nclust, cudaStream_t s);
+void launch_tail_final(const DevState &st, const DevIn &in, const TailState &ts, const BudParams &bp, int greedy, int detect_singletons,
+                       int last_pass, int nclust, cudaStream_t s);
+
 // per-round control kernels (dd_round.cu)
 struct BudParams { double min_fold; int min_hamming, min_abund; };
 void launch_round_begin(const DevState &st, int apply, uint32_t r, uint32_t from, uint32_t newi, uint32_t reads_r, cudaStream_t s);

@@ -1,0 +1,245 @@
+// Fused round tail (product code, sm_100a) -- EXPERIMENTAL, selected with DADA2B_FUSED_TAIL=1; checked on the host SIMT
+// emulator of tests/emu, not yet on hardware.  dd_round.cu stays the default.
+//
+// dd_round.cu spends ~17 small launches per round on b_shuffle2 / b_p_update / b_bud (4 per shuffle pass, 5 after).
+// Here the same work is 1 + NP + 1 launches:
+//
+//   k_tail_link    threads the round's new stored comparisons onto per-raw chains (newest first) and clears the scratch
+//   k_tail_pass    one b_shuffle2 pass (cluster.cpp:210-266) in ONE kernel: every raw walks its own chain for the
+//                  arg-max of lambda * reads(cluster); the pass-wide frozen reads (Appendix A.4 of SURVEY.md) are
+//                  rebuilt per block in shared memory as reads_at_round_start + sum of the earlier passes' deltas,
+//                  and a pass only ever adds to its own delta row, so no commit kernel is needed
+//   k_tail_final   b_p_update (pval.cpp:14-40) + the b_bud scan (cluster.cpp:274-308) + the report: per-block
+//                  lexicographic (p asc, reads desc) minima with their tie candidates, reduced by the last block to
+//                  finish (ticket counter), which also commits the cluster reads and clears the per-cluster flags
+//
+// Results are identical to dd_round.cu: the arg-max prefers the lowest cluster index among equal e (chain walked from
+// the newest entry with '>='), moves are recorded per pass (the host replays them in the reference's order) and the
+// host still resolves exact (p, reads) ties by (cluster, slot).
+#include "dd_common.h"
+#include "dd_kernels.h"
+#include "ppois.cuh"
+
+namespace dd2 {
+
+constexpr uint32_t CHAIN_END = 0xFFFFFFFFu;
+
+__global__ void k_tail_link(DevState st, TailState ts, unsigned long long base, uint32_t cluster_i, int nraw, int nclust) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long t0 = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (cluster_i == 0) {                       // cluster 0 owns slots [0, nraw): one entry per raw, the chain's tail
+    for (unsigned long long x = t0; x < (unsigned long long)nraw; x += stride) { ts.head[x] = (uint32_t)x; ts.cs_prev[x] = CHAIN_END; }
+  } else {
+    const unsigned long long n = st.ctr[CTR_CS_COUNT];
+    for (unsigned long long x = base + t0; x < n; x += stride) {       // at most one new entry per raw and round
+      const uint32_t r = st.cs_index[x];
+      ts.cs_prev[x] = ts.head[r];
+      ts.head[r] = (uint32_t)x;
+    }
+  }
+  for (unsigned long long x = t0; x < (unsigned long long)MAX_PASS * ts.cl_cap; x += stride)
+    if ((int)(x % ts.cl_cap) < nclust) ts.delta[x] = 0;
+  if (t0 < MAX_PASS) ts.nmove_pass[t0] = 0;
+  if (t0 == 0) *ts.done = 0;
+}
+
+// reads of every cluster as frozen at the start of shuffle pass `pass` (pass == npasses: after the last one)
+__device__ __forceinline__ void stage_reads(const DevState &st, const TailState &ts, int pass, int nclust, uint32_t *s_reads) {
+  for (int c = threadIdx.x; c < nclust; c += blockDim.x) {
+    int v = (int)st.cl_reads[c];
+    for (int k = 0; k < pass; k++) v += ts.delta[(size_t)k * ts.cl_cap + c];
+    s_reads[c] = (uint32_t)v;
+  }
+  __syncthreads();
+}
+
+__global__ void k_tail_pass(DevState st, DevIn in, TailState ts, int pass, int nclust) {
+  extern __shared__ uint32_t s_reads[];
+  if (pass > 0 && ts.nmove_pass[pass - 1] == 0) return;             // previous pass moved nothing: b_shuffle2 returned false
+  stage_reads(st, ts, pass, nclust, s_reads);
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= in.nraw) return;
+  double best_e = -1.0;
+  uint32_t best_x = CHAIN_END;
+  for (uint32_t x = ts.head[r]; x != CHAIN_END; x = ts.cs_prev[x]) {   // clusters descending: '>=' keeps the lowest index among ties
+    const double e = st.cs_lambda[x] * (double)s_reads[st.cs_i[x]];
+    if (e >= best_e) { best_e = e; best_x = x; }
+  }
+  if (best_x == CHAIN_END) return;
+  const uint32_t to = st.cs_i[best_x], from = st.cluster_of[r];
+  if (to != from && !st.is_center[r]) {                                 // cluster.cpp:248-260
+    const unsigned long long s = atomicAdd(&st.ctr[CTR_NMOVE], 1ull);
+    if (s < st.move_cap) { st.moves[2 * s] = (uint32_t)r; st.moves[2 * s + 1] = to; }
+    atomicAdd(&ts.nmove_pass[pass], 1u);
+    st.cluster_of[r] = to;
+    st.comp_lambda[r] = st.cs_lambda[best_x];
+    st.comp_ham[r] = st.cs_ham[best_x];
+    const int rd = (int)in.reads[r];
+    atomicAdd(&ts.delta[(size_t)pass * ts.cl_cap + from], -rd);
+    atomicAdd(&ts.delta[(size_t)pass * ts.cl_cap + to], rd);
+    st.cl_update_e[from] = 1; st.cl_update_e[to] = 1;
+  }
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const uint32_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  return v;
+}
+
+// blockDim.x must be TAIL_BLOCK (a multiple of 32, at most 1024)
+__global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, int greedy, int detect_singletons, int last_pass, int nclust) {
+  extern __shared__ uint32_t s_reads[];
+  __shared__ unsigned long long s_pb[32], s_pbp[32];
+  __shared__ uint32_t s_rd[32], s_rdp[32];
+  __shared__ unsigned s_n, s_np, s_last;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+  const bool converged = last_pass < 0 || ts.nmove_pass[last_pass] == 0;
+  if (tid == 0) { s_n = 0; s_np = 0; }
+  stage_reads(st, ts, last_pass + 1, nclust, s_reads);               // also the barrier behind s_n / s_np
+  const int r = blockIdx.x * blockDim.x + tid;
+  unsigned long long pb = ~0ull, pbp = ~0ull;
+  uint32_t rd = 0;
+  bool elig = false, prior = false;
+  if (converged && r < in.nraw) {
+    const uint32_t ci = st.cluster_of[r];
+    rd = in.reads[r];
+    prior = in.prior[r] != 0;
+    const double lambda = st.comp_lambda[r];
+    const uint32_t ham = st.comp_ham[r];
+    double pval = st.p[r];
+    if (st.cl_update_e[ci]) {                                          // get_pA pval.cpp:67-89
+      if (rd == 1 && !prior && !detect_singletons) pval = 1.;
+      else if (ham == 0) pval = 1.;
+      else if (lambda == 0) pval = 0.;
+      else pval = calc_pA((int)rd, lambda * (double)s_reads[ci], prior || detect_singletons);
+      st.p[r] = pval;
+    }
+    if (greedy && st.cl_check_locks[ci]) {                             // pval.cpp:29-38
+      const uint32_t cen = st.cl_center[ci];
+      if ((double)in.reads[cen] * lambda > (double)rd) st.lock[r] = 1;
+      if ((uint32_t)r == cen) st.lock[r] = 1;
+    }
+    // b_bud candidate (cluster.cpp:285-294)
+    elig = !st.slot0[r] && (int)rd >= bp.min_abund && (int)ham >= bp.min_hamming &&
+           (bp.min_fold <= 1 || ((double)rd) >= bp.min_fold * lambda * (double)s_reads[ci]);
+    if (elig) { pb = (unsigned long long)__double_as_longlong(pval); if (prior) pbp = pb; }
+  }
+  // block minimum of p, then maximum of reads among the raws attaining it; all of those are tie candidates
+  unsigned long long w = warp_min_u64(pb), wp = warp_min_u64(pbp);
+  if (lane == 0) { s_pb[wid] = w; s_pbp[wid] = wp; }
+  __syncthreads();
+  unsigned long long bmin = ~0ull, bminp = ~0ull;
+  for (int k = 0; k < nwarp; k++) { bmin = s_pb[k] < bmin ? s_pb[k] : bmin; bminp = s_pbp[k] < bminp ? s_pbp[k] : bminp; }
+  const bool ca = elig && pb == bmin, cp = elig && prior && pb == bminp;
+  uint32_t wr = warp_max_u32(ca ? rd : 0u), wrp = warp_max_u32(cp ? rd : 0u);
+  if (lane == 0) { s_rd[wid] = wr; s_rdp[wid] = wrp; }
+  __syncthreads();
+  uint32_t bmax = 0, bmaxp = 0;
+  for (int k = 0; k < nwarp; k++) { bmax = s_rd[k] > bmax ? s_rd[k] : bmax; bmaxp = s_rdp[k] > bmaxp ? s_rdp[k] : bmaxp; }
+  if (ca && rd == bmax) { const unsigned k = atomicAdd(&s_n, 1u); if (k < TIE_MAX) ts.blk_ties[(size_t)blockIdx.x * TIE_MAX + k] = (uint32_t)r; }
+  if (cp && rd == bmaxp) { const unsigned k = atomicAdd(&s_np, 1u); if (k < TIE_MAX) ts.blk_ties_pr[(size_t)blockIdx.x * TIE_MAX + k] = (uint32_t)r; }
+  __syncthreads();
+  if (tid == 0) {
+    BlkBest b;
+    b.pb = bmin; b.pbp = bminp; b.rd = bmax; b.rdp = bmaxp; b.n = s_n; b.np = s_np;
+    ts.blk[blockIdx.x] = b;
+    __threadfence();                                                   // results visible before the ticket
+    s_last = atomicAdd(ts.done, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+
+  // ---- the last block to finish: commit, global reduction, report ----
+  __threadfence();
+  const volatile BlkBest *blk = ts.blk;
+  const volatile uint32_t *bt = ts.blk_ties, *btp = ts.blk_ties_pr;
+  for (int c = tid; c < nclust; c += blockDim.x) { st.cl_reads[c] = s_reads[c]; st.cl_reads_next[c] = s_reads[c]; }
+  if (tid == 0) {
+    uint32_t acc = 0;                                                  // pinfo[p+1] = moves recorded up to and including pass p
+    st.pinfo[0] = 0;
+    for (int p = 0; p <= last_pass; p++) { acc += ts.nmove_pass[p]; st.pinfo[p + 1] = acc; }
+  }
+  if (converged) {
+    unsigned long long gmin = ~0ull, gminp = ~0ull;
+    for (unsigned b = tid; b < gridDim.x; b += blockDim.x) {
+      const unsigned long long x = blk[b].pb, xp = blk[b].pbp;
+      gmin = x < gmin ? x : gmin; gminp = xp < gminp ? xp : gminp;
+    }
+    gmin = warp_min_u64(gmin); gminp = warp_min_u64(gminp);
+    if (lane == 0) { s_pb[wid] = gmin; s_pbp[wid] = gminp; }
+    __syncthreads();
+    gmin = ~0ull; gminp = ~0ull;
+    for (int k = 0; k < nwarp; k++) { gmin = s_pb[k] < gmin ? s_pb[k] : gmin; gminp = s_pbp[k] < gminp ? s_pbp[k] : gminp; }
+    uint32_t gmax = 0, gmaxp = 0;
+    for (unsigned b = tid; b < gridDim.x; b += blockDim.x) {
+      if (blk[b].n && blk[b].pb == gmin) gmax = blk[b].rd > gmax ? blk[b].rd : gmax;
+      if (blk[b].np && blk[b].pbp == gminp) gmaxp = blk[b].rdp > gmaxp ? blk[b].rdp : gmaxp;
+    }
+    gmax = warp_max_u32(gmax); gmaxp = warp_max_u32(gmaxp);
+    if (lane == 0) { s_rd[wid] = gmax; s_rdp[wid] = gmaxp; }
+    if (tid == 0) { s_n = 0; s_np = 0; }
+    __syncthreads();
+    gmax = 0; gmaxp = 0;
+    for (int k = 0; k < nwarp; k++) { gmax = s_rd[k] > gmax ? s_rd[k] : gmax; gmaxp = s_rdp[k] > gmaxp ? s_rdp[k] : gmaxp; }
+    for (unsigned b = tid; b < gridDim.x; b += blockDim.x) {
+      if (blk[b].n && blk[b].pb == gmin && blk[b].rd == gmax) {
+        const unsigned cnt = blk[b].n, at = atomicAdd(&s_n, cnt);
+        for (unsigned k = 0; k < cnt && k < TIE_MAX && at + k < TIE_MAX; k++) {
+          const uint32_t rr = bt[(size_t)b * TIE_MAX + k];
+          st.report->tie_r[at + k] = rr; st.report->tie_lam[at + k] = st.comp_lambda[rr]; st.report->tie_ham[at + k] = st.comp_ham[rr];
+        }
+      }
+      if (blk[b].np && blk[b].pbp == gminp && blk[b].rdp == gmaxp) {
+        const unsigned cnt = blk[b].np, at = atomicAdd(&s_np, cnt);
+        for (unsigned k = 0; k < cnt && k < TIE_MAX && at + k < TIE_MAX; k++) {
+          const uint32_t rr = btp[(size_t)b * TIE_MAX + k];
+          st.report->tiep_r[at + k] = rr; st.report->tiep_lam[at + k] = st.comp_lambda[rr]; st.report->tiep_ham[at + k] = st.comp_ham[rr];
+        }
+      }
+    }
+    for (int c = tid; c < nclust; c += blockDim.x) { st.cl_update_e[c] = 0; st.cl_check_locks[c] = 0; }   // consumed above
+    __syncthreads();
+    if (tid == 0) {
+      st.ctr[CTR_PMIN] = gmin; st.ctr[CTR_RMAX] = gmax; st.ctr[CTR_NTIE] = s_n;
+      st.ctr[CTR_PMIN_PR] = gminp; st.ctr[CTR_RMAX_PR] = gmaxp; st.ctr[CTR_NTIE_PR] = s_np;
+    }
+  }
+  __syncthreads();
+  if (tid < CTR_N) st.report->ctr[tid] = st.ctr[tid];
+  if (tid < MAX_PASS + 2) st.report->pinfo[tid] = st.pinfo[tid];
+  if (tid == 0) { st.report->converged = converged ? 1u : 0u; *ts.done = 0; }
+}
+
+// ------------------------------- launch wrappers --------------------------------------
+constexpr int TAIL_BLOCK = 256;
+constexpr size_t TAIL_SMEM_MAX = 160 * 1024;
+
+bool tail_fits(int nclust) { return (size_t)nclust * 4 <= TAIL_SMEM_MAX; }
+int tail_grid(int nraw) { return std::max(1, (nraw + TAIL_BLOCK - 1) / TAIL_BLOCK); }
+
+void launch_tail_link(const DevState &st, const TailState &ts, unsigned long long base, uint32_t cluster_i, int nraw, int nclust, cudaStream_t s) {
+  count_launch(1);
+  const unsigned g = (unsigned)std::min<unsigned long long>(((unsigned long long)nraw + 255) / 256 + 1, 148ull * 8);
+  k_tail_link<<<g, 256, 0, s>>>(st, ts, base, cluster_i, nraw, nclust);
+}
+void launch_tail_pass(const DevState &st, const DevIn &in, const TailState &ts, int pass, int nclust, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_tail_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX); attr_set = true; }
+  count_launch(1);
+  k_tail_pass<<<tail_grid(in.nraw), TAIL_BLOCK, (size_t)nclust * 4, s>>>(st, in, ts, pass, nclust);
+}
+void launch_tail_final(const DevState &st, const DevIn &in, const TailState &ts, const BudParams &bp, int greedy, int detect_singletons,
+                       int last_pass, int nclust, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_tail_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX); attr_set = true; }
+  count_launch(1);
+  k_tail_final<<<tail_grid(in.nraw), TAIL_BLOCK, (size_t)nclust * 4, s>>>(st, in, ts, bp, greedy, detect_singletons, last_pass, nclust);
+}
+
+}  // namespace dd2

@@ -144,3 +144,35 @@ def test_emu_sharded_ranks(emu, world, name):
         if isinstance(results[r], Exception):
             raise results[r]
         cases.assert_same(results[r], want, rtol=1e-10, prior_born=pb, label=f"{name} rank {r}/{world}")
+
+
+FUSED_E2E = ["syn800_default", "syn800_nogreedy", "syn800_priors", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES)
+
+
+@pytest.mark.parametrize("np_passes", [1, 3])
+@pytest.mark.parametrize("name", FUSED_E2E)
+def test_emu_e2e_fused_tail(emu, monkeypatch, name, np_passes):
+    """The fused round tail (dd_round2.cu, DADA2B_FUSED_TAIL=1): 1 + NP + 1 launches instead of ~17 per round.  NP=1
+    forces the hand-over to the unfused kernels in every round that needs a second shuffle pass."""
+    if np_passes == 1 and name not in ("syn800_default", "syn800_priors") and not os.environ.get("DADA2B_EMU_FULL"):
+        pytest.skip("quick subset")
+    monkeypatch.setenv("DADA2B_FUSED_TAIL", "1")
+    monkeypatch.setenv("DADA2B_NP", str(np_passes))
+    _gpu_tests().test_e2e_matches_reference_golden(name)
+    assert emu.cuemu_launches(b"k_tail_final") > 0
+    if np_passes >= 3:
+        assert emu.cuemu_launches(b"k_shuffle_max") == 0 and emu.cuemu_launches(b"k_p_update") == 0
+    else:
+        assert emu.cuemu_launches(b"k_shuffle_max") > 0
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["default", "fused_tail"])
+def test_emu_large_tie_sets(emu, monkeypatch, fused):
+    """b_bud tie sets larger than TIE_MAX: the host fetches the whole set (k_bud_collect) and applies the scan order."""
+    import tests.test_gpu_zz_ties as TT
+    if fused:
+        monkeypatch.setenv("DADA2B_FUSED_TAIL", "1")
+    for opts in (dict(), dict(greedy=False), dict(max_clust=30)):
+        TT.test_large_tie_sets_follow_scan_order(opts)
+    assert emu.cuemu_launches(b"k_bud_collect") > 0
+    assert (emu.cuemu_launches(b"k_tail_final") > 0) == fused
