@@ -311,6 +311,10 @@ struct Run {
   DBuf<uint32_t> fb_list, surv_list;
   DBuf<double> raw_S, raw_rho;           // two-phase loop NW (experimental, DADA2B_TWOPHASE=1): per-raw bound factors
   bool two_phase = false;
+  // pivot pre-filter of the k-mer screen (experimental, DADA2B_PIVOT=1; dd_classify2.cu)
+  bool pivot = false;
+  DBuf<uint32_t> pv_cluster;
+  DBuf<uint16_t> pv_ms, seed_ms;
   // fused round tail (experimental, DADA2B_FUSED_TAIL=1; dd_round2.cu)
   bool fused_tail = false;
   TailState ts{};
@@ -522,6 +526,8 @@ void Run::alloc_state() {
   move_cap = (unsigned)(4 * n + 1024); fb_list.alloc(n);
   two_phase = getenv("DADA2B_TWOPHASE") != nullptr;      // off by default: not yet validated on hardware
   if (two_phase) { surv_list.alloc(n); raw_S.alloc(n); raw_rho.alloc(n); }
+  pivot = getenv("DADA2B_PIVOT") != nullptr;             // off by default: not yet validated on hardware
+  if (pivot) { pv_cluster.alloc(n); pv_ms.alloc(n); CK(cudaMemsetAsync(pv_cluster.p, 0xFF, n * 4, s)); pv_ms.zero(s); }
   if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
   fused_tail = getenv("DADA2B_FUSED_TAIL") != nullptr;   // off by default: not yet validated on hardware
   if (fused_tail) {
@@ -609,6 +615,16 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   ca.greedy = o->greedy != 0; ca.lock = st.lock; ca.nw_list = st.nw_list; ca.gl_list = st.gl_list; ca.ctr = st.ctr;
   ca.kind_out = nullptr; ca.kord_words = kord_words; ca.shard_rank = cx->rank; ca.shard_world = cx->world;
   int cgrid = std::min((nraw / cx->world + 8) / 8, cx->num_sms * 4);
+  if (pivot && P.use_kmers) {
+    const int nclust_before = (int)i;                    // centres 0..i-1 exist; the seed is centre i
+    if (seed_ms.n < cl_cap) seed_ms.alloc(cl_cap);
+    PivotArgs pa{pv_cluster.p, pv_ms.p, seed_ms.p, st.cl_center, i};
+    cgrid = std::min((nraw / cx->world + 255) / 256 + 1, cx->num_sms * 4);
+    timed(T_CLASSIFY, [&]() {
+      launch_seed_dists(in, st.cl_center, nclust_before, c, seed_ms.p, cx->num_sms, s);
+      launch_classify2(ca, pa, cgrid, 256, classify_smem, s);
+    });
+  } else
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   bool fwd_done = false;
   if (!P.homo && P.band >= 0 && !getenv("DADA2B_NO_NWFWD")) {       // register-resident forward-carry NW (dd_nwfwd.cu)
@@ -1115,7 +1131,8 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
                      R.cl_center_h[newi], now_ms() - tr, ran, R.cs_count, R.h_report->ctr[CTR_NW], R.h_report->ctr[CTR_GL],
                      R.h_report->ctr[CTR_NMOVE]);
   }
-  if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters\n", (int)R.members.size());
+  if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters; screened %llu, shrouded %llu (pivot bound %llu)\n", (int)R.members.size(),
+                   R.h_report->ctr[CTR_ALIGN], R.h_report->ctr[CTR_SHROUD], R.pivot ? R.h_report->ctr[CTR_GLTOT] : 0ull);
   R.sync();
   const double t2 = now_ms();
   dada2b_out *out = (dada2b_out *)calloc(1, sizeof(dada2b_out));

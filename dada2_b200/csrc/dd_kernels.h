@@ -23,6 +23,16 @@ struct ClassifyArgs {
   int shard_rank, shard_world;
 };
 
+// pivot pre-filter of the k-mer screen (dd_classify2.cu; EXPERIMENTAL, DADA2B_PIVOT=1)
+struct PivotArgs {
+  uint32_t *pv_cluster;        // [nraw] cluster index of the raw's pivot centre, 0xFFFFFFFF = none yet
+  uint16_t *pv_ms;             // [nraw] exact 5-mer min-sum between the raw and its pivot centre
+  const uint16_t *seed_ms;     // [nclust] min-sum between every existing centre and the round's seed (k_seed_dists)
+  const uint32_t *cl_center;   // [nclust] raw index of each centre
+  uint32_t cluster_i;          // index of the cluster being seeded
+};
+void launch_seed_dists(const DevIn &in, const uint32_t *cl_center, int nclust, uint32_t seed, uint16_t *seed_ms, int num_sms, cudaStream_t s);
+
 struct AlignArgs {
   DevIn in;
   AlnParams P;
@@ -81,6 +91,7 @@ inline bool launch_nwfwd_sel(const FwdArgs &a, int slots_needed, unsigned long l
 void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, cudaStream_t s);
 void count_launch(int n);
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);
+void launch_classify2(const ClassifyArgs &a, const PivotArgs &pv, int grid, int block, size_t smem, cudaStream_t s);
 void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 cudaError_t align_set_smem(size_t bytes);
 

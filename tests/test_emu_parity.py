@@ -107,10 +107,7 @@ def test_emu_long_reads_band32_homopolymer(emu):
         cases.assert_same(got, want, rtol=1e-10, label=str(opts))
 
 
-@pytest.mark.parametrize("world,name", [(2, "syn800_default"), (3, "syn700_ragged"), (8, "syn800_priors")])
-def test_emu_sharded_ranks(emu, world, name):
-    """The sharded multi-GPU path (raw r aligned by rank r % world, one all-gather per split round, final all-reduces)
-    with the ranks as threads and the emulator's in-process NCCL stand-in: every rank returns the reference's result."""
+def _run_sharded(world, name):
     import threading
 
     import numpy as np
@@ -146,6 +143,13 @@ def test_emu_sharded_ranks(emu, world, name):
         cases.assert_same(results[r], want, rtol=1e-10, prior_born=pb, label=f"{name} rank {r}/{world}")
 
 
+@pytest.mark.parametrize("world,name", [(2, "syn800_default"), (3, "syn700_ragged"), (8, "syn800_priors")])
+def test_emu_sharded_ranks(emu, world, name):
+    """The sharded multi-GPU path (raw r aligned by rank r % world, one all-gather per split round, final all-reduces)
+    with the ranks as threads and the emulator's in-process NCCL stand-in: every rank returns the reference's result."""
+    _run_sharded(world, name)
+
+
 FUSED_E2E = ["syn800_default", "syn800_nogreedy", "syn800_priors", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES)
 
 
@@ -176,3 +180,22 @@ def test_emu_large_tie_sets(emu, monkeypatch, fused):
         TT.test_large_tie_sets_follow_scan_order(opts)
     assert emu.cuemu_launches(b"k_bud_collect") > 0
     assert (emu.cuemu_launches(b"k_tail_final") > 0) == fused
+
+
+@pytest.mark.parametrize("name", ["syn800_default", "syn800_kdist", "syn700_ragged", "syn800_sse0"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
+def test_emu_e2e_pivot_screen(emu, monkeypatch, name):
+    """The pivot pre-filter of the k-mer screen (dd_classify2.cu, DADA2B_PIVOT=1): triangle-inequality bound on the
+    5-mer min-sum from the closest centre seen so far; must classify every pair exactly like k_classify."""
+    monkeypatch.setenv("DADA2B_PIVOT", "1")
+    _gpu_tests().test_e2e_matches_reference_golden(name)
+    if cases.E2E_CASES[name][1].get("use_kmers", True):
+        assert emu.cuemu_launches(b"k_classify2") > 0 and emu.cuemu_launches(b"k_seed_dists") > 0
+
+
+def test_emu_all_experimental_paths_together(emu, monkeypatch):
+    """Every experimental path at once (pivot screen, two-phase + restructured NW, fused tail), single rank and sharded."""
+    for k in ("DADA2B_PIVOT", "DADA2B_TWOPHASE", "DADA2B_NWFWD_V2", "DADA2B_FUSED_TAIL"):
+        monkeypatch.setenv(k, "1")
+    _gpu_tests().test_e2e_matches_reference_golden("syn800_default")
+    _run_sharded(2, "syn700_ragged")
+    assert emu.cuemu_launches(b"k_classify2") > 0 and emu.cuemu_launches(b"k_nwfwd2") > 0 and emu.cuemu_launches(b"k_tail_final") > 0
