@@ -84,6 +84,15 @@ void park(const volatile int *gen_ptr, int gen) {
   f->wait_ptr = nullptr;
 }
 
+void reorder(std::vector<int> &order, int sched, uint64_t &rng) {
+  const int n = (int)order.size();
+  if (sched == 1) { for (int t = 0; t < n; t++) order[t] = n - 1 - t; return; }
+  for (int t = n - 1; t > 0; t--) {                    // Fisher-Yates with xorshift64
+    rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+    std::swap(order[t], order[(int)(rng % (uint64_t)(t + 1))]);
+  }
+}
+
 [[noreturn]] void fiber_main() {
   R.tramp(R.closure);
   Fiber *f = R.cur;
@@ -162,6 +171,14 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, void (*tramp)(void *), void
     if (t_stacks == (char *)MAP_FAILED) { std::perror("cuda_emu: mmap"); std::abort(); }
   }
   const int nwarps = (nthreads + 31) / 32;
+  // CUEMU_SCHED: order in which the runnable threads of a block get the CPU between two collectives.
+  //   unset/0 = thread order; 1 = reverse; N >= 2 = a fresh pseudo-random permutation (seed N) before every pass.
+  // Code that is correct on the GPU cannot depend on it, so results must not change -- a cheap detector for missing
+  // __syncwarp()/__syncthreads() and other order assumptions.
+  static const int sched = [] { const char *e = std::getenv("CUEMU_SCHED"); return e ? std::atoi(e) : 0; }();
+  static thread_local std::vector<int> order;
+  static thread_local uint64_t rng = 0;
+  if (sched != 0) { order.resize(nthreads); for (int t = 0; t < nthreads; t++) order[t] = t; if (!rng) rng = 0x9E3779B97F4A7C15ull * (uint64_t)sched; }
   R.fibers.resize(nthreads);
   R.warps.resize(nwarps);
   R.tramp = tramp;
@@ -190,7 +207,9 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, void (*tramp)(void *), void
         }
         while (R.blive > 0) {
           const unsigned long long before = R.progress;
-          for (int t = 0; t < nthreads; t++) {
+          if (sched != 0) reorder(order, sched, rng);
+          for (int k = 0; k < nthreads; k++) {
+            const int t = sched != 0 ? order[k] : k;
             Fiber &f = R.fibers[t];
             if (f.done || (f.wait_ptr && *f.wait_ptr == f.wait_val)) continue;
             R.cur = &f;
