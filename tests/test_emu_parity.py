@@ -199,3 +199,10 @@ def test_emu_all_experimental_paths_together(emu, monkeypatch):
     _gpu_tests().test_e2e_matches_reference_golden("syn800_default")
     _run_sharded(2, "syn700_ragged")
     assert emu.cuemu_launches(b"k_classify2") > 0 and emu.cuemu_launches(b"k_nwfwd2") > 0 and emu.cuemu_launches(b"k_tail_final") > 0
+
+
+def test_emu_edge_cases(emu):
+    """tests/cases.py:edge_cases() on the emulated library (the GPU suite runs the same table in test_gpu_zz_edge.py)."""
+    import dada2_b200
+    for case in cases.edge_cases():
+        cases.check_edge_case(case, dada2_b200.dada_uniques)
