@@ -627,16 +627,17 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   } else
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   bool fwd_done = false;
-  if (!P.homo && P.band >= 0 && !getenv("DADA2B_NO_NWFWD")) {       // register-resident forward-carry NW (dd_nwfwd.cu)
+  const bool fwd_homo_ok = getenv("DADA2B_NWFWD_V2") != nullptr;       // only the restructured kernel knows homopolymer gap costs
+  if ((!P.homo || fwd_homo_ok) && P.band >= 0 && !getenv("DADA2B_NO_NWFWD")) {       // register-resident forward-carry NW (dd_nwfwd.cu)
     FwdArgs f{};
     f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
     f.centre_idx = c; f.centre_reads = cx->reads[c]; f.cluster_i = i; f.total_reads = cx->total_reads;
     f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes; f.mode = 0; f.job_mul = 1; f.job_add = 0;
     {  // the fast path replaces the reference's sentinel by a larger penalty: only valid while no real score can come near it
-      const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::abs(P.gap) + 16;
+      const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::max(std::abs(P.gap), std::abs(P.hgap)) + 16;
       f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
     }
-    if (two_phase && i > 0) {
+    if (two_phase && i > 0 && !P.homo) {
       // pass 1: scores + substitution counts only; lambda <= S_r * rho_r^nsubs decides which pairs can pass the store rule
       FwdArgs fbnd = f;
       fbnd.raw_S = raw_S.p; fbnd.raw_rho = raw_rho.p; fbnd.surv_list = surv_list.p; fbnd.surv_count = st.ctr + CTR_SURV;
@@ -848,7 +849,7 @@ void Run::finish(dada2b_out *out) {
   if (cx->world > 1) nsubs_final.zero(s);
   {  // FinalSubsParallel: sub_new(centre, raw, use_kmers=false) for every raw
     bool split = false;
-    if (P.band > 0 && !P.homo && !getenv("DADA2B_NO_NWFWD")) {
+    if (P.band > 0 && (!P.homo || getenv("DADA2B_NWFWD_V2")) && !getenv("DADA2B_NO_NWFWD")) {
       // 1) forward-carry NW of every raw against its own centre: nsubs + "is the optimal path the pure diagonal?"
       FwdArgs f{};
       unsigned long long nn = (unsigned long long)n_owned;
@@ -859,7 +860,7 @@ void Run::finish(dada2b_out *out) {
       f.gl_out = st.gl_list; f.nw_out = st.nw_list; f.gl_count = st.ctr + CTR_GL; f.nw_count = st.ctr + CTR_NW;
       f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_NMOVE;   // (scratch counter; pairs that do not fit -> traceback list below)
       { unsigned long long z = 0; h2d(ctr.p + CTR_NMOVE, &z, 8); }
-      const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::abs(P.gap) + 16;
+      const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::max(std::abs(P.gap), std::abs(P.hgap)) + 16;
       f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
       timed(T_FINAL, [&]() { split = launch_nwfwd_sel(f, fwd_slots, (unsigned long long)nraw, (unsigned long long)nraw, cx->num_sms, s); });
     }

@@ -46,14 +46,16 @@ __device__ __forceinline__ long long band_cells2(int n, int m, int l, int r) {
 // FAST = interior step (no boundary cell, no free end gap, every pair running): branch-free, out-of-band slots kept
 // below any real score by PEN.  Otherwise every cell is checked against the matrix borders and the band.
 struct StepCtx {
-  int gl, len1, len2, tlo, thi, nsteps, SENT, match, mismatch, gap, ncol4, ONE_IDX;
+  int gl, len1, len2, tlo, thi, nsteps, SENT, match, mismatch, gap, hgap, ncol4, ONE_IDX;
   const uint16_t *s_b2;
   const double *s_err;
 };
 
-template <int G, int ND, bool WL, int PAR, bool FAST>
+// HM = homopolymer gap costs (nwalign_endsfree.cpp:220-396): a gap opposite a base that lies in a run >= 3 costs hgap; HA / HB
+// carry that flag for the centre / raw base of every slot (bit cc <-> slot cc), like A / B carry the bases.
+template <int G, int ND, bool WL, bool HM, int PAR, bool FAST>
 __device__ __forceinline__ void nw_step(int (&H)[ND], int (&NSUB)[ND], double (&LAM)[ND], const int (&PEN)[ND], uint32_t A,
-                                        uint32_t B, int I, int J, int k, const StepCtx &c) {
+                                        uint32_t B, uint32_t HA, uint32_t HB, int I, int J, int k, const StepCtx &c) {
   constexpr int NSL = ND / 2;
   constexpr int BIGPEN = 1 << 20, GAPFLAG = 1 << 30, PADL = 64;
   // neighbour exchange: identical in both paths, unconditional
@@ -85,7 +87,8 @@ __device__ __forceinline__ void nw_step(int (&H)[ND], int (&NSUB)[ND], double (&
     const uint32_t nt1 = (A >> (2 * cc)) & 3u, nt2 = (B >> (2 * cc)) & 3u;
     const bool eq = ((X >> (2 * cc)) & 3u) == 0u;
     if (FAST) {
-      const int left = hl + c.gap, up = hu + c.gap, diag = H[t] + (eq ? c.match : c.mismatch);
+      const int gl_ = (HM && ((HB >> cc) & 1u)) ? c.hgap : c.gap, gu_ = (HM && ((HA >> cc) & 1u)) ? c.hgap : c.gap;   // :303-320
+      const int left = hl + gl_, up = hu + gu_, diag = H[t] + (eq ? c.match : c.mismatch);
       const int m = __vimax3_s32(left, up, diag);
       const bool isU = up == m;                      // precedence up > left > diag (nwalign_endsfree.cpp:147-156)
       const bool isL = (left == m) && !isU;
@@ -99,8 +102,9 @@ __device__ __forceinline__ void nw_step(int (&H)[ND], int (&NSUB)[ND], double (&
     } else {
       const int i = I - cc, j = Jp + cc;
       const bool valid = (t >= c.tlo) && (t <= c.thi) && i >= 0 && j >= 0 && i <= c.len1 && j <= c.len2 && k <= c.nsteps;
-      const int left = hl + ((i == c.len1) ? 0 : c.gap);                   // nwalign_endsfree.cpp:128-156
-      const int up = hu + ((j == c.len2) ? 0 : c.gap);
+      const int gl_ = (HM && ((HB >> cc) & 1u)) ? c.hgap : c.gap, gu_ = (HM && ((HA >> cc) & 1u)) ? c.hgap : c.gap;
+      const int left = hl + ((i == c.len1) ? 0 : gl_);                     // nwalign_endsfree.cpp:128-156 (homo :303-320)
+      const int up = hu + ((j == c.len2) ? 0 : gu_);
       const int diag = H[t] + (eq ? c.match : c.mismatch);
       const int m = max(max(left, up), diag);
       int pmove = (up == m) ? 3 : ((left == m) ? 2 : 1);
@@ -124,9 +128,19 @@ __device__ __forceinline__ void nw_step(int (&H)[ND], int (&NSUB)[ND], double (&
   }
 }
 
+// bit 2 of a staged base byte = "inside a homopolymer run of length >= 3" (nwalign_endsfree.cpp:230-255).  Writers only touch
+// bit 2 and readers of the neighbours only use bits 1:0, so the flags of one sequence can be set concurrently.
+__device__ __forceinline__ void homo_flag(uint8_t *seq, int p, int len) {
+  const int b = seq[p] & 3;
+  int L = 0, R = 0;
+  while (L < 2 && p - L - 1 >= 0 && (seq[p - L - 1] & 3) == b) L++;
+  while (R < 2 && p + R + 1 < len && (seq[p + R + 1] & 3) == b) R++;
+  if (L + R >= 2) seq[p] |= 4;
+}
+
 // WL = carry lambda (the exact kernel).  WL = false is the bound pass of the two-phase scheme: scores and
 // substitution counts only; pairs that provably fail the store rule are dropped, the rest are listed for the exact kernel.
-template <int G, int ND, bool WL>
+template <int G, int ND, bool WL, bool HM>
 __global__ void __launch_bounds__(128) k_nwfwd2(FwdArgs a) {
   constexpr int NSL = ND / 2;             // cells per lane per step
   constexpr int PPW = 32 / G;             // pairs per warp
@@ -158,6 +172,10 @@ __global__ void __launch_bounds__(128) k_nwfwd2(FwdArgs a) {
   if (!final_mode) {
     const uint32_t *crow = a.in.seq2 + (size_t)a.centre_idx * a.in.SW;
     for (int p = threadIdx.x; p < len1_shared; p += blockDim.x) s_cen_shared[p] = (uint8_t)((crow[p >> 4] >> (2 * (p & 15))) & 3u);
+    if (HM) {
+      __syncthreads();
+      for (int p = threadIdx.x; p < len1_shared; p += blockDim.x) homo_flag(s_cen_shared, p, len1_shared);
+    }
   }
   __syncthreads();
   const int ONE_IDX = 16 * ncol, ncol4 = 4 * ncol;
@@ -178,6 +196,10 @@ __global__ void __launch_bounds__(128) k_nwfwd2(FwdArgs a) {
       const uint32_t *crow = a.in.seq2 + (size_t)c * a.in.SW;
       for (int p = gl; p < len1; p += G) s_cen_own[p] = (uint8_t)((crow[p >> 4] >> (2 * (p & 15))) & 3u);
     }
+    if (HM && final_mode) {
+      __syncwarp();
+      if (act) for (int p = gl; p < len1; p += G) homo_flag(s_cen_own, p, len1);
+    }
     // ---- stage raw bases + qualities (group-cooperative) ----
     if (act) {
       const uint32_t *rrow = a.in.seq2 + (size_t)r * a.in.SW;
@@ -194,6 +216,10 @@ __global__ void __launch_bounds__(128) k_nwfwd2(FwdArgs a) {
       for (int p = gl; p < a.seq_bytes + 2 * PAD; p += G) s_b2[p - PAD] = 0;
     }
     __syncwarp();
+    if (HM) {
+      if (act) for (int p = gl; p < len2; p += G) homo_flag(s_raw, p, len2);
+      __syncwarp();
+    }
     // ---- band geometry (nwalign_endsfree.cpp:101-111) ----
     int lband, rband;
     if (len2 > len1) { lband = P.band; rband = P.band + len2 - len1; }
@@ -219,13 +245,14 @@ __global__ void __launch_bounds__(128) k_nwfwd2(FwdArgs a) {
     for (int t = 0; t < ND; t++) { H[t] = SENT; NSUB[t] = 0; LAM[t] = 1.0; }
     // windows for step k = 0: I = -D/2, J = D/2 ; slot c: s1[I-1-c], s2[J-1+c]
     int I = -(D / 2), J = D / 2;      // D even; exact
-    uint32_t A = 0, B = 0;
+    uint32_t A = 0, B = 0, HA = 0, HB = 0;
 #pragma unroll
     for (int cc = 0; cc < NSL; cc++) {
       const int i1 = I - 1 - cc, j1 = J - 1 + cc;
       const uint32_t b1 = (i1 >= 0 && i1 < len1) ? s_cen[i1] : 0u;
       const uint32_t b2 = (act && j1 >= 0 && j1 < len2) ? s_raw[j1] : 0u;
-      A |= b1 << (2 * cc); B |= b2 << (2 * cc);
+      A |= (b1 & 3u) << (2 * cc); B |= (b2 & 3u) << (2 * cc);
+      if (HM) { HA |= (b1 >> 2) << cc; HB |= (b2 >> 2) << cc; }
     }
 
     // Interior steps (no boundary cell, no free end gap, every pair still running) take a branch-free path;
@@ -245,31 +272,35 @@ __global__ void __launch_bounds__(128) k_nwfwd2(FwdArgs a) {
     // ---- main loop in three phases: checked prologue, branch-free interior, checked epilogue ----
     auto advB = [&]() {            // even -> odd: raw window moves one base (J -> J+1)
       uint32_t nbB = __shfl_down_sync(0xffffffffu, B, 1, G);
-      uint32_t newb = nbB & 3u;
-      if (gl == G - 1) { const int jn = J + NSL - 1; newb = (act && jn >= 0 && jn < len2) ? s_raw[jn] : 0u; }
+      uint32_t newb = nbB & 3u, newh = 0;
+      if (HM) newh = __shfl_down_sync(0xffffffffu, HB, 1, G) & 1u;
+      if (gl == G - 1) { const int jn = J + NSL - 1; const uint32_t v = (act && jn >= 0 && jn < len2) ? s_raw[jn] : 0u; newb = v & 3u; newh = v >> 2; }
       B = (B >> 2) | (newb << (2 * (NSL - 1)));
+      if (HM) HB = (HB >> 1) | (newh << (NSL - 1));
     };
     auto advA = [&]() {            // odd -> even: centre window moves one base (I -> I+1), J -> J+1 completes
       uint32_t nbA = __shfl_up_sync(0xffffffffu, A, 1, G);
-      uint32_t newa = (nbA >> (2 * (NSL - 1))) & 3u;
-      if (gl == 0) newa = (I >= 0 && I < len1) ? s_cen[I] : 0u;
+      uint32_t newa = (nbA >> (2 * (NSL - 1))) & 3u, newh = 0;
+      if (HM) newh = (__shfl_up_sync(0xffffffffu, HA, 1, G) >> (NSL - 1)) & 1u;
+      if (gl == 0) { const uint32_t v = (I >= 0 && I < len1) ? s_cen[I] : 0u; newa = v & 3u; newh = v >> 2; }
       A = ((A << 2) | newa) & (NSL == 16 ? 0xffffffffu : ((1u << (2 * NSL)) - 1u));
+      if (HM) HA = ((HA << 1) | newh) & ((1u << NSL) - 1u);
       I += 1; J += 1;
     };
-    const StepCtx cx{gl, len1, len2, tlo, thi, nsteps, SENT, match, mismatch, gap, ncol4, ONE_IDX, s_b2, s_err};
+    const StepCtx cx{gl, len1, len2, tlo, thi, nsteps, SENT, match, mismatch, gap, P.hgap, ncol4, ONE_IDX, s_b2, s_err};
     int kk = 0;
     const int kfa = (kf_lo + 1) & ~1;                       // first even step index inside the interior range
     for (; kk < kfa && kk <= maxsteps; kk += 2) {
-      nw_step<G, ND, WL, 0, false>(H, NSUB, LAM, PEN, A, B, I, J, kk, cx); advB();
-      nw_step<G, ND, WL, 1, false>(H, NSUB, LAM, PEN, A, B, I, J, kk + 1, cx); advA();
+      nw_step<G, ND, WL, HM, 0, false>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk, cx); advB();
+      nw_step<G, ND, WL, HM, 1, false>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk + 1, cx); advA();
     }
     for (; kk + 1 <= kf_hi && kk <= maxsteps; kk += 2) {
-      nw_step<G, ND, WL, 0, true>(H, NSUB, LAM, PEN, A, B, I, J, kk, cx); advB();
-      nw_step<G, ND, WL, 1, true>(H, NSUB, LAM, PEN, A, B, I, J, kk + 1, cx); advA();
+      nw_step<G, ND, WL, HM, 0, true>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk, cx); advB();
+      nw_step<G, ND, WL, HM, 1, true>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk + 1, cx); advA();
     }
     for (; kk <= maxsteps; kk += 2) {
-      nw_step<G, ND, WL, 0, false>(H, NSUB, LAM, PEN, A, B, I, J, kk, cx); advB();
-      nw_step<G, ND, WL, 1, false>(H, NSUB, LAM, PEN, A, B, I, J, kk + 1, cx); advA();
+      nw_step<G, ND, WL, HM, 0, false>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk, cx); advB();
+      nw_step<G, ND, WL, HM, 1, false>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk + 1, cx); advA();
     }
     // ---- result: cell (len1, len2) on dd = len2 - len1 + LB ----
     const int ddf = len2 - len1 + LB;
@@ -332,20 +363,22 @@ __global__ void __launch_bounds__(128) k_nwfwd2(FwdArgs a) {
   if (lane == 0 && cells_lane) atomicAdd(&a.st.ctr[CTR_CELLS], (unsigned long long)cells_lane);
 }
 
-template <int G, int ND, bool WL> static void launch_one2(const FwdArgs &a, int grid, size_t smem, cudaStream_t s) {
+template <int G, int ND, bool WL, bool HM> static void launch_one2(const FwdArgs &a, int grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_nwfwd2<G, ND, WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
-  k_nwfwd2<G, ND, WL><<<grid, 128, smem, s>>>(a);
+  if (!attr_set) { cudaFuncSetAttribute(k_nwfwd2<G, ND, WL, HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+  k_nwfwd2<G, ND, WL, HM><<<grid, 128, smem, s>>>(a);
 }
 template <int G, int ND> static void launch_wl2(const FwdArgs &a, bool bound_only, int grid, size_t smem, cudaStream_t s) {
-  if (bound_only) launch_one2<G, ND, false>(a, grid, smem, s);
-  else launch_one2<G, ND, true>(a, grid, smem, s);
+  if (a.P.homo) launch_one2<G, ND, true, true>(a, grid, smem, s);        // homopolymer costs: exact kernel only (no bound pass)
+  else if (bound_only) launch_one2<G, ND, false, false>(a, grid, smem, s);
+  else launch_one2<G, ND, true, false>(a, grid, smem, s);
 }
 
 // Picks the instantiation: smallest G*ND >= needed band slots, preferring few lanes per pair for
 // large batches (throughput) and many lanes for small batches (latency).
 bool launch_nwfwd2(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s,
                   bool bound_only) {
+  if (a.P.homo && bound_only) return false;
   int G, ND;
   const bool big = njobs_hint > (unsigned long long)num_sms * 512;
   const char *force = getenv("DADA2B_NWFWD");          // tuning override, e.g. "8x6"

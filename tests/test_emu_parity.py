@@ -74,13 +74,13 @@ def test_emu_e2e(emu, name):
     _gpu_tests().test_e2e_matches_reference_golden(name)
 
 
-@pytest.mark.parametrize("name", ["syn800_default", "syn800_band8", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
+@pytest.mark.parametrize("name", ["syn800_default", "syn800_band8", "syn700_ragged", "syn700_ragged_homo"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
 def test_emu_e2e_nwfwd_v2(emu, monkeypatch, name):
     """The restructured loop-NW kernel (dd_nwfwd2.cu, DADA2B_NWFWD_V2=1) gives the reference's results."""
     monkeypatch.setenv("DADA2B_NWFWD_V2", "1")
     _gpu_tests().test_e2e_matches_reference_golden(name)
     opts = cases.E2E_CASES[name][1]
-    if opts.get("band_size", 16) >= 0 and "homo_gap" not in opts:
+    if opts.get("band_size", 16) >= 0:          # homopolymer gap costs included (the default kernel hands those to k_align)
         assert emu.cuemu_launches(b"k_nwfwd2") > 0 and emu.cuemu_launches(b"k_nwfwd<") == 0
 
 
@@ -91,7 +91,7 @@ def test_emu_e2e_twophase(emu, monkeypatch, name):
     _gpu_tests().test_e2e_matches_reference_golden(name)
 
 
-def test_emu_long_reads_band32_homopolymer(emu):
+def test_emu_long_reads_band32_homopolymer(emu, monkeypatch):
     """BASELINE config 5 flavour at toy size: ~1.5 kb uniques, band 32, 94 quality columns; the homopolymer-gap scalar
     path (nwalign_endsfree.cpp:220-396) and the vectorized path with ragged lengths."""
     from oracle import port
@@ -99,12 +99,15 @@ def test_emu_long_reads_band32_homopolymer(emu):
     import dada2_b200
     seqs, ab, q = synth.pacbio(60, L=1500, nvar=4, seed=5)
     err = synth.extend_err(cases.tperr1(), 94)
-    for opts in (dict(band_size=32, vectorized_alignment=False, homo_gap=-1), dict(band_size=32)):
-        o = dict(opts)
-        o.setdefault("homo_gap", -8)
-        got = dada2_b200.dada_uniques(seqs, ab, None, err, q, **opts)
-        want = port.dada_uniques(seqs, ab, None, err, q, **o)
-        cases.assert_same(got, want, rtol=1e-10, label=str(opts))
+    for v2 in (False, True):                      # default kernels, then the restructured NW kernel (register path for homo gaps)
+        if v2:
+            monkeypatch.setenv("DADA2B_NWFWD_V2", "1")
+        for opts in (dict(band_size=32, vectorized_alignment=False, homo_gap=-1), dict(band_size=32)):
+            o = dict(opts)
+            o.setdefault("homo_gap", -8)
+            got = dada2_b200.dada_uniques(seqs, ab, None, err, q, **opts)
+            want = port.dada_uniques(seqs, ab, None, err, q, **o)
+            cases.assert_same(got, want, rtol=1e-10, label=str(opts) + (" v2" if v2 else ""))
 
 
 def _run_sharded(world, name):
