@@ -45,10 +45,20 @@ __device__ __forceinline__ long long band_cells2(int n, int m, int l, int r) {
 // PAR reads its neighbours of the other parity (unchanged during this step) and its own previous value only.
 // FAST = interior step (no boundary cell, no free end gap, every pair running): branch-free, out-of-band slots kept
 // below any real score by PEN.  Otherwise every cell is checked against the matrix borders and the band.
+// select without a branch: ptxas otherwise turns the rare 'up' move into a divergent branch around the table lookup
+__device__ __forceinline__ int sel_i32(bool p, int a, int b) {
+#ifdef DADA2B_EMU
+  return p ? a : b;
+#else
+  int r;
+  asm("{.reg .pred q; setp.ne.s32 q, %3, 0; selp.s32 %0, %1, %2, q;}" : "=r"(r) : "r"(a), "r"(b), "r"((int)p));
+  return r;
+#endif
+}
+
 struct StepCtx {
   int gl, len1, len2, tlo, thi, nsteps, SENT, match, mismatch, gap, hgap, ncol4, ONE_IDX;
-  const uint16_t *s_b2;
-  const double *s_err;
+  int b2_off;            // byte offset of the pair's b2 table (entry 0) from the start of dynamic shared memory
 };
 
 // HM = homopolymer gap costs (nwalign_endsfree.cpp:220-396): a gap opposite a base that lies in a run >= 3 costs hgap; HA / HB
@@ -74,7 +84,10 @@ __device__ __forceinline__ void nw_step(int (&H)[ND], int (&NSUB)[ND], double (&
   }
   const uint32_t X = A ^ B;
   const int Jp = J + PAR;
-  const uint16_t *b2p = c.s_b2 + (Jp - 1);
+  extern __shared__ uint32_t smem[];                     // named directly: no generic-to-shared address conversion per load
+  const double *s_err = (const double *)smem;             // the error table sits at offset 0
+  const uint16_t *s_b2 = (const uint16_t *)((const unsigned char *)smem + c.b2_off);
+  const uint16_t *b2p = s_b2 + (Jp - 1);
 #pragma unroll
   for (int cc = 0; cc < NSL; cc++) {
     const int t = 2 * cc + PAR;
@@ -93,11 +106,11 @@ __device__ __forceinline__ void nw_step(int (&H)[ND], int (&NSUB)[ND], double (&
       const bool isU = up == m;                      // precedence up > left > diag (nwalign_endsfree.cpp:147-156)
       const bool isL = (left == m) && !isU;
       if (WL) {
-        const int idx = isU ? c.ONE_IDX : (int)b2p[cc] + (int)(isL ? nt2 : nt1) * c.ncol4;
+        const int idx = sel_i32(isU, c.ONE_IDX, (int)b2p[cc] + (int)(isL ? nt2 : nt1) * c.ncol4);
         const double lp = isU ? lu : (isL ? ll : LAM[t]);
-        LAM[t] = lp * c.s_err[idx];
+        LAM[t] = lp * s_err[idx];
       }
-      NSUB[t] = isU ? (nu | GAPFLAG) : (isL ? (nl | GAPFLAG) : NSUB[t] + (eq ? 0 : 1));
+      NSUB[t] = sel_i32(isU, nu | GAPFLAG, sel_i32(isL, nl | GAPFLAG, NSUB[t] + (eq ? 0 : 1)));
       H[t] = m + PEN[t];
     } else {
       const int i = I - cc, j = Jp + cc;
@@ -116,11 +129,11 @@ __device__ __forceinline__ void nw_step(int (&H)[ND], int (&NSUB)[ND], double (&
       if (pmove == 1 && !eq) np++;
       if (pmove == 2 || pmove == 3) np |= GAPFLAG;
       if (WL) {
-        const int b2 = c.s_b2[min(max(j - 1, -PADL), c.len2 + PADL - 1)];
+        const int b2 = s_b2[min(max(j - 1, -PADL), c.len2 + PADL - 1)];
         const int idx = (pmove == 1 || pmove == 2) ? b2 + (int)((pmove == 1) ? nt1 : nt2) * c.ncol4 : c.ONE_IDX;
         double lp = (pmove == 3) ? lu : ((pmove == 2) ? ll : LAM[t]);
         if (pmove == 0) lp = 1.0;
-        LAM[t] = valid ? lp * c.s_err[idx] : LAM[t];
+        LAM[t] = valid ? lp * s_err[idx] : LAM[t];
       }
       H[t] = valid ? val : H[t];
       NSUB[t] = valid ? np : NSUB[t];
@@ -267,7 +280,10 @@ __global__ void __launch_bounds__(128) k_nwfwd2(FwdArgs a) {
     constexpr int BIGPEN = 1 << 20;
     int PEN[ND];
 #pragma unroll
-    for (int t = 0; t < ND; t++) PEN[t] = (t >= tlo && t <= thi) ? 0 : -BIGPEN;
+    for (int t = 0; t < ND; t++) {
+      PEN[t] = (t >= tlo && t <= thi) ? 0 : -BIGPEN;
+      PEN[t] = __shfl_sync(0xffffffffu, PEN[t], lane);   // opaque to ptxas: stays an addend (one IADD per cell), not a predicate + select
+    }
 
     // ---- main loop in three phases: checked prologue, branch-free interior, checked epilogue ----
     auto advB = [&]() {            // even -> odd: raw window moves one base (J -> J+1)
@@ -287,7 +303,7 @@ __global__ void __launch_bounds__(128) k_nwfwd2(FwdArgs a) {
       if (HM) HA = ((HA << 1) | newh) & ((1u << NSL) - 1u);
       I += 1; J += 1;
     };
-    const StepCtx cx{gl, len1, len2, tlo, thi, nsteps, SENT, match, mismatch, gap, P.hgap, ncol4, ONE_IDX, s_b2, s_err};
+    const StepCtx cx{gl, len1, len2, tlo, thi, nsteps, SENT, match, mismatch, gap, P.hgap, ncol4, ONE_IDX, (int)((const unsigned char *)s_b2 - (const unsigned char *)smem)};
     int kk = 0;
     const int kfa = (kf_lo + 1) & ~1;                       // first even step index inside the interior range
     for (; kk < kfa && kk <= maxsteps; kk += 2) {
