@@ -22,8 +22,8 @@ sys.path.insert(0, os.path.join(HERE, "emu"))
 
 pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="the emulator's fiber switch is x86-64 only")
 
-QUICK = ["syn800_default", "syn800_nogreedy", "syn800_nokmers", "syn600_band0", "syn800_maxclust5", "syn800_kdist",
-         "syn800_ones_err", "syn700_ragged", "syn500_usequals0"]
+QUICK = ["syn800_default", "syn800_nogreedy", "syn600_band0", "syn800_maxclust5", "syn800_kdist", "syn800_ones_err", "syn700_ragged",
+         "syn500_usequals0"]
 E2E = list(cases.E2E_CASES) if os.environ.get("DADA2B_EMU_FULL") else QUICK
 
 
@@ -97,12 +97,14 @@ def test_emu_long_reads_band32_homopolymer(emu, monkeypatch):
     from oracle import port
     from tools import synth
     import dada2_b200
-    seqs, ab, q = synth.pacbio(60, L=1500, nvar=4, seed=5)
+    seqs, ab, q = synth.pacbio(36, L=1500, nvar=3, seed=5)
     err = synth.extend_err(cases.tperr1(), 94)
     for v2 in (False, True):                      # default kernels, then the restructured NW kernel (register path for homo gaps)
         if v2:
             monkeypatch.setenv("DADA2B_NWFWD_V2", "1")
         for opts in (dict(band_size=32, vectorized_alignment=False, homo_gap=-1), dict(band_size=32)):
+            if v2 and "homo_gap" not in opts and not os.environ.get("DADA2B_EMU_FULL"):
+                continue
             o = dict(opts)
             o.setdefault("homo_gap", -8)
             got = dada2_b200.dada_uniques(seqs, ab, None, err, q, **opts)
@@ -146,14 +148,14 @@ def _run_sharded(world, name):
         cases.assert_same(results[r], want, rtol=1e-10, prior_born=pb, label=f"{name} rank {r}/{world}")
 
 
-@pytest.mark.parametrize("world,name", [(2, "syn800_default"), (3, "syn700_ragged"), (8, "syn800_priors")])
+@pytest.mark.parametrize("world,name", [(2, "syn800_default"), (3, "syn700_ragged"), (8, "syn800_maxclust5")])
 def test_emu_sharded_ranks(emu, world, name):
     """The sharded multi-GPU path (raw r aligned by rank r % world, one all-gather per split round, final all-reduces)
     with the ranks as threads and the emulator's in-process NCCL stand-in: every rank returns the reference's result."""
     _run_sharded(world, name)
 
 
-FUSED_E2E = ["syn800_default", "syn800_nogreedy", "syn800_priors", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES)
+FUSED_E2E = ["syn800_default", "syn800_nogreedy", "syn800_maxclust5", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES)
 
 
 @pytest.mark.parametrize("np_passes", [1, 3])
@@ -161,7 +163,7 @@ FUSED_E2E = ["syn800_default", "syn800_nogreedy", "syn800_priors", "syn700_ragge
 def test_emu_e2e_fused_tail(emu, monkeypatch, name, np_passes):
     """The fused round tail (dd_round2.cu, DADA2B_FUSED_TAIL=1): 1 + NP + 1 launches instead of ~17 per round.  NP=1
     forces the hand-over to the unfused kernels in every round that needs a second shuffle pass."""
-    if np_passes == 1 and name not in ("syn800_default", "syn800_priors") and not os.environ.get("DADA2B_EMU_FULL"):
+    if np_passes == 1 and name not in ("syn800_default", "syn800_maxclust5") and not os.environ.get("DADA2B_EMU_FULL"):
         pytest.skip("quick subset")
     monkeypatch.setenv("DADA2B_FUSED_TAIL", "1")
     monkeypatch.setenv("DADA2B_NP", str(np_passes))
@@ -185,7 +187,7 @@ def test_emu_large_tie_sets(emu, monkeypatch, fused):
     assert (emu.cuemu_launches(b"k_tail_final") > 0) == fused
 
 
-@pytest.mark.parametrize("name", ["syn800_default", "syn800_kdist", "syn700_ragged", "syn800_sse0"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
+@pytest.mark.parametrize("name", ["syn800_default", "syn800_kdist", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
 def test_emu_e2e_pivot_screen(emu, monkeypatch, name):
     """The pivot pre-filter of the k-mer screen (dd_classify2.cu, DADA2B_PIVOT=1): triangle-inequality bound on the
     5-mer min-sum from the closest centre seen so far; must classify every pair exactly like k_classify."""
@@ -204,8 +206,13 @@ def test_emu_all_experimental_paths_together(emu, monkeypatch):
     assert emu.cuemu_launches(b"k_classify2") > 0 and emu.cuemu_launches(b"k_nwfwd2") > 0 and emu.cuemu_launches(b"k_tail_final") > 0
 
 
-def test_emu_edge_cases(emu):
-    """tests/cases.py:edge_cases() on the emulated library (the GPU suite runs the same table in test_gpu_zz_edge.py)."""
+@pytest.mark.parametrize("experimental", [False, True], ids=["default", "experimental"])
+def test_emu_edge_cases(emu, monkeypatch, experimental):
+    """tests/cases.py:edge_cases() on the emulated library (the GPU suite runs the same table in test_gpu_zz_edge.py),
+    with the default kernels and with every experimental path switched on."""
     import dada2_b200
+    if experimental:
+        for k in ("DADA2B_PIVOT", "DADA2B_TWOPHASE", "DADA2B_NWFWD_V2", "DADA2B_FUSED_TAIL"):
+            monkeypatch.setenv(k, "1")
     for case in cases.edge_cases():
         cases.check_edge_case(case, dada2_b200.dada_uniques)

@@ -49,9 +49,9 @@ def test_collectives_under_every_schedule_and_missing_syncwarp_is_exposed(selfte
     assert len(set(stale.values())) > 2      # random orders land in between: the bug shows as schedule dependence
 
 
-@pytest.mark.parametrize("sched", [1, 7])
+@pytest.mark.parametrize("sched", [7])
 def test_real_kernels_are_schedule_invariant(sched):
-    """One e2e golden with every experimental path on, under a reversed and a random thread schedule (own process: the
+    """One e2e golden with every experimental path on, under a random thread schedule (CUEMU_SCHED=1 reverses it) (own process: the
     emulator reads CUEMU_SCHED once)."""
     import build_emu
     lib = build_emu.build()
