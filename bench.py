@@ -328,7 +328,8 @@ def main():
                                        "new stored comparisons per split round, final tallies all-reduced" % (nraw, world)) if shard else
                                       "one sample per GPU (reference's per-sample loop); no data-path collective",
                            "l2": "256 MB buffer written between timed iterations (inputs 32 MB < 126 MB L2)",
-                           "nclust": len(last["clustering"]["sequence"]), "rounds": st["n_rounds"], "shuffles": st["n_shuffles"]},
+                           "nclust": len(last["clustering"]["sequence"]), "rounds": st["n_rounds"], "shuffles": st["n_shuffles"],
+                           "experimental": sorted(k for k in os.environ if k.startswith("DADA2B_") and k not in ("DADA2B_VERBOSE", "DADA2B_AB_TAG"))},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "uniques/s", "h2d_bytes_per_step": int(est["h2d_bytes"]),
                         "d2h_bytes_per_step": int(est["d2h_bytes"]), "ms_per_step": 1e3 * t_e2e / args.steps},
