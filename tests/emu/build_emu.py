@@ -46,26 +46,43 @@ def sources():
     return list(SOURCES)
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def needs_build(lib=LIB):
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "build_emu.py")]
     deps += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, extra_sources=(), lib=LIB, opt="-O1"):
-    if not force and not needs_build() and not extra_sources:
+def build(force=False, extra_sources=(), lib=LIB, opt="-O1", asan=False):
+    """asan=True builds libdada2b_emu_asan.so with AddressSanitizer (load it with LD_PRELOAD=`g++ -print-file-name=libasan.so`):
+    every out-of-bounds access of a kernel to a "device" buffer or beyond its dynamic shared memory is reported."""
+    if asan:
+        lib = LIB.replace(".so", "_asan.so")
+    if not force and not needs_build(lib) and not extra_sources:
         return lib
     os.makedirs(OUT, exist_ok=True)
     cxx = os.environ.get("CXX", "g++")
+    asan_dir = []
+    if asan:                                 # a compiler wrapper earlier on PATH may not know where libasan lives
+        for probe in (cxx, "/usr/bin/g++"):
+            try:
+                f = subprocess.run([probe, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+            except OSError:
+                continue
+            if os.path.isabs(f):
+                asan_dir = ["-L", os.path.dirname(f)]
+                break
     flags = [opt, "-g1", "-std=c++17", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-strict-aliasing", "-w", "-DDADA2B_EMU=1",
              "-I", os.path.join(HERE, "stub"), "-I", CSRC, "-include", os.path.join(HERE, "cuda_emu.h")]
+    san = ["-fsanitize=address", "-fno-omit-frame-pointer", "--param", "asan-stack=0"] if asan else []     # heap + shared memory checks; fiber stacks stay uninstrumented
+    flags += san
+    tag = ".asan" if asan else ""
     procs, objs = [], []
     for src in list(sources()) + list(extra_sources):
         path = src if os.path.isabs(src) else os.path.join(CSRC, src)
-        cpp = os.path.join(OUT, os.path.basename(src).replace(".cu", ".emu.cpp"))
+        cpp = os.path.join(OUT, os.path.basename(src).replace(".cu", tag + ".emu.cpp"))
         with open(path) as f:
             body = transform(f.read())
         # keep relative includes of the original directory working
@@ -75,8 +92,8 @@ def build(force=False, extra_sources=(), lib=LIB, opt="-O1"):
         cmd = [cxx] + flags + ["-I", os.path.dirname(path), "-c", cpp, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
-    obj = os.path.join(OUT, "cuda_emu.o")
-    cmd = [cxx, "-O2", "-g1", "-std=c++17", "-fPIC", "-c", os.path.join(HERE, "cuda_emu.cpp"), "-o", obj]
+    obj = os.path.join(OUT, "cuda_emu" + tag + ".o")
+    cmd = [cxx, "-O2", "-g1", "-std=c++17", "-fPIC"] + san + ["-c", os.path.join(HERE, "cuda_emu.cpp"), "-o", obj]
     procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     objs.append(obj)
     for cmd, p in procs:
@@ -84,9 +101,9 @@ def build(force=False, extra_sources=(), lib=LIB, opt="-O1"):
         if p.returncode:
             sys.stderr.write(out[-6000:])
             raise RuntimeError("emulator build failed: " + " ".join(cmd))
-    subprocess.check_call([cxx, "-shared", "-o", lib] + objs + ["-ldl", "-pthread"])
+    subprocess.check_call([cxx, "-shared", "-o", lib] + san + asan_dir + objs + ["-ldl", "-pthread"])
     return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))

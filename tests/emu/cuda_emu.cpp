@@ -38,6 +38,17 @@ cuemu_switch:
 .size cuemu_switch,.-cuemu_switch
 )");
 
+// AddressSanitizer build (build_emu.build(asan=True)): "device" allocations are ordinary heap blocks, so every
+// out-of-bounds global load/store of a kernel is reported; the unused tail of the dynamic shared memory window is
+// poisoned per launch; fiber switches are announced to the runtime.
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#include <sanitizer/common_interface_defs.h>
+#define CUEMU_ASAN 1
+#else
+#define CUEMU_ASAN 0
+#endif
+
 namespace cuemu {
 thread_local uint3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 thread_local int t_lane;
@@ -75,12 +86,40 @@ struct BlockRt {
 thread_local BlockRt R;
 thread_local unsigned char *t_smem = nullptr;
 thread_local char *t_stacks = nullptr;
+#if CUEMU_ASAN
+thread_local const void *t_main_bottom = nullptr;
+thread_local size_t t_main_size = 0;
+#endif
+
+// fiber -> scheduler
+inline void to_main(Fiber *f) {
+#if CUEMU_ASAN
+  void *fake = nullptr;
+  __sanitizer_start_switch_fiber(&fake, t_main_bottom, t_main_size);
+  cuemu_switch(&f->sp, R.main_sp);
+  __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#else
+  cuemu_switch(&f->sp, R.main_sp);
+#endif
+}
+// scheduler -> fiber t
+inline void to_fiber(Fiber &f, int t) {
+#if CUEMU_ASAN
+  void *fake = nullptr;
+  __sanitizer_start_switch_fiber(&fake, t_stacks + STACK_BYTES * (size_t)t, STACK_BYTES);
+  cuemu_switch(&R.main_sp, f.sp);
+  __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#else
+  (void)t;
+  cuemu_switch(&R.main_sp, f.sp);
+#endif
+}
 
 void park(const volatile int *gen_ptr, int gen) {
   Fiber *f = R.cur;
   f->wait_ptr = gen_ptr;
   f->wait_val = gen;
-  while (*gen_ptr == gen) cuemu_switch(&f->sp, R.main_sp);
+  while (*gen_ptr == gen) to_main(f);
   f->wait_ptr = nullptr;
 }
 
@@ -94,6 +133,9 @@ void reorder(std::vector<int> &order, int sched, uint64_t &rng) {
 }
 
 [[noreturn]] void fiber_main() {
+#if CUEMU_ASAN
+  __sanitizer_finish_switch_fiber(nullptr, &t_main_bottom, &t_main_size);    // first entry: learn the scheduler's stack
+#endif
   R.tramp(R.closure);
   Fiber *f = R.cur;
   f->done = true;
@@ -103,7 +145,7 @@ void reorder(std::vector<int> &order, int sched, uint64_t &rng) {
   if (w.arrived > 0 && w.arrived == w.live) { w.arrived = 0; w.gen++; }        // the rest of the warp was waiting for us
   R.blive--;
   if (R.barrived > 0 && R.barrived == R.blive) { R.barrived = 0; R.bgen++; }
-  for (;;) cuemu_switch(&f->sp, R.main_sp);
+  for (;;) to_main(f);
 }
 }  // namespace
 
@@ -145,10 +187,17 @@ void note_launch(const char *kernel) {
 
 void *dev_alloc(size_t bytes) {
   if (!bytes) return nullptr;
+#if CUEMU_ASAN
+  void *p = nullptr;                                   // exact size: the red zone starts right behind the last byte
+  if (posix_memalign(&p, 256, bytes)) return nullptr;
+  std::memset(p, 0xCD, bytes);
+  return p;
+#else
   const size_t n = (bytes + 255) / 256 * 256;
   void *p = std::aligned_alloc(256, n);
   if (p) std::memset(p, 0xCD, n);
   return p;
+#endif
 }
 void dev_free(void *p) { std::free(p); }
 
@@ -189,7 +238,13 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, void (*tramp)(void *), void
     for (unsigned by = 0; by < grid.y; by++)
       for (unsigned bx = 0; bx < grid.x; bx++) {
         t_blockIdx = {bx, by, bz};
+#if CUEMU_ASAN
+        __asan_unpoison_memory_region(t_smem, SMEM_BYTES);
+#endif
         std::memset(t_smem, 0xCD, smem);
+#if CUEMU_ASAN
+        __asan_poison_memory_region(t_smem + smem, SMEM_BYTES - smem);               // beyond what this launch asked for
+#endif
         for (int w = 0; w < nwarps; w++) { R.warps[w].gen = 0; R.warps[w].arrived = 0; R.warps[w].live = std::min(32, nthreads - 32 * w); }
         R.bgen = 0; R.barrived = 0; R.blive = nthreads; R.progress = 0;
         for (int t = 0; t < nthreads; t++) {
@@ -215,7 +270,7 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, void (*tramp)(void *), void
             R.cur = &f;
             t_threadIdx = f.tid;
             t_lane = f.lane;
-            cuemu_switch(&R.main_sp, f.sp);
+            to_fiber(f, t);
           }
           if (R.progress == before && R.blive > 0) {
             std::fprintf(stderr, "cuda_emu: deadlock in block (%u,%u,%u): threads wait on a barrier the others never reach\n", bx, by, bz);
