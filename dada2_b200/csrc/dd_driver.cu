@@ -317,6 +317,16 @@ struct Run {
   DBuf<uint16_t> pv_ms, seed_ms;
   // fused round tail (experimental, DADA2B_FUSED_TAIL=1; dd_round2.cu)
   bool fused_tail = false;
+  // owner mode (experimental, DADA2B_OWNER=1 on top of the fused tail, sharded runs): every rank keeps the stored comparisons and
+  // runs shuffle / p-update / bud scan for its own raws only; per pass one all-reduce of the cluster read deltas, per round one
+  // all-gather of the ranks' reports (bud candidates, move counts) and, when raws moved, one of the move lists.
+  bool owner = false;
+  int tail_last = -1;                    // last shuffle pass launched in the current round
+  DBuf<RoundReport> d_report_all;
+  PBuf<RoundReport> h_report_all;
+  DBuf<uint32_t> d_moves_all;
+  PBuf<uint32_t> h_moves_all;
+  void sync_report_owner();
   TailState ts{};
   DBuf<uint32_t> t_head, t_prev, t_nmove, t_bt, t_btp;
   DBuf<int> t_delta;
@@ -461,8 +471,10 @@ void Run::tail_sync_caps() {
     sync();
     std::swap(t_prev.p, np.p); std::swap(t_prev.n, np.n); std::swap(t_prev.cap, np.cap);
   }
-  if (t_delta.n < (size_t)MAX_PASS * cl_cap) { t_delta.alloc((size_t)MAX_PASS * cl_cap); t_delta.zero(s); }   // cleared every round by k_tail_link
-  ts.cs_prev = t_prev.p; ts.delta = t_delta.p; ts.cl_cap = (uint32_t)cl_cap;
+  const size_t stride = 2 * cl_cap + 4;
+  if (t_delta.n < (size_t)MAX_PASS * stride) { t_delta.alloc((size_t)MAX_PASS * stride); t_delta.zero(s); }   // cleared every round by k_tail_link
+  ts.cs_prev = t_prev.p; ts.rows = t_delta.p; ts.cl_cap = (uint32_t)cl_cap; ts.row_stride = (uint32_t)stride;
+  ts.rank = owner ? cx->rank : 0; ts.world = owner ? cx->world : 1;
 }
 
 void Run::ensure_cluster_cap(size_t n) {
@@ -530,6 +542,7 @@ void Run::alloc_state() {
   if (pivot) { pv_cluster.alloc(n); pv_ms.alloc(n); CK(cudaMemsetAsync(pv_cluster.p, 0xFF, n * 4, s)); pv_ms.zero(s); }
   if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
   fused_tail = getenv("DADA2B_FUSED_TAIL") != nullptr;   // off by default: not yet validated on hardware
+  owner = fused_tail && cx->world > 1 && getenv("DADA2B_OWNER") != nullptr;
   if (fused_tail) {
     const size_t g = (size_t)tail_grid(nraw);
     t_head.alloc(n); t_nmove.alloc(MAX_PASS); t_done.alloc(1); t_blk.alloc(g); t_bt.alloc(g * TIE_MAX); t_btp.alloc(g * TIE_MAX);
@@ -631,6 +644,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   if ((!P.homo || fwd_homo_ok) && P.band >= 0 && !getenv("DADA2B_NO_NWFWD")) {       // register-resident forward-carry NW (dd_nwfwd.cu)
     FwdArgs f{};
     f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
+    if (owner) { f.st.shard_world = 1; f.st.shard_rank = 0; }       // this rank's comparisons go straight into its own store
     f.centre_idx = c; f.centre_reads = cx->reads[c]; f.cluster_i = i; f.total_reads = cx->total_reads;
     f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes; f.mode = 0; f.job_mul = 1; f.job_add = 0;
     {  // the fast path replaces the reference's sentinel by a larger penalty: only valid while no real score can come near it
@@ -654,9 +668,10 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     if (kind == KIND_NW && fwd_done) { a.jobs = fb_list.p; a.njobs_ptr = st.ctr + CTR_FB; }
     else a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
     a.centre_idx = c; a.centre_reads = cx->reads[c]; a.cluster_i = i; a.total_reads = cx->total_reads;
+    if (owner) { a.st.shard_world = 1; a.st.shard_rank = 0; }
     timed(kind == KIND_NW ? T_NW : T_GL, [&]() { launch_align_jobs(MODE_LOOP, a, (unsigned long long)nraw); });
   }
-  if (cx->world > 1) {
+  if (cx->world > 1 && !owner) {
     // The one collective of a split round: all-gather of the new stored comparisons (count first, then the
     // payload padded to the largest count), appended on every rank in rank-major order.
     NC(g_nccl.AllGather(ctr.p + CTR_NE, d_counts.p, 1, ncclUint64, cx->comm, s));
@@ -677,10 +692,15 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
 void Run::launch_round_tail(int first_pass, int npass) {
   const int nclust = (int)members.size();
   const unsigned long long upper = cs_count + (unsigned long long)nraw;
-  if (fused_tail && first_pass == 0 && tail_fits(nclust)) {
-    for (int p = 0; p < npass; p++) launch_tail_pass(st, in, ts, p, nclust, s);
+  if (fused_tail) {
+    if (!tail_fits(nclust)) throw Err{"dada2b: too many clusters for the fused round tail (unset DADA2B_FUSED_TAIL)"};
+    for (int p = first_pass; p < first_pass + npass; p++) {
+      launch_tail_pass(st, in, ts, p, nclust, s);
+      if (owner) NC(g_nccl.AllReduce(ts.rows + (size_t)p * ts.row_stride, ts.rows + (size_t)p * ts.row_stride, ts.row_stride, ncclInt32, ncclSum, cx->comm, s));
+    }
+    tail_last = first_pass + npass - 1;
     BudParams bp{o->min_fold, o->min_hamming, o->min_abund};
-    launch_tail_final(st, in, ts, bp, o->greedy != 0, o->detect_singletons != 0, npass - 1, nclust, s);
+    launch_tail_final(st, in, ts, bp, o->greedy != 0, o->detect_singletons != 0, tail_last, nclust, tail_last == MAX_PASS - 1 ? 2 : 0, s);
     return;
   }
   for (int p = first_pass; p < first_pass + npass; p++) launch_shuffle_pass(st, in, upper, nclust, p, s);
@@ -702,7 +722,76 @@ void Run::launch_round_tail_noshuffle() {
   launch_report(st, -1, s);
 }
 
+// Owner mode: gather every rank's report, keep the local counters, merge the bud candidates and the move lists so that
+// replay_moves / decide_bud see exactly what a single-GPU run would have reported.  Every rank computes the same merge.
+void Run::sync_report_owner() {
+  const int W = cx->world;
+  d_report_all.alloc(W); h_report_all.alloc(W);
+  NC(g_nccl.AllGather(d_report.p, d_report_all.p, sizeof(RoundReport), ncclChar, cx->comm, s));
+  d2h_pinned(h_report_all.p, d_report_all.p, (size_t)W * sizeof(RoundReport));
+  sync();
+  const RoundReport *rep = h_report_all.p;
+  *h_report = rep[cx->rank];
+  memcpy(h_ctr.p, h_report->ctr, sizeof(unsigned long long) * CTR_N);
+  for (int q = 0; q < W; q++) h_ctr.p[CTR_ERR] = std::max(h_ctr.p[CTR_ERR], rep[q].ctr[CTR_ERR]);
+  check_dev_error();
+  cs_count = h_report->ctr[CTR_CS_COUNT];
+  if (count_round) { tot_nw += h_report->ctr[CTR_NW]; tot_gl += h_report->ctr[CTR_GL]; count_round = false; }
+  est_active = std::max<unsigned long long>(1024, 2 * h_report->ctr[CTR_NW]);
+  if (cs_count > st.cs_cap) throw Err{"dada2b: comparison store overflow"};
+  for (int q = 0; q < W; q++) if (rep[q].ctr[CTR_NMOVE] > move_cap) throw Err{"dada2b: move list overflow"};
+  // ---- moves: rank q's list is grouped by pass through its local pinfo; merge pass by pass ----
+  const int last = tail_last;
+  uint32_t maxM = 0;
+  for (int q = 0; q < W && last >= 0; q++) maxM = std::max(maxM, rep[q].pinfo[last + 1]);
+  uint32_t gp[MAX_PASS + 2] = {0};
+  if (maxM) {
+    d_moves_all.alloc((size_t)W * maxM * 2); h_moves_all.alloc((size_t)W * maxM * 2);
+    NC(g_nccl.AllGather(d_moves.p, d_moves_all.p, (size_t)maxM * 8, ncclChar, cx->comm, s));
+    d2h_pinned(h_moves_all.p, d_moves_all.p, (size_t)W * maxM * 8);
+    sync();
+    size_t at = 0;
+    for (int p = 0; p <= last; p++) {
+      for (int q = 0; q < W; q++) {
+        const uint32_t b = rep[q].pinfo[p], e = rep[q].pinfo[p + 1];
+        if (at + (e - b) > move_cap) throw Err{"dada2b: move list overflow"};
+        memcpy(h_moves + 2 * at, h_moves_all.p + 2 * ((size_t)q * maxM + b), (size_t)(e - b) * 8);
+        at += e - b;
+      }
+      gp[p + 1] = (uint32_t)at;
+    }
+  }
+  for (int p = 0; p <= last + 1 && p < MAX_PASS + 2; p++) h_report->pinfo[p] = gp[p];
+  h_report->ctr[CTR_NMOVE] = last >= 0 ? gp[last + 1] : 0;
+  // ---- bud candidates: lexicographic (p asc, reads desc) over the ranks' local optima ----
+  auto merge = [&](int iP, int iR, int iN, uint32_t RoundReport::*tr, uint32_t RoundReport::*th, double RoundReport::*tl, int tie_off) {
+    (void)tr; (void)th; (void)tl; (void)tie_off;
+    unsigned long long gmin = ~0ull, gmax = 0, n = 0;
+    for (int q = 0; q < W; q++) if (rep[q].ctr[iN]) gmin = std::min(gmin, rep[q].ctr[iP]);
+    for (int q = 0; q < W; q++) if (rep[q].ctr[iN] && rep[q].ctr[iP] == gmin) gmax = std::max(gmax, rep[q].ctr[iR]);
+    h_report->ctr[iP] = gmin; h_report->ctr[iR] = gmax;
+    return std::make_pair(gmin, gmax);
+  };
+  auto a = merge(CTR_PMIN, CTR_RMAX, CTR_NTIE, nullptr, nullptr, nullptr, 0);
+  auto b = merge(CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR, nullptr, nullptr, nullptr, 0);
+  unsigned long long nt = 0, ntp = 0;
+  for (int q = 0; q < W; q++) {
+    if (rep[q].ctr[CTR_NTIE] && rep[q].ctr[CTR_PMIN] == a.first && rep[q].ctr[CTR_RMAX] == a.second) {
+      for (unsigned long long k = 0; k < rep[q].ctr[CTR_NTIE] && k < TIE_MAX; k++)
+        if (nt + k < TIE_MAX) { h_report->tie_r[nt + k] = rep[q].tie_r[k]; h_report->tie_lam[nt + k] = rep[q].tie_lam[k]; h_report->tie_ham[nt + k] = rep[q].tie_ham[k]; }
+      nt += rep[q].ctr[CTR_NTIE];
+    }
+    if (rep[q].ctr[CTR_NTIE_PR] && rep[q].ctr[CTR_PMIN_PR] == b.first && rep[q].ctr[CTR_RMAX_PR] == b.second) {
+      for (unsigned long long k = 0; k < rep[q].ctr[CTR_NTIE_PR] && k < TIE_MAX; k++)
+        if (ntp + k < TIE_MAX) { h_report->tiep_r[ntp + k] = rep[q].tiep_r[k]; h_report->tiep_lam[ntp + k] = rep[q].tiep_lam[k]; h_report->tiep_ham[ntp + k] = rep[q].tiep_ham[k]; }
+      ntp += rep[q].ctr[CTR_NTIE_PR];
+    }
+  }
+  h_report->ctr[CTR_NTIE] = nt; h_report->ctr[CTR_NTIE_PR] = ntp;
+}
+
 void Run::sync_report() {
+  if (owner) { sync_report_owner(); return; }
   d2h_pinned(h_report, d_report.p, sizeof(RoundReport));
   const unsigned eager = std::min<unsigned>(MOVES_EAGER, move_cap);
   d2h_pinned(h_moves, d_moves.p, (size_t)eager * 8);
@@ -763,7 +852,36 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
   unsigned long long nt = R.ctr[CTR_NTIE], ntp = R.ctr[CTR_NTIE_PR];
   std::vector<uint32_t> big, bigp;
   const uint32_t *tr = R.tie_r, *trp = R.tiep_r;
-  if (nt > TIE_MAX || ntp > TIE_MAX) {                          // pathological tie set: fetch all of it
+  if (owner && (nt > TIE_MAX || ntp > TIE_MAX)) {
+    // every rank lists its own candidates at the global optimum; the lists are exchanged padded to the longest one
+    const int W = cx->world;
+    const RoundReport *rep = h_report_all.p;
+    std::vector<unsigned long long> na(W, 0), np(W, 0);
+    unsigned long long maxn = 1;
+    for (int q = 0; q < W; q++) {
+      if (rep[q].ctr[CTR_NTIE] && rep[q].ctr[CTR_PMIN] == R.ctr[CTR_PMIN] && rep[q].ctr[CTR_RMAX] == R.ctr[CTR_RMAX]) na[q] = rep[q].ctr[CTR_NTIE];
+      if (rep[q].ctr[CTR_NTIE_PR] && rep[q].ctr[CTR_PMIN_PR] == R.ctr[CTR_PMIN_PR] && rep[q].ctr[CTR_RMAX_PR] == R.ctr[CTR_RMAX_PR]) np[q] = rep[q].ctr[CTR_NTIE_PR];
+      maxn = std::max(maxn, std::max(na[q], np[q]));
+    }
+    DBuf<uint32_t> d1, d2, g1, g2;
+    d1.alloc(maxn); d2.alloc(maxn); g1.alloc(maxn * W); g2.alloc(maxn * W);
+    unsigned long long gl[6] = {R.ctr[CTR_PMIN], R.ctr[CTR_RMAX], 0ull, R.ctr[CTR_PMIN_PR], R.ctr[CTR_RMAX_PR], 0ull};
+    static_assert(CTR_RMAX == CTR_PMIN + 1 && CTR_NTIE == CTR_PMIN + 2 && CTR_PMIN_PR == CTR_PMIN + 3 && CTR_NTIE_PR == CTR_PMIN + 5, "counter layout");
+    h2d(ctr.p + CTR_PMIN, gl, sizeof(gl));
+    BudParams bp{o->min_fold, o->min_hamming, o->min_abund};
+    launch_bud_collect_owned(st, in, ts, bp, d1.p, d2.p, (unsigned)maxn, s);
+    NC(g_nccl.AllGather(d1.p, g1.p, (size_t)maxn * 4, ncclChar, cx->comm, s));
+    NC(g_nccl.AllGather(d2.p, g2.p, (size_t)maxn * 4, ncclChar, cx->comm, s));
+    std::vector<uint32_t> h1(maxn * W), h2(maxn * W);
+    d2h(h1.data(), g1.p, h1.size() * 4); d2h(h2.data(), g2.p, h2.size() * 4);
+    sync();
+    for (int q = 0; q < W; q++) {
+      big.insert(big.end(), h1.begin() + (size_t)q * maxn, h1.begin() + (size_t)q * maxn + na[q]);
+      bigp.insert(bigp.end(), h2.begin() + (size_t)q * maxn, h2.begin() + (size_t)q * maxn + np[q]);
+    }
+    if (big.size() != nt || bigp.size() != ntp) throw Err{"dada2b: inconsistent tie lists across ranks"};
+    tr = big.data(); trp = bigp.data();
+  } else if (nt > TIE_MAX || ntp > TIE_MAX) {                          // pathological tie set: fetch all of it
     const unsigned cap = (unsigned)std::max(nt, ntp);
     DBuf<uint32_t> d1, d2; d1.alloc(cap); d2.alloc(cap);
     unsigned long long z[2] = {0ull, 0ull};
@@ -808,7 +926,18 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
     if (R.tie_r[k] == r && type == 'A') { lam = R.tie_lam[k]; ham = R.tie_ham[k]; have = true; }
   for (unsigned long long k = 0; k < std::min<unsigned long long>(ntp, TIE_MAX) && !have; k++)
     if (R.tiep_r[k] == r && type == 'P') { lam = R.tiep_lam[k]; ham = R.tiep_ham[k]; have = true; }
-  if (!have) {
+  if (!have && owner) {            // only the winner's owner holds its comparison: sum all-reduce of (lambda bits, hamming) with zeros elsewhere
+    DBuf<unsigned long long> w2; w2.alloc(2); w2.zero(s);
+    if ((int)(r % (uint32_t)cx->world) == cx->rank) {
+      CK(cudaMemcpyAsync(w2.p, comp_lambda.p + r, 8, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(w2.p + 1, comp_ham.p + r, 4, cudaMemcpyDeviceToDevice, s));
+    }
+    NC(g_nccl.AllReduce(w2.p, w2.p, 2, ncclUint64, ncclSum, cx->comm, s));
+    unsigned long long hw[2];
+    d2h(hw, w2.p, 16);
+    sync();
+    memcpy(&lam, &hw[0], 8); ham = (uint32_t)hw[1];
+  } else if (!have) {
     d2h(&lam, comp_lambda.p + r, 8); d2h(&ham, comp_ham.p + r, 4);
     sync();
   }
@@ -883,6 +1012,11 @@ void Run::finish(dada2b_out *out) {
     NC(g_nccl.AllReduce(cq_sum.p, cq_sum.p, (size_t)nclust * maxlen, ncclUint64, ncclSum, cx->comm, s));
     NC(g_nccl.AllReduce(cq_cnt.p, cq_cnt.p, (size_t)nclust * maxlen, ncclUint64, ncclSum, cx->comm, s));
     NC(g_nccl.AllReduce(nsubs_final.p, nsubs_final.p, (size_t)nraw, ncclUint32, ncclSum, cx->comm, s));
+    if (owner) {       // final p / correct are only meaningful on a raw's owner: zero the rest, then the sum is the full array
+      launch_mask_unowned(this->p.p, correct.p, nraw, cx->rank, cx->world, s);
+      NC(g_nccl.AllReduce(this->p.p, this->p.p, (size_t)nraw, ncclFloat64, ncclSum, cx->comm, s));
+      NC(g_nccl.AllReduce(correct.p, correct.p, (size_t)nraw, ncclUint8, ncclSum, cx->comm, s));
+    }
   }
   // birth subs: sub_new(centre of birth_comp.i, centre i, use_kmers, cutoff 1.0)   Rmain.cpp:206-209
   const uint32_t npair = nclust - 1;
@@ -937,17 +1071,47 @@ void Run::finish(dada2b_out *out) {
     DBuf<unsigned long long> dcount; dcount.alloc(1);
     for (;;) {
       trip_ij.alloc((size_t)cap * 2); trip_v.alloc(cap); dcount.zero(s);
-      launch_posthoc(st, nraw, cs_count, center_cluster.p, trip_ij.p, trip_v.p, cap, dcount.p, s);
+      if (owner) launch_posthoc_owned(st, nraw, cs_count, center_cluster.p, trip_ij.p, trip_v.p, cap, dcount.p, cx->rank, cx->world, s);
+      else launch_posthoc(st, nraw, cs_count, center_cluster.p, trip_ij.p, trip_v.p, cap, dcount.p, s);
       d2h(&cnt, dcount.p, 8);
       sync();
       if (cnt <= cap) break;
       cap = (unsigned)cnt + 16;
     }
+    if (owner) {       // every rank found the triples of the centres it owns: exchange them (counts first, then padded payloads)
+      const int W = cx->world;
+      DBuf<unsigned long long> dall; dall.alloc(W);
+      NC(g_nccl.AllGather(dcount.p, dall.p, 1, ncclUint64, cx->comm, s));
+      std::vector<unsigned long long> cq(W);
+      d2h(cq.data(), dall.p, (size_t)W * 8);
+      sync();
+      unsigned long long maxc = 1, tot = 0;
+      for (int q = 0; q < W; q++) { maxc = std::max(maxc, cq[q]); tot += cq[q]; }
+      DBuf<uint32_t> sij, gij; DBuf<double> sv, gv;
+      sij.alloc((size_t)maxc * 2); sv.alloc((size_t)maxc); sij.zero(s); sv.zero(s);
+      if (cnt) {
+        CK(cudaMemcpyAsync(sij.p, trip_ij.p, cnt * 8, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(sv.p, trip_v.p, cnt * 8, cudaMemcpyDeviceToDevice, s));
+      }
+      gij.alloc((size_t)maxc * 2 * W); gv.alloc((size_t)maxc * W);
+      NC(g_nccl.AllGather(sij.p, gij.p, (size_t)maxc * 8, ncclChar, cx->comm, s));
+      NC(g_nccl.AllGather(sv.p, gv.p, (size_t)maxc * 8, ncclChar, cx->comm, s));
+      std::vector<uint32_t> hij((size_t)maxc * 2 * W); std::vector<double> hv((size_t)maxc * W);
+      d2h(hij.data(), gij.p, hij.size() * 4); d2h(hv.data(), gv.p, hv.size() * 8);
+      sync();
+      tij.clear(); tv.clear();
+      for (int q = 0; q < W; q++) {
+        tij.insert(tij.end(), hij.begin() + (size_t)q * maxc * 2, hij.begin() + (size_t)q * maxc * 2 + cq[q] * 2);
+        tv.insert(tv.end(), hv.begin() + (size_t)q * maxc, hv.begin() + (size_t)q * maxc + cq[q]);
+      }
+      cnt = tot;
+    } else {
     tij.resize(cnt * 2); tv.resize(cnt);
     if (cnt) {
       d2h(tij.data(), trip_ij.p, cnt * 8);
       d2h(tv.data(), trip_v.p, cnt * 8);
       sync();
+    }
     }
     std::vector<size_t> ord(cnt);
     for (size_t k = 0; k < cnt; k++) ord[k] = k;
@@ -1116,7 +1280,14 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
     R.sync_report();
     int last = R.NP - 1;
     int ran = R.replay_moves(0, last);
-    if (!R.h_report->converged) {            // rare: more than NP passes needed (MAX_SHUFFLE = 10, dada.h:30)
+    if (!R.h_report->converged && R.fused_tail) {     // rare: more than NP passes needed: one more fused pass at a time
+      while (!R.h_report->converged && last + 1 < MAX_PASS) {
+        last++;
+        R.launch_round_tail(last, 1);        // at pass MAX_SHUFFLE - 1 the tail proceeds regardless (dada.h:30, Rmain.cpp:322-325)
+        R.sync_report();
+        ran += R.replay_moves(last, last);
+      }
+    } else if (!R.h_report->converged) {     // rare: more than NP passes needed (MAX_SHUFFLE = 10, dada.h:30)
       while (last + 1 < MAX_PASS) {
         last++;
         R.launch_shuffle_only(last);

@@ -100,9 +100,10 @@ struct BlkBest { unsigned long long pb, pbp; uint32_t rd, rdp, n, np; };
 struct TailState {
   uint32_t *head;          // [nraw] newest stored comparison of the raw
   uint32_t *cs_prev;       // [cs_cap] the same raw's previous stored comparison (lower cluster index); chain ends at the cluster-0 entry
-  int *delta;              // [MAX_PASS][cl_cap] net change of each cluster's reads made by shuffle pass k of the current round
-  uint32_t cl_cap;
-  uint32_t *nmove_pass;    // [MAX_PASS] moves made by pass k of the current round
+  int *rows;               // [MAX_PASS][row_stride] per shuffle pass: reads delta per cluster | touched flag per cluster | moves
+  uint32_t cl_cap, row_stride;      // row_stride = 2 * cl_cap + 4
+  uint32_t *nmove_pass;    // [MAX_PASS] moves THIS rank made in pass k of the current round
+  int rank, world;         // owner mode: this rank shuffles / scans raws r % world == rank only (1 rank: every raw)
   unsigned *done;          // block tickets of k_tail_final
   BlkBest *blk;            // [grid of k_tail_final] per-block bud minima
   uint32_t *blk_ties, *blk_ties_pr;   // [grid][TIE_MAX] their tie candidates
@@ -113,7 +114,13 @@ int tail_grid(int nraw);
 void launch_tail_link(const DevState &st, const TailState &ts, unsigned long long base, uint32_t cluster_i, int nraw, int nclust, cudaStream_t s);
 void launch_tail_pass(const DevState &st, const DevIn &in, const TailState &ts, int pass, int nclust, cudaStream_t s);
 void launch_tail_final(const DevState &st, const DevIn &in, const TailState &ts, const BudParams &bp, int greedy, int detect_singletons,
-                       int last_pass, int nclust, cudaStream_t s);
+                       int last_pass, int nclust, int mode, cudaStream_t s);
+
+void launch_bud_collect_owned(const DevState &st, const DevIn &in, const TailState &ts, const BudParams &bp, uint32_t *ties, uint32_t *ties_pr,
+                              unsigned cap, cudaStream_t s);
+void launch_mask_unowned(double *p, uint8_t *correct, int nraw, int rank, int world, cudaStream_t s);
+void launch_posthoc_owned(const DevState &st, int nraw, unsigned long long n_entries, const int *center_cluster, uint32_t *trip_ij, double *trip_v,
+                          unsigned cap, unsigned long long *count, int rank, int world, cudaStream_t s);
 
 // per-round control kernels (dd_round.cu)
 struct BudParams { double min_fold; int min_hamming, min_abund; };

@@ -24,6 +24,14 @@ namespace dd2 {
 
 constexpr uint32_t CHAIN_END = 0xFFFFFFFFu;
 
+// Per-pass scratch rows (TailState::rows): [delta(cl_cap) | touched(cl_cap) | moves of the pass (1) | pad].  One row is one
+// NCCL all-reduce in owner mode (every rank shuffles its own raws only).
+__device__ __forceinline__ int &row_delta(const TailState &ts, int pass, uint32_t c) { return ts.rows[(size_t)pass * ts.row_stride + c]; }
+__device__ __forceinline__ int &row_touched(const TailState &ts, int pass, uint32_t c) { return ts.rows[(size_t)pass * ts.row_stride + ts.cl_cap + c]; }
+__device__ __forceinline__ int &row_nmove(const TailState &ts, int pass) { return ts.rows[(size_t)pass * ts.row_stride + 2 * (size_t)ts.cl_cap]; }
+// the raw handled by global thread `it`: every raw, or this rank's raws only (owner mode)
+__device__ __forceinline__ long long tail_raw(const TailState &ts, long long it) { return it * ts.world + ts.rank; }
+
 __global__ void k_tail_link(DevState st, TailState ts, unsigned long long base, uint32_t cluster_i, int nraw, int nclust) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   const unsigned long long t0 = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -37,8 +45,10 @@ __global__ void k_tail_link(DevState st, TailState ts, unsigned long long base, 
       ts.head[r] = (uint32_t)x;
     }
   }
-  for (unsigned long long x = t0; x < (unsigned long long)MAX_PASS * ts.cl_cap; x += stride)
-    if ((int)(x % ts.cl_cap) < nclust) ts.delta[x] = 0;
+  for (unsigned long long x = t0; x < (unsigned long long)MAX_PASS * ts.row_stride; x += stride) {
+    const unsigned c = (unsigned)(x % ts.row_stride);
+    if (c >= 2 * ts.cl_cap || (int)(c % ts.cl_cap) < nclust) ts.rows[x] = 0;
+  }
   if (t0 < MAX_PASS) ts.nmove_pass[t0] = 0;
   if (t0 == 0) *ts.done = 0;
 }
@@ -47,7 +57,7 @@ __global__ void k_tail_link(DevState st, TailState ts, unsigned long long base, 
 __device__ __forceinline__ void stage_reads(const DevState &st, const TailState &ts, int pass, int nclust, uint32_t *s_reads) {
   for (int c = threadIdx.x; c < nclust; c += blockDim.x) {
     int v = (int)st.cl_reads[c];
-    for (int k = 0; k < pass; k++) v += ts.delta[(size_t)k * ts.cl_cap + c];
+    for (int k = 0; k < pass; k++) v += row_delta(ts, k, c);
     s_reads[c] = (uint32_t)v;
   }
   __syncthreads();
@@ -55,10 +65,11 @@ __device__ __forceinline__ void stage_reads(const DevState &st, const TailState 
 
 __global__ void k_tail_pass(DevState st, DevIn in, TailState ts, int pass, int nclust) {
   extern __shared__ uint32_t s_reads[];
-  if (pass > 0 && ts.nmove_pass[pass - 1] == 0) return;             // previous pass moved nothing: b_shuffle2 returned false
+  if (pass > 0 && row_nmove(ts, pass - 1) == 0) return;             // previous pass moved nothing (anywhere): b_shuffle2 returned false
   stage_reads(st, ts, pass, nclust, s_reads);
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= in.nraw) return;
+  const long long rl = tail_raw(ts, blockIdx.x * (long long)blockDim.x + threadIdx.x);
+  if (rl >= in.nraw) return;
+  const int r = (int)rl;
   double best_e = -1.0;
   uint32_t best_x = CHAIN_END;
   for (uint32_t x = ts.head[r]; x != CHAIN_END; x = ts.cs_prev[x]) {   // clusters descending: '>=' keeps the lowest index among ties
@@ -70,14 +81,15 @@ __global__ void k_tail_pass(DevState st, DevIn in, TailState ts, int pass, int n
   if (to != from && !st.is_center[r]) {                                 // cluster.cpp:248-260
     const unsigned long long s = atomicAdd(&st.ctr[CTR_NMOVE], 1ull);
     if (s < st.move_cap) { st.moves[2 * s] = (uint32_t)r; st.moves[2 * s + 1] = to; }
-    atomicAdd(&ts.nmove_pass[pass], 1u);
+    atomicAdd(&ts.nmove_pass[pass], 1u);                                // this rank's moves of the pass (splits the local move list)
+    atomicAdd(&row_nmove(ts, pass), 1);                                 // all ranks' after the all-reduce
     st.cluster_of[r] = to;
     st.comp_lambda[r] = st.cs_lambda[best_x];
     st.comp_ham[r] = st.cs_ham[best_x];
     const int rd = (int)in.reads[r];
-    atomicAdd(&ts.delta[(size_t)pass * ts.cl_cap + from], -rd);
-    atomicAdd(&ts.delta[(size_t)pass * ts.cl_cap + to], rd);
-    st.cl_update_e[from] = 1; st.cl_update_e[to] = 1;
+    atomicAdd(&row_delta(ts, pass, from), -rd);
+    atomicAdd(&row_delta(ts, pass, to), rd);
+    row_touched(ts, pass, from) = 1; row_touched(ts, pass, to) = 1;     // -> cl_update_e (bi_pop_raw / bi_add_raw set update_e)
   }
 }
 
@@ -93,16 +105,28 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
 }
 
 // blockDim.x must be TAIL_BLOCK (a multiple of 32, at most 1024)
-__global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, int greedy, int detect_singletons, int last_pass, int nclust) {
-  extern __shared__ uint32_t s_reads[];
+// mode 0: p-update + bud scan only if the last launched pass moved nothing (anywhere); otherwise just report and leave the
+//         state for further k_tail_pass launches
+// mode 2: MAX_SHUFFLE passes are done: proceed as if converged (Rmain.cpp:322-325 stops shuffling there)
+__global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, int greedy, int detect_singletons, int last_pass, int nclust,
+                             int mode) {
+  extern __shared__ uint32_t s_reads[];                 // [nclust] reads, then [nclust] bytes: cluster needs a p-update
+  uint8_t *s_upd = (uint8_t *)(s_reads + nclust);
   __shared__ unsigned long long s_pb[32], s_pbp[32];
   __shared__ uint32_t s_rd[32], s_rdp[32];
   __shared__ unsigned s_n, s_np, s_last;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
-  const bool converged = last_pass < 0 || ts.nmove_pass[last_pass] == 0;
+  const bool moved_nothing = last_pass < 0 || row_nmove(ts, last_pass) == 0;
+  const bool converged = moved_nothing || mode == 2;
   if (tid == 0) { s_n = 0; s_np = 0; }
-  stage_reads(st, ts, last_pass + 1, nclust, s_reads);               // also the barrier behind s_n / s_np
-  const int r = blockIdx.x * blockDim.x + tid;
+  for (int c = tid; c < nclust; c += blockDim.x) {
+    int u = st.cl_update_e[c];
+    for (int k = 0; k <= last_pass; k++) u |= row_touched(ts, k, c);
+    s_upd[c] = u ? 1 : 0;
+  }
+  stage_reads(st, ts, last_pass + 1, nclust, s_reads);               // also the barrier behind s_n / s_np / s_upd
+  const long long rl = tail_raw(ts, blockIdx.x * (long long)blockDim.x + tid);
+  const int r = (int)(rl < in.nraw ? rl : in.nraw);
   unsigned long long pb = ~0ull, pbp = ~0ull;
   uint32_t rd = 0;
   bool elig = false, prior = false;
@@ -113,7 +137,7 @@ __global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, 
     const double lambda = st.comp_lambda[r];
     const uint32_t ham = st.comp_ham[r];
     double pval = st.p[r];
-    if (st.cl_update_e[ci]) {                                          // get_pA pval.cpp:67-89
+    if (s_upd[ci]) {                                                   // get_pA pval.cpp:67-89
       if (rd == 1 && !prior && !detect_singletons) pval = 1.;
       else if (ham == 0) pval = 1.;
       else if (lambda == 0) pval = 0.;
@@ -159,7 +183,8 @@ __global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, 
   __threadfence();
   const volatile BlkBest *blk = ts.blk;
   const volatile uint32_t *bt = ts.blk_ties, *btp = ts.blk_ties_pr;
-  for (int c = tid; c < nclust; c += blockDim.x) { st.cl_reads[c] = s_reads[c]; st.cl_reads_next[c] = s_reads[c]; }
+  if (converged)
+    for (int c = tid; c < nclust; c += blockDim.x) { st.cl_reads[c] = s_reads[c]; st.cl_reads_next[c] = s_reads[c]; }
   if (tid == 0) {
     uint32_t acc = 0;                                                  // pinfo[p+1] = moves recorded up to and including pass p
     st.pinfo[0] = 0;
@@ -214,14 +239,57 @@ __global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, 
   if (tid < CTR_N) st.report->ctr[tid] = st.ctr[tid];
   if (tid < MAX_PASS + 2) st.report->pinfo[tid] = st.pinfo[tid];
   if (tid == 0) { st.report->converged = converged ? 1u : 0u; *ts.done = 0; }
+  (void)moved_nothing;
+}
+
+
+// ---- owner mode helpers (sharded runs where every rank keeps the comparisons / state of its own raws only) ----
+// b_bud tie sets larger than TIE_MAX: this rank's candidates at the GLOBAL (p, reads) optimum (ctr[CTR_PMIN..] set by the host).
+__global__ void k_bud_collect_owned(DevState st, DevIn in, TailState ts, BudParams bp, uint32_t *ties, uint32_t *ties_pr, unsigned cap) {
+  const long long rl = tail_raw(ts, blockIdx.x * (long long)blockDim.x + threadIdx.x);
+  if (rl >= in.nraw) return;
+  const int r = (int)rl;
+  const uint32_t rd = in.reads[r];
+  const bool elig = !st.slot0[r] && (int)rd >= bp.min_abund && (int)st.comp_ham[r] >= bp.min_hamming &&
+                    (bp.min_fold <= 1 || ((double)rd) >= bp.min_fold * st.comp_lambda[r] * (double)st.cl_reads[st.cluster_of[r]]);
+  if (!elig) return;
+  const unsigned long long pb = (unsigned long long)__double_as_longlong(st.p[r]);
+  if (pb == st.ctr[CTR_PMIN] && (unsigned long long)rd == st.ctr[CTR_RMAX]) {
+    const unsigned long long k = atomicAdd(&st.ctr[CTR_NTIE], 1ull);
+    if (k < cap) ties[k] = (uint32_t)r;
+  }
+  if (in.prior[r] && pb == st.ctr[CTR_PMIN_PR] && (unsigned long long)rd == st.ctr[CTR_RMAX_PR]) {
+    const unsigned long long k = atomicAdd(&st.ctr[CTR_NTIE_PR], 1ull);
+    if (k < cap) ties_pr[k] = (uint32_t)r;
+  }
+}
+// final per-raw results of raws this rank does not own -> 0, so that a sum all-reduce assembles the full arrays
+__global__ void k_mask_unowned(double *p, uint8_t *correct, int nraw, int rank, int world) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nraw && r % world != rank) { p[r] = 0.0; correct[r] = 0; }
+}
+// k_posthoc (error.cpp:101-119) over this rank's own stored comparisons only
+__global__ void k_posthoc_owned(DevState st, unsigned long long n, const int *center_cluster, uint32_t *trip_ij, double *trip_v, unsigned cap,
+                                unsigned long long *count, int rank, int world, int nraw) {
+  const unsigned long long x = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  if (x < (unsigned long long)nraw && (int)(x % (unsigned long long)world) != rank) return;      // cluster-0 slot of somebody else's raw: never written
+  const int j = center_cluster[st.cs_index[x]];
+  if (j < 0) return;
+  const uint32_t i = st.cs_i[x];
+  if ((int)i == j) return;
+  const unsigned long long s = atomicAdd(count, 1ull);
+  if (s < cap) { trip_ij[2 * s] = i; trip_ij[2 * s + 1] = (uint32_t)j; trip_v[s] = st.cs_lambda[x] * (double)st.cl_reads[i]; }
 }
 
 // ------------------------------- launch wrappers --------------------------------------
 constexpr int TAIL_BLOCK = 256;
 constexpr size_t TAIL_SMEM_MAX = 160 * 1024;
 
-bool tail_fits(int nclust) { return (size_t)nclust * 4 <= TAIL_SMEM_MAX; }
+bool tail_fits(int nclust) { return (size_t)nclust * 5 + 16 <= TAIL_SMEM_MAX; }
 int tail_grid(int nraw) { return std::max(1, (nraw + TAIL_BLOCK - 1) / TAIL_BLOCK); }
+static int tail_grid_owned(const DevIn &in, const TailState &ts) { return tail_grid((in.nraw - ts.rank + ts.world - 1) / ts.world); }
+bool tail_fits(int nclust);
 
 void launch_tail_link(const DevState &st, const TailState &ts, unsigned long long base, uint32_t cluster_i, int nraw, int nclust, cudaStream_t s) {
   count_launch(1);
@@ -232,14 +300,30 @@ void launch_tail_pass(const DevState &st, const DevIn &in, const TailState &ts, 
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_tail_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX); attr_set = true; }
   count_launch(1);
-  k_tail_pass<<<tail_grid(in.nraw), TAIL_BLOCK, (size_t)nclust * 4, s>>>(st, in, ts, pass, nclust);
+  k_tail_pass<<<tail_grid_owned(in, ts), TAIL_BLOCK, (size_t)nclust * 4, s>>>(st, in, ts, pass, nclust);
 }
 void launch_tail_final(const DevState &st, const DevIn &in, const TailState &ts, const BudParams &bp, int greedy, int detect_singletons,
-                       int last_pass, int nclust, cudaStream_t s) {
+                       int last_pass, int nclust, int mode, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_tail_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX); attr_set = true; }
   count_launch(1);
-  k_tail_final<<<tail_grid(in.nraw), TAIL_BLOCK, (size_t)nclust * 4, s>>>(st, in, ts, bp, greedy, detect_singletons, last_pass, nclust);
+  k_tail_final<<<tail_grid_owned(in, ts), TAIL_BLOCK, (size_t)nclust * 5 + 16, s>>>(st, in, ts, bp, greedy, detect_singletons, last_pass, nclust, mode);
+}
+
+void launch_bud_collect_owned(const DevState &st, const DevIn &in, const TailState &ts, const BudParams &bp, uint32_t *ties, uint32_t *ties_pr,
+                              unsigned cap, cudaStream_t s) {
+  count_launch(1);
+  k_bud_collect_owned<<<tail_grid_owned(in, ts), TAIL_BLOCK, 0, s>>>(st, in, ts, bp, ties, ties_pr, cap);
+}
+void launch_mask_unowned(double *p, uint8_t *correct, int nraw, int rank, int world, cudaStream_t s) {
+  count_launch(1);
+  k_mask_unowned<<<(nraw + 255) / 256, 256, 0, s>>>(p, correct, nraw, rank, world);
+}
+void launch_posthoc_owned(const DevState &st, int nraw, unsigned long long n_entries, const int *center_cluster, uint32_t *trip_ij, double *trip_v,
+                          unsigned cap, unsigned long long *count, int rank, int world, cudaStream_t s) {
+  if (!n_entries) return;
+  count_launch(1);
+  k_posthoc_owned<<<(unsigned)((n_entries + 255) / 256), 256, 0, s>>>(st, n_entries, center_cluster, trip_ij, trip_v, cap, count, rank, world, nraw);
 }
 
 }  // namespace dd2

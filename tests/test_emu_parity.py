@@ -112,15 +112,21 @@ def test_emu_long_reads_band32_homopolymer(emu, monkeypatch):
             cases.assert_same(got, want, rtol=1e-10, label=str(opts) + (" v2" if v2 else ""))
 
 
-def _run_sharded(world, name):
+def _run_sharded(world, name, case=None):
     import threading
 
     import numpy as np
 
     import dada2_b200.api as api
     from tests.test_oracle import load_golden
-    seqs, ab, pri, err, q, opts = cases.build_case(name)
-    want = load_golden(name)
+    if case is None:
+        seqs, ab, pri, err, q, opts = cases.build_case(name)
+        want = load_golden(name)
+    else:                                   # (seqs, abund, priors, quals, opts): expected result from the CPU oracle
+        from oracle import port
+        seqs, ab, pri, q, opts = case
+        err = cases.tperr1()
+        want = port.dada_uniques(seqs, ab, pri, err, q, **dict(opts, homo_gap=opts.get("homo_gap", -8)))
     uid = api.nccl_unique_id()
     results = [None] * world
 
@@ -162,17 +168,16 @@ FUSED_E2E = ["syn800_default", "syn800_nogreedy", "syn800_maxclust5", "syn700_ra
 @pytest.mark.parametrize("name", FUSED_E2E)
 def test_emu_e2e_fused_tail(emu, monkeypatch, name, np_passes):
     """The fused round tail (dd_round2.cu, DADA2B_FUSED_TAIL=1): 1 + NP + 1 launches instead of ~17 per round.  NP=1
-    forces the hand-over to the unfused kernels in every round that needs a second shuffle pass."""
+    makes every round that needs a second shuffle pass continue with one more fused pass at a time."""
     if np_passes == 1 and name not in ("syn800_default", "syn800_maxclust5") and not os.environ.get("DADA2B_EMU_FULL"):
         pytest.skip("quick subset")
     monkeypatch.setenv("DADA2B_FUSED_TAIL", "1")
     monkeypatch.setenv("DADA2B_NP", str(np_passes))
     _gpu_tests().test_e2e_matches_reference_golden(name)
     assert emu.cuemu_launches(b"k_tail_final") > 0
-    if np_passes >= 3:
-        assert emu.cuemu_launches(b"k_shuffle_max") == 0 and emu.cuemu_launches(b"k_p_update") == 0
-    else:
-        assert emu.cuemu_launches(b"k_shuffle_max") > 0
+    assert emu.cuemu_launches(b"k_shuffle_max") == 0 and emu.cuemu_launches(b"k_p_update") == 0
+    if np_passes == 1:      # rounds that moved raws in pass 0 continue with one more fused pass (and final) at a time
+        assert emu.cuemu_launches(b"k_tail_final") > emu.cuemu_launches(b"k_tail_link")
 
 
 @pytest.mark.parametrize("fused", [False, True], ids=["default", "fused_tail"])
@@ -216,3 +221,26 @@ def test_emu_edge_cases(emu, monkeypatch, experimental):
             monkeypatch.setenv(k, "1")
     for case in cases.edge_cases():
         cases.check_edge_case(case, dada2_b200.dada_uniques)
+
+
+@pytest.mark.parametrize("world,name", [(2, "syn800_default"), (3, "syn700_ragged"), (8, "syn800_nogreedy")])
+def test_emu_sharded_owner_mode(emu, monkeypatch, world, name):
+    """Owner mode (DADA2B_OWNER=1 on top of the fused tail): every rank keeps the stored comparisons and runs shuffle /
+    p-update / bud scan for its own raws only; per pass one all-reduce of the cluster read deltas, per round one
+    all-gather of the ranks' reports and (when raws moved) of the move lists.  No exchange of comparisons at all."""
+    monkeypatch.setenv("DADA2B_FUSED_TAIL", "1")
+    monkeypatch.setenv("DADA2B_OWNER", "1")
+    _run_sharded(world, name)
+    assert emu.cuemu_launches(b"k_cs_append") == 0 and emu.cuemu_launches(b"k_posthoc_owned") > 0
+
+
+def test_emu_sharded_owner_mode_ties_and_extra_passes(emu, monkeypatch):
+    """Owner mode corner paths: tie sets larger than TIE_MAX (per-rank candidate lists exchanged), and NP=1 so that rounds
+    needing more shuffle passes continue with one fused pass at a time; plus every other experimental path."""
+    for k in ("DADA2B_FUSED_TAIL", "DADA2B_OWNER", "DADA2B_NWFWD_V2", "DADA2B_PIVOT", "DADA2B_TWOPHASE"):
+        monkeypatch.setenv(k, "1")
+    monkeypatch.setenv("DADA2B_NP", "1")
+    seqs, ab, q = cases.tie_case()
+    _run_sharded(2, "ties", case=(seqs, ab, None, q, dict(max_clust=40)))
+    assert emu.cuemu_launches(b"k_bud_collect_owned") > 0
+    _run_sharded(3, "syn800_maxclust5")
