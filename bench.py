@@ -106,6 +106,44 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+AB_VARIANTS = [("nwfwd2", {"DADA2B_NWFWD_V2": "1"}),
+               ("fused_tail", {"DADA2B_FUSED_TAIL": "1"}),
+               ("pivot", {"DADA2B_PIVOT": "1"}),
+               ("twophase", {"DADA2B_TWOPHASE": "1"}),
+               ("all", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1"})]
+
+
+def experimental_ab(seqs, ab, q, err, last, budget_s, device, leg_cmd=None, steps=3, warmup=2, variants=None):
+    """After the measured region (N=1 only): every off-by-default kernel variant runs the same workload
+    in its own subprocess under a timeout, and its outputs are diffed against the default path's.  Reported under
+    "experimental_ab"; never part of `value`/`e2e`.  Bounded by `budget_s` seconds in total."""
+    import tempfile
+    from tests import cases
+    t_start = time.time()
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        wl, ref = os.path.join(td, "wl.npz"), os.path.join(td, "ref.npz")
+        np.savez(wl, seqs=np.array(seqs), ab=np.asarray(ab), q=np.asarray(q), err=np.asarray(err))
+        np.savez(ref, **cases.flatten(last))
+        for tag, env in (variants or AB_VARIANTS):
+            left = budget_s - (time.time() - t_start)
+            if left < 20:
+                res[tag] = {"skipped": "A/B time budget spent"}
+                continue
+            e = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)), **env)
+            try:
+                out = subprocess.run((leg_cmd or [sys.executable, os.path.join(ROOT, "tools", "ab_leg.py")]) + [wl, ref, str(steps), str(warmup)], env=e,
+                                     capture_output=True, text=True, timeout=min(75, left))
+                rows = [l for l in out.stdout.splitlines() if l.startswith("ABLEG ")]
+                res[tag] = json.loads(rows[-1][6:]) if rows else {"failed": (out.stderr or out.stdout)[-300:]}
+            except subprocess.TimeoutExpired:
+                res[tag] = {"failed": "timeout"}
+            except Exception as ex:                      # never let the A/B leg take the bench line down
+                res[tag] = {"failed": repr(ex)[:200]}
+            res[tag]["switches"] = sorted(env)
+    return res
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation, all host threads, same workload."""
     if rank != 0:
@@ -150,6 +188,8 @@ def main():
     ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
                     help="N>1: shard ONE sample of N x nuniques uniques over the ranks (NCCL all-gather per split round; weak scaling) "
                          "or run one independent sample per rank (no collective)")
+    ap.add_argument("--ab-seconds", type=int, default=150,
+                    help="N=1: total wall budget for the post-measurement A/B of the experimental kernel variants (0 = off)")
     ap.add_argument("--watchdog", type=int, default=1500, help="dump stacks and exit after this many seconds")
     args = ap.parse_args()
     import faulthandler
@@ -318,6 +358,12 @@ def main():
                     parity = "outputs identical to the CPU reference on this workload (ints exact, fp64 <= 1e-10)"
                 except AssertionError as e:
                     parity = "MISMATCH: %s" % e
+        ab_res = None
+        if world == 1 and args.ab_seconds > 0 and not any(k.startswith("DADA2B_") and k not in ("DADA2B_VERBOSE", "DADA2B_AB_TAG", "DADA2B_BENCH_NOCLOCKS") for k in os.environ):
+            try:
+                ab_res = experimental_ab(seqs, ab, q, err, last, args.ab_seconds, local_rank)
+            except Exception as ex:
+                ab_res = {"failed": repr(ex)[:200]}
         line = {"metric": "unique-reads/sec through dada()", "value": value, "unit": "uniques/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_val / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 DP + f64 lambda/p-value",
@@ -338,7 +384,8 @@ def main():
                 "step_ms": step_ms, "step_host_ms": step_host, "e2e_step_ms": e2e_ms,
                 "kernel_ms": {k: st[k] for k in ("ms_k_classify", "ms_k_align_nw", "ms_k_align_gl", "ms_k_align_final")},
                 "host_ms": {k: st[k] for k in ("ms_setup", "ms_loop", "ms_final", "ms_total")},
-                "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+                "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+                "experimental_ab": ab_res}
         print(json.dumps(line))
     res.close()
     if world > 1:

@@ -627,6 +627,66 @@ dada2b_out *run(const dada2b_in *in, const dada2b_opts *o) {
   return out;
 }
 
+
+// =====================================================================================
+// Bimera detection: restatement of /root/reference/src/chimera.cpp.
+// The alignment there is nwalign_vectorized2(query, parent, match, mismatch, gap_p, end_gap 0, band = max_shift)
+// (chimera.cpp:27, :122), which computes the same alignment as the banded ends-free NW restated above.
+// =====================================================================================
+struct BimPair { int left, right, left_oo, right_oo, ham; };
+
+// get_lr, chimera.cpp:239-269.  The integer conversions of the original are kept: `pos < len` and
+// `pos > +(len - max_shift)` compare an int with a size_t (unsigned 64-bit arithmetic; the second wraps when
+// len < max_shift), `pos < max_shift` and `pos >= 0` are int comparisons.  The one-off credit looks at the column
+// AFTER the first mismatch (:254-256, :266-268).  Reads at al[.][len] see the terminating NUL, like the original.
+void get_lr(const std::string &a0, const std::string &a1, int &left, int &right, int &left_oo, int &right_oo,
+            bool allow_one_off, int max_shift) {
+  const size_t len = a0.size();
+  const char *al0 = a0.c_str(), *al1 = a1.c_str();
+  int pos = 0; left = 0;
+  while (al0[pos] == '-' && (size_t)pos < len) pos++;                                  // :242-244
+  while (al1[pos] == '-' && pos < max_shift) { pos++; left++; }                        // :245-247
+  while ((size_t)pos < len && al0[pos] == al1[pos]) { pos++; left++; }                 // :248-250
+  if (allow_one_off) {                                                                 // :251-258
+    left_oo = left; pos++;
+    if ((size_t)pos < len && al0[pos] != '-') left_oo++;
+    while ((size_t)pos < len && al0[pos] == al1[pos]) { pos++; left_oo++; }
+  }
+  pos = (int)len - 1; right = 0;
+  while (al0[pos] == '-' && pos >= 0) pos--;                                           // :261-263
+  while (al1[pos] == '-' && (size_t)pos > +(len - (size_t)max_shift)) { pos--; right++; }   // :264-266
+  while (pos >= 0 && al0[pos] == al1[pos]) { pos--; right++; }                         // :267-269
+  if (allow_one_off) {
+    right_oo = right; pos--;
+    if (pos >= 0 && al0[pos] != '-') right_oo++;
+    while (pos >= 0 && al0[pos] == al1[pos]) { pos--; right_oo++; }
+  }
+}
+
+// get_ham_endsfree, chimera.cpp:210-236: mismatching columns (internal gaps included) between the end-gap runs.
+int get_ham_endsfree(const std::string &s1, const std::string &s2) {
+  int i = 0, j = (int)s2.size() - 1;
+  bool g1 = s1[i] == '-', g2 = s2[i] == '-';
+  while (g1 || g2) { i++; g1 = g1 && s1[i] == '-'; g2 = g2 && s2[i] == '-'; }
+  g1 = s1[j] == '-'; g2 = s2[j] == '-';
+  while (g1 || g2) { j--; g1 = g1 && s1[j] == '-'; g2 = g2 && s2[j] == '-'; }
+  int ham = 0;
+  for (int pos = i; pos <= j; pos++) if (s1[pos] != s2[pos]) ham++;
+  return ham;
+}
+
+BimPair bimera_pair(const std::string &sq, const std::string &par, bool allow_one_off, int match, int mismatch, int gap_p,
+                    int max_shift, std::string *o0 = nullptr, std::string *o1 = nullptr) {
+  std::string a0, a1;
+  nw_endsfree(sq, par, match, mismatch, gap_p, gap_p, false, max_shift, a0, a1);
+  BimPair r{0, 0, 0, 0, 0};
+  get_lr(a0, a1, r.left, r.right, r.left_oo, r.right_oo, allow_one_off, max_shift);
+  r.ham = get_ham_endsfree(a0, a1);
+  if (o0) *o0 = a0;
+  if (o1) *o1 = a1;
+  return r;
+}
+
 }  // namespace
 
 extern "C" {
@@ -679,6 +739,85 @@ int port_pair(const char *seq0, const uint8_t *q0, const char *seq1, const uint8
     }
     return kind;
   } catch (std::exception &e) { if (errbuf) snprintf(errbuf, 256, "%s", e.what()); return -1; }
+}
+
+// C_table_bimera2 / BimeraTableParallel, chimera.cpp:61-207.  mat: nrow (samples) x ncol (sequences), column-major.
+int port_table_bimera(int nrow, int ncol, const int *vals, const char **seqs, double min_fold, int min_abund,
+                      int allow_one_off, int min_one_off_par_dist, int match, int mismatch, int gap_p, int max_shift,
+                      int *nflag_out, int *nsam_out) {
+  std::vector<std::string> sq(ncol);
+  for (int j = 0; j < ncol; j++) sq[j] = seqs[j];
+  std::vector<int> lefts(ncol), rights(ncol), lefts_oo(ncol), rights_oo(ncol);
+  std::vector<char> allowed(ncol);
+  for (int j = 0; j < ncol; j++) {                                                       // :105
+    int nsam = 0, nflag = 0;
+    const int sqlen = (int)sq[j].size();
+    std::fill(lefts.begin(), lefts.end(), -1); std::fill(rights.begin(), rights.end(), -1);
+    std::fill(lefts_oo.begin(), lefts_oo.end(), -1); std::fill(rights_oo.begin(), rights_oo.end(), -1);
+    std::fill(allowed.begin(), allowed.end(), 0);
+    for (int i = 0; i < nrow; i++) {                                                     // :116
+      if (vals[i + (size_t)j * nrow] <= 0) continue;
+      nsam++;
+      int max_left = 0, max_right = 0, oo_max_left = 0, oo_max_right = 0, oo_max_left_oo = 0, oo_max_right_oo = 0;
+      for (int k = 0; k < ncol; k++) {                                                   // :121
+        if (vals[i + (size_t)k * nrow] > (min_fold * vals[i + (size_t)j * nrow]) && vals[i + (size_t)k * nrow] >= min_abund) {
+          if (lefts[k] < 0) {                                                            // :123-147
+            BimPair r = bimera_pair(sq[j], sq[k], allow_one_off != 0, match, mismatch, gap_p, max_shift);
+            if (allow_one_off && r.ham >= min_one_off_par_dist) allowed[k] = 1;
+            if (r.left + r.right < sqlen) { lefts[k] = r.left; rights[k] = r.right; if (allow_one_off) { lefts_oo[k] = r.left_oo; rights_oo[k] = r.right_oo; } }
+            else { lefts[k] = 0; rights[k] = 0; if (allow_one_off) { lefts_oo[k] = 0; rights_oo[k] = 0; } }
+          }
+          if (lefts[k] > max_left) max_left = lefts[k];                                  // :149-157
+          if (rights[k] > max_right) max_right = rights[k];
+          if (allow_one_off && allowed[k]) {
+            if (lefts[k] > oo_max_left) oo_max_left = lefts[k];
+            if (rights[k] > oo_max_right) oo_max_right = rights[k];
+            if (lefts_oo[k] > oo_max_left_oo) oo_max_left_oo = lefts_oo[k];
+            if (rights_oo[k] > oo_max_right_oo) oo_max_right_oo = rights_oo[k];
+          }
+        }
+      }
+      if (max_right + max_left >= sqlen) nflag++;                                        // :162-169
+      else if (allow_one_off) {
+        if (oo_max_left + oo_max_right_oo >= sqlen || oo_max_left_oo + oo_max_right >= sqlen) nflag++;
+      }
+    }
+    nflag_out[j] = nflag; nsam_out[j] = nsam;                                            // :172-173
+  }
+  return 0;
+}
+
+// C_is_bimera, chimera.cpp:18-59 (the early exit once a model is found does not change the result: the maxima only grow).
+int port_is_bimera(const char *sq_c, int npar, const char **pars, int allow_one_off, int min_one_off_par_dist, int match,
+                   int mismatch, int gap_p, int max_shift) {
+  const std::string sq(sq_c);
+  int max_left = 0, max_right = 0, oo_max_left = 0, oo_max_right = 0, oo_max_left_oo = 0, oo_max_right_oo = 0;
+  bool rval = false;
+  for (int i = 0; i < npar && !rval; i++) {
+    BimPair r = bimera_pair(sq, pars[i], allow_one_off != 0, match, mismatch, gap_p, max_shift);
+    if ((size_t)(r.left + r.right) >= sq.size()) continue;                               // :30-32
+    if (r.left > max_left) max_left = r.left;
+    if (r.right > max_right) max_right = r.right;
+    if (allow_one_off && r.ham >= min_one_off_par_dist) {                                // :37-42
+      if (r.left > oo_max_left) oo_max_left = r.left;
+      if (r.right > oo_max_right) oo_max_right = r.right;
+      if (r.left_oo > oo_max_left_oo) oo_max_left_oo = r.left_oo;
+      if (r.right_oo > oo_max_right_oo) oo_max_right_oo = r.right_oo;
+    }
+    if ((size_t)(max_right + max_left) >= sq.size()) rval = true;                        // :45-52
+    if (allow_one_off && ((size_t)(oo_max_left + oo_max_right_oo) >= sq.size() || (size_t)(oo_max_left_oo + oo_max_right) >= sq.size())) rval = true;
+  }
+  return rval ? 1 : 0;
+}
+
+int port_bimera_pair(const char *sq, const char *par, int allow_one_off, int match, int mismatch, int gap_p, int max_shift,
+                     int *out5, char *al0, char *al1) {
+  std::string a0, a1;
+  BimPair r = bimera_pair(sq, par, allow_one_off != 0, match, mismatch, gap_p, max_shift, &a0, &a1);
+  out5[0] = r.left; out5[1] = r.right; out5[2] = r.left_oo; out5[3] = r.right_oo; out5[4] = r.ham;
+  if (al0) strcpy(al0, a0.c_str());
+  if (al1) strcpy(al1, a1.c_str());
+  return 0;
 }
 
 double port_calc_pA(int reads, double E_reads, int prior) { return calc_pA(reads, E_reads, prior != 0); }

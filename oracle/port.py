@@ -68,3 +68,41 @@ def pair(seq0, q0, seq1, q1, err, use_kmers=True, kdist_cutoff=0.42, **opts):
     return dict(kind=kind, shrouded=(kind == 0), lam=lam.value, nsubs=ns.value, map=mp[:l0].copy(),
                 pos=pos[:n].copy(), nt0=bytes(nt0.raw[:n]), nt1=bytes(nt1.raw[:n]), q0=sq0[:n].copy(),
                 q1=sq1[:n].copy(), al0=al0.value.decode(), al1=al1.value.decode())
+
+
+# ---------------- bimera detection (restatement of src/chimera.cpp in port.cpp) ----------------
+BIMERA_DEFAULTS = dict(min_fold=1.5, min_abund=2, allow_one_off=False, min_one_off_par_dist=4,
+                       match=5, mismatch=-4, gap_p=-8, max_shift=16)
+
+
+def table_bimera(mat, seqs, **opts):
+    o = dict(BIMERA_DEFAULTS); o.update(opts)
+    m = np.asfortranarray(np.asarray(mat, dtype=np.int32))
+    nrow, ncol = m.shape
+    assert ncol == len(seqs)
+    arr = (C.c_char_p * ncol)(*[s.encode() for s in seqs])
+    nflag, nsam = np.zeros(ncol, np.int32), np.zeros(ncol, np.int32)
+    lib().port_table_bimera(C.c_int(nrow), C.c_int(ncol), m.ctypes.data_as(C.c_void_p), arr, C.c_double(o["min_fold"]),
+                            C.c_int(o["min_abund"]), C.c_int(o["allow_one_off"]), C.c_int(o["min_one_off_par_dist"]),
+                            C.c_int(o["match"]), C.c_int(o["mismatch"]), C.c_int(o["gap_p"]), C.c_int(o["max_shift"]),
+                            nflag.ctypes.data_as(C.c_void_p), nsam.ctypes.data_as(C.c_void_p))
+    return nflag, nsam
+
+
+def is_bimera(sq, pars, **opts):
+    o = dict(BIMERA_DEFAULTS); o.update(opts)
+    arr = (C.c_char_p * len(pars))(*[s.encode() for s in pars])
+    return bool(lib().port_is_bimera(sq.encode(), C.c_int(len(pars)), arr, C.c_int(o["allow_one_off"]),
+                                     C.c_int(o["min_one_off_par_dist"]), C.c_int(o["match"]), C.c_int(o["mismatch"]),
+                                     C.c_int(o["gap_p"]), C.c_int(o["max_shift"])))
+
+
+def bimera_pair(sq, par, **opts):
+    o = dict(BIMERA_DEFAULTS); o.update(opts)
+    out = np.zeros(5, np.int32)
+    n = len(sq) + len(par) + 2
+    a0, a1 = C.create_string_buffer(n), C.create_string_buffer(n)
+    lib().port_bimera_pair(sq.encode(), par.encode(), C.c_int(o["allow_one_off"]), C.c_int(o["match"]), C.c_int(o["mismatch"]),
+                           C.c_int(o["gap_p"]), C.c_int(o["max_shift"]), out.ctypes.data_as(C.c_void_p), a0, a1)
+    return dict(left=int(out[0]), right=int(out[1]), left_oo=int(out[2]), right_oo=int(out[3]), ham=int(out[4]),
+                al0=a0.value.decode(), al1=a1.value.decode())

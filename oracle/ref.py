@@ -182,3 +182,57 @@ def align(seq0, seq1, match=5, mismatch=-4, gap=-8, homo_gap=-8, band=16, mode=0
     if rc:
         raise RuntimeError("ref_align failed")
     return a0.value.decode(), a1.value.decode()
+
+
+# ---------------- bimera detection (src/chimera.cpp) ----------------
+BIMERA_DEFAULTS = dict(min_fold=1.5, min_abund=2, allow_one_off=False, min_one_off_par_dist=4,
+                       match=5, mismatch=-4, gap_p=-8, max_shift=16)       # R/chimeras.R:220, R/dada.R:1-26
+
+
+def _bimera_table(fn, mat, seqs, o):
+    m = np.asfortranarray(np.asarray(mat, dtype=np.int32))          # nrow (samples) x ncol (sequences), column-major like R
+    nrow, ncol = m.shape
+    assert ncol == len(seqs)
+    arr = (C.c_char_p * ncol)(*[s.encode() for s in seqs])
+    nflag = np.zeros(ncol, np.int32)
+    nsam = np.zeros(ncol, np.int32)
+    return m, nrow, ncol, arr, nflag, nsam
+
+
+def table_bimera(mat, seqs, **opts):
+    """The reference's C_table_bimera2 (chimera.cpp:194-207).  mat: [nsample, nseq] counts.  -> (nflag, nsam)"""
+    o = dict(BIMERA_DEFAULTS); o.update(opts)
+    m, nrow, ncol, arr, nflag, nsam = _bimera_table(None, mat, seqs, o)
+    eb = C.create_string_buffer(256)
+    rc = lib().ref_table_bimera(C.c_int(nrow), C.c_int(ncol), m.ctypes.data_as(C.c_void_p), arr, C.c_double(o["min_fold"]),
+                                C.c_int(o["min_abund"]), C.c_int(o["allow_one_off"]), C.c_int(o["min_one_off_par_dist"]),
+                                C.c_int(o["match"]), C.c_int(o["mismatch"]), C.c_int(o["gap_p"]), C.c_int(o["max_shift"]),
+                                nflag.ctypes.data_as(C.c_void_p), nsam.ctypes.data_as(C.c_void_p), eb)
+    if rc:
+        raise RuntimeError(eb.value.decode())
+    return nflag, nsam
+
+
+def is_bimera(sq, pars, **opts):
+    """The reference's C_is_bimera (chimera.cpp:18-59)."""
+    o = dict(BIMERA_DEFAULTS); o.update(opts)
+    arr = (C.c_char_p * len(pars))(*[s.encode() for s in pars])
+    rc = lib().ref_is_bimera(sq.encode(), C.c_int(len(pars)), arr, C.c_int(o["allow_one_off"]), C.c_int(o["min_one_off_par_dist"]),
+                             C.c_int(o["match"]), C.c_int(o["mismatch"]), C.c_int(o["gap_p"]), C.c_int(o["max_shift"]))
+    if rc < 0:
+        raise RuntimeError("ref_is_bimera failed")
+    return bool(rc)
+
+
+def bimera_pair(sq, par, **opts):
+    """nwalign_vectorized2 + get_lr + get_ham_endsfree for one (query, parent) pair -> dict."""
+    o = dict(BIMERA_DEFAULTS); o.update(opts)
+    out = np.zeros(5, np.int32)
+    n = len(sq) + len(par) + 2
+    a0, a1 = C.create_string_buffer(n), C.create_string_buffer(n)
+    rc = lib().ref_bimera_pair(sq.encode(), par.encode(), C.c_int(o["allow_one_off"]), C.c_int(o["match"]), C.c_int(o["mismatch"]),
+                               C.c_int(o["gap_p"]), C.c_int(o["max_shift"]), out.ctypes.data_as(C.c_void_p), a0, a1)
+    if rc:
+        raise RuntimeError("ref_bimera_pair failed")
+    return dict(left=int(out[0]), right=int(out[1]), left_oo=int(out[2]), right_oo=int(out[3]), ham=int(out[4]),
+                al0=a0.value.decode(), al1=a1.value.decode())

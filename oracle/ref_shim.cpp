@@ -16,6 +16,13 @@ Rcpp::List dada_uniques(std::vector<std::string> seqs, std::vector<int> abundanc
                         int min_abund, bool use_quals, bool final_consensus, bool vectorized_alignment,
                         int homo_gap, bool multithread, bool verbose, int SSE, bool gapless, bool greedy);
 
+Rcpp::DataFrame C_table_bimera2(Rcpp::IntegerMatrix mat, std::vector<std::string> seqs, double min_fold, int min_abund,
+                                bool allow_one_off, int min_one_off_par_dist, int match, int mismatch, int gap_p, int max_shift);
+bool C_is_bimera(std::string sq, std::vector<std::string> pars, bool allow_one_off, int min_one_off_par_dist, int match,
+                 int mismatch, int gap_p, int max_shift);
+int get_ham_endsfree(const char *seq1, const char *seq2);
+void get_lr(char **al, int &left, int &right, int &left_oo, int &right_oo, bool allow_one_off, int max_shift);
+
 static std::atomic<int> g_threads(1);
 extern "C" int oracle_get_threads(void) { return g_threads.load(); }
 extern "C" void oracle_set_threads(int n) { g_threads.store(n < 1 ? 1 : n); }
@@ -208,6 +215,51 @@ int ref_align(const char *seq0, const char *seq1, int match, int mismatch, int g
   }
   free(s0); free(s1);
   return rc;
+}
+
+// ---------------- bimera detection (src/chimera.cpp) ----------------
+// C_table_bimera2 (chimera.cpp:194-207): mat is nrow (samples) x ncol (sequences), column-major.
+int ref_table_bimera(int nrow, int ncol, const int *mat, const char **seqs, double min_fold, int min_abund,
+                     int allow_one_off, int min_one_off_par_dist, int match, int mismatch, int gap_p, int max_shift,
+                     int *nflag, int *nsam, char *errbuf) {
+  try {
+    Rcpp::IntegerMatrix M(nrow, ncol);
+    for (size_t i = 0; i < (size_t)nrow * ncol; i++) (*M.d)[i] = mat[i];
+    std::vector<std::string> s(ncol);
+    for (int i = 0; i < ncol; i++) s[i] = seqs[i];
+    Rcpp::DataFrame df = C_table_bimera2(M, s, min_fold, min_abund, allow_one_off != 0, min_one_off_par_dist, match,
+                                         mismatch, gap_p, max_shift);
+    const Rcpp::Any *f = df.get("nflag"), *n = df.get("nsam");
+    memcpy(nflag, f->iv->data(), ncol * sizeof(int));
+    memcpy(nsam, n->iv->data(), ncol * sizeof(int));
+  } catch (std::exception &e) {
+    if (errbuf) { strncpy(errbuf, e.what(), 255); errbuf[255] = 0; }
+    return -1;
+  }
+  return 0;
+}
+// C_is_bimera (chimera.cpp:18-59)
+int ref_is_bimera(const char *sq, int npar, const char **pars, int allow_one_off, int min_one_off_par_dist, int match,
+                  int mismatch, int gap_p, int max_shift) {
+  std::vector<std::string> p(npar);
+  for (int i = 0; i < npar; i++) p[i] = pars[i];
+  try {
+    return C_is_bimera(std::string(sq), p, allow_one_off != 0, min_one_off_par_dist, match, mismatch, gap_p, max_shift) ? 1 : 0;
+  } catch (std::exception &e) { return -1; }
+}
+// One (query, parent) pair: the alignment of chimera.cpp:122 followed by get_lr (:239-269) and get_ham_endsfree (:210-236).
+int ref_bimera_pair(const char *sq, const char *par, int allow_one_off, int match, int mismatch, int gap_p, int max_shift,
+                    int *out5, char *al0, char *al1) {
+  try {
+    char **al = nwalign_vectorized2(sq, strlen(sq), par, strlen(par), (int16_t)match, (int16_t)mismatch, (int16_t)gap_p, 0, max_shift);
+    int left = 0, right = 0, left_oo = 0, right_oo = 0;
+    get_lr(al, left, right, left_oo, right_oo, allow_one_off != 0, max_shift);
+    out5[0] = left; out5[1] = right; out5[2] = left_oo; out5[3] = right_oo; out5[4] = get_ham_endsfree(al[0], al[1]);
+    if (al0) strcpy(al0, al[0]);
+    if (al1) strcpy(al1, al[1]);
+    free(al[0]); free(al[1]); free(al);
+  } catch (std::exception &e) { return -1; }
+  return 0;
 }
 
 double ref_ppois_upper(int reads_minus_1, double E) { return oracle_ppois((double)reads_minus_1, E, 0, 0); }

@@ -53,6 +53,7 @@ template <typename T> class Vec {
   std::shared_ptr<std::vector<T>> d;
   Vec() : d(std::make_shared<std::vector<T>>()) {}
   explicit Vec(size_t n) : d(std::make_shared<std::vector<T>>(n, T())) {}
+  Vec(size_t n, const T &v) : d(std::make_shared<std::vector<T>>(n, v)) {}
   size_t size() const { return d->size(); }
   T &operator[](size_t i) { return (*d)[i]; }
   const T &operator[](size_t i) const { return (*d)[i]; }

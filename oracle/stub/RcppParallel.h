@@ -12,6 +12,26 @@
 extern "C" int oracle_get_threads(void);
 
 namespace RcppParallel {
+// Thin views over the stub Rcpp containers (chimera.cpp:63-68 uses RMatrix<int> / RVector<int>).
+template <typename T> class RMatrix {
+ public:
+  template <typename M> RMatrix(const M &m) : p_(m.d->data()), nr_(m.nr), nc_(m.nc) {}
+  const T *begin() const { return p_; }
+  T *begin() { return p_; }
+  std::size_t nrow() const { return nr_; }
+  std::size_t ncol() const { return nc_; }
+ private:
+  T *p_; std::size_t nr_, nc_;
+};
+template <typename T> class RVector {
+ public:
+  template <typename V> RVector(const V &v) : p_(v.d->data()), n_(v.d->size()) {}
+  T &operator[](std::size_t i) { return p_[i]; }
+  const T &operator[](std::size_t i) const { return p_[i]; }
+  std::size_t size() const { return n_; }
+ private:
+  T *p_; std::size_t n_;
+};
 struct Worker {
   virtual ~Worker() {}
   virtual void operator()(std::size_t begin, std::size_t end) = 0;

@@ -1,0 +1,59 @@
+"""Experimental kernel variants on hardware (all OFF by default): DADA2B_NWFWD_V2 (restructured register
+NW, dd_nwfwd2.cu), DADA2B_TWOPHASE (bound pass before the fp64 NW), DADA2B_FUSED_TAIL (dd_round2.cu), DADA2B_PIVOT
+(dd_classify2.cu) and their combination.  They were written after round 1's GPU budget was spent and are validated on
+the host SIMT emulator only (tests/test_emu_parity.py), so their first execution on a B200 is this file:
+xfail(strict=False) -- XPASS means "reference goldens reproduced on hardware", XFAIL carries the diff -- and each
+variant runs in its own subprocess with a timeout so that a device fault or a hang cannot touch the validated suite.
+The default path does not read any of these switches' code."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = textwrap.dedent('''
+    import sys, time
+    sys.path.insert(0, %r)
+    import numpy as np
+    from tests import cases
+    from tests.test_oracle import load_golden
+    import dada2_b200
+    t0 = time.time()
+    for name in ("syn2000_default", "syn800_nogreedy", "syn700_ragged", "syn800_scores", "syn800_priors",
+                 "syn500_usequals0", "syn800_homo", "syn800_band32", "syn800_nogapless", "syn800_singletons"):
+        seqs, ab, pri, err, q, opts = cases.build_case(name)
+        got = dada2_b200.dada_uniques(seqs, ab, pri, err, q, **opts)
+        want = load_golden(name)
+        pb = None
+        if pri is not None:
+            pb = np.zeros(len(want["clustering"]["sequence"]), dtype=bool)
+            pb[1:] = want["clustering"]["birth_pval"][1:] >= opts.get("omegaA", 1e-40)
+        cases.assert_same(got, want, rtol=1e-10, prior_born=pb, label=name)
+        print(name, "ok", "%%.1f ms device" %% got["stats"]["ms_device"], flush=True)
+    seqs, ab, q = cases.load_config1()
+    got = dada2_b200.dada_uniques(seqs, ab, None, cases.tperr1(), q)
+    cases.assert_same(got, load_golden("config1"), rtol=1e-10, label="config1")
+    print("VARIANT OK %%.1f s" %% (time.time() - t0))
+''') % ROOT
+
+VARIANTS = {
+    "nwfwd2": dict(DADA2B_NWFWD_V2="1"),
+    "twophase": dict(DADA2B_TWOPHASE="1"),
+    "nwfwd2_twophase": dict(DADA2B_NWFWD_V2="1", DADA2B_TWOPHASE="1"),
+    "fused_tail": dict(DADA2B_FUSED_TAIL="1"),
+    "fused_tail_np1": dict(DADA2B_FUSED_TAIL="1", DADA2B_NP="1"),
+    "pivot": dict(DADA2B_PIVOT="1"),
+    "all": dict(DADA2B_NWFWD_V2="1", DADA2B_FUSED_TAIL="1", DADA2B_PIVOT="1"),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.xfail(strict=False, reason="experimental path, first run on hardware happens at round end")
+def test_experimental_variant_matches_reference_goldens(variant):
+    env = dict(os.environ, **VARIANTS[variant])
+    out = subprocess.run([sys.executable, "-c", SCRIPT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "VARIANT OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -154,3 +154,68 @@ def extend_err(err, ncol):
     if err.shape[1] >= ncol:
         return err
     return np.concatenate([err, np.repeat(err[:, -1:], ncol - err.shape[1], axis=1)], axis=1)
+
+
+def bimera_table(nseq, nsample=8, L=250, npar=None, seed=1, frac_bimera=0.4, frac_oneoff=0.15, frac_indel=0.1, frac_shift=0.05,
+                 lenvar=0):
+    """Synthetic sequence table for bimera detection (input of the reference's isBimeraDenovoTable, R/chimeras.R:220-238):
+    -> (seqs, mat[nsample, nseq] int32).  `npar` true variants (substitution variants of one root, like illumina());
+    the rest are two-parent bimeras at a random breakpoint (some with one extra substitution = "one-off", some with a
+    1-3 nt indel, some with shifted ends) plus plain substitution variants.  Abundances: Zipf over sequences, log-normal
+    sample depths, ~60 % of the cells zero for the rarer sequences.  Sequences are distinct; column order is by
+    decreasing total abundance (what makeSequenceTable + dada() produce is unordered; the algorithm does not care)."""
+    rng = np.random.default_rng(seed)
+    npar = npar or max(4, nseq // 8)
+    root = rng.integers(0, 4, L)
+    pars = []
+    for _ in range(npar):
+        s = root.copy()
+        k = int(rng.integers(1, 40))
+        pos = rng.choice(L, k, replace=False)
+        s[pos] = (s[pos] + rng.integers(1, 4, k)) % 4
+        if lenvar:
+            s = s[:L - int(rng.integers(0, lenvar + 1))]
+        pars.append(s)
+    out = {}
+
+    def add(s):
+        key = "".join("ACGT"[x] for x in s)
+        if len(key) >= 8 and key not in out:
+            out[key] = len(out)
+
+    for s in pars:
+        add(s)
+    guard = 0
+    while len(out) < nseq and guard < 50 * nseq:
+        guard += 1
+        u = rng.random()
+        a, b = pars[int(rng.integers(0, npar))], pars[int(rng.integers(0, npar))]
+        if u < frac_bimera + frac_oneoff + frac_indel + frac_shift:
+            bp = int(rng.integers(10, min(len(a), len(b)) - 10))
+            s = np.concatenate([a[:bp], b[bp:]])
+            v = u - frac_bimera
+            if 0 <= v < frac_oneoff:
+                p = int(rng.integers(0, len(s)))
+                s = s.copy(); s[p] = (s[p] + int(rng.integers(1, 4))) % 4
+            elif frac_oneoff <= v < frac_oneoff + frac_indel:
+                p = int(rng.integers(5, len(s) - 5)); k = int(rng.integers(1, 4))
+                s = np.concatenate([s[:p], rng.integers(0, 4, k), s[p:]]) if rng.random() < 0.5 else np.concatenate([s[:p], s[p + k:]])
+            elif v >= frac_oneoff + frac_indel:
+                k = int(rng.integers(1, 20))
+                s = s[k:] if rng.random() < 0.5 else np.concatenate([rng.integers(0, 4, k), s])
+        else:
+            s = a.copy()
+            k = int(rng.integers(1, 4))
+            pos = rng.choice(len(s), k, replace=False)
+            s[pos] = (s[pos] + rng.integers(1, 4, k)) % 4
+        add(s)
+    seqs = list(out)
+    n = len(seqs)
+    w = 1.0 / np.arange(1, n + 1)
+    depth = rng.lognormal(9.0, 0.6, nsample)
+    lam = depth[:, None] * (w / w.sum())[None, :]
+    mat = rng.poisson(lam).astype(np.int32)
+    drop = rng.random((nsample, n)) < np.minimum(0.6, np.arange(n)[None, :] / max(1, n) + 0.05)
+    mat[drop] = 0
+    mat[0, mat.sum(axis=0) == 0] = 1            # every sequence occurs somewhere
+    return seqs, mat
