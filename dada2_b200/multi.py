@@ -49,3 +49,30 @@ def sharded_resident(seqs, abundances, priors, quals, device=None, group=None):
     dist.broadcast_object_list(box, src=0, group=group)
     res.comm_init(rank, world, box[0])
     return res
+
+
+def table_bimera_sharded(mat, seqs, device=None, group=None, runner=None, **opts):
+    """C_table_bimera2 over all ranks of `group`: the queries shard with no data-path collective (rank r evaluates the
+    sequences j with j % world == r against the replicated table, chimera.cpp:105 is an independent loop over j); one
+    SUM all-reduce of the two int32 result vectors at the end.  Every rank gets the complete {"nflag", "nsam"}.
+    `runner` is injectable for the CPU logic tests (default: dada2_b200.bimera.C_table_bimera2 on this rank's GPU)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if runner is None:
+        from .bimera import C_table_bimera2 as runner
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    kw = dict(opts)
+    if device is not None:
+        kw["device"] = device
+    r = runner(mat, seqs, shard_rank=rank, shard_world=world, **kw)
+    if world == 1:
+        return {"nflag": r["nflag"], "nsam": r["nsam"]}
+    on_gpu = dist.get_backend(group) == "nccl"
+    t = torch.from_numpy(np.stack([r["nflag"], r["nsam"]]).astype(np.int32))
+    if on_gpu:
+        t = t.cuda(device if device is not None else torch.cuda.current_device())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    t = t.cpu().numpy()
+    return {"nflag": t[0].copy(), "nsam": t[1].copy()}

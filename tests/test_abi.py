@@ -23,12 +23,13 @@ def _lib():
 def test_library_exports_every_declared_symbol():
     L = _lib()
     names = set()
-    for h in ("dada2b.h", "dada2b_test.h"):
+    for h in sorted(f for f in os.listdir(os.path.join(ROOT, "include")) if f.endswith(".h")):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(dada2b_[a-z_A-Z0-9]+)\s*\(", src))
     assert {"dada2b_run", "dada2b_free", "dada2b_upload", "dada2b_run_resident", "dada2b_ctx_free",
-            "dada2b_default_opts", "dada2b_test_pairs", "dada2b_test_calc_pA"} <= names
+            "dada2b_default_opts", "dada2b_test_pairs", "dada2b_test_calc_pA", "dada2b_table_bimera", "dada2b_is_bimera",
+            "dada2b_bimera_default_opts", "dada2b_test_bimera_pairs"} <= names
     for n in sorted(names):
         assert hasattr(L, n), "libdada2b.so does not export %s" % n
 
@@ -55,6 +56,31 @@ def test_struct_layouts_match_ctypes_mirror():
     assert got == want
 
 
+def test_bimera_struct_layouts_and_defaults():
+    from dada2_b200 import bimera
+    prog = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "dada2b_bimera.h"
+    int main() {
+      printf("%zu %zu %zu %zu %zu\n", sizeof(dada2b_bimera_opts), sizeof(dada2b_bimera_stats), offsetof(dada2b_bimera_opts, max_shift),
+             offsetof(dada2b_bimera_opts, shard_world), offsetof(dada2b_bimera_stats, ms_k_align));
+      return 0;
+    }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert got == [ctypes.sizeof(bimera.BimeraOpts), ctypes.sizeof(bimera.BimeraStats), bimera.BimeraOpts.max_shift.offset,
+                   bimera.BimeraOpts.shard_world.offset, bimera.BimeraStats.ms_k_align.offset]
+    _lib()
+    o = bimera._opts()                                          # R/chimeras.R:220, R/dada.R:1-26
+    assert (o.min_fold, o.min_abund, o.allow_one_off, o.min_one_off_par_dist, o.match, o.mismatch, o.gap_p, o.max_shift,
+            o.shard_rank, o.shard_world) == (1.5, 2, 0, 4, 5, -4, -8, 16, 0, 1)
+
+
 def test_default_opts_are_the_reference_defaults():
     from dada2_b200 import _abi
     L = _lib()
@@ -72,6 +98,10 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback():
     import dada2_b200
     with pytest.raises(dada2_b200.Dada2bError, match="no CUDA device"):
         dada2_b200.dada_uniques(["ACGTACGTAC"], [1], None, np.ones((16, 41)), np.full((1, 10), 30.0))
+    with pytest.raises(dada2_b200.Dada2bError, match="no CUDA device"):
+        dada2_b200.bimera.C_table_bimera2(np.ones((1, 2), np.int32), ["ACGTACGTAC", "ACGTACGTAA"])
+    with pytest.raises(dada2_b200.Dada2bError, match="no CUDA device"):
+        dada2_b200.bimera.C_is_bimera("ACGTACGTAC", ["ACGTACGTAA", "ACGTACGTTT"])
 
 
 def test_product_sources_do_not_touch_the_oracle():

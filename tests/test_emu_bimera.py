@@ -1,0 +1,67 @@
+"""The bimera kernels (dd_bimera.cu) on the host SIMT emulator against the reference goldens -- CPU suite.  Same assertions
+as tests/test_gpu_zz_bimera.py, at sizes the emulator finishes in seconds (about 5 ms per emulated alignment)."""
+import os
+import platform
+import sys
+
+import numpy as np
+import pytest
+
+from tests import bimera_cases as B
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="the emulator's fiber switch is x86-64 only")
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    import build_emu
+    import dada2_b200.api as api
+    lib = build_emu.build()
+    monkeypatch.setattr(api, "_LIBPATH", lib)
+    monkeypatch.setattr(api, "_LIB", None)
+    import dada2_b200.bimera as bm
+    monkeypatch.setattr(bm, "_BOUND", False)
+    yield lib
+
+
+def test_emu_bimera_pairs(emu):
+    B.check_pairs(B.product_pair_fn, limit=None if os.environ.get("DADA2B_EMU_FULL") else 120)
+
+
+@pytest.mark.parametrize("name,opt_ids", [("t40_one_sample", None), ("t120", [1])] if not os.environ.get("DADA2B_EMU_FULL")
+                         else [(n, None) for n in B.table_names()])
+def test_emu_bimera_table(emu, name, opt_ids):
+    B.check_table(name, B.product_table_fn, opt_ids)
+
+
+def test_emu_bimera_denovo_and_sharding(emu):
+    from dada2_b200 import bimera
+    B.check_is_bimera("t40_one_sample", B.product_denovo_fn)
+    g = B.golden()
+    seqs, mat = g["t40_one_sample_seqs"].tolist(), g["t40_one_sample_mat"]
+    tot = [np.zeros(len(seqs), np.int32), np.zeros(len(seqs), np.int32)]
+    for r in range(3):                                   # three shards, summed like multi.table_bimera_sharded does
+        x = bimera.C_table_bimera2(mat, seqs, shard_rank=r, shard_world=3)
+        owned = np.arange(len(seqs)) % 3 == r
+        assert not x["nflag"][~owned].any() and not x["nsam"][~owned].any()
+        tot[0] += x["nflag"]; tot[1] += x["nsam"]
+    assert np.array_equal(tot[0], g["t40_one_sample_o0_nflag"]) and np.array_equal(tot[1], g["t40_one_sample_o0_nsam"])
+
+
+def test_emu_bimera_errors_and_corners(emu):
+    from dada2_b200 import bimera, Dada2bError
+    with pytest.raises(Dada2bError, match="A/C/G/T"):
+        bimera.C_table_bimera2(np.ones((1, 2), np.int32), ["ACGTNACGTA", "ACGTAACGTA"])
+    with pytest.raises(Dada2bError, match="valid sequence table"):
+        bimera.C_table_bimera2(np.ones((1, 3), np.int32), ["ACGTAACGTA", "ACGTTACGTA"])
+    r = bimera.C_table_bimera2(np.array([[5], [0], [7]], np.int32), ["ACGTAACGTAGG"])        # one sequence: no parents
+    assert r["nflag"].tolist() == [0] and r["nsam"].tolist() == [2]
+    assert bimera.C_is_bimera("ACGTAACGTAGG", []) is False
+    # exact two-parent bimera, and the same with the parents given in the other order
+    a = "GTATCGGCTACCGCAAAAATAGTACCCTATTTACGCGGGATGTCCTAACGATCAGTTTCATGTAAGCCTAGCCTACAACG"
+    b = "GCATTAACATGGCGTATACTTATTCCTTGCATCGGACGAGTGGCTACGGAAGTGTCCTAAACATTCAGAGATGTGGCTAA"
+    chim = a[:36] + b[36:]
+    assert bimera.C_is_bimera(chim, [a, b]) is True and bimera.C_is_bimera(chim, [b, a]) is True
+    assert bimera.C_is_bimera(chim, [a]) is False
