@@ -20,6 +20,7 @@
 #include "dd_common.h"
 #include "dd_kernels.h"
 #include "dd_nw_warp.cuh"
+#include "dd_bimera.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -30,103 +31,6 @@
 #include <vector>
 
 namespace dd2 {
-
-// Packed per-(query, parent) record: bits 0-14 left, 15-29 right, 30-44 left_oo, 45-59 right_oo, 60 allowed
-// (get_ham_endsfree >= min_one_off_par_dist), 63 valid.  Alignments have < 2 * 9999 columns, so 15 bits suffice.
-constexpr unsigned long long BIM_VALID = 1ull << 63, BIM_ALLOWED = 1ull << 60;
-__host__ __device__ inline unsigned long long bim_pack(int l, int r, int lo, int ro, bool allowed) {
-  return BIM_VALID | (allowed ? BIM_ALLOWED : 0ull) | (unsigned long long)(l & 0x7FFF) | ((unsigned long long)(r & 0x7FFF) << 15) |
-         ((unsigned long long)(lo & 0x7FFF) << 30) | ((unsigned long long)(ro & 0x7FFF) << 45);
-}
-
-struct BimSeqs {
-  int n, maxlen, minlen, SW;
-  const uint32_t *seq2;     // [n][SW] 2-bit packed, like DevIn::seq2
-  const uint16_t *len;      // [n]
-};
-
-struct BimAlignArgs {
-  BimSeqs sq;
-  AlnParams P;
-  int allow_one_off, min_one_off_par_dist, max_shift;
-  const uint32_t *jq, *jk;                  // job -> (query sequence, parent sequence)
-  const unsigned long long *njobs_ptr;      // device-side count (NULL => njobs_fixed)
-  unsigned long long njobs_fixed;
-  int dst_mode;                             // 0: record index = job;  1: slot(jq) * ncol + jk  (table batches)
-  uint32_t j0; int ncol;
-  int q_mul, q_add;                         //    batch slot of query q = (q - q_add) / q_mul - j0  (sharded table calls)
-  unsigned long long *rec;                  // packed records (may be NULL)
-  int32_t *raw5;                            // [job][5] unpacked get_lr / ham values (test hook; may be NULL)
-  unsigned long long *ctr;                  // [0] jobs (k_bim_need), [1] cells, [2] error flag
-  int warp_words, seq_bytes, H_words, ops_words, mask_words, ptr_in_smem;
-  uint32_t *ptr_scratch; unsigned long long ptr_words;
-};
-
-// run of set bits of mask M starting at pos and going up, never past position n - 1
-__device__ __forceinline__ int run_fwd(const uint32_t *M, int pos, int n) {
-  int cnt = 0;
-  while (pos < n) {
-    const int sh = pos & 31, avail = 32 - sh;
-    const uint32_t w = ~(M[pos >> 5] >> sh);
-    const int t = w ? __ffs((int)w) - 1 : 32;
-    const int r = min(min(t, avail), n - pos);
-    cnt += r; pos += r;
-    if (r < avail) break;
-  }
-  return cnt;
-}
-// run of set bits starting at pos and going down to 0
-__device__ __forceinline__ int run_bwd(const uint32_t *M, int pos) {
-  int cnt = 0;
-  while (pos >= 0) {
-    const int avail = (pos & 31) + 1;
-    const uint32_t w = ~(M[pos >> 5] << (31 - (pos & 31)));
-    const int t = __clz((int)w);
-    const int r = min(t, avail);
-    cnt += r; pos -= r;
-    if (r < avail) break;
-  }
-  return cnt;
-}
-__device__ __forceinline__ int bit_at(const uint32_t *M, int pos) { return (M[pos >> 5] >> (pos & 31)) & 1; }
-
-// get_lr (chimera.cpp:239-269) and get_ham_endsfree (:210-236) on the column masks of an alignment of n columns:
-// Q = query row has '-', Pm = parent row has '-', E = both rows hold the same base.  Warp-uniform (every lane computes
-// the same scalars from shared memory).  Integer conversions of the original are kept: `pos > +(len - max_shift)` is an
-// unsigned 64-bit comparison (false for every pos when len < max_shift); the one-off credit inspects the column after
-// the first mismatch.
-__device__ void bim_scan(const uint32_t *Q, const uint32_t *Pm, const uint32_t *E, int n, int neq, bool one_off, int max_shift, int out[5]) {
-  int pos = run_fwd(Q, 0, n);                                                   // :242-244
-  int left = run_fwd(Pm, pos, min(n, max(max_shift, 0)));                       // :245-247 (pos < max_shift)
-  pos += left;
-  { const int r = run_fwd(E, pos, n); left += r; pos += r; }                    // :248-250
-  int left_oo = 0, right_oo = 0;
-  if (one_off) {                                                                // :251-258
-    left_oo = left; pos++;
-    if (pos < n && !bit_at(Q, pos)) left_oo++;
-    if (pos < n) left_oo += run_fwd(E, pos, n);
-  }
-  pos = n - 1;
-  pos -= run_bwd(Q, pos);                                                       // :261-263
-  int right = 0;
-  {                                                                             // :264-266
-    const unsigned long long thr = (unsigned long long)n - (unsigned long long)(long long)max_shift;
-    if (pos >= 0 && (unsigned long long)pos > thr) {
-      const int r = min(run_bwd(Pm, pos), (int)((unsigned long long)pos - thr));
-      right += r; pos -= r;
-    }
-  }
-  { const int r = run_bwd(E, pos); right += r; pos -= r; }                      // :267-269
-  if (one_off) {
-    right_oo = right; pos--;
-    if (pos >= 0 && !bit_at(Q, pos)) right_oo++;
-    if (pos >= 0) right_oo += run_bwd(E, pos);
-  }
-  // get_ham_endsfree: the end-gap run on either side belongs to whichever row starts (ends) with a gap
-  const int i = bit_at(Q, 0) ? run_fwd(Q, 0, n) : run_fwd(Pm, 0, n);
-  const int j = n - 1 - (bit_at(Q, n - 1) ? run_bwd(Q, n - 1) : run_bwd(Pm, n - 1));
-  out[0] = left; out[1] = right; out[2] = left_oo; out[3] = right_oo; out[4] = (j - i + 1) - neq;
-}
 
 __global__ void __launch_bounds__(128) k_bim_align(BimAlignArgs a) {
   extern __shared__ uint32_t smem[];
@@ -144,7 +48,8 @@ __global__ void __launch_bounds__(128) k_bim_align(BimAlignArgs a) {
   uint32_t *ptr = a.ptr_in_smem ? ptr_s : a.ptr_scratch + (size_t)gw * a.ptr_words;
   int errflag = 0;
   unsigned long long cells_lane = 0;
-  for (unsigned long long jb = gw; jb < njobs; jb += tw) {
+  for (unsigned long long jx = gw; jx < njobs; jx += tw) {
+    const unsigned long long jb = a.job_list ? (unsigned long long)a.job_list[jx] : jx;
     const uint32_t q = a.jq[jb], k = a.jk[jb];
     const int len1 = a.sq.len[q], len2 = a.sq.len[k];
     unpack_row(a.sq.seq2 + (size_t)q * a.sq.SW, len1, s1, false);       // s1 = query  (al[0]),  rows i
@@ -346,7 +251,8 @@ struct BimRun {
   int device = 0, num_sms = 148;
   cudaStream_t s = nullptr;
   BimSeqs sq{};
-  BBuf<uint32_t> d_seq2, d_jq, d_jk, d_ptr;
+  BBuf<uint32_t> d_seq2, d_jq, d_jk, d_ptr, d_fwd_moves, d_fb;
+  bool use_fwd = false; int fwd_slots = 0;
   BBuf<uint16_t> d_len;
   BBuf<unsigned long long> d_ctr, d_rec;
   std::vector<uint16_t> len;
@@ -437,6 +343,16 @@ struct BimRun {
     d_ctr.alloc(8);
     BCK(cudaMemsetAsync(d_ctr.p, 0, 8 * 8, s));
     aa.ctr = d_ctr.p;
+    // register-resident kernel (dd_bimfwd.cu; EXPERIMENTAL, off by default: not yet run on hardware)
+    use_fwd = getenv("DADA2B_BIMFWD") != nullptr && P.band >= 0;
+    fwd_slots = ((lbmax + 1) & ~1) + rbmax + 1;
+    if (use_fwd) {
+      const size_t w = bimfwd_scratch_words(fwd_slots, maxlen, num_sms);
+      if (!w) use_fwd = false;
+      else { d_fwd_moves.alloc(w); }
+      const long worst = (long)maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::abs(P.gap) + 16;
+      aa.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
+    }
   }
 
   void launch_align(unsigned long long njobs_upper) {
@@ -445,9 +361,25 @@ struct BimRun {
     align_ev.emplace_back(a, b);
     const int g = (int)std::min<unsigned long long>((unsigned long long)grid, std::max<unsigned long long>(1, (njobs_upper + 3) / 4));
     BCK(cudaEventRecord(a, s));
-    k_bim_align<<<g, 128, smem, s>>>(aa);
+    bool done = false;
+    if (use_fwd) {
+      // pass 1: every job through the register kernel; jobs whose band does not fit are listed in d_fb (count in ctr[4]) ...
+      if (d_fb.n < njobs_upper) d_fb.alloc((size_t)njobs_upper);
+      BCK(cudaMemsetAsync(d_ctr.p + 4, 0, 8, s));
+      BimAlignArgs f = aa;
+      f.ptr_scratch = d_fwd_moves.p; f.fb_list = d_fb.p; f.fb_count = d_ctr.p + 4; f.job_list = nullptr;
+      done = launch_bimfwd(f, fwd_slots, njobs_upper, num_sms, s, nullptr);
+      if (done) {
+        launches++;
+        // ... pass 2: and go through the warp-per-pair traceback kernel
+        BimAlignArgs r = aa;
+        r.job_list = d_fb.p; r.njobs_ptr = d_ctr.p + 4;
+        k_bim_align<<<g, 128, smem, s>>>(r);
+        launches++;
+      }
+    }
+    if (!done) { k_bim_align<<<g, 128, smem, s>>>(aa); launches++; }
     BCK(cudaEventRecord(b, s));
-    launches++;
   }
 
   void finish(dada2b_bimera_stats *st, double t0) {

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="the emul
 
 @pytest.fixture()
 def emu(monkeypatch):
+    monkeypatch.delenv("DADA2B_BIMFWD", raising=False)
     import build_emu
     import dada2_b200.api as api
     lib = build_emu.build()
@@ -65,3 +66,23 @@ def test_emu_bimera_errors_and_corners(emu):
     chim = a[:36] + b[36:]
     assert bimera.C_is_bimera(chim, [a, b]) is True and bimera.C_is_bimera(chim, [b, a]) is True
     assert bimera.C_is_bimera(chim, [a]) is False
+
+
+def test_emu_bimera_register_kernel(emu, monkeypatch):
+    """DADA2B_BIMFWD=1: the register-resident kernel (dd_bimfwd.cu) in every instantiation (<4,10> .. <32,8>), with and
+    without its interior fast path, against the CPU oracle and the goldens; pairs it cannot hold fall back to k_bim_align."""
+    import ctypes
+    h = ctypes.CDLL(emu)
+    h.cuemu_launches.restype = ctypes.c_long
+    h.cuemu_launches.argtypes = [ctypes.c_char_p]
+    monkeypatch.setenv("DADA2B_BIMFWD", "1")
+    n0 = h.cuemu_launches(b"k_bimfwd")
+    B.check_pairs_vs_oracle(B.product_pair_fn, npairs=24)
+    assert h.cuemu_launches(b"k_bimfwd") - n0 == 5
+    monkeypatch.setenv("DADA2B_NO_FAST", "1")
+    B.check_pairs_vs_oracle(B.product_pair_fn, shifts=(16,), npairs=24)
+    monkeypatch.delenv("DADA2B_NO_FAST")
+    B.check_pairs(B.product_pair_fn, shifts=[16], limit=60)            # ragged corpus: everything falls back
+    B.check_table("t40_one_sample", B.product_table_fn)
+    B.check_table("t160_ragged", B.product_table_fn, [1])
+    B.check_is_bimera("t40_one_sample", B.product_denovo_fn)

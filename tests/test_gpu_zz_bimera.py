@@ -19,6 +19,7 @@ SCRIPT = textwrap.dedent('''
     from tests import bimera_cases as B
     from dada2_b200 import bimera
     B.check_pairs(B.product_pair_fn)
+    B.check_pairs_vs_oracle(B.product_pair_fn, npairs=400)
     for name in B.table_names():
         B.check_table(name, B.product_table_fn)
         B.check_is_bimera(name, B.product_denovo_fn)
@@ -37,7 +38,12 @@ SCRIPT = textwrap.dedent('''
 ''') % ROOT
 
 
+@pytest.mark.parametrize("variant", ["traceback", "register"])
 @pytest.mark.xfail(strict=False, reason="new kernels, first run on hardware happens at round end")
-def test_bimera_kernels_match_reference_goldens_and_oracle():
-    out = subprocess.run([sys.executable, "-c", SCRIPT], cwd=ROOT, capture_output=True, text=True, timeout=600)
+def test_bimera_kernels_match_reference_goldens_and_oracle(variant):
+    env = dict(os.environ)
+    env.pop("DADA2B_BIMFWD", None)
+    if variant == "register":                       # dd_bimfwd.cu (register-resident wavefront + per-pair traceback)
+        env["DADA2B_BIMFWD"] = "1"
+    out = subprocess.run([sys.executable, "-c", SCRIPT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "BIMERA OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
