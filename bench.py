@@ -144,6 +144,22 @@ def experimental_ab(seqs, ab, q, err, last, budget_s, device, leg_cmd=None, step
     return res
 
 
+def bimera_leg(budget_s, device, cmd=None):
+    """After the measured region (N=1 only): SURVEY.md 8(f3)'s bimera detection timed through its C-ABI on a synthetic
+    sequence table, next to the reference's C_table_bimera2 on the host cores, in a subprocess under a timeout (the
+    kernels are new: first run on hardware).  Reported under "bimera"; never part of `value`/`e2e`."""
+    e = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)))
+    try:
+        out = subprocess.run(cmd or [sys.executable, os.path.join(ROOT, "tools", "bimera_leg.py")], env=e, capture_output=True, text=True,
+                             timeout=budget_s)
+        rows = [l for l in out.stdout.splitlines() if l.startswith("BIMLEG ")]
+        return json.loads(rows[-1][7:]) if rows else {"failed": (out.stderr or out.stdout)[-300:]}
+    except subprocess.TimeoutExpired:
+        return {"failed": "timeout"}
+    except Exception as ex:
+        return {"failed": repr(ex)[:200]}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation, all host threads, same workload."""
     if rank != 0:
@@ -190,6 +206,8 @@ def main():
                          "or run one independent sample per rank (no collective)")
     ap.add_argument("--ab-seconds", type=int, default=150,
                     help="N=1: total wall budget for the post-measurement A/B of the experimental kernel variants (0 = off)")
+    ap.add_argument("--bimera-seconds", type=int, default=90,
+                    help="N=1: timeout of the post-measurement bimera-detection leg (0 = off)")
     ap.add_argument("--watchdog", type=int, default=1500, help="dump stacks and exit after this many seconds")
     args = ap.parse_args()
     import faulthandler
@@ -359,11 +377,15 @@ def main():
                 except AssertionError as e:
                     parity = "MISMATCH: %s" % e
         ab_res = None
-        if world == 1 and args.ab_seconds > 0 and not any(k.startswith("DADA2B_") and k not in ("DADA2B_VERBOSE", "DADA2B_AB_TAG", "DADA2B_BENCH_NOCLOCKS") for k in os.environ):
+        clean_env = not any(k.startswith("DADA2B_") and k not in ("DADA2B_VERBOSE", "DADA2B_AB_TAG", "DADA2B_BENCH_NOCLOCKS") for k in os.environ)
+        if world == 1 and args.ab_seconds > 0 and clean_env:
             try:
                 ab_res = experimental_ab(seqs, ab, q, err, last, args.ab_seconds, local_rank)
             except Exception as ex:
                 ab_res = {"failed": repr(ex)[:200]}
+        bim_res = None
+        if world == 1 and args.bimera_seconds > 0 and clean_env:
+            bim_res = bimera_leg(args.bimera_seconds, local_rank)
         line = {"metric": "unique-reads/sec through dada()", "value": value, "unit": "uniques/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_val / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 DP + f64 lambda/p-value",
@@ -385,7 +407,7 @@ def main():
                 "kernel_ms": {k: st[k] for k in ("ms_k_classify", "ms_k_align_nw", "ms_k_align_gl", "ms_k_align_final")},
                 "host_ms": {k: st[k] for k in ("ms_setup", "ms_loop", "ms_final", "ms_total")},
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-                "experimental_ab": ab_res}
+                "experimental_ab": ab_res, "bimera": bim_res}
         print(json.dumps(line))
     res.close()
     if world > 1:
