@@ -687,6 +687,52 @@ BimPair bimera_pair(const std::string &sq, const std::string &par, bool allow_on
   return r;
 }
 
+// =====================================================================================
+// mergePairs' native steps: restatement of /root/reference/src/evaluate.cpp:18-174.
+// =====================================================================================
+// C_eval_pair, evaluate.cpp:73-120: matches / mismatches / indels between the end-gap runs.
+void eval_pair(const std::string &s1, const std::string &s2, int &match, int &mismatch, int &indel) {
+  bool s1gap = true, s2gap = true;
+  int start = -1, end;
+  do {                                                                     // :85-91
+    start++;
+    s1gap = s1gap && (s1.c_str()[start] == '-');
+    s2gap = s2gap && (s2.c_str()[start] == '-');
+  } while ((s1gap || s2gap) && (size_t)start < s1.size());
+  s1gap = s2gap = true;
+  end = (int)s1.size();
+  do {                                                                     // :94-101
+    end--;
+    if (end < 0) break;                                                    // the original would read s1[-1] (empty input only)
+    s1gap = s1gap && (s1[end] == '-');
+    s2gap = s2gap && (s2[end] == '-');
+  } while ((s1gap || s2gap) && end >= start);
+  match = mismatch = indel = 0;
+  for (int i = start; i <= end; i++) {                                     // :104-113
+    if (s1[i] == '-' || s2[i] == '-') indel++;
+    else if (s1[i] == s2[i]) match++;
+    else mismatch++;
+  }
+}
+
+// C_pair_consensus, evaluate.cpp:131-174
+std::string pair_consensus(const std::string &s1, const std::string &s2, int prefer, bool trim_overhang) {
+  std::string o(s1.size(), '-');
+  for (size_t i = 0; i < s1.size(); i++) {
+    if (s1[i] == s2[i]) o[i] = s1[i];
+    else if (s2[i] == '-') o[i] = s1[i];
+    else if (s1[i] == '-') o[i] = s2[i];
+    else o[i] = prefer == 1 ? s1[i] : (prefer == 2 ? s2[i] : 'N');
+  }
+  if (trim_overhang) {                                                     // :152-160
+    for (size_t i = 0; i < s1.size(); i++) { if (s1[i] != '-') break; o[i] = '-'; }
+    for (int i = (int)s1.size() - 1; i >= 0; i--) { if (s2[i] != '-') break; o[i] = '-'; }
+  }
+  std::string r;
+  for (char c : o) if (c != '-') r.push_back(c);                           // :162-168
+  return r;
+}
+
 }  // namespace
 
 extern "C" {
@@ -818,6 +864,20 @@ int port_bimera_pair(const char *sq, const char *par, int allow_one_off, int mat
   if (al0) strcpy(al0, a0.c_str());
   if (al1) strcpy(al1, a1.c_str());
   return 0;
+}
+
+// C_nwalign (endsfree) + C_eval_pair + C_pair_consensus for one pair, as chained by R/paired.R:153-164.
+int port_merge_pair(const char *s1, const char *s2, int match, int mismatch, int gap_p, int homo_gap_p, int band, int prefer,
+                    int trim_overhang, int *counts3, char *cons, char *al0, char *al1) {
+  try {
+    std::string a0, a1;
+    nw_endsfree(s1, s2, match, mismatch, gap_p, homo_gap_p, gap_p != homo_gap_p, band, a0, a1);      // evaluate.cpp:40-46
+    eval_pair(a0, a1, counts3[0], counts3[1], counts3[2]);
+    strcpy(cons, pair_consensus(a0, a1, prefer, trim_overhang != 0).c_str());
+    if (al0) strcpy(al0, a0.c_str());
+    if (al1) strcpy(al1, a1.c_str());
+    return 0;
+  } catch (std::exception &e) { return -1; }
 }
 
 double port_calc_pA(int reads, double E_reads, int prior) { return calc_pA(reads, E_reads, prior != 0); }

@@ -106,3 +106,20 @@ def bimera_pair(sq, par, **opts):
                            C.c_int(o["gap_p"]), C.c_int(o["max_shift"]), out.ctypes.data_as(C.c_void_p), a0, a1)
     return dict(left=int(out[0]), right=int(out[1]), left_oo=int(out[2]), right_oo=int(out[3]), ham=int(out[4]),
                 al0=a0.value.decode(), al1=a1.value.decode())
+
+
+MERGE_DEFAULTS = dict(match=1, mismatch=-64, gap_p=-64, homo_gap_p=None, band=-1, prefer=1, trim_overhang=False)
+
+
+def merge_pair(s1, s2, **opts):
+    """Restatement of C_nwalign(endsfree) -> C_eval_pair -> C_pair_consensus (evaluate.cpp:18-174)."""
+    o = dict(MERGE_DEFAULTS); o.update(opts)
+    hg = o["gap_p"] if o["homo_gap_p"] is None else o["homo_gap_p"]
+    n = len(s1) + len(s2) + 2
+    cnt = np.zeros(3, np.int32)
+    cons, a0, a1 = C.create_string_buffer(n), C.create_string_buffer(n), C.create_string_buffer(n)
+    rc = lib().port_merge_pair(s1.encode(), s2.encode(), C.c_int(o["match"]), C.c_int(o["mismatch"]), C.c_int(o["gap_p"]), C.c_int(hg),
+                               C.c_int(o["band"]), C.c_int(o["prefer"]), C.c_int(o["trim_overhang"]), cnt.ctypes.data_as(C.c_void_p), cons, a0, a1)
+    if rc:
+        raise RuntimeError("port_merge_pair failed")
+    return dict(nmatch=int(cnt[0]), nmismatch=int(cnt[1]), nindel=int(cnt[2]), sequence=cons.value.decode(), al0=a0.value.decode(), al1=a1.value.decode())

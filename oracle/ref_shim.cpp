@@ -20,6 +20,9 @@ Rcpp::DataFrame C_table_bimera2(Rcpp::IntegerMatrix mat, std::vector<std::string
                                 bool allow_one_off, int min_one_off_par_dist, int match, int mismatch, int gap_p, int max_shift);
 bool C_is_bimera(std::string sq, std::vector<std::string> pars, bool allow_one_off, int min_one_off_par_dist, int match,
                  int mismatch, int gap_p, int max_shift);
+Rcpp::CharacterVector C_nwalign(std::string s1, std::string s2, int match, int mismatch, int gap_p, int homo_gap_p, int band, bool endsfree);
+Rcpp::IntegerVector C_eval_pair(std::string s1, std::string s2);
+Rcpp::CharacterVector C_pair_consensus(std::string s1, std::string s2, int prefer, bool trim_overhang);
 int get_ham_endsfree(const char *seq1, const char *seq2);
 void get_lr(char **al, int &left, int &right, int &left_oo, int &right_oo, bool allow_one_off, int max_shift);
 
@@ -258,6 +261,23 @@ int ref_bimera_pair(const char *sq, const char *par, int allow_one_off, int matc
     if (al0) strcpy(al0, al[0]);
     if (al1) strcpy(al1, al[1]);
     free(al[0]); free(al[1]); free(al);
+  } catch (std::exception &e) { return -1; }
+  return 0;
+}
+
+// ---------------- mergePairs' native steps (src/evaluate.cpp) ----------------
+// R/paired.R:153-164 for one pair: C_nwalign(s1, s2, ...) -> C_eval_pair(al0, al1) -> C_pair_consensus(al0, al1, prefer, trim).
+// counts3 = match, mismatch, indel; cons / al0 / al1 need capacity len1 + len2 + 1.
+int ref_merge_pair(const char *s1, const char *s2, int match, int mismatch, int gap_p, int homo_gap_p, int band, int endsfree,
+                   int prefer, int trim_overhang, int *counts3, char *cons, char *al0, char *al1) {
+  try {
+    Rcpp::CharacterVector al = C_nwalign(s1, s2, match, mismatch, gap_p, homo_gap_p, band, endsfree != 0);
+    Rcpp::IntegerVector ev = C_eval_pair(al[0], al[1]);
+    counts3[0] = ev[0]; counts3[1] = ev[1]; counts3[2] = ev[2];
+    Rcpp::CharacterVector c = C_pair_consensus(al[0], al[1], prefer, trim_overhang != 0);
+    strcpy(cons, c[0].c_str());
+    if (al0) strcpy(al0, al[0].c_str());
+    if (al1) strcpy(al1, al[1].c_str());
   } catch (std::exception &e) { return -1; }
   return 0;
 }

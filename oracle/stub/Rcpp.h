@@ -48,10 +48,14 @@ inline void stop(const char *fmt, ...) {
 }
 inline void checkUserInterrupt() {}
 
+struct Nil {};                      // R_NilValue (evaluate.cpp returns it from vector-valued functions on bad input)
+#define R_NilValue (Rcpp::Nil())
+
 template <typename T> class Vec {
  public:
   std::shared_ptr<std::vector<T>> d;
   Vec() : d(std::make_shared<std::vector<T>>()) {}
+  Vec(Nil) : d(std::make_shared<std::vector<T>>()) {}
   explicit Vec(size_t n) : d(std::make_shared<std::vector<T>>(n, T())) {}
   Vec(size_t n, const T &v) : d(std::make_shared<std::vector<T>>(n, v)) {}
   size_t size() const { return d->size(); }
@@ -60,12 +64,21 @@ template <typename T> class Vec {
   T &operator()(size_t i) { return (*d)[i]; }
   void push_back(const T &v) { d->push_back(v); }
 };
-class IntegerVector : public Vec<int> { public: using Vec<int>::Vec; };
+struct Any;
+class IntegerVector : public Vec<int> {
+ public: using Vec<int>::Vec;
+  template <typename... A> static IntegerVector create(const A &...a);       // IntegerVector::create(_["match"]=m, ...) (evaluate.cpp:118)
+};
+class LogicalVector : public Vec<int> { public: using Vec<int>::Vec; };
 class NumericVector : public Vec<double> {
  public: using Vec<double>::Vec;
   static double get_na() { return NA_REAL; }
 };
-class CharacterVector : public Vec<std::string> { public: using Vec<std::string>::Vec; };
+class CharacterVector : public Vec<std::string> {
+ public: using Vec<std::string>::Vec;
+  CharacterVector() : Vec<std::string>() {}
+  CharacterVector(const std::string &one) : Vec<std::string>() { d->push_back(one); }     // `return(ostr);` (evaluate.cpp:173)
+};
 
 template <typename T> class Mat {  // column-major like R
  public:
@@ -110,6 +123,7 @@ class DataFrame : public List {
 
 struct NamedPlaceholder {
   std::string name;
+  Any operator=(int v) const { Any a; a.name = name; a.iv = std::make_shared<std::vector<int>>(1, v); return a; }
   Any operator=(const IntegerVector &v) const { Any a; a.name = name; a.iv = v.d; return a; }
   Any operator=(const NumericVector &v) const { Any a; a.name = name; a.nv = v.d; return a; }
   Any operator=(const CharacterVector &v) const { Any a; a.name = name; a.sv = v.d; return a; }
@@ -124,6 +138,10 @@ struct Placeholder {
   NamedPlaceholder operator[](const char *nm) const { NamedPlaceholder p; p.name = nm; return p; }
 };
 static const Placeholder _ = Placeholder();
+
+template <typename... A> IntegerVector IntegerVector::create(const A &...a) {
+  IntegerVector v; int dummy[] = {0, (v.push_back((*a.iv)[0]), 0)...}; (void)dummy; return v;
+}
 
 inline NumericVector ppois(const IntegerVector &x, double lambda, bool lower = true, bool log_p = false) {
   NumericVector r(x.size());

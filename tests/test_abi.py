@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol():
         names |= set(re.findall(r"\b(dada2b_[a-z_A-Z0-9]+)\s*\(", src))
     assert {"dada2b_run", "dada2b_free", "dada2b_upload", "dada2b_run_resident", "dada2b_ctx_free",
             "dada2b_default_opts", "dada2b_test_pairs", "dada2b_test_calc_pA", "dada2b_table_bimera", "dada2b_is_bimera",
-            "dada2b_bimera_default_opts", "dada2b_test_bimera_pairs"} <= names
+            "dada2b_bimera_default_opts", "dada2b_test_bimera_pairs", "dada2b_merge_pairs", "dada2b_merge_free",
+            "dada2b_merge_default_opts"} <= names
     for n in sorted(names):
         assert hasattr(L, n), "libdada2b.so does not export %s" % n
 
@@ -81,6 +82,30 @@ def test_bimera_struct_layouts_and_defaults():
             o.shard_rank, o.shard_world) == (1.5, 2, 0, 4, 5, -4, -8, 16, 0, 1)
 
 
+def test_merge_struct_layouts_and_defaults():
+    from dada2_b200 import merge
+    prog = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "dada2b_merge.h"
+    int main() {
+      printf("%zu %zu %zu %zu %zu\n", sizeof(dada2b_merge_opts), sizeof(dada2b_merge_out), offsetof(dada2b_merge_out, cons_off),
+             offsetof(dada2b_merge_out, n_cells), offsetof(dada2b_merge_out, ms_total));
+      return 0;
+    }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert got == [ctypes.sizeof(merge.MergeOpts), ctypes.sizeof(merge.MergeOut), merge.MergeOut.cons_off.offset,
+                   merge.MergeOut.n_cells.offset, merge.MergeOut.ms_total.offset]
+    o = merge.MergeOpts()
+    merge._lib().dada2b_merge_default_opts(ctypes.byref(o))      # R/paired.R:153-155, nwalign(band=-1)
+    assert (o.match, o.mismatch, o.gap_p, o.homo_gap_p, o.band, o.trim_overhang) == (1, -64, -64, -64, -1, 0)
+
+
 def test_default_opts_are_the_reference_defaults():
     from dada2_b200 import _abi
     L = _lib()
@@ -102,6 +127,8 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback():
         dada2_b200.bimera.C_table_bimera2(np.ones((1, 2), np.int32), ["ACGTACGTAC", "ACGTACGTAA"])
     with pytest.raises(dada2_b200.Dada2bError, match="no CUDA device"):
         dada2_b200.bimera.C_is_bimera("ACGTACGTAC", ["ACGTACGTAA", "ACGTACGTTT"])
+    with pytest.raises(dada2_b200.Dada2bError, match="no CUDA device"):
+        dada2_b200.merge.merge_align(["ACGTACGTAC", "ACGTACGTAA"], [0], [1], [1])
 
 
 def test_product_sources_do_not_touch_the_oracle():
