@@ -4,3 +4,4 @@ from . import api  # noqa: F401
 from .api import Dada2bError, PackedCall, Resident, dada_uniques  # noqa: F401
 from . import bimera  # noqa: F401,E402
 from . import merge  # noqa: F401,E402
+from . import derep  # noqa: F401,E402

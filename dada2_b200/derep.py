@@ -1,0 +1,100 @@
+"""Host-side mirror of the reference's dereplication for the B200 path.
+
+`derep_reads` is what derepFastq() computes once ShortRead has parsed the fastq (qtables2 + the chunk loop,
+/root/reference/R/sequenceIO.R:45-124, :150-183); `derepFastq` adds a plain fastq(.gz) reader for the tests.  All
+computation happens in libdada2b.so behind include/dada2b_derep.h; this module only marshals.  No CPU fallback.
+The result feeds dada2_b200.dada_uniques(uniques, abundances, None, err, quals) unchanged.
+"""
+import ctypes as C
+import gzip
+
+import numpy as np
+
+from . import api
+
+ERRLEN = 256
+
+
+class DerepIn(C.Structure):
+    _fields_ = [("nreads", C.c_int32), ("seq_concat", C.c_char_p), ("seq_off", C.c_void_p), ("qual_concat", C.c_void_p), ("chunk_n", C.c_int64)]
+
+
+class DerepOut(C.Structure):
+    _fields_ = [("nuniq", C.c_int32), ("maxlen", C.c_int32), ("nreads", C.c_int32), ("seq_concat", C.POINTER(C.c_char)),
+                ("seq_off", C.POINTER(C.c_int64)), ("abund", C.POINTER(C.c_int32)), ("quals", C.POINTER(C.c_double)), ("map", C.POINTER(C.c_int32)),
+                ("gpu_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("ms_device", C.c_double), ("ms_sort", C.c_double), ("ms_total", C.c_double)]
+
+
+_BOUND = False
+
+
+def _lib():
+    global _BOUND
+    L = api.lib()
+    if not _BOUND:
+        P = C.POINTER
+        L.dada2b_derep.argtypes = [P(DerepIn), C.c_int32, P(P(DerepOut)), C.c_char_p]
+        L.dada2b_derep_free.argtypes = [P(DerepOut)]
+        _BOUND = True
+    return L
+
+
+def derep_reads(seqs, quals, n=1000000, device=0, return_stats=False):
+    """seqs: list[str] (A/C/G/T); quals: list of integer arrays or one uint8 array of all bases concatenated (numeric
+    quality, Phred offset removed).  -> dict(uniques list[str], abundances int32[nuniq], quals float64[nuniq, maxlen]
+    NaN/NA-padded, map int32[nreads] 1-based with NA = INT32_MIN) in derepFastq's order."""
+    L = _lib()
+    nreads = len(seqs)
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=nreads)
+    off = np.zeros(nreads + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    buf = "".join(seqs).encode()
+    if isinstance(quals, np.ndarray) and quals.ndim == 1:
+        q = np.ascontiguousarray(quals, dtype=np.uint8)
+    else:
+        q = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint8).ravel()[:l] for x, l in zip(quals, lens)]) if nreads else np.zeros(0, np.uint8))
+    if len(q) != off[-1]:
+        raise api.Dada2bError("dada2b: qualities and sequences have different lengths.")
+    inp = DerepIn(nreads, buf, off.ctypes.data, q.ctypes.data, int(n))
+    out = C.POINTER(DerepOut)()
+    eb = C.create_string_buffer(ERRLEN)
+    rc = L.dada2b_derep(C.byref(inp), int(device), C.byref(out), eb)
+    if rc:
+        raise api.Dada2bError(eb.value.decode())
+    try:
+        r = out.contents
+        nu, ml = r.nuniq, r.maxlen
+        so = np.ctypeslib.as_array(r.seq_off, shape=(nu + 1,)).copy()
+        raw = C.string_at(r.seq_concat, int(so[-1])).decode()
+        res = {"uniques": [raw[so[i]:so[i + 1]] for i in range(nu)],
+               "abundances": np.ctypeslib.as_array(r.abund, shape=(nu,)).copy(),
+               "quals": np.ctypeslib.as_array(r.quals, shape=(nu, ml)).copy(),          # maxlen x nuniq column-major == [nuniq, maxlen] row-major
+               "map": np.ctypeslib.as_array(r.map, shape=(max(r.nreads, 1),))[:r.nreads].copy()}
+        if return_stats:
+            res["stats"] = {k: getattr(r, k) for k in ("gpu_launches", "h2d_bytes", "d2h_bytes", "ms_device", "ms_sort", "ms_total")}
+        return res
+    finally:
+        L.dada2b_derep_free(out)
+
+
+def read_fastq(path, phred=33):
+    """Plain four-line fastq(.gz) reader (host side; the reference uses ShortRead's FastqStreamer here)."""
+    op = gzip.open if str(path).endswith(".gz") else open
+    seqs, quals = [], []
+    with op(path, "rt") as f:
+        while True:
+            if not f.readline():
+                break
+            s = f.readline().strip()
+            f.readline()
+            q = f.readline().strip()
+            seqs.append(s)
+            quals.append(np.frombuffer(q.encode(), dtype=np.uint8) - phred)
+    return seqs, quals
+
+
+def derepFastq(path, n=1000000, device=0):
+    """derepFastq(fl, n) (R/sequenceIO.R:45) for one file: host fastq parsing + dada2b_derep."""
+    seqs, quals = read_fastq(path)
+    return derep_reads(seqs, quals, n=n, device=device)

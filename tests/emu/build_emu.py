@@ -51,7 +51,7 @@ def needs_build(lib=LIB):
         return True
     t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "build_emu.py")]
-    deps += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
+    deps += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))] + [os.path.join(ROOT, "dada2_b200", "build.py")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

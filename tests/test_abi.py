@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert {"dada2b_run", "dada2b_free", "dada2b_upload", "dada2b_run_resident", "dada2b_ctx_free",
             "dada2b_default_opts", "dada2b_test_pairs", "dada2b_test_calc_pA", "dada2b_table_bimera", "dada2b_is_bimera",
             "dada2b_bimera_default_opts", "dada2b_test_bimera_pairs", "dada2b_merge_pairs", "dada2b_merge_free",
-            "dada2b_merge_default_opts"} <= names
+            "dada2b_merge_default_opts", "dada2b_derep", "dada2b_derep_free"} <= names
     for n in sorted(names):
         assert hasattr(L, n), "libdada2b.so does not export %s" % n
 
@@ -106,6 +106,27 @@ def test_merge_struct_layouts_and_defaults():
     assert (o.match, o.mismatch, o.gap_p, o.homo_gap_p, o.band, o.trim_overhang) == (1, -64, -64, -64, -1, 0)
 
 
+def test_derep_struct_layouts():
+    from dada2_b200 import derep
+    prog = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "dada2b_derep.h"
+    int main() {
+      printf("%zu %zu %zu %zu %zu\n", sizeof(dada2b_derep_in), sizeof(dada2b_derep_out), offsetof(dada2b_derep_in, chunk_n),
+             offsetof(dada2b_derep_out, map), offsetof(dada2b_derep_out, ms_total));
+      return 0;
+    }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert got == [ctypes.sizeof(derep.DerepIn), ctypes.sizeof(derep.DerepOut), derep.DerepIn.chunk_n.offset, derep.DerepOut.map.offset,
+                   derep.DerepOut.ms_total.offset]
+
+
 def test_default_opts_are_the_reference_defaults():
     from dada2_b200 import _abi
     L = _lib()
@@ -129,6 +150,8 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback():
         dada2_b200.bimera.C_is_bimera("ACGTACGTAC", ["ACGTACGTAA", "ACGTACGTTT"])
     with pytest.raises(dada2_b200.Dada2bError, match="no CUDA device"):
         dada2_b200.merge.merge_align(["ACGTACGTAC", "ACGTACGTAA"], [0], [1], [1])
+    with pytest.raises(dada2_b200.Dada2bError, match="no CUDA device"):
+        dada2_b200.derep.derep_reads(["ACGTACGTAC"], [np.full(10, 30, np.uint8)])
 
 
 def test_product_sources_do_not_touch_the_oracle():

@@ -55,3 +55,33 @@ def test_kernels_are_memory_clean_under_asan(flags):
     out = subprocess.run([sys.executable, "-c", SCRIPT % (ROOT, lib, names)], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert "AddressSanitizer" not in out.stderr, out.stderr[-4000:]
     assert out.returncode == 0 and "ASAN RUN OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+SCRIPT_F = """
+import sys
+sys.path.insert(0, %r)
+import dada2_b200.api as api
+api._LIBPATH = %r; api._LIB = None
+from tests import bimera_cases as B, merge_cases as M, derep_cases as D
+B.check_pairs(B.product_pair_fn, shifts=[16, -1], limit=40)
+B.check_pairs_vs_oracle(B.product_pair_fn, shifts=(16, 50), npairs=12)
+B.check_table("t40_one_sample", B.product_table_fn, [0, 1])
+B.check_is_bimera("t40_one_sample", B.product_denovo_fn)
+M.check(M.product_fn, opt_ids=[0, 2, 3, 4], limit=25, maxlen=160)
+D.check_all(D.product_fn, sizes=(1200,))
+print('ASAN RUN OK')
+"""
+
+
+@pytest.mark.parametrize("flags", [{}, {"DADA2B_BIMFWD": "1"}], ids=["default", "bimfwd"])
+def test_bimera_and_merge_kernels_are_memory_clean_under_asan(flags):
+    """dd_bimera.cu / dd_bimfwd.cu / dd_merge.cu / dd_derep.cu under the same memcheck stand-in."""
+    asan = _preload()
+    if asan is None:
+        pytest.skip("libasan not found")
+    import build_emu
+    lib = build_emu.build(asan=True)
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", **flags)
+    out = subprocess.run([sys.executable, "-c", SCRIPT_F % (ROOT, lib)], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert "AddressSanitizer" not in out.stderr, out.stderr[-4000:]
+    assert out.returncode == 0 and "ASAN RUN OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
