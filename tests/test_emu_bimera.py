@@ -31,7 +31,7 @@ def test_emu_bimera_pairs(emu):
     B.check_pairs(B.product_pair_fn, limit=None if os.environ.get("DADA2B_EMU_FULL") else 120)
 
 
-@pytest.mark.parametrize("name,opt_ids", [("t40_one_sample", None), ("t120", [1])] if not os.environ.get("DADA2B_EMU_FULL")
+@pytest.mark.parametrize("name,opt_ids", [("t40_one_sample", None)] if not os.environ.get("DADA2B_EMU_FULL")
                          else [(n, None) for n in B.table_names()])
 def test_emu_bimera_table(emu, name, opt_ids):
     B.check_table(name, B.product_table_fn, opt_ids)
@@ -84,5 +84,5 @@ def test_emu_bimera_register_kernel(emu, monkeypatch):
     monkeypatch.delenv("DADA2B_NO_FAST")
     B.check_pairs(B.product_pair_fn, shifts=[16], limit=60)            # ragged corpus: everything falls back
     B.check_table("t40_one_sample", B.product_table_fn)
-    B.check_table("t160_ragged", B.product_table_fn, [1])
+    B.check_table("t150_short", B.product_table_fn, [1])
     B.check_is_bimera("t40_one_sample", B.product_denovo_fn)

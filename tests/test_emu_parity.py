@@ -213,7 +213,7 @@ def test_emu_all_experimental_paths_together(emu, monkeypatch):
 
 @pytest.mark.parametrize("experimental", [False, True], ids=["default", "experimental"])
 def test_emu_edge_cases(emu, monkeypatch, experimental):
-    """tests/cases.py:edge_cases() on the emulated library (the GPU suite runs the same table in test_gpu_zz_edge.py),
+    """tests/cases.py:edge_cases() on the emulated library (the GPU suite runs the same table in test_gpu_zzz_edge.py),
     with the default kernels and with every experimental path switched on."""
     import dada2_b200
     if experimental:
