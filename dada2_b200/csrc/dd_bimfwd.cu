@@ -107,13 +107,52 @@ __global__ void __launch_bounds__(128) k_bimfwd(BimAlignArgs a) {
     for (int t = 0; t < ND; t++) PEN[t] = (t >= tlo && t <= thi) ? 0 : -BIGPEN;
 
     for (int kk = 0; kk <= maxsteps; kk += 2) {
-      const bool fast = kk >= kf_lo && kk + 1 <= kf_hi;
+      if (kk >= kf_lo && kk + 1 <= kf_hi) {
+        // ---- interior: branch-free, ~11 instructions per cell (3 adds, VIMNMX3, 2 compares + 2 selects for the move, shift/or, penalty)
+#pragma unroll
+        for (int PAR = 0; PAR < 2; PAR++) {
+          int Hn;
+          if (PAR == 0) { Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G); if (gl == 0) Hn = -BIGPEN; }
+          else { Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G); if (gl == G - 1) Hn = -BIGPEN; }
+          const uint32_t X = A ^ B;
+          const uint32_t EQ = ~(X | (X >> 1));                                  // bit 2cc set <=> bases of slot cc are equal
+          int Hnew[NSL];
+          uint32_t mv = 0;
+#pragma unroll
+          for (int cc = 0; cc < NSL; cc++) {
+            const int t = 2 * cc + PAR;
+            const int hl = (PAR == 0 && cc == 0) ? Hn : H[t - 1 < 0 ? 0 : t - 1];
+            const int hu = (PAR == 1 && cc == NSL - 1) ? Hn : H[t + 1 >= ND ? ND - 1 : t + 1];
+            const int left = hl + gap, up = hu + gap, diag = H[t] + (((EQ >> (2 * cc)) & 1u) ? match : mismatch);
+            const int m = __vimax3_s32(left, up, diag);
+            const uint32_t pm = (up == m) ? 3u : ((left == m) ? 2u : 1u);       // precedence up > left > diag (nwalign_endsfree.cpp:147-156)
+            mv |= pm << (2 * cc);
+            Hnew[cc] = m + PEN[t];
+          }
+#pragma unroll
+          for (int cc = 0; cc < NSL; cc++) H[2 * cc + PAR] = Hnew[cc];
+          moves[(size_t)(kk + PAR) * G + gl] = mv;                             // every pair of the warp is inside its interior here
+          if (PAR == 0) {
+            uint32_t nbB = __shfl_down_sync(0xffffffffu, B, 1, G);
+            uint32_t newb = nbB & 3u;
+            if (gl == G - 1) { const int jn = J + NSL - 1; newb = (jn >= 0 && jn < len2) ? s_p[jn] : 0u; }
+            B = (B >> 2) | (newb << (2 * (NSL - 1)));
+          } else {
+            uint32_t nbA = __shfl_up_sync(0xffffffffu, A, 1, G);
+            uint32_t newa = (nbA >> (2 * (NSL - 1))) & 3u;
+            if (gl == 0) newa = (I >= 0 && I < len1) ? s_q[I] : 0u;
+            A = ((A << 2) | newa) & (NSL == 16 ? 0xffffffffu : ((1u << (2 * NSL)) - 1u));
+            I += 1; J += 1;
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int PAR = 0; PAR < 2; PAR++) {
         const int k = kk + PAR;
         int Hn;
-        if (PAR == 0) { Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G); if (gl == 0) Hn = fast ? -BIGPEN : SENT; }
-        else { Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G); if (gl == G - 1) Hn = fast ? -BIGPEN : SENT; }
+        if (PAR == 0) { Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G); if (gl == 0) Hn = SENT; }
+        else { Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G); if (gl == G - 1) Hn = SENT; }
         const uint32_t X = A ^ B;
         const int Jp = J + PAR;
         int Hnew[NSL];
@@ -125,24 +164,16 @@ __global__ void __launch_bounds__(128) k_bimfwd(BimAlignArgs a) {
           const int hu = (PAR == 1 && cc == NSL - 1) ? Hn : H[t + 1 >= ND ? ND - 1 : t + 1];
           const bool eq = ((X >> (2 * cc)) & 3u) == 0u;
           const int diag = H[t] + (eq ? match : mismatch);
-          if (fast) {
-            const int left = hl + gap, up = hu + gap;
-            const int m = __vimax3_s32(left, up, diag);
-            const uint32_t pm = (up == m) ? 3u : ((left == m) ? 2u : 1u);       // precedence up > left > diag
-            mv |= pm << (2 * cc);
-            Hnew[cc] = m + PEN[t];
-          } else {
-            const int i = I - cc, j = Jp + cc;
-            const bool valid = (t >= tlo) && (t <= thi) && i >= 0 && j >= 0 && i <= len1 && j <= len2 && k <= nsteps;
-            const int left = hl + ((i == len1) ? 0 : gap);                      // free end gaps, nwalign_endsfree.cpp:130-141
-            const int up = hu + ((j == len2) ? 0 : gap);
-            const int m = max(max(left, up), diag);
-            const uint32_t pm = (up == m) ? 3u : ((left == m) ? 2u : 1u);
-            int val = m;
-            if (i == 0 || j == 0) val = 0;                                      // first row / column: ends-free (:91-101)
-            mv |= pm << (2 * cc);
-            Hnew[cc] = valid ? val : H[t];
-          }
+          const int i = I - cc, j = Jp + cc;
+          const bool valid = (t >= tlo) && (t <= thi) && i >= 0 && j >= 0 && i <= len1 && j <= len2 && k <= nsteps;
+          const int left = hl + ((i == len1) ? 0 : gap);                        // free end gaps, nwalign_endsfree.cpp:130-141
+          const int up = hu + ((j == len2) ? 0 : gap);
+          const int m = max(max(left, up), diag);
+          const uint32_t pm = (up == m) ? 3u : ((left == m) ? 2u : 1u);
+          int val = m;
+          if (i == 0 || j == 0) val = 0;                                        // first row / column: ends-free (:91-101)
+          mv |= pm << (2 * cc);
+          Hnew[cc] = valid ? val : H[t];
         }
 #pragma unroll
         for (int cc = 0; cc < NSL; cc++) H[2 * cc + PAR] = Hnew[cc];
