@@ -308,7 +308,9 @@ struct Run {
   static constexpr unsigned MOVES_EAGER = 8192;   // moves copied back with the report; more => one extra copy
   int NP = 3;                            // shuffle passes launched speculatively per round
   unsigned move_cap = 0;
-  DBuf<uint32_t> fb_list, surv_list;
+  DBuf<uint32_t> fb_list, surv_list, uneq_list;
+  DBuf<unsigned long long> uneq_ctr;
+  bool bound16 = false;                  // two raws per lane group in the bound pass (experimental, DADA2B_BOUND16=1; dd_nwbound.cu)
   DBuf<double> raw_S, raw_rho;           // two-phase loop NW (experimental, DADA2B_TWOPHASE=1): per-raw bound factors
   bool two_phase = false;
   // pivot pre-filter of the k-mer screen (experimental, DADA2B_PIVOT=1; dd_classify2.cu)
@@ -538,6 +540,8 @@ void Run::alloc_state() {
   move_cap = (unsigned)(4 * n + 1024); fb_list.alloc(n);
   two_phase = getenv("DADA2B_TWOPHASE") != nullptr;      // off by default: not yet validated on hardware
   if (two_phase) { surv_list.alloc(n); raw_S.alloc(n); raw_rho.alloc(n); }
+  bound16 = two_phase && getenv("DADA2B_BOUND16") != nullptr;
+  if (bound16) { uneq_list.alloc(n + 2); uneq_ctr.alloc(1); }
   pivot = getenv("DADA2B_PIVOT") != nullptr;             // off by default: not yet validated on hardware
   if (pivot) { pv_cluster.alloc(n); pv_ms.alloc(n); CK(cudaMemsetAsync(pv_cluster.p, 0xFF, n * 4, s)); pv_ms.zero(s); }
   if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
@@ -656,7 +660,13 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       FwdArgs fbnd = f;
       fbnd.raw_S = raw_S.p; fbnd.raw_rho = raw_rho.p; fbnd.surv_list = surv_list.p; fbnd.surv_count = st.ctr + CTR_SURV;
       CK(cudaMemsetAsync(ctr.p + CTR_SURV, 0, 8, s));
-      timed(T_NW, [&]() { fwd_done = launch_nwfwd_sel(fbnd, fwd_slots, (unsigned long long)nraw, est_active, cx->num_sms, s, true); });
+      bool done16 = false;
+      if (bound16) {              // two raws per lane group on the 16-bit SIMD datapath; unequal-length neighbours come back in uneq_list
+        CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
+        timed(T_NW, [&]() { done16 = launch_nwbound16(fbnd, uneq_list.p, uneq_ctr.p, fwd_slots, (unsigned long long)nraw, est_active, cx->num_sms, s); });
+        if (done16) { fbnd.jobs = uneq_list.p; fbnd.njobs_ptr = uneq_ctr.p; }
+      }
+      timed(T_NW, [&]() { fwd_done = launch_nwfwd_sel(fbnd, fwd_slots, (unsigned long long)nraw, done16 ? 0 : est_active, cx->num_sms, s, true); });
       // pass 2: the exact forward-carry kernel on the survivors
       if (fwd_done) { f.jobs = surv_list.p; f.njobs_ptr = st.ctr + CTR_SURV; }
     }

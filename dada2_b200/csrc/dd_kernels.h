@@ -88,6 +88,9 @@ inline bool launch_nwfwd_sel(const FwdArgs &a, int slots_needed, unsigned long l
   return getenv("DADA2B_NWFWD_V2") ? launch_nwfwd2(a, slots_needed, njobs_upper, njobs_hint, num_sms, s, bound_only)
                                    : launch_nwfwd(a, slots_needed, njobs_upper, njobs_hint, num_sms, s, bound_only);
 }
+// dd_nwbound.cu: the bound pass on the 16-bit SIMD datapath, two raws per lane group (EXPERIMENTAL, DADA2B_BOUND16=1 with DADA2B_TWOPHASE=1)
+bool launch_nwbound16(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, int slots_needed, unsigned long long njobs_upper,
+                      unsigned long long njobs_hint, int num_sms, cudaStream_t s);
 void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, cudaStream_t s);
 void count_launch(int n);
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);

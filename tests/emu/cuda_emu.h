@@ -151,6 +151,19 @@ inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; i++
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) { return (unsigned)((((uint64_t)hi << 32) | lo) >> (shift & 31)); }
 inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) { return (unsigned)(((((uint64_t)hi << 32) | lo) << (shift & 31)) >> 32); }
 inline int __vimax3_s32(int a, int b, int c) { return std::max(std::max(a, b), c); }
+// 16-bit SIMD (two signed halves per word): VIADD.16x2 / VIMNMX.S16x2 with per-half predicate outputs / PRMT
+inline unsigned __vadd2(unsigned a, unsigned b) { return ((a + b) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16); }
+inline unsigned __vibmax_s16x2(unsigned a, unsigned b, bool *pred_hi, bool *pred_lo) {
+  const short al = (short)(a & 0xFFFFu), ah = (short)(a >> 16), bl = (short)(b & 0xFFFFu), bh = (short)(b >> 16);
+  *pred_lo = al >= bl; *pred_hi = ah >= bh;
+  return ((unsigned)(unsigned short)(al >= bl ? al : bl)) | ((unsigned)(unsigned short)(ah >= bh ? ah : bh) << 16);
+}
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+  const uint64_t v = ((uint64_t)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) { const unsigned n = (sel >> (4 * i)) & 0xFu; unsigned b = (unsigned)((v >> (8 * (n & 7))) & 0xFFu); if (n & 8) b = (b & 0x80u) ? 0xFFu : 0u; r |= b << (8 * i); }
+  return r;
+}
 inline int __vimin3_s32(int a, int b, int c) { return std::min(std::min(a, b), c); }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long x) { double r; std::memcpy(&r, &x, 8); return r; }

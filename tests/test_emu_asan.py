@@ -42,7 +42,7 @@ def _preload():
     return None
 
 
-@pytest.mark.parametrize("flags", [{}, {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1"}],
+@pytest.mark.parametrize("flags", [{}, {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"}],
                          ids=["default", "experimental"])
 def test_kernels_are_memory_clean_under_asan(flags):
     asan = _preload()

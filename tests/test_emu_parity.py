@@ -244,3 +244,19 @@ def test_emu_sharded_owner_mode_ties_and_extra_passes(emu, monkeypatch):
     _run_sharded(2, "ties", case=(seqs, ab, None, q, dict(max_clust=40)))
     assert emu.cuemu_launches(b"k_bud_collect_owned") > 0
     _run_sharded(3, "syn800_maxclust5")
+
+
+@pytest.mark.parametrize("name", ["syn800_default", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
+def test_emu_e2e_bound16(emu, monkeypatch, name):
+    """DADA2B_BOUND16=1 (dd_nwbound.cu): the bound pass of the two-phase loop NW with two raws per lane group on the 16-bit
+    SIMD datapath.  Goldens reproduced, and its survivor set equals the scalar bound pass's (same DP-cell total: the exact
+    pass aligned exactly the same pairs); ragged lengths exercise the unequal-length hand-over to the scalar pass."""
+    import dada2_b200
+    monkeypatch.setenv("DADA2B_TWOPHASE", "1")
+    seqs, ab, pri, err, q, opts = cases.build_case(name)
+    scalar = dada2_b200.dada_uniques(seqs, ab, pri, err, q, **opts)["stats"]["nw_cells"]
+    monkeypatch.setenv("DADA2B_BOUND16", "1")
+    n0 = emu.cuemu_launches(b"k_nwbound16")
+    _gpu_tests().test_e2e_matches_reference_golden(name)
+    assert emu.cuemu_launches(b"k_nwbound16") > n0
+    assert dada2_b200.dada_uniques(seqs, ab, pri, err, q, **opts)["stats"]["nw_cells"] == scalar

@@ -1,5 +1,5 @@
 """Experimental kernel variants on hardware (all OFF by default): DADA2B_NWFWD_V2 (restructured register
-NW, dd_nwfwd2.cu), DADA2B_TWOPHASE (bound pass before the fp64 NW), DADA2B_FUSED_TAIL (dd_round2.cu), DADA2B_PIVOT
+NW, dd_nwfwd2.cu), DADA2B_TWOPHASE (bound pass before the fp64 NW), DADA2B_BOUND16 (that bound pass on the 16-bit SIMD datapath, dd_nwbound.cu), DADA2B_FUSED_TAIL (dd_round2.cu), DADA2B_PIVOT
 (dd_classify2.cu) and their combination.  They were written after round 1's GPU budget was spent and are validated on
 the host SIMT emulator only (tests/test_emu_parity.py), so their first execution on a B200 is this file:
 xfail(strict=False) -- XPASS means "reference goldens reproduced on hardware", XFAIL carries the diff -- and each
@@ -44,6 +44,8 @@ VARIANTS = {
     "nwfwd2": dict(DADA2B_NWFWD_V2="1"),
     "twophase": dict(DADA2B_TWOPHASE="1"),
     "nwfwd2_twophase": dict(DADA2B_NWFWD_V2="1", DADA2B_TWOPHASE="1"),
+    "twophase_bound16": dict(DADA2B_TWOPHASE="1", DADA2B_BOUND16="1"),
+    "nwfwd2_twophase_bound16": dict(DADA2B_NWFWD_V2="1", DADA2B_TWOPHASE="1", DADA2B_BOUND16="1"),
     "fused_tail": dict(DADA2B_FUSED_TAIL="1"),
     "fused_tail_np1": dict(DADA2B_FUSED_TAIL="1", DADA2B_NP="1"),
     "pivot": dict(DADA2B_PIVOT="1"),

@@ -32,6 +32,7 @@ run_variant fused DADA2B_FUSED_TAIL=1
 run_variant pivot DADA2B_PIVOT=1
 run_variant twophase DADA2B_TWOPHASE=1
 run_variant nwfwd2_twophase DADA2B_NWFWD_V2=1 DADA2B_TWOPHASE=1
+run_variant nwfwd2_twophase_bound16 DADA2B_NWFWD_V2=1 DADA2B_TWOPHASE=1 DADA2B_BOUND16=1
 run_variant all DADA2B_NWFWD_V2=1 DADA2B_FUSED_TAIL=1 DADA2B_PIVOT=1
 run_variant all_np2 DADA2B_NWFWD_V2=1 DADA2B_FUSED_TAIL=1 DADA2B_PIVOT=1 DADA2B_NP=2
 # multi-GPU variants (only when the box has more than one GPU): replicated control vs fused tail vs owner mode
