@@ -111,7 +111,8 @@ AB_VARIANTS = [("nwfwd2", {"DADA2B_NWFWD_V2": "1"}),
                ("pivot", {"DADA2B_PIVOT": "1"}),
                ("twophase", {"DADA2B_TWOPHASE": "1"}),
                ("nwfwd2_twophase_bound16", {"DADA2B_NWFWD_V2": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"}),
-               ("all", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1"})]
+               ("all", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1"}),
+               ("everything", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"})]
 
 
 def experimental_ab(seqs, ab, q, err, last, budget_s, device, leg_cmd=None, steps=3, warmup=2, variants=None):

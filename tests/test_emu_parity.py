@@ -203,12 +203,14 @@ def test_emu_e2e_pivot_screen(emu, monkeypatch, name):
 
 
 def test_emu_all_experimental_paths_together(emu, monkeypatch):
-    """Every experimental path at once (pivot screen, two-phase + restructured NW, fused tail), single rank and sharded."""
-    for k in ("DADA2B_PIVOT", "DADA2B_TWOPHASE", "DADA2B_NWFWD_V2", "DADA2B_FUSED_TAIL"):
+    """Every experimental path at once (pivot screen, two-phase with the 16-bit SIMD bound pass + restructured NW, fused tail),
+    single rank and sharded."""
+    for k in ("DADA2B_PIVOT", "DADA2B_TWOPHASE", "DADA2B_BOUND16", "DADA2B_NWFWD_V2", "DADA2B_FUSED_TAIL"):
         monkeypatch.setenv(k, "1")
     _gpu_tests().test_e2e_matches_reference_golden("syn800_default")
     _run_sharded(2, "syn700_ragged")
     assert emu.cuemu_launches(b"k_classify2") > 0 and emu.cuemu_launches(b"k_nwfwd2") > 0 and emu.cuemu_launches(b"k_tail_final") > 0
+    assert emu.cuemu_launches(b"k_nwbound16") > 0
 
 
 @pytest.mark.parametrize("experimental", [False, True], ids=["default", "experimental"])
@@ -217,7 +219,7 @@ def test_emu_edge_cases(emu, monkeypatch, experimental):
     with the default kernels and with every experimental path switched on."""
     import dada2_b200
     if experimental:
-        for k in ("DADA2B_PIVOT", "DADA2B_TWOPHASE", "DADA2B_NWFWD_V2", "DADA2B_FUSED_TAIL"):
+        for k in ("DADA2B_PIVOT", "DADA2B_TWOPHASE", "DADA2B_BOUND16", "DADA2B_NWFWD_V2", "DADA2B_FUSED_TAIL"):
             monkeypatch.setenv(k, "1")
     for case in cases.edge_cases():
         cases.check_edge_case(case, dada2_b200.dada_uniques)

@@ -50,6 +50,7 @@ VARIANTS = {
     "fused_tail_np1": dict(DADA2B_FUSED_TAIL="1", DADA2B_NP="1"),
     "pivot": dict(DADA2B_PIVOT="1"),
     "all": dict(DADA2B_NWFWD_V2="1", DADA2B_FUSED_TAIL="1", DADA2B_PIVOT="1"),
+    "everything": dict(DADA2B_NWFWD_V2="1", DADA2B_FUSED_TAIL="1", DADA2B_PIVOT="1", DADA2B_TWOPHASE="1", DADA2B_BOUND16="1"),
 }
 
 
