@@ -237,8 +237,8 @@ struct BimRun {
   int device = 0, num_sms = 148;
   cudaStream_t s = nullptr;
   BimSeqs sq{};
-  BBuf<uint32_t> d_seq2, d_jq, d_jk, d_ptr, d_fwd_moves, d_fb;
-  bool use_fwd = false; int fwd_slots = 0;
+  BBuf<uint32_t> d_seq2, d_jq, d_jk, d_ptr, d_fwd_moves, d_fb, d_uneq;
+  bool use_fwd = false, use_fwd16 = false; int fwd_slots = 0;
   BBuf<uint16_t> d_len;
   BBuf<unsigned long long> d_ctr, d_rec;
   std::vector<uint16_t> len;
@@ -301,6 +301,7 @@ struct BimRun {
     aa.ctr = d_ctr.p;
     // register-resident kernel (dd_bimfwd.cu; EXPERIMENTAL, off by default: not yet run on hardware)
     use_fwd = getenv("DADA2B_BIMFWD") != nullptr && P.band >= 0;
+    use_fwd16 = use_fwd && atoi(getenv("DADA2B_BIMFWD")) == 2;       // two jobs per lane group on the 16-bit SIMD datapath (dd_bimfwd16.cu)
     fwd_slots = ((lbmax + 1) & ~1) + rbmax + 1;
     if (use_fwd) {
       const size_t w = bimfwd_scratch_words(fwd_slots, maxlen, num_sms);
@@ -324,6 +325,13 @@ struct BimRun {
       BCK(cudaMemsetAsync(d_ctr.p + 4, 0, 8, s));
       BimAlignArgs f = aa;
       f.ptr_scratch = d_fwd_moves.p; f.fb_list = d_fb.p; f.fb_count = d_ctr.p + 4; f.job_list = nullptr;
+      bool done16 = false;
+      if (use_fwd16) {          // pass 0: matching neighbours two at a time; the rest comes back in d_uneq (count in ctr[5]) for pass 1
+        if (d_uneq.n < njobs_upper + 2) d_uneq.alloc((size_t)njobs_upper + 2);
+        BCK(cudaMemsetAsync(d_ctr.p + 5, 0, 8, s));
+        done16 = launch_bimfwd16(f, d_uneq.p, d_ctr.p + 5, fwd_slots, njobs_upper, num_sms, s);
+        if (done16) { launches++; f.job_list = d_uneq.p; f.njobs_ptr = d_ctr.p + 5; }
+      }
       done = launch_bimfwd(f, fwd_slots, njobs_upper, num_sms, s, nullptr);
       if (done) {
         launches++;

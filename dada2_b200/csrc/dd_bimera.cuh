@@ -111,5 +111,9 @@ __device__ inline void bim_scan(const uint32_t *Q, const uint32_t *Pm, const uin
 // DADA2B_BIMFWD=1).  Pairs whose band does not fit an instantiation are appended to fb_list for k_bim_align.
 bool launch_bimfwd(const BimAlignArgs &a, int slots_needed, unsigned long long njobs_upper, int num_sms, cudaStream_t s, int *grid_out);
 size_t bimfwd_scratch_words(int slots_needed, int maxlen, int num_sms);
+// dd_bimfwd16.cu: two jobs per lane group on the 16-bit SIMD datapath (EXPERIMENTAL, DADA2B_BIMFWD=2); jobs whose neighbour has
+// another query / parent length come back in uneq_list for k_bimfwd.
+bool launch_bimfwd16(const BimAlignArgs &a, uint32_t *uneq_list, unsigned long long *uneq_count, int slots_needed,
+                     unsigned long long njobs_upper, int num_sms, cudaStream_t s);
 
 }  // namespace dd2

@@ -50,8 +50,9 @@ __global__ void __launch_bounds__(128) k_bimfwd(BimAlignArgs a) {
 
   for (unsigned long long base = (unsigned long long)(blockIdx.x * nwarps + wid) * PPW; base < njobs;
        base += (unsigned long long)gridDim.x * nwarps * PPW) {
-    const unsigned long long jb = base + gid;
-    bool act = jb < njobs;
+    const unsigned long long jx = base + gid;
+    bool act = jx < njobs;
+    const unsigned long long jb = act ? (a.job_list ? (unsigned long long)a.job_list[jx] : jx) : 0;   // job_list: hand-over from k_bimfwd16
     const uint32_t q = act ? a.jq[jb] : 0, par = act ? a.jk[jb] : 0;
     const int len1 = act ? (int)a.sq.len[q] : 16;
     const int len2 = act ? (int)a.sq.len[par] : len1;   // idle groups run a benign geometry (their lanes still execute)

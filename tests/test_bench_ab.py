@@ -56,6 +56,6 @@ def test_bimera_leg_runs_on_the_emulator_and_failures_are_contained():
     wrap = ("import sys, runpy; sys.path.insert(0, %r); import dada2_b200.api as api; api._LIBPATH = %r; "
             "sys.argv = ['bimera_leg.py', '40', '2']; runpy.run_path(%r, run_name='__main__')")
     r = bench.bimera_leg(300, 0, cmd=[sys.executable, "-c", wrap % (ROOT, lib, os.path.join(ROOT, "tools", "bimera_leg.py"))])
-    assert r["traceback"]["parity_vs_cpu"] is True and r["register"]["parity_vs_cpu"] is True, r
+    assert all(r[t]["parity_vs_cpu"] is True for t in ("traceback", "register", "simd16")), r
     assert r["traceback"]["pairs"] == r["register"]["pairs"] > 0 and r["cpu_baseline"]["kind"] in ("reference", "port")
     assert "failed" in bench.bimera_leg(30, 0, cmd=[sys.executable, "-c", "import sys; sys.exit('boom')"])

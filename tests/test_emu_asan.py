@@ -73,7 +73,7 @@ print('ASAN RUN OK')
 """
 
 
-@pytest.mark.parametrize("flags", [{}, {"DADA2B_BIMFWD": "1"}], ids=["default", "bimfwd"])
+@pytest.mark.parametrize("flags", [{}, {"DADA2B_BIMFWD": "1"}, {"DADA2B_BIMFWD": "2"}], ids=["default", "bimfwd", "bimfwd16"])
 def test_bimera_and_merge_kernels_are_memory_clean_under_asan(flags):
     """dd_bimera.cu / dd_bimfwd.cu / dd_merge.cu / dd_derep.cu under the same memcheck stand-in."""
     asan = _preload()

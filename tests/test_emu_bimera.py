@@ -86,3 +86,32 @@ def test_emu_bimera_register_kernel(emu, monkeypatch):
     B.check_table("t40_one_sample", B.product_table_fn)
     B.check_table("t150_short", B.product_table_fn, [1])
     B.check_is_bimera("t40_one_sample", B.product_denovo_fn)
+
+
+def test_emu_bimera_simd_kernel(emu, monkeypatch):
+    """DADA2B_BIMFWD=2: two jobs per lane group on the 16-bit SIMD datapath (dd_bimfwd16.cu); neighbours with another query or
+    parent length are handed to k_bimfwd, bands that do not fit to k_bim_align -- every route against goldens and oracle."""
+    import ctypes
+    from oracle import port
+    from dada2_b200 import bimera
+    h = ctypes.CDLL(emu)
+    h.cuemu_launches.restype = ctypes.c_long
+    h.cuemu_launches.argtypes = [ctypes.c_char_p]
+    monkeypatch.setenv("DADA2B_BIMFWD", "2")
+    n0 = h.cuemu_launches(b"k_bimfwd16")
+    B.check_pairs_vs_oracle(B.product_pair_fn, npairs=24)                       # random neighbours: mostly handed over
+    g = B.golden()
+    seqs = g["t120_seqs"].tolist()                                              # all 250 nt: runs of one query with equally long parents
+    q, p = np.repeat(np.arange(0, 8), 6), np.tile(np.arange(20, 26), 8)
+    for ms, fast in ((16, True), (16, False), (3, True)):
+        if not fast:
+            monkeypatch.setenv("DADA2B_NO_FAST", "1")
+        got = bimera.test_bimera_pairs(seqs, q, p, allow_one_off=True, max_shift=ms)
+        monkeypatch.delenv("DADA2B_NO_FAST", raising=False)
+        for n, (a, b) in enumerate(zip(q, p)):
+            r = port.bimera_pair(seqs[a], seqs[b], allow_one_off=True, max_shift=ms)
+            assert list(got[n]) == [r["left"], r["right"], r["left_oo"], r["right_oo"], r["ham"]], (ms, fast, n)
+    assert h.cuemu_launches(b"k_bimfwd16") - n0 == 8
+    B.check_pairs(B.product_pair_fn, shifts=[16], limit=40)                     # ragged corpus: falls through to k_bim_align
+    B.check_table("t40_one_sample", B.product_table_fn)
+    B.check_table("t150_short", B.product_table_fn, [1])

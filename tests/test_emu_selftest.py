@@ -68,7 +68,7 @@ def test_real_kernels_are_schedule_invariant(sched):
     assert out.returncode == 0 and "SCHED OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
 
 
-@pytest.mark.parametrize("sched,bimfwd", [(1, "0"), (7, "1")])
+@pytest.mark.parametrize("sched,bimfwd", [(1, "0"), (7, "1"), (5, "2")])
 def test_new_kernels_are_schedule_invariant(sched, bimfwd):
     """dd_bimera.cu / dd_bimfwd.cu / dd_merge.cu / dd_derep.cu under a reversed (1) and a pseudo-random (7) thread schedule: a
     missing __syncwarp() / __syncthreads() between a shared-memory (or scratch) write and its reader would show here."""
@@ -82,12 +82,13 @@ def test_new_kernels_are_schedule_invariant(sched, bimfwd):
         "B.check_pairs(B.product_pair_fn, shifts=[16], limit=40)\n"
         "B.check_pairs_vs_oracle(B.product_pair_fn, shifts=(16, 50), npairs=10)\n"
         "B.check_table('t40_one_sample', B.product_table_fn, [1])\n"
+        "B.check_table('t150_short', B.product_table_fn, [0])\n"
         "M.check(M.product_fn, opt_ids=[0, 4], limit=20, maxlen=160)\n"
         "D.check_all(D.product_fn, sizes=(1200,))\n"
         "print('SCHED OK')\n") % (os.path.dirname(HERE), lib)
     env = dict(os.environ, CUEMU_SCHED=str(sched))
     env.pop("DADA2B_BIMFWD", None)
-    if bimfwd == "1":
-        env["DADA2B_BIMFWD"] = "1"
+    if bimfwd != "0":
+        env["DADA2B_BIMFWD"] = bimfwd
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(HERE))
     assert out.returncode == 0 and "SCHED OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -38,12 +38,14 @@ SCRIPT = textwrap.dedent('''
 ''') % ROOT
 
 
-@pytest.mark.parametrize("variant", ["traceback", "register"])
+@pytest.mark.parametrize("variant", ["traceback", "register", "simd16"])
 @pytest.mark.xfail(strict=False, reason="new kernels, first run on hardware happens at round end")
 def test_bimera_kernels_match_reference_goldens_and_oracle(variant):
     env = dict(os.environ)
     env.pop("DADA2B_BIMFWD", None)
     if variant == "register":                       # dd_bimfwd.cu (register-resident wavefront + per-pair traceback)
         env["DADA2B_BIMFWD"] = "1"
+    if variant == "simd16":                         # dd_bimfwd16.cu (two jobs per lane group on the 16-bit SIMD datapath)
+        env["DADA2B_BIMFWD"] = "2"
     out = subprocess.run([sys.executable, "-c", SCRIPT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "BIMERA OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -1,6 +1,6 @@
 """Bimera detection on one synthetic sequence table: the C-ABI call dada2b_table_bimera on host buffers
-(pack + H2D + need / align / flag kernels + D2H inside the timed call) with the default traceback kernel and with the
-register-resident kernel (DADA2B_BIMFWD=1), next to the reference's own C_table_bimera2 (oracle/_ref, all host threads; the
+(pack + H2D + need / align / flag kernels + D2H inside the timed call) with the default traceback kernel, with the
+register-resident kernel (DADA2B_BIMFWD=1) and with its 16-bit SIMD form (DADA2B_BIMFWD=2), next to the reference's own C_table_bimera2 (oracle/_ref, all host threads; the
 CPU restatement when the compiled reference is absent), outputs diffed.  Prints one line `BIMLEG {json}`.  Run by bench.py
 in a subprocess with a timeout after the measured region; never part of `value`."""
 import json
@@ -23,7 +23,7 @@ def main():
     L = len(seqs[0])
     out = {"workload": "%d synthetic %d nt sequences x %d samples (tools/synth.py bimera_table seed 21), isBimeraDenovoTable defaults" % (len(seqs), L, nsample)}
     res = {}
-    for tag, env in (("traceback", None), ("register", "1")):
+    for tag, env in (("traceback", None), ("register", "1"), ("simd16", "2")):
         if env:
             os.environ["DADA2B_BIMFWD"] = env
         else:
@@ -55,7 +55,7 @@ def main():
         else:
             t0 = time.perf_counter(); want = port.table_bimera(mat, seqs); dt = time.perf_counter() - t0
             kind, ncores = "port", 1
-        npairs = next((out[t]["pairs"] for t in ("traceback", "register") if "pairs" in out.get(t, {})), None)
+        npairs = next((out[t]["pairs"] for t in ("traceback", "register", "simd16") if "pairs" in out.get(t, {})), None)
         out["cpu_baseline"] = {"kind": kind, "cores": ncores, "s": round(dt, 3), "pairs_per_s": (npairs / dt) if npairs else None}
         for tag, r in res.items():
             ok = bool(np.array_equal(r["nflag"], want[0]) and np.array_equal(r["nsam"], want[1]))
