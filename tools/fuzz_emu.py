@@ -38,8 +38,12 @@ while time.time() < t_end:
     q = rng.integers(0, len(seqs), 40); p = rng.integers(0, len(seqs), 40)
     o = dict(allow_one_off=bool(rng.integers(0, 2)), max_shift=int(rng.choice([0, 1, 5, 16, 16, 30, 64])), match=int(rng.integers(1, 7)),
              mismatch=-int(rng.integers(1, 9)), gap_p=-int(rng.integers(1, 12)))
-    for fwd in (False, True):
-        if fwd: os.environ["DADA2B_BIMFWD"] = "1"
+    if it % 2 == 0:                      # every other round: runs of one query against equally long parents (what dd_bimfwd16.cu pairs up)
+        same = [x for x in range(len(seqs)) if len(seqs[x]) == len(base)]
+        if len(same) >= 2:
+            q = np.repeat(rng.integers(0, len(seqs), 5), 8); p = rng.choice(same, 40)
+    for fwd in (None, "1", "2"):
+        if fwd: os.environ["DADA2B_BIMFWD"] = fwd
         else: os.environ.pop("DADA2B_BIMFWD", None)
         got = bimera.test_bimera_pairs(seqs, q, p, **o)
         for n, (a, b) in enumerate(zip(q, p)):
@@ -53,8 +57,8 @@ while time.time() < t_end:
     to = dict(allow_one_off=bool(rng.integers(0, 2)), min_fold=float(rng.choice([0.5, 1.0, 1.5, 2.0])), min_abund=int(rng.integers(1, 9)),
               max_shift=int(rng.choice([0, 4, 16, 32])), min_one_off_par_dist=int(rng.integers(1, 6)))
     want = port.table_bimera(mat, sq, **to)
-    for fwd in (False, True):
-        if fwd: os.environ["DADA2B_BIMFWD"] = "1"
+    for fwd in (None, "1", "2"):
+        if fwd: os.environ["DADA2B_BIMFWD"] = fwd
         else: os.environ.pop("DADA2B_BIMFWD", None)
         g = bimera.C_table_bimera2(mat, sq, **to)
         assert np.array_equal(g["nflag"], want[0]) and np.array_equal(g["nsam"], want[1]), ("table", fwd, to)
