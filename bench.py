@@ -107,6 +107,8 @@ def measured_peak_gbs():
 
 
 AB_VARIANTS = [("nwfwd2", {"DADA2B_NWFWD_V2": "1"}),
+               ("small16x4", {"DADA2B_NWFWD_SMALL": "1"}),
+               ("nwfwd2_small16x4", {"DADA2B_NWFWD_V2": "1", "DADA2B_NWFWD_SMALL": "1"}),
                ("fused_tail", {"DADA2B_FUSED_TAIL": "1"}),
                ("pivot", {"DADA2B_PIVOT": "1"}),
                ("twophase", {"DADA2B_TWOPHASE": "1"}),
@@ -206,7 +208,7 @@ def main():
     ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
                     help="N>1: shard ONE sample of N x nuniques uniques over the ranks (NCCL all-gather per split round; weak scaling) "
                          "or run one independent sample per rank (no collective)")
-    ap.add_argument("--ab-seconds", type=int, default=180,
+    ap.add_argument("--ab-seconds", type=int, default=210,
                     help="N=1: total wall budget for the post-measurement A/B of the experimental kernel variants (0 = off)")
     ap.add_argument("--bimera-seconds", type=int, default=90,
                     help="N=1: timeout of the post-measurement bimera-detection leg (0 = off)")

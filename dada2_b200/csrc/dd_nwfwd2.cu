@@ -399,7 +399,12 @@ bool launch_nwfwd2(const FwdArgs &a, int slots_needed, unsigned long long njobs_
   const bool big = njobs_hint > (unsigned long long)num_sms * 512;
   const char *force = getenv("DADA2B_NWFWD");          // tuning override, e.g. "8x6"
   int fg = 0, fnd = 0;
+  // EXPERIMENTAL (DADA2B_NWFWD_SMALL=<pairs>, "1" = 4096): rounds with few pairs are bound by the latency of ~500 dependent
+  // anti-diagonal steps (ncu: 6.8 % warp occupancy), so they take 16 lanes x 4 diagonals: 2 cells per lane and step instead of 3-5
+  const char *small_env = getenv("DADA2B_NWFWD_SMALL");
+  const unsigned long long small_thr = small_env ? (atoll(small_env) > 1 ? (unsigned long long)atoll(small_env) : 4096ull) : 0ull;
   if (force && sscanf(force, "%dx%d", &fg, &fnd) == 2) { G = fg; ND = fnd; }
+  else if (small_thr && njobs_hint <= small_thr && slots_needed <= 64) { G = 16; ND = 4; }
   else if (slots_needed <= 40) { G = big ? 4 : 8; ND = big ? 10 : 6; }
   else if (slots_needed <= 48) { G = 8; ND = 6; }
   else if (slots_needed <= 64) { G = 8; ND = 8; }

@@ -262,3 +262,12 @@ def test_emu_e2e_bound16(emu, monkeypatch, name):
     _gpu_tests().test_e2e_matches_reference_golden(name)
     assert emu.cuemu_launches(b"k_nwbound16") > n0
     assert dada2_b200.dada_uniques(seqs, ab, pri, err, q, **opts)["stats"]["nw_cells"] == scalar
+
+
+@pytest.mark.parametrize("v2", [False, True], ids=["nwfwd", "nwfwd2"])
+def test_emu_e2e_small_round_instantiation(emu, monkeypatch, v2):
+    """DADA2B_NWFWD_SMALL=1: rounds with few pairs run the <16, 4> instantiation (2 cells per lane and step) of k_nwfwd / k_nwfwd2."""
+    monkeypatch.setenv("DADA2B_NWFWD_SMALL", "1")
+    if v2:
+        monkeypatch.setenv("DADA2B_NWFWD_V2", "1")
+    _gpu_tests().test_e2e_matches_reference_golden("syn700_ragged")

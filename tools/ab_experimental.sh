@@ -28,6 +28,8 @@ PY
 }
 run_variant base DADA2B_NONE=1
 run_variant nwfwd2 DADA2B_NWFWD_V2=1
+run_variant small16x4 DADA2B_NWFWD_SMALL=1
+run_variant nwfwd2_small16x4 DADA2B_NWFWD_V2=1 DADA2B_NWFWD_SMALL=1
 run_variant fused DADA2B_FUSED_TAIL=1
 run_variant pivot DADA2B_PIVOT=1
 run_variant twophase DADA2B_TWOPHASE=1
