@@ -23,8 +23,7 @@ SCRIPT = textwrap.dedent('''
     from tests.test_oracle import load_golden
     import dada2_b200
     t0 = time.time()
-    for name in ("syn2000_default", "syn800_nogreedy", "syn700_ragged", "syn800_scores", "syn800_priors",
-                 "syn500_usequals0", "syn800_homo", "syn800_band32", "syn800_nogapless", "syn800_singletons"):
+    for name in ("syn2000_default", "syn800_nogreedy", "syn700_ragged", "syn800_priors", "syn800_homo", "syn800_band32"):
         seqs, ab, pri, err, q, opts = cases.build_case(name)
         got = dada2_b200.dada_uniques(seqs, ab, pri, err, q, **opts)
         want = load_golden(name)
