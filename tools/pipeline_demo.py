@@ -32,7 +32,7 @@ def main():
     prof = np.clip(np.round(38 - 18 * (np.arange(L) / (L - 1)) ** 2), 2, 40)
     q = np.clip(np.round(prof[None, :] + rng.normal(0, 3, (nreads, L))), 2, 40).astype(np.uint8)
     reads = np.stack([var[v] for v in pick])
-    err = rng.random((nreads, L)) < 10.0 ** (-q / 10.0)
+    err = rng.random((nreads, L)) < 10.0 ** (-q.astype(np.float64) / 10.0)
     reads = np.where(err, (reads + rng.integers(1, 4, (nreads, L))) % 4, reads)
     nt = np.frombuffer(b"ACGT", dtype=np.uint8)
     seqs = [bytes(nt[r]).decode() for r in reads]

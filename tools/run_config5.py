@@ -32,7 +32,8 @@ line = {"n_uniques": len(seqs), "maxlen": max(map(len, seqs)), "ms": [round(x, 1
         "nclust": len(out["clustering"]["sequence"]), "stats": {k: (round(v, 2) if isinstance(v, float) else int(v)) for k, v in st.items()}}
 if nsub:
     from oracle import port
-    s2, a2, q2 = seqs[:nsub], ab[:nsub], q[:nsub]
+    s2, a2 = seqs[:nsub], ab[:nsub]
+    q2 = q[:nsub, :max(len(x) for x in s2)]          # the quality matrix must be exactly as wide as the longest read of the call
     got = dada2_b200.dada_uniques(s2, a2, None, err, q2, **opts)
     t0 = time.perf_counter(); want = port.dada_uniques(s2, a2, None, err, q2, **opts); line["oracle_s"] = round(time.perf_counter() - t0, 1)
     try:
