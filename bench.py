@@ -117,6 +117,12 @@ AB_VARIANTS = [("nwfwd2", {"DADA2B_NWFWD_V2": "1"}),
                ("everything", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"})]
 
 
+def _last_lines(txt, n=2, width=300):
+    """The end of a failed leg's output: the exception line, not the middle of its traceback."""
+    rows = [l.strip() for l in txt.strip().splitlines() if l.strip()]
+    return " | ".join(rows[-n:])[-width:]
+
+
 def experimental_ab(seqs, ab, q, err, last, budget_s, device, leg_cmd=None, steps=3, warmup=2, variants=None):
     """After the measured region (N=1 only): every off-by-default kernel variant runs the same workload
     in its own subprocess under a timeout, and its outputs are diffed against the default path's.  Reported under
@@ -139,7 +145,7 @@ def experimental_ab(seqs, ab, q, err, last, budget_s, device, leg_cmd=None, step
                 out = subprocess.run((leg_cmd or [sys.executable, os.path.join(ROOT, "tools", "ab_leg.py")]) + [wl, ref, str(steps), str(warmup)], env=e,
                                      capture_output=True, text=True, timeout=min(75, left))
                 rows = [l for l in out.stdout.splitlines() if l.startswith("ABLEG ")]
-                res[tag] = json.loads(rows[-1][6:]) if rows else {"failed": (out.stderr or out.stdout)[-300:]}
+                res[tag] = json.loads(rows[-1][6:]) if rows else {"failed": _last_lines(out.stderr or out.stdout)}
             except subprocess.TimeoutExpired:
                 res[tag] = {"failed": "timeout"}
             except Exception as ex:                      # never let the A/B leg take the bench line down
@@ -157,7 +163,7 @@ def bimera_leg(budget_s, device, cmd=None):
         out = subprocess.run(cmd or [sys.executable, os.path.join(ROOT, "tools", "bimera_leg.py")], env=e, capture_output=True, text=True,
                              timeout=budget_s)
         rows = [l for l in out.stdout.splitlines() if l.startswith("BIMLEG ")]
-        return json.loads(rows[-1][7:]) if rows else {"failed": (out.stderr or out.stdout)[-300:]}
+        return json.loads(rows[-1][7:]) if rows else {"failed": _last_lines(out.stderr or out.stdout)}
     except subprocess.TimeoutExpired:
         return {"failed": "timeout"}
     except Exception as ex:
