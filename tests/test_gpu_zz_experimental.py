@@ -42,14 +42,10 @@ SCRIPT = textwrap.dedent('''
 VARIANTS = {
     "nwfwd2": dict(DADA2B_NWFWD_V2="1"),
     "twophase": dict(DADA2B_TWOPHASE="1"),
-    "nwfwd2_twophase": dict(DADA2B_NWFWD_V2="1", DADA2B_TWOPHASE="1"),
-    "twophase_bound16": dict(DADA2B_TWOPHASE="1", DADA2B_BOUND16="1"),
     "nwfwd2_twophase_bound16": dict(DADA2B_NWFWD_V2="1", DADA2B_TWOPHASE="1", DADA2B_BOUND16="1"),
     "fused_tail": dict(DADA2B_FUSED_TAIL="1"),
-    "fused_tail_np1": dict(DADA2B_FUSED_TAIL="1", DADA2B_NP="1"),
     "pivot": dict(DADA2B_PIVOT="1"),
     "small16x4": dict(DADA2B_NWFWD_SMALL="1"),
-    "nwfwd2_small16x4": dict(DADA2B_NWFWD_V2="1", DADA2B_NWFWD_SMALL="1"),
     "all": dict(DADA2B_NWFWD_V2="1", DADA2B_FUSED_TAIL="1", DADA2B_PIVOT="1"),
     "everything": dict(DADA2B_NWFWD_V2="1", DADA2B_FUSED_TAIL="1", DADA2B_PIVOT="1", DADA2B_TWOPHASE="1", DADA2B_BOUND16="1"),
 }
