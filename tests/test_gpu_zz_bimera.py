@@ -34,7 +34,7 @@ SCRIPT = textwrap.dedent('''
         got = bimera.C_table_bimera2(mat, seqs, return_stats=True, **o)
         assert np.array_equal(got["nflag"], want[0]) and np.array_equal(got["nsam"], want[1]), o
         st = got["stats"]
-        print("table %dx%d" % (len(seqs), mat.shape[0]), o, "pairs", st["n_pairs"], "gpu %%.1f ms (align %%.1f ms), oracle %%.1f s" %% (st["ms_total"], st["ms_k_align"], t1 - t0), flush=True)
+        print("table %%dx%%d" %% (len(seqs), mat.shape[0]), o, "pairs", st["n_pairs"], "gpu %%.1f ms (align %%.1f ms), oracle %%.1f s" %% (st["ms_total"], st["ms_k_align"], t1 - t0), flush=True)
     print("BIMERA OK")
 ''') % ROOT
 
