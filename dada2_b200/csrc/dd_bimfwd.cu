@@ -15,13 +15,6 @@
 
 namespace dd2 {
 
-__device__ __forceinline__ long long bim_band_cells(int n, int m, int l, int r) {     // SURVEY.md 8d, closed form
-  const long long k = min(max(m - r, 0), n);
-  const long long A = k * (k + 1) / 2 + k * r + (long long)(n - k) * m;
-  const long long k2 = min(max(l + 1, 0), n);
-  const long long B = k2 + ((long long)n * (n + 1) / 2 - k2 * (k2 + 1) / 2) - (long long)l * (n - k2);
-  return A - B + n;
-}
 
 template <int G, int ND>
 __global__ void __launch_bounds__(128) k_bimfwd(BimAlignArgs a) {
@@ -242,7 +235,7 @@ __global__ void __launch_bounds__(128) k_bimfwd(BimAlignArgs a) {
           a.rec[dst] = keep ? bim_pack(v[0], v[1], a.allow_one_off ? v[2] : 0, a.allow_one_off ? v[3] : 0, allowed) : bim_pack(0, 0, 0, 0, allowed);
         }
       }
-      cells_lane += bim_band_cells(len1, len2, lband, rband);
+      cells_lane += band_cells_cf(len1, len2, lband, rband);
     }
     __syncwarp();
   }

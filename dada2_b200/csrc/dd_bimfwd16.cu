@@ -21,13 +21,6 @@ __device__ __forceinline__ uint32_t b16_sel2(bool p_hi, bool p_lo, uint32_t a, u
   if (p_hi) r = __byte_perm(r, a, 0x7610);
   return r;
 }
-__device__ __forceinline__ long long b16_band_cells(int n, int m, int l, int r) {
-  const long long k = min(max(m - r, 0), n);
-  const long long A = k * (k + 1) / 2 + k * r + (long long)(n - k) * m;
-  const long long k2 = min(max(l + 1, 0), n);
-  const long long B = k2 + ((long long)n * (n + 1) / 2 - k2 * (k2 + 1) / 2) - (long long)l * (n - k2);
-  return A - B + n;
-}
 constexpr int B16_NEG = -16000;
 
 struct B16Args {
@@ -230,7 +223,7 @@ __global__ void __launch_bounds__(128) k_bimfwd16(B16Args ba) {
           const size_t dst = a.dst_mode ? (size_t)((q - (uint32_t)a.q_add) / (uint32_t)a.q_mul - a.j0) * a.ncol + par : (size_t)jb;
           a.rec[dst] = keep ? bim_pack(v[0], v[1], a.allow_one_off ? v[2] : 0, a.allow_one_off ? v[3] : 0, allowed) : bim_pack(0, 0, 0, 0, allowed);
         }
-        cells_lane += b16_band_cells(len1, len2, lband, rband);
+        cells_lane += band_cells_cf(len1, len2, lband, rband);
       }
     }
     __syncwarp();

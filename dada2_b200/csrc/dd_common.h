@@ -99,6 +99,16 @@ struct DevState {
 
 
 
+// DP cells of a banded alignment: sum_i [min(len2, i + rband) - max(1, i - lband) + 1], closed form.
+// (dd_nwfwd.cu / dd_nwfwd2.cu keep their own copies: their SASS is pinned to the hardware-validated build.)
+__host__ __device__ inline long long band_cells_cf(int n, int m, int l, int r) {
+  const long long k = (m - r < 0 ? 0 : (m - r > n ? n : m - r));
+  const long long A = k * (k + 1) / 2 + k * r + (long long)(n - k) * m;
+  const long long k2 = (l + 1 < 0 ? 0 : (l + 1 > n ? n : l + 1));
+  const long long B = k2 + ((long long)n * (n + 1) / 2 - k2 * (k2 + 1) / 2) - (long long)l * (n - k2);
+  return A - B + n;
+}
+
 constexpr int CTR_SURV = CTR_NWTOT;   // survivor count of the two-phase bound pass (slot otherwise unused by kernels)
 
 enum ErrCode : int { ERR_NONE = 0, ERR_LAMBDA = 1, ERR_QUAL = 2, ERR_TRACE = 3 };

@@ -34,13 +34,6 @@ __device__ __forceinline__ uint32_t sel2(bool p_hi, bool p_lo, uint32_t a, uint3
   if (p_hi) r = __byte_perm(r, a, 0x7610);
   return r;
 }
-__device__ __forceinline__ long long nb_band_cells(int n, int m, int l, int r) {
-  const long long k = min(max(m - r, 0), n);
-  const long long A = k * (k + 1) / 2 + k * r + (long long)(n - k) * m;
-  const long long k2 = min(max(l + 1, 0), n);
-  const long long B = k2 + ((long long)n * (n + 1) / 2 - k2 * (k2 + 1) / 2) - (long long)l * (n - k2);
-  return A - B + n;
-}
 
 constexpr int NEG16 = -16000;          // out-of-band / unreached slots: far below any real score, far above INT16_MIN
 
@@ -214,7 +207,7 @@ __global__ void __launch_bounds__(128) k_nwbound16(BoundArgs ba) {
     const bool owner = act && tf >= 0 && tf < ND;
     bool s0 = false, s1 = false;
     if (owner) {
-      cells_lane += nb_band_cells(len1, len2, lband, rband) * (two ? 2 : 1);
+      cells_lane += band_cells_cf(len1, len2, lband, rband) * (two ? 2 : 1);
       const double b0 = a.raw_S[r0] * pow(a.raw_rho[r0], (double)(nsw & 0xFFFFu)) * (double)a.total_reads * (1.0 + 1e-9);
       s0 = !(b0 <= a.st.E_minmax[r0]) || b0 < 1e-280;
       if (two) {
