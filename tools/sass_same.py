@@ -12,6 +12,8 @@ def split(path):
         if m:
             cur = m.group(1)
             d[cur] = []
+        elif re.match(r"\s*Fatbin (elf|ptx) code", ln):
+            cur = None                      # next object of the fat binary: not part of the previous function
         elif cur and "identifier" not in ln and not re.match(r"\s*/\* 0x", ln):
             d[cur].append(ln)
     return d
