@@ -19,6 +19,7 @@
 #include "../../include/dada2b_derep.h"
 #include "dd_bimera.cuh"
 #include "dd_hostutil.h"
+#include "dd_ctx.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -253,6 +254,42 @@ __global__ void __launch_bounds__(256) k_dr_map(const uint32_t *head, const uint
   map[id] = (int32_t)rank_of[seg[p] + head[p] - 1] + 1;
 }
 
+// dereplication -> dada(): fill a context's packed arrays from the device-side result (one thread per 16-base word / per quality byte)
+struct DrToCtx {
+  DevIn in; unsigned nuniq; int maxlen, S;
+  const char *seq; const long long *off; const int32_t *rep, *abund; const double *quals; const uint32_t *keys;
+  unsigned long long *maxq;
+};
+__global__ void __launch_bounds__(256) k_dr_to_ctx(DrToCtx a) {
+  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)a.in.SW + a.in.QS;
+  if (x >= (size_t)a.nuniq * per) return;
+  const unsigned r = (unsigned)(x / per); const int w = (int)(x % per);
+  const int rd = a.rep[r];
+  const int len = (int)a.keys[(size_t)rd * a.S + a.S - 1];
+  if (w < a.in.SW) {                                     // 2-bit packing, 16 bases per word, base b at bits 2(b%16) (DevIn::seq2)
+    uint32_t v = 0;
+    const long long o = a.off[rd];
+    for (int b = 0; b < 16; b++) {
+      const int p = 16 * w + b;
+      if (p < len) { const char c = a.seq[o + p]; v |= (uint32_t)(c == 'C' ? 1 : (c == 'G' ? 2 : (c == 'T' ? 3 : 0))) << (2 * b); }
+    }
+    a.in.seq2[(size_t)r * a.in.SW + w] = v;
+    if (w == 0) { a.in.len[r] = (uint16_t)len; a.in.reads[r] = (uint32_t)a.abund[r]; a.in.prior[r] = 0; }
+  } else {                                               // (uint8_t) round(mean quality), containers.cpp:34 (same rounding as do_upload)
+    const int p = w - a.in.SW;
+    uint8_t q = 0;
+    if (p < len) {
+      const double xq = a.quals[(size_t)r * a.maxlen + p];
+      int rv = (int)(xq + 0.5);
+      if ((double)rv - xq > 0.5) rv--;
+      q = (uint8_t)rv;
+      atomicMax(a.maxq, (unsigned long long)q);
+    }
+    a.in.qual[(size_t)r * a.in.QS + p] = q;
+  }
+}
+
 }  // namespace dd2
 
 using namespace dd2;
@@ -291,13 +328,16 @@ struct Sorter {                       // stable LSD radix sort of an index array
 
 extern "C" {
 
+void dada2b_ctx_free(dada2b_ctx *ctx);       // include/dada2b.h (dd_driver.cu)
+
 void dada2b_derep_free(dada2b_derep_out *o) {
   if (!o) return;
   free(o->seq_concat); free(o->seq_off); free(o->abund); free(o->quals); free(o->map); free(o);
 }
 
-int dada2b_derep(const dada2b_derep_in *in, int32_t device, dada2b_derep_out **out, char errbuf[DADA2B_ERRLEN]) {
+static int derep_impl(const dada2b_derep_in *in, int32_t device, dada2b_derep_out **out, dada2b_ctx **ctx_out, int want_quals, char errbuf[DADA2B_ERRLEN]) {
   const double t0 = bnow_ms();
+  dada2b_ctx *ctx = nullptr;
   cudaStream_t s = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   dada2b_derep_out *res = nullptr;
@@ -395,14 +435,14 @@ int dada2b_derep(const dada2b_derep_in *in, int32_t device, dada2b_derep_out **o
     }
     res = (dada2b_derep_out *)calloc(1, sizeof(dada2b_derep_out));
     res->nuniq = (int32_t)nuniq; res->maxlen = maxlen; res->nreads = in->nreads;
-    res->abund = (int32_t *)malloc((size_t)nuniq * 4); res->quals = (double *)malloc((size_t)nuniq * maxlen * 8);
+    res->abund = (int32_t *)malloc((size_t)nuniq * 4); res->quals = want_quals ? (double *)malloc((size_t)nuniq * maxlen * 8) : nullptr;
     res->map = (int32_t *)malloc((size_t)n * 4); res->seq_off = (int64_t *)malloc(((size_t)nuniq + 1) * 8);
     std::vector<int32_t> rep(nuniq);
     BCK(cudaMemcpyAsync(res->abund, d_abund.p, (size_t)nuniq * 4, cudaMemcpyDeviceToHost, s));
-    BCK(cudaMemcpyAsync(res->quals, d_quals.p, (size_t)nuniq * maxlen * 8, cudaMemcpyDeviceToHost, s));
+    if (want_quals) BCK(cudaMemcpyAsync(res->quals, d_quals.p, (size_t)nuniq * maxlen * 8, cudaMemcpyDeviceToHost, s));
     BCK(cudaMemcpyAsync(res->map, d_map.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     BCK(cudaMemcpyAsync(rep.data(), d_rep.p, (size_t)nuniq * 4, cudaMemcpyDeviceToHost, s));
-    d2h += (long long)nuniq * (8 + (long long)maxlen * 8) + (long long)n * 4 + 16;
+    d2h += (long long)nuniq * (8 + (want_quals ? (long long)maxlen * 8 : 0)) + (long long)n * 4 + 16;
     BCK(cudaEventRecord(ev[3], s));
     BCK(cudaStreamSynchronize(s));
     BCK(cudaGetLastError());
@@ -413,17 +453,50 @@ int dada2b_derep(const dada2b_derep_in *in, int32_t device, dada2b_derep_out **o
     res->seq_concat = (char *)malloc((size_t)std::max<int64_t>(tot, 1));
     for (unsigned r = 0; r < nuniq; r++)
       memcpy(res->seq_concat + res->seq_off[r], in->seq_concat + in->seq_off[rep[r]], (size_t)(res->seq_off[r + 1] - res->seq_off[r]));
+    if (ctx_out) {
+      // ---- hand the uniques over to dada() on the device (dd_ctx.h): no D2H of the means, no host re-pack, no H2D ----
+      int minlen = maxlen;
+      for (unsigned r = 0; r < nuniq; r++) minlen = std::min<int>(minlen, (int)(res->seq_off[r + 1] - res->seq_off[r]));
+      DevIn arrays{}; cudaStream_t cs = nullptr;
+      ctx = ctx_create_device(device, (int)nuniq, maxlen, minlen, res->seq_concat, res->seq_off, res->abund, &arrays, &cs);
+      BBuf<unsigned long long> d_maxq; d_maxq.alloc(1);
+      BCK(cudaMemsetAsync(d_maxq.p, 0, 8, cs));
+      DrToCtx tc{arrays, nuniq, maxlen, S, d_seq.p, d_off.p, d_rep.p, d_abund.p, d_quals.p, d_keys.p, d_maxq.p};
+      const size_t work = (size_t)nuniq * ((size_t)arrays.SW + arrays.QS);
+      k_dr_to_ctx<<<(unsigned)((work + 255) / 256), 256, 0, cs>>>(tc);
+      unsigned long long mq = 0;
+      BCK(cudaMemcpyAsync(&mq, d_maxq.p, 8, cudaMemcpyDeviceToHost, cs));
+      BCK(cudaStreamSynchronize(cs));
+      BCK(cudaGetLastError());
+      ctx_finish_device(ctx, (int)mq);
+      so.launches += 1;
+    }
     float ms = 0;
     BCK(cudaEventElapsedTime(&ms, ev[1], ev[2])); res->ms_sort = ms;
     BCK(cudaEventElapsedTime(&ms, ev[0], ev[3])); res->ms_device = ms;
     res->gpu_launches = so.launches; res->h2d_bytes = h2d; res->d2h_bytes = d2h; res->ms_total = bnow_ms() - t0;
     *out = res;
+    if (ctx_out) *ctx_out = ctx;
   } catch (BErr &e) { msg = e.msg; rc = 1; }
   catch (std::exception &e) { msg = e.what(); rc = 1; }
   for (auto &e : ev) if (e) cudaEventDestroy(e);
   if (s) cudaStreamDestroy(s);
-  if (rc) { if (res) dada2b_derep_free(res); if (errbuf) snprintf(errbuf, DADA2B_ERRLEN, "%s", msg.c_str()); }
+  if (rc) {
+    if (res) dada2b_derep_free(res);
+    if (ctx) dada2b_ctx_free(ctx);
+    if (errbuf) snprintf(errbuf, DADA2B_ERRLEN, "%s", msg.c_str());
+  }
   return rc;
+}
+
+int dada2b_derep(const dada2b_derep_in *in, int32_t device, dada2b_derep_out **out, char errbuf[DADA2B_ERRLEN]) {
+  return derep_impl(in, device, out, nullptr, 1, errbuf);
+}
+int dada2b_derep_resident(const dada2b_derep_in *in, int32_t device, int32_t want_quals, dada2b_derep_out **out, dada2b_ctx **ctx,
+                          char errbuf[DADA2B_ERRLEN]) {
+  if (!ctx) { if (errbuf) snprintf(errbuf, DADA2B_ERRLEN, "dada2b: NULL context pointer."); return 1; }
+  *ctx = nullptr;
+  return derep_impl(in, device, out, ctx, want_quals != 0, errbuf);
 }
 
 }  // extern "C"

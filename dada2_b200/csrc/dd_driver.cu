@@ -9,10 +9,12 @@
 #include "../../include/dada2b.h"
 #include "../../include/dada2b_test.h"
 #include <memory>
+#include <stdexcept>
 #include <dlfcn.h>
 #include <nccl.h>
 #include "dd_common.h"
 #include "dd_kernels.h"
+#include "dd_ctx.h"
 
 #include <algorithm>
 #include <chrono>
@@ -265,6 +267,47 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   if (fresh) fresh.release();
   return cx;
 }
+
+// Device-resident constructor (dd_ctx.h): the uniques come from kernels of another driver (dereplication), not from the host.
+namespace dd2 {
+dada2b_ctx *ctx_create_device(int device, int nraw, int maxlen, int minlen, const char *seq_concat, const int64_t *seq_off,
+                              const int32_t *abund, DevIn *arrays, cudaStream_t *stream) {
+  try {
+    if (nraw <= 0) throw Err{"Zero input sequences."};
+    if (maxlen >= 9999) throw Err{"Input sequences exceed the maximum allowed string length."};
+    if (minlen <= KMER) throw Err{"Input sequences must all be longer than the kmer-size (5)."};
+    CK(cudaSetDevice(device));
+    std::unique_ptr<dada2b_ctx> cx(new dada2b_ctx());
+    cx->device = device;
+    int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    cx->num_sms = sms;
+    CK(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
+    cx->has_quals = true; cx->bad_nt = false; cx->maxq = 0;
+    cx->len.resize(nraw); cx->reads.resize(nraw); cx->prior.assign(nraw, 0);
+    cx->seq_off.assign(seq_off, seq_off + nraw + 1);
+    cx->seq_concat.assign(seq_concat + seq_off[0], seq_concat + seq_off[nraw]);
+    const int64_t off0 = seq_off[0];
+    unsigned tot = 0;
+    for (int i = 0; i < nraw; i++) {
+      cx->len[i] = (uint16_t)(seq_off[i + 1] - seq_off[i]);
+      cx->reads[i] = (uint32_t)abund[i]; tot += cx->reads[i];
+    }
+    for (auto &o : cx->seq_off) o -= off0;
+    cx->total_reads = tot;
+    DevIn &d = cx->in;
+    d.nraw = nraw; d.maxlen = maxlen; d.minlen = minlen;
+    d.SW = ((maxlen + 15) / 16 + 3) & ~3;
+    d.QS = (maxlen + 15) & ~15;
+    cx->d_seq2.alloc((size_t)nraw * d.SW); cx->d_qual.alloc((size_t)nraw * d.QS);
+    cx->d_len.alloc(nraw); cx->d_reads.alloc(nraw); cx->d_prior.alloc(nraw);
+    d.seq2 = cx->d_seq2.p; d.qual = cx->d_qual.p; d.len = cx->d_len.p; d.reads = cx->d_reads.p; d.prior = cx->d_prior.p;
+    cx->upload_h2d = 0;
+    *arrays = d; *stream = cx->stream;
+    return cx.release();
+  } catch (Err &e) { throw std::runtime_error(e.msg); }
+}
+void ctx_finish_device(dada2b_ctx *ctx, int maxq) { ctx->maxq = maxq; }
+}  // namespace dd2
 
 // ------------------------------------------------------------------------------------
 namespace {

@@ -36,14 +36,18 @@ def _lib():
         P = C.POINTER
         L.dada2b_derep.argtypes = [P(DerepIn), C.c_int32, P(P(DerepOut)), C.c_char_p]
         L.dada2b_derep_free.argtypes = [P(DerepOut)]
+        L.dada2b_derep_resident.argtypes = [P(DerepIn), C.c_int32, C.c_int32, P(P(DerepOut)), P(C.c_void_p), C.c_char_p]
         _BOUND = True
     return L
 
 
-def derep_reads(seqs, quals, n=1000000, device=0, return_stats=False):
+def derep_reads(seqs, quals, n=1000000, device=0, return_stats=False, resident=False, want_quals=True):
     """seqs: list[str] (A/C/G/T); quals: list of integer arrays or one uint8 array of all bases concatenated (numeric
     quality, Phred offset removed).  -> dict(uniques list[str], abundances int32[nuniq], quals float64[nuniq, maxlen]
-    NaN/NA-padded, map int32[nreads] 1-based with NA = INT32_MIN) in derepFastq's order."""
+    NaN/NA-padded, map int32[nreads] 1-based with NA = INT32_MIN) in derepFastq's order.
+    resident=True: additionally leaves the uniques packed on the device and returns (dict, dada2_b200.Resident) -- run(err) on
+    it is dada() on the dereplicated reads without the quality means ever visiting the host (want_quals=False drops them from
+    the dict as well)."""
     L = _lib()
     nreads = len(seqs)
     lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=nreads)
@@ -59,7 +63,11 @@ def derep_reads(seqs, quals, n=1000000, device=0, return_stats=False):
     inp = DerepIn(nreads, buf, off.ctypes.data, q.ctypes.data, int(n))
     out = C.POINTER(DerepOut)()
     eb = C.create_string_buffer(ERRLEN)
-    rc = L.dada2b_derep(C.byref(inp), int(device), C.byref(out), eb)
+    ctx = C.c_void_p()
+    if resident:
+        rc = L.dada2b_derep_resident(C.byref(inp), int(device), int(bool(want_quals)), C.byref(out), C.byref(ctx), eb)
+    else:
+        rc = L.dada2b_derep(C.byref(inp), int(device), C.byref(out), eb)
     if rc:
         raise api.Dada2bError(eb.value.decode())
     try:
@@ -69,10 +77,15 @@ def derep_reads(seqs, quals, n=1000000, device=0, return_stats=False):
         raw = C.string_at(r.seq_concat, int(so[-1])).decode()
         res = {"uniques": [raw[so[i]:so[i + 1]] for i in range(nu)],
                "abundances": np.ctypeslib.as_array(r.abund, shape=(nu,)).copy(),
-               "quals": np.ctypeslib.as_array(r.quals, shape=(nu, ml)).copy(),          # maxlen x nuniq column-major == [nuniq, maxlen] row-major
+               "quals": np.ctypeslib.as_array(r.quals, shape=(nu, ml)).copy() if r.quals else None,   # maxlen x nuniq column-major == [nuniq, maxlen] row-major
                "map": np.ctypeslib.as_array(r.map, shape=(max(r.nreads, 1),))[:r.nreads].copy()}
         if return_stats:
             res["stats"] = {k: getattr(r, k) for k in ("gpu_launches", "h2d_bytes", "d2h_bytes", "ms_device", "ms_sort", "ms_total")}
+        if resident:
+            rs = api.Resident.__new__(api.Resident)                 # adopt the context the library built on the device
+            rs._pin = None
+            rs._ctx = ctx
+            return res, rs
         return res
     finally:
         L.dada2b_derep_free(out)

@@ -48,6 +48,15 @@ typedef struct {
 } dada2b_derep_out;
 
 int dada2b_derep(const dada2b_derep_in *in, int32_t device, dada2b_derep_out **out, char errbuf[DADA2B_ERRLEN]);
+
+/* Dereplicate and leave the uniques packed and RESIDENT on the device as a dada2b_ctx (include/dada2b.h) for
+ * dada2b_run_resident: the quality means are rounded to dada()'s uint8 on the device ((uint8_t)round(q), containers.cpp:34)
+ * and never travel to the host and back, the sequences are re-packed on the device.  `out` receives the same result as
+ * dada2b_derep except that `quals` is NULL when want_quals == 0 (derep$quals is then never materialised on the host).
+ * Free the context with dada2b_ctx_free.  A dada() run on the context equals dada2b_run on dada2b_derep's output. */
+struct dada2b_ctx;
+int dada2b_derep_resident(const dada2b_derep_in *in, int32_t device, int32_t want_quals, dada2b_derep_out **out,
+                          struct dada2b_ctx **ctx, char errbuf[DADA2B_ERRLEN]);
 void dada2b_derep_free(dada2b_derep_out *out);
 
 #ifdef __cplusplus

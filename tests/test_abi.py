@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert {"dada2b_run", "dada2b_free", "dada2b_upload", "dada2b_run_resident", "dada2b_ctx_free",
             "dada2b_default_opts", "dada2b_test_pairs", "dada2b_test_calc_pA", "dada2b_table_bimera", "dada2b_is_bimera",
             "dada2b_bimera_default_opts", "dada2b_test_bimera_pairs", "dada2b_merge_pairs", "dada2b_merge_free",
-            "dada2b_merge_default_opts", "dada2b_derep", "dada2b_derep_free"} <= names
+            "dada2b_merge_default_opts", "dada2b_derep", "dada2b_derep_free", "dada2b_derep_resident"} <= names
     for n in sorted(names):
         assert hasattr(L, n), "libdada2b.so does not export %s" % n
 

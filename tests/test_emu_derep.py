@@ -39,6 +39,16 @@ def test_emu_derep_feeds_dada_and_corners(emu):
     d = derep.derep_reads(seqs, quals)
     got = dada2_b200.dada_uniques(d["uniques"], d["abundances"], None, cases.tperr1(), d["quals"])       # derep -> dada, both on the "device"
     cases.assert_same(got, load_golden("config1"), rtol=1e-10, label="derep+dada config1")
+    # the same without the host round trip: uniques stay packed on the device, dada() runs on that context
+    d2, res = derep.derep_reads(seqs, quals, resident=True, want_quals=False)
+    assert d2["quals"] is None and d2["uniques"] == d["uniques"] and np.array_equal(d2["abundances"], d["abundances"])
+    cases.assert_same(res.run(cases.tperr1()), got, rtol=0, label="derep_resident + run_resident")
+    res.close()
+    s2, q2 = D.synthetic(900, seed=5, L=70, nvar=20, zero_len=2)            # ragged lengths, fractional means, NA map entries
+    dd, rr = derep.derep_reads(s2, q2, n=300, resident=True)
+    err = np.full((16, 45), 0.01); err[[0, 5, 10, 15]] = 0.97
+    cases.assert_same(rr.run(err), dada2_b200.dada_uniques(dd["uniques"], dd["abundances"], None, err, dd["quals"]), rtol=0, label="resident ragged")
+    rr.close()
     with pytest.raises(Dada2bError, match="A/C/G/T"):
         derep.derep_reads(["ACGTN", "ACGTA"], [np.full(5, 30, np.uint8)] * 2)
     with pytest.raises(Dada2bError, match="Only zero-length"):

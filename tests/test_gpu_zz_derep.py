@@ -28,6 +28,15 @@ SCRIPT = textwrap.dedent('''
     st = got["stats"]
     print("2e5 x 250 nt reads -> %%d uniques: gpu %%.1f ms (device %%.1f, sort %%.1f, %%d launches), oracle %%.1f s" %% (
         len(got["uniques"]), st["ms_total"], st["ms_device"], st["ms_sort"], st["gpu_launches"], t1), flush=True)
+    import dada2_b200
+    from tests import cases
+    seqs, quals = D.sam1F_reads()                       # derep -> dada without the host round trip == the two-call form
+    d, res = derep.derep_reads(seqs, quals, resident=True)
+    a = res.run(cases.tperr1()); b = dada2_b200.dada_uniques(d["uniques"], d["abundances"], None, cases.tperr1(), d["quals"])
+    cases.assert_same(a, b, rtol=0, label="derep_resident")
+    from tests.test_oracle import load_golden
+    cases.assert_same(a, load_golden("config1"), rtol=1e-10, label="derep_resident vs config-1 golden")
+    res.close()
     print("DEREP OK")
 ''') % ROOT
 

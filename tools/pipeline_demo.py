@@ -1,5 +1,5 @@
 """The accelerated steps chained on one GPU, host buffers between them (each step is its own C-ABI call, as the R package
-would drive them): dereplication (8(f1)) -> dada() core (8(a)-(e)) -> bimera detection on the resulting ASV table (8(f3)),
+would drive them): dereplication (8(f1), uniques left resident on the device) -> dada() core (8(a)-(e)) -> bimera detection on the resulting ASV table (8(f3)),
 with per-step wall / device times.  Synthetic reads: `nreads` Illumina-like 250 nt reads of 100 variants plus bimeras of
 them.   python tools/pipeline_demo.py [nreads=200000]"""
 import os
@@ -36,10 +36,10 @@ def main():
     reads = np.where(err, (reads + rng.integers(1, 4, (nreads, L))) % 4, reads)
     nt = np.frombuffer(b"ACGT", dtype=np.uint8)
     seqs = [bytes(nt[r]).decode() for r in reads]
-    t0 = time.perf_counter(); d = derep.derep_reads(seqs, q.ravel(), return_stats=True); t1 = time.perf_counter()
+    t0 = time.perf_counter(); d, res = derep.derep_reads(seqs, q.ravel(), return_stats=True, resident=True, want_quals=False); t1 = time.perf_counter()
     print("derep : %d reads -> %d uniques   %.1f ms wall (device %.1f ms, sort %.1f ms, %d launches)" % (
         nreads, len(d["uniques"]), (t1 - t0) * 1e3, d["stats"]["ms_device"], d["stats"]["ms_sort"], d["stats"]["gpu_launches"]))
-    t0 = time.perf_counter(); r = dada2_b200.dada_uniques(d["uniques"], d["abundances"], None, cases.tperr1(), d["quals"]); t1 = time.perf_counter()
+    t0 = time.perf_counter(); r = res.run(cases.tperr1()); t1 = time.perf_counter()          # the uniques never left the device
     asv = r["clustering"]["sequence"]; ab = np.asarray(r["clustering"]["abundance"])
     print("dada  : %d uniques -> %d ASVs   %.1f ms wall (device %.1f ms, %d launches)" % (
         len(d["uniques"]), len(asv), (t1 - t0) * 1e3, r["stats"]["ms_device"], r["stats"]["gpu_launches"]))
