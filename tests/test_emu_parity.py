@@ -74,7 +74,7 @@ def test_emu_e2e(emu, name):
     _gpu_tests().test_e2e_matches_reference_golden(name)
 
 
-@pytest.mark.parametrize("name", ["syn800_default", "syn800_band8", "syn700_ragged", "syn700_ragged_homo"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
+@pytest.mark.parametrize("name", ["syn800_band8", "syn700_ragged_homo"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
 def test_emu_e2e_nwfwd_v2(emu, monkeypatch, name):
     """The restructured loop-NW kernel (dd_nwfwd2.cu, DADA2B_NWFWD_V2=1) gives the reference's results."""
     monkeypatch.setenv("DADA2B_NWFWD_V2", "1")
@@ -192,7 +192,7 @@ def test_emu_large_tie_sets(emu, monkeypatch, fused):
     assert (emu.cuemu_launches(b"k_tail_final") > 0) == fused
 
 
-@pytest.mark.parametrize("name", ["syn800_default", "syn800_kdist", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
+@pytest.mark.parametrize("name", ["syn800_kdist", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
 def test_emu_e2e_pivot_screen(emu, monkeypatch, name):
     """The pivot pre-filter of the k-mer screen (dd_classify2.cu, DADA2B_PIVOT=1): triangle-inequality bound on the
     5-mer min-sum from the closest centre seen so far; must classify every pair exactly like k_classify."""
@@ -213,7 +213,7 @@ def test_emu_all_experimental_paths_together(emu, monkeypatch):
     assert emu.cuemu_launches(b"k_nwbound16") > 0
 
 
-@pytest.mark.parametrize("experimental", [False, True], ids=["default", "experimental"])
+@pytest.mark.parametrize("experimental", [False, True] if os.environ.get("DADA2B_EMU_FULL") else [False], ids=lambda e: "experimental" if e else "default")
 def test_emu_edge_cases(emu, monkeypatch, experimental):
     """tests/cases.py:edge_cases() on the emulated library (the GPU suite runs the same table in test_gpu_zzz_edge.py),
     with the default kernels and with every experimental path switched on."""
@@ -248,7 +248,7 @@ def test_emu_sharded_owner_mode_ties_and_extra_passes(emu, monkeypatch):
     _run_sharded(3, "syn800_maxclust5")
 
 
-@pytest.mark.parametrize("name", ["syn800_default", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
+@pytest.mark.parametrize("name", ["syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
 def test_emu_e2e_bound16(emu, monkeypatch, name):
     """DADA2B_BOUND16=1 (dd_nwbound.cu): the bound pass of the two-phase loop NW with two raws per lane group on the 16-bit
     SIMD datapath.  Goldens reproduced, and its survivor set equals the scalar bound pass's (same DP-cell total: the exact
