@@ -18,5 +18,5 @@ step ncu_bimera 900 ncu --set full --clock-control none --import-source on -k re
 # 5. BASELINE configs[4] flavour (1.5 kb, band 32, homopolymer gaps): default vs DADA2B_NWFWD_V2
 step config5 1800 python tools/run_config5.py 20000 1500
 # 6. the accelerated steps chained on the device: derep (resident) -> dada -> bimera, per-step wall / device times
-step pipeline 600 python tools/pipeline_demo.py 1000000
+step pipeline 600 python tools/pipeline_demo.py 400000
 cat "$OUT/summary.txt"
