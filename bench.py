@@ -114,7 +114,9 @@ AB_VARIANTS = [("nwfwd2", {"DADA2B_NWFWD_V2": "1"}),
                ("twophase", {"DADA2B_TWOPHASE": "1"}),
                ("nwfwd2_twophase_bound16", {"DADA2B_NWFWD_V2": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"}),
                ("all", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1"}),
-               ("everything", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"})]
+               ("everything", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"}),
+               ("everything_small16x4", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1",
+                                         "DADA2B_NWFWD_SMALL": "1"})]
 
 
 def _last_lines(txt, n=2, width=300):
@@ -214,7 +216,7 @@ def main():
     ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
                     help="N>1: shard ONE sample of N x nuniques uniques over the ranks (NCCL all-gather per split round; weak scaling) "
                          "or run one independent sample per rank (no collective)")
-    ap.add_argument("--ab-seconds", type=int, default=210,
+    ap.add_argument("--ab-seconds", type=int, default=240,
                     help="N=1: total wall budget for the post-measurement A/B of the experimental kernel variants (0 = off)")
     ap.add_argument("--bimera-seconds", type=int, default=90,
                     help="N=1: timeout of the post-measurement bimera-detection leg (0 = off)")
