@@ -177,7 +177,8 @@ def test_emu_e2e_fused_tail(emu, monkeypatch, name, np_passes):
     assert emu.cuemu_launches(b"k_tail_final") > 0
     assert emu.cuemu_launches(b"k_shuffle_max") == 0 and emu.cuemu_launches(b"k_p_update") == 0
     if np_passes == 1:      # rounds that moved raws in pass 0 continue with one more fused pass (and final) at a time
-        assert emu.cuemu_launches(b"k_tail_final") > emu.cuemu_launches(b"k_tail_link")
+        extra = emu.cuemu_launches(b"k_tail_final") - emu.cuemu_launches(b"k_tail_link")
+        assert extra >= 0 and (extra > 0 or name not in ("syn800_default", "syn800_maxclust5"))      # e.g. max_clust=1: nothing ever moves
 
 
 @pytest.mark.parametrize("fused", [False, True], ids=["default", "fused_tail"])
