@@ -145,7 +145,7 @@ def experimental_ab(seqs, ab, q, err, last, budget_s, device, leg_cmd=None, step
             e = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)), **env)
             try:
                 out = subprocess.run((leg_cmd or [sys.executable, os.path.join(ROOT, "tools", "ab_leg.py")]) + [wl, ref, str(steps), str(warmup)], env=e,
-                                     capture_output=True, text=True, timeout=min(75, left))
+                                     capture_output=True, text=True, timeout=min(45, left))
                 rows = [l for l in out.stdout.splitlines() if l.startswith("ABLEG ")]
                 res[tag] = json.loads(rows[-1][6:]) if rows else {"failed": _last_lines(out.stderr or out.stdout)}
             except subprocess.TimeoutExpired:
@@ -216,9 +216,9 @@ def main():
     ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
                     help="N>1: shard ONE sample of N x nuniques uniques over the ranks (NCCL all-gather per split round; weak scaling) "
                          "or run one independent sample per rank (no collective)")
-    ap.add_argument("--ab-seconds", type=int, default=240,
+    ap.add_argument("--ab-seconds", type=int, default=150,
                     help="N=1: total wall budget for the post-measurement A/B of the experimental kernel variants (0 = off)")
-    ap.add_argument("--bimera-seconds", type=int, default=90,
+    ap.add_argument("--bimera-seconds", type=int, default=60,
                     help="N=1: timeout of the post-measurement bimera-detection leg (0 = off)")
     ap.add_argument("--watchdog", type=int, default=1500, help="dump stacks and exit after this many seconds")
     args = ap.parse_args()
