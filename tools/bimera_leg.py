@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 
 
 def main():
-    nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+    nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
     nsample = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     from tools import synth
     from dada2_b200 import bimera
