@@ -86,4 +86,13 @@ while time.time() < t_end:
     s, qq = D.synthetic(int(rng.integers(50, 900)), seed=int(rng.integers(0, 1 << 30)), L=int(rng.integers(14, 90)), nvar=int(rng.integers(2, 30)), zero_len=int(rng.integers(0, 3)))
     n = int(rng.choice([1000000, 7, 64, 300]))
     D.assert_same(derep.derep_reads(s, qq, n=n), OD.derep_reads(s, qq, n=n), "derep fuzz")
+    if it % 8 == 0:                      # derep left resident on the device -> dada() == the two-call form (bit-identical)
+        import dada2_b200
+        from tests import cases
+        keep = [i for i in range(len(s)) if len(s[i]) > 10 or len(s[i]) == 0]
+        s3, q3 = [s[i] for i in keep], [qq[i] for i in keep]
+        d3, r3 = derep.derep_reads(s3, q3, n=n, resident=True)
+        e3 = np.full((16, 45), 0.01); e3[[0, 5, 10, 15]] = 0.97
+        cases.assert_same(r3.run(e3), dada2_b200.dada_uniques(d3["uniques"], d3["abundances"], None, e3, d3["quals"]), rtol=0, label="derep resident fuzz")
+        r3.close()
 print("FUZZ OK iterations", it, "bimera pairs", npairs)
