@@ -353,8 +353,10 @@ struct Run {
   unsigned move_cap = 0;
   DBuf<uint32_t> fb_list, surv_list, uneq_list;
   DBuf<unsigned long long> uneq_ctr;
-  bool bound16 = false;                  // two raws per lane group in the bound pass (experimental, DADA2B_BOUND16=1; dd_nwbound.cu)
-  DBuf<double> raw_S, raw_rho;           // two-phase loop NW (experimental, DADA2B_TWOPHASE=1): per-raw bound factors
+  DBuf<double> raw_S, raw_rho;           // two-phase loop NW: per-raw bound factors (dd_round.cu:k_raw_bounds)
+  DBuf<uint32_t> row_mv;                 // thread-per-pair exact NW (dd_nwrow.cu): per-thread scratch columns for the moves ...
+  DBuf<uint16_t> row_sub;                // ... and the substitutions found by the traceback
+  int row_grid_cap = 0;
   bool two_phase = false;
   // pivot pre-filter of the k-mer screen (experimental, DADA2B_PIVOT=1; dd_classify2.cu)
   bool pivot = false;
@@ -399,7 +401,7 @@ struct Run {
   struct Ev { cudaEvent_t a, b; int tag; };
   std::vector<Ev> evs;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  enum { T_CLASSIFY = 0, T_NW, T_GL, T_FINAL, T_N };
+  enum { T_CLASSIFY = 0, T_NW, T_GL, T_FINAL, T_NWB, T_N };
   template <typename F> void timed(int tag, F f) {
     Ev e{cx->get_event(), cx->get_event(), tag};
     cudaEventRecord(e.a, s); f(); cudaEventRecord(e.b, s);
@@ -581,10 +583,13 @@ void Run::alloc_state() {
   ctr.alloc(CTR_N); h_ctr.alloc(CTR_N);
   DBG("alloc: ctr done");
   move_cap = (unsigned)(4 * n + 1024); fb_list.alloc(n);
-  two_phase = getenv("DADA2B_TWOPHASE") != nullptr;      // off by default: not yet validated on hardware
-  if (two_phase) { surv_list.alloc(n); raw_S.alloc(n); raw_rho.alloc(n); }
-  bound16 = two_phase && getenv("DADA2B_BOUND16") != nullptr;
-  if (bound16) { uneq_list.alloc(n + 2); uneq_ctr.alloc(1); }
+  two_phase = getenv("DADA2B_NO_TWOPHASE") == nullptr;    // bound pass first, exact lambda for the survivors only
+  if (two_phase) { surv_list.alloc(n); raw_S.alloc(n); raw_rho.alloc(n); uneq_list.alloc(n + 2); uneq_ctr.alloc(1); }
+  if (nwrow_usable(P, in.maxlen) && P.band >= 0) {
+    row_grid_cap = nwrow_exact_grid(cx->num_sms, nraw);
+    row_mv.alloc(nwrow_mv_words(P.band, in.maxlen, row_grid_cap)); row_sub.alloc(nwrow_sub_halfwords(in.maxlen, row_grid_cap));
+    if (!uneq_list.p) { uneq_list.alloc(n + 2); uneq_ctr.alloc(1); }
+  } else { row_mv.free(); row_sub.free(); }
   pivot = getenv("DADA2B_PIVOT") != nullptr;             // off by default: not yet validated on hardware
   if (pivot) { pv_cluster.alloc(n); pv_ms.alloc(n); CK(cudaMemsetAsync(pv_cluster.p, 0xFF, n * 4, s)); pv_ms.zero(s); }
   if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
@@ -703,17 +708,27 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       FwdArgs fbnd = f;
       fbnd.raw_S = raw_S.p; fbnd.raw_rho = raw_rho.p; fbnd.surv_list = surv_list.p; fbnd.surv_count = st.ctr + CTR_SURV;
       CK(cudaMemsetAsync(ctr.p + CTR_SURV, 0, 8, s));
-      bool done16 = false;
-      if (bound16) {              // two raws per lane group on the 16-bit SIMD datapath; unequal-length neighbours come back in uneq_list
-        CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
-        timed(T_NW, [&]() { done16 = launch_nwbound16(fbnd, uneq_list.p, uneq_ctr.p, fwd_slots, (unsigned long long)nraw, est_active, cx->num_sms, s); });
-        if (done16) { fbnd.jobs = uneq_list.p; fbnd.njobs_ptr = uneq_ctr.p; }
-      }
-      timed(T_NW, [&]() { fwd_done = launch_nwfwd_sel(fbnd, fwd_slots, (unsigned long long)nraw, done16 ? 0 : est_active, cx->num_sms, s, true); });
+      CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
+      // thread-per-pair row kernel (dd_nwrow.cu) for raws as long as the centre; the others come back in uneq_list
+      bool done_row = false;
+      timed(T_NWB, [&]() { done_row = launch_nwrow_bound(fbnd, uneq_list.p, uneq_ctr.p, (int)cx->len[c], (unsigned long long)nraw, cx->num_sms, s); });
+      if (done_row) { fbnd.jobs = uneq_list.p; fbnd.njobs_ptr = uneq_ctr.p; }
+      bool done_rest = done_row && in.minlen == in.maxlen;          // every raw has the centre's length: nothing was handed back
+      if (!done_rest)
+        timed(T_NWB, [&]() { done_rest = launch_nwfwd(fbnd, fwd_slots, (unsigned long long)nraw, done_row ? 0 : est_active, cx->num_sms, s, true); });
       // pass 2: the exact forward-carry kernel on the survivors
-      if (fwd_done) { f.jobs = surv_list.p; f.njobs_ptr = st.ctr + CTR_SURV; }
+      if (done_rest) { f.jobs = surv_list.p; f.njobs_ptr = st.ctr + CTR_SURV; f.no_cells = 1; }
     }
-    timed(T_NW, [&]() { fwd_done = launch_nwfwd_sel(f, fwd_slots, (unsigned long long)nraw, i == 0 ? (unsigned long long)nraw : est_active, cx->num_sms, s); });
+    // exact pass: thread-per-pair row kernel with recorded moves + traceback (dd_nwrow.cu); what it hands back (raws not as
+    // long as the centre) and every configuration it does not cover go through the lane-group forward-carry kernel
+    bool ex_done = false;
+    if (row_mv.p) {
+      CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
+      timed(T_NW, [&]() { ex_done = launch_nwrow_exact(f, uneq_list.p, uneq_ctr.p, row_mv.p, row_sub.p, (int)cx->len[c], (unsigned long long)nraw, row_grid_cap, s); });
+      if (ex_done) { f.jobs = uneq_list.p; f.njobs_ptr = uneq_ctr.p; }
+    }
+    if (ex_done && in.minlen == in.maxlen) fwd_done = true;       // nothing was handed back; fb_list stays empty
+    else timed(T_NW, [&]() { fwd_done = launch_nwfwd_sel(f, fwd_slots, (unsigned long long)nraw, ex_done ? 0 : (i == 0 ? (unsigned long long)nraw : est_active), cx->num_sms, s); });
   }
   for (int kind : {KIND_NW, KIND_GAPLESS}) {
     AlignArgs a = align_args(MODE_LOOP, kind);
@@ -1044,7 +1059,13 @@ void Run::finish(dada2b_out *out) {
       { unsigned long long z = 0; h2d(ctr.p + CTR_NMOVE, &z, 8); }
       const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::max(std::abs(P.gap), std::abs(P.hgap)) + 16;
       f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
-      timed(T_FINAL, [&]() { split = launch_nwfwd_sel(f, fwd_slots, (unsigned long long)nraw, (unsigned long long)nraw, cx->num_sms, s); });
+      bool row_done = false;
+      if (uneq_list.p) {       // thread-per-pair row kernel when every sequence has the same length (dd_nwrow.cu), else the lane-group kernel
+        CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
+        timed(T_FINAL, [&]() { row_done = launch_nwrow_final(f, uneq_list.p, uneq_ctr.p, (unsigned long long)nraw, cx->num_sms, s); });
+      }
+      if (row_done) split = true;
+      else timed(T_FINAL, [&]() { split = launch_nwfwd_sel(f, fwd_slots, (unsigned long long)nraw, (unsigned long long)nraw, cx->num_sms, s); });
     }
     if (split) {
       // 2) gapless column list for the pure-diagonal pairs, 3) traceback kernel for the rest (+ pairs that did not fit)
@@ -1257,8 +1278,10 @@ void Run::finish(dada2b_out *out) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
   out->ms_device = ms;
-  double sum[T_N] = {0, 0, 0, 0}; int cnt[T_N] = {0, 0, 0, 0};
+  double sum[T_N] = {0, 0, 0, 0, 0}; int cnt[T_N] = {0, 0, 0, 0, 0};
   for (const Ev &e : evs) { float t = 0; if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) { sum[e.tag] += t; cnt[e.tag]++; } }
+  if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] loop NW: bound pass %.3f ms (%d launches), exact %.3f ms (%d launches)\n", sum[T_NWB], cnt[T_NWB], sum[T_NW], cnt[T_NW]);
+  sum[T_NW] += sum[T_NWB]; cnt[T_NW] += cnt[T_NWB];
   out->ms_k_classify = sum[T_CLASSIFY]; out->ms_k_align_nw = sum[T_NW]; out->ms_k_align_gl = sum[T_GL]; out->ms_k_align_final = sum[T_FINAL];
   out->n_k_classify = cnt[T_CLASSIFY]; out->n_k_align_nw = cnt[T_NW]; out->n_k_align_gl = cnt[T_GL]; out->n_k_align_final = cnt[T_FINAL];
   out->n_final_nw = (P.band == 0) ? 0 : nraw;

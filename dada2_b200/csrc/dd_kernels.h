@@ -76,6 +76,7 @@ struct FwdArgs {
   const double *raw_S, *raw_rho;
   uint32_t *surv_list;
   unsigned long long *surv_count;
+  int no_cells;                         // pass 2 of the two-phase scheme: the bound pass already counted these pairs' DP cells
 };
 bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s,
                   bool bound_only = false);
@@ -91,6 +92,18 @@ inline bool launch_nwfwd_sel(const FwdArgs &a, int slots_needed, unsigned long l
 // dd_nwbound.cu: the bound pass on the 16-bit SIMD datapath, two raws per lane group (EXPERIMENTAL, DADA2B_BOUND16=1 with DADA2B_TWOPHASE=1)
 bool launch_nwbound16(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, int slots_needed, unsigned long long njobs_upper,
                       unsigned long long njobs_hint, int num_sms, cudaStream_t s);
+// dd_nwrow.cu: thread-per-pair row kernel, bound pass over f.jobs (raws as long as the centre; the rest -> uneq_list)
+bool launch_nwrow_bound(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, int len1, unsigned long long njobs_upper, int num_sms,
+                        cudaStream_t s);
+bool launch_nwrow_final(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, unsigned long long njobs_upper, int num_sms,
+                        cudaStream_t s);
+// exact pass: per-thread scratch columns for the recorded moves / substitutions; the grid is capped by what was allocated
+int nwrow_exact_grid(int num_sms, int nraw);
+size_t nwrow_mv_words(int band, int maxlen, int grid);
+size_t nwrow_sub_halfwords(int maxlen, int grid);
+bool nwrow_usable(const AlnParams &P, int len1);
+bool launch_nwrow_exact(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, uint32_t *mv_scratch, uint16_t *sub_scratch, int len1,
+                        unsigned long long njobs_upper, int grid_cap, cudaStream_t s);
 void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, cudaStream_t s);
 void count_launch(int n);
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
 #pragma unroll
     for (int t = 0; t < ND; t++) if (t == tf) { lam = LAM[t]; ns = NSUB[t]; }
     const bool owner = act && tf >= 0 && tf < ND;
-    if (owner) cells_lane += band_cells(len1, len2, lband, rband);
+    if (owner && !a.no_cells) cells_lane += band_cells(len1, len2, lband, rband);
     if (final_mode) {
       // FinalSubsParallel (Rmain.cpp:179-236): nsubs of the final alignment; pairs whose optimal path is the pure
       // diagonal get the trivial (gapless) column list, the rest go to the traceback kernel.

@@ -151,6 +151,8 @@ inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; i++
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) { return (unsigned)((((uint64_t)hi << 32) | lo) >> (shift & 31)); }
 inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) { return (unsigned)(((((uint64_t)hi << 32) | lo) << (shift & 31)) >> 32); }
 inline int __vimax3_s32(int a, int b, int c) { return std::max(std::max(a, b), c); }
+inline int __viaddmax_s32(int a, int b, int c) { return std::max((int)((unsigned)a + (unsigned)b), c); }   // VIADDMNMX: wrapping add, signed max
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * (uint64_t)b) >> 32); }
 // 16-bit SIMD (two signed halves per word): VIADD.16x2 / VIMNMX.S16x2 with per-half predicate outputs / PRMT
 inline unsigned __vadd2(unsigned a, unsigned b) { return ((a + b) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16); }
 inline unsigned __vibmax_s16x2(unsigned a, unsigned b, bool *pred_hi, bool *pred_lo) {
