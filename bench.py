@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- unique-reads/s through the dada() core (BASELINE.json metric) on N B200s.
 
-A "step" is one dada_uniques()-equivalent pass over one batch of synthetic dereplicated
-reads (BASELINE.json configs[1]: 1e5 synthetic 250 nt uniques, Zipf abundances, 100 true
-variants, Illumina-like qualities, tperr1 error matrix, selfConsist=FALSE, default options).
+A "step" is one dada_uniques()-equivalent pass over one batch of synthetic dereplicated reads.
+
+Workload (the configuration BASELINE.json's targets are quoted on): 1e6 synthetic 250 nt uniques (Zipf abundances, 100
+true variants, Illumina-like qualities, seed 12345), tperr1 error matrix, default options, one dada() pass
+(selfConsist=FALSE; the selfConsist loop of configs[2] is the separate "selfconsist" leg).  BASELINE configs[1]
+(1e5 uniques) is reported as the secondary "configs1" object at N = 1.
 
   value  : uniques/s with the packed uniques already resident in HBM (Resident.run)
-  e2e    : uniques/s through the one-shot C-ABI call dada2b_run() on HOST buffers
-           (pack + H2D + loop + D2H of every output inside the timed region)
-  N > 1  : one process per GPU (torchrun); each rank denoises its own sample -- the
-           reference's per-sample loop (R/dada.R:266) -- no data-path collective, "weak".
-  --impl reference : the reference's own C++ (oracle/_ref, compiled unmodified from
-           /root/reference/src in the build container) on the host cores, same workload.
+  e2e    : uniques/s through the C-ABI on HOST buffers: N = 1: the one-shot dada2b_run() (pack + H2D + loop + D2H of every
+           output inside the timed region); N > 1: dada2b_reupload() + dada2b_run_resident() on every rank
+  N > 1  : one process per GPU (torchrun); the SAME 1e6 sample sharded over the ranks (raw r on rank r % N) -- BASELINE
+           configs[3] -- "strong" scaling
+  parity : at every N, rank 0 runs the reference's own C++ on the same sample once and diffs the full output; a mismatch
+           makes the run exit non-zero
+  --impl reference : the reference's own C++ (oracle/_ref, compiled unmodified from /root/reference/src in the build
+           container) on the host cores, same workload, full size.
 """
 import argparse
 import json
@@ -26,7 +31,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NUNIQ_DEFAULT = 100000
+NUNIQ_DEFAULT = 1000000
+WORKLOAD = ("BASELINE configs[2]/[3] size: %d synthetic 250 nt uniques in ONE sample (100 variants, Zipf abundances, Illumina-like quals, seed 12345), "
+            "tperr1, dada() default options, one pass (selfConsist=FALSE)")
 
 
 def workload(n_uniques, seed):
@@ -106,103 +113,142 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-AB_VARIANTS = [("nwfwd2", {"DADA2B_NWFWD_V2": "1"}),
-               ("small16x4", {"DADA2B_NWFWD_SMALL": "1"}),
-               ("nwfwd2_small16x4", {"DADA2B_NWFWD_V2": "1", "DADA2B_NWFWD_SMALL": "1"}),
-               ("fused_tail", {"DADA2B_FUSED_TAIL": "1"}),
-               ("pivot", {"DADA2B_PIVOT": "1"}),
-               ("twophase", {"DADA2B_TWOPHASE": "1"}),
-               ("nwfwd2_twophase_bound16", {"DADA2B_NWFWD_V2": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"}),
-               ("all", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1"}),
-               ("everything", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"}),
-               ("everything_small16x4", {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1",
-                                         "DADA2B_NWFWD_SMALL": "1"})]
-
-
 def _last_lines(txt, n=2, width=300):
     """The end of a failed leg's output: the exception line, not the middle of its traceback."""
     rows = [l.strip() for l in txt.strip().splitlines() if l.strip()]
     return " | ".join(rows[-n:])[-width:]
 
 
-def experimental_ab(seqs, ab, q, err, last, budget_s, device, leg_cmd=None, steps=3, warmup=2, variants=None):
-    """After the measured region (N=1 only): every off-by-default kernel variant runs the same workload
-    in its own subprocess under a timeout, and its outputs are diffed against the default path's.  Reported under
-    "experimental_ab"; never part of `value`/`e2e`.  Bounded by `budget_s` seconds in total."""
-    import tempfile
-    from tests import cases
-    t_start = time.time()
-    res = {}
-    with tempfile.TemporaryDirectory() as td:
-        wl, ref = os.path.join(td, "wl.npz"), os.path.join(td, "ref.npz")
-        np.savez(wl, seqs=np.array(seqs), ab=np.asarray(ab), q=np.asarray(q), err=np.asarray(err))
-        np.savez(ref, **cases.flatten(last))
-        for tag, env in (variants or AB_VARIANTS):
-            left = budget_s - (time.time() - t_start)
-            if left < 20:
-                res[tag] = {"skipped": "A/B time budget spent"}
-                continue
-            e = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)), **env)
-            try:
-                out = subprocess.run((leg_cmd or [sys.executable, os.path.join(ROOT, "tools", "ab_leg.py")]) + [wl, ref, str(steps), str(warmup)], env=e,
-                                     capture_output=True, text=True, timeout=min(45, left))
-                rows = [l for l in out.stdout.splitlines() if l.startswith("ABLEG ")]
-                res[tag] = json.loads(rows[-1][6:]) if rows else {"failed": _last_lines(out.stderr or out.stdout)}
-            except subprocess.TimeoutExpired:
-                res[tag] = {"failed": "timeout"}
-            except Exception as ex:                      # never let the A/B leg take the bench line down
-                res[tag] = {"failed": repr(ex)[:200]}
-            res[tag]["switches"] = sorted(env)
-    return res
-
-
-def bimera_leg(budget_s, device, cmd=None):
-    """After the measured region (N=1 only): SURVEY.md 8(f3)'s bimera detection timed through its C-ABI on a synthetic
-    sequence table, next to the reference's C_table_bimera2 on the host cores, in a subprocess under a timeout (the
-    kernels are new: first run on hardware).  Reported under "bimera"; never part of `value`/`e2e`."""
+def subprocess_leg(tag, cmd, budget_s, device):
+    """A post-measurement leg in its own process under a timeout (N = 1 only); prints one `<TAG> {json}` line.
+    Reported under its own key; never part of `value` / `e2e`."""
     e = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)))
     try:
-        out = subprocess.run(cmd or [sys.executable, os.path.join(ROOT, "tools", "bimera_leg.py")], env=e, capture_output=True, text=True,
-                             timeout=budget_s)
-        rows = [l for l in out.stdout.splitlines() if l.startswith("BIMLEG ")]
-        return json.loads(rows[-1][7:]) if rows else {"failed": _last_lines(out.stderr or out.stdout)}
+        out = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=budget_s)
+        rows = [l for l in out.stdout.splitlines() if l.startswith(tag + " ")]
+        return json.loads(rows[-1][len(tag) + 1:]) if rows else {"failed": _last_lines(out.stderr or out.stdout)}
     except subprocess.TimeoutExpired:
         return {"failed": "timeout"}
     except Exception as ex:
         return {"failed": repr(ex)[:200]}
 
 
+def bimera_leg(budget_s, device, cmd=None):
+    """SURVEY.md 8(f3)'s bimera detection timed through its C-ABI on a synthetic sequence table, next to the reference's
+    C_table_bimera2 on the host cores."""
+    return subprocess_leg("BIMLEG", cmd or [sys.executable, os.path.join(ROOT, "tools", "bimera_leg.py")], budget_s, device)
+
+
+def cpu_reference(seqs, ab, err, q):
+    """One pass of the reference's own C++ (or of the port when oracle/_ref is absent) on all host cores."""
+    from oracle import ref
+    ncores = os.cpu_count() or 1
+    if ref.available():
+        ref.set_threads(ncores)
+        t0 = time.perf_counter()
+        cres = ref.dada_uniques(seqs, ab, None, err, q, multithread=True)
+        return cres, time.perf_counter() - t0, ncores, "reference"
+    from oracle import port
+    t0 = time.perf_counter()
+    cres = port.dada_uniques(seqs, ab, None, err, q)
+    return cres, time.perf_counter() - t0, 1, "port"
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation, all host threads, same workload."""
+    """--impl reference: the reference's CPU implementation, all host threads, the SAME full-size workload.  One step = one
+    full pass.  The run is bounded in wall time (N = 1: ~23 min, N > 1: ~7 min, where the same CPU measurement would only
+    be repeated): warm-up is cut to one pass first, then the number of timed passes -- never the size; `steps` is what ran."""
     if rank != 0:
         return
     from oracle import ref
     ncores = os.cpu_count() or 1
     ref.set_threads(ncores)
-    # same workload as the B200 arm (N x nuniques uniques in one sample when sharded), bounded to 2 x nuniques so that
-    # warmup + steps passes of the CPU implementation end within a few minutes
-    total = args.nuniques * (world if args.mode == "shard" else 1)
-    n_s = min(total, 2 * args.nuniques)
-    seqs, ab, q, err = workload(n_s, 12345)
+    seqs, ab, q, err = workload(args.nuniques, 12345)
+    budget = float(os.environ.get("DADA2B_REF_BUDGET_S", 1400 if world == 1 else 420))
+    t_begin = time.perf_counter()
+    warm = min(args.warmup, 1) if args.nuniques >= 500000 else args.warmup
     times = []
-    for it in range(args.warmup + args.steps):
+    it = 0
+    while len(times) < args.steps:
         t0 = time.perf_counter()
         ref.dada_uniques(seqs, ab, None, err, q, multithread=True)
         dt = time.perf_counter() - t0
-        if it >= args.warmup:
+        if it >= warm:
             times.append(dt)
+        it += 1
+        if times and (time.perf_counter() - t_begin) + dt > budget:
+            break
     tsum = sum(times)
-    val = n_s * len(times) / tsum
+    val = args.nuniques * len(times) / tsum
     line = {"impl": "reference", "metric": "unique-reads/sec through dada()", "value": val, "unit": "uniques/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tsum / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 + f64",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": 1e3 * tsum / len(times),
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "int16/int32 + f64",
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: %d synthetic 250 nt uniques per GPU (%d in total), 100 variants (Zipf), Illumina-like quals, "
-                                   "tperr1, dada() selfConsist=FALSE, default options" % (args.nuniques, total)},
+            "config": {"workload": WORKLOAD % args.nuniques},
             "cpu_baseline": {"value": val, "unit": "uniques/s", "cores": ncores, "kind": "reference",
-                             "sample": "%d-unique sample (%s) per step, multithread=TRUE on %d threads (parallelFor shim over std::thread)" % (n_s, "the full workload" if n_s == total else "bounded from %d" % total, ncores)},
+                             "sample": "the full %d-unique workload per step, multithread=TRUE on %d threads (parallelFor shim over a "
+                                       "persistent std::thread pool); %d timed passes inside a %.0f s budget" % (args.nuniques, ncores, len(times), budget)},
             "e2e": {"value": val, "unit": "uniques/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def measure(res, err, steps, warmup, flush, barrier, torch):
+    """`warmup` untimed + exactly `steps` timed resident passes -> (seconds, per-step ms, device ms sum, last result)."""
+    last = None
+    for _ in range(warmup):
+        last = res.run(err)
+        flush.zero_()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, step_ms, step_host = 0.0, [], []
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ts = time.perf_counter()
+        last = res.run(err)
+        step_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
+        step_host.append([round(last["stats"][k], 2) for k in ("ms_setup", "ms_loop", "ms_final")])
+        dev_ms += last["stats"]["ms_device"]
+    barrier()
+    return time.perf_counter() - t0, step_ms, step_host, dev_ms, last
+
+
+def configs1_leg(local_rank, flush, torch, do_cpu):
+    """BASELINE configs[1] (1e5 uniques, one GPU) as a secondary object: value, e2e, parity against the CPU reference."""
+    import dada2_b200
+    from tests import cases
+    n = 100000
+    seqs, ab, q, err = workload(n, 12345)
+    res = dada2_b200.Resident(seqs, ab, None, q, device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+    t_val, step_ms, _h, dev_ms, last = measure(res, err, 10, 3, flush, barrier, torch)
+    res.close()
+    call = dada2_b200.PackedCall(seqs, ab, None, err, q)
+    call.run(unpack=False)
+    e2e_ms = []
+    for _ in range(10):
+        flush.zero_()
+        torch.cuda.synchronize()
+        _r, ms = call.run(unpack=False)
+        e2e_ms.append(ms)
+    st = last["stats"]
+    out = {"workload": "BASELINE configs[1]: 100000 synthetic 250 nt uniques, 1 GPU, 10 timed steps after 3 warm-up",
+           "value": n * 10 / t_val, "unit": "uniques/s", "ms_per_step": 1e3 * t_val / 10, "ms_per_step_median": float(np.median(step_ms)),
+           "e2e": {"value": n / (float(np.mean(e2e_ms)) / 1e3), "ms_per_step": float(np.mean(e2e_ms)), "ms_per_step_median": float(np.median(e2e_ms))},
+           "device_ms_per_step": dev_ms / 10, "gpu_launches_per_step": int(st["gpu_launches"]),
+           "kernel_ms": {k: st[k] for k in st if k.startswith("ms_k_")}}
+    if do_cpu:
+        cres, dt, ncores, kind = cpu_reference(seqs, ab, err, q)
+        out["cpu_baseline"] = {"value": n / dt, "unit": "uniques/s", "cores": ncores, "kind": kind, "sample": "all 100000 uniques, one pass, %.1f s" % dt}
+        try:
+            cases.assert_same(last, cres, rtol=1e-10, label="configs1")
+            out["parity"] = "identical"
+        except AssertionError as e:
+            out["parity"] = "MISMATCH: %s" % str(e)[:300]
+    return out
 
 
 def main():
@@ -212,15 +258,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nuniques", type=int, default=NUNIQ_DEFAULT)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
-                    help="N>1: shard ONE sample of N x nuniques uniques over the ranks (NCCL all-gather per split round; weak scaling) "
-                         "or run one independent sample per rank (no collective)")
-    ap.add_argument("--ab-seconds", type=int, default=150,
-                    help="N=1: total wall budget for the post-measurement A/B of the experimental kernel variants (0 = off)")
-    ap.add_argument("--bimera-seconds", type=int, default=60,
-                    help="N=1: timeout of the post-measurement bimera-detection leg (0 = off)")
-    ap.add_argument("--watchdog", type=int, default=1500, help="dump stacks and exit after this many seconds")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference pass (no parity diff, no cpu_baseline)")
+    ap.add_argument("--no-legs", action="store_true", help="N=1: skip the secondary legs (configs1, selfconsist, config5, bimera)")
+    ap.add_argument("--bimera-seconds", type=int, default=60, help="N=1: timeout of the post-measurement bimera-detection leg (0 = off)")
+    ap.add_argument("--watchdog", type=int, default=1700, help="dump stacks and exit after this many seconds")
     args = ap.parse_args()
     import faulthandler
     faulthandler.dump_traceback_later(args.watchdog, exit=True)
@@ -231,11 +272,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import datetime
     import torch
     import torch.distributed as dist
     import dada2_b200
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=30))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
@@ -244,11 +286,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    shard = world > 1 and args.mode == "shard"
-    if shard:
-        seqs, ab, q, err = workload(args.nuniques * world, 12345)       # same sample on every rank
-    else:
-        seqs, ab, q, err = workload(args.nuniques, 12345 + rank)
+    shard = world > 1
+    seqs, ab, q, err = workload(args.nuniques, 12345)                      # the same sample on every rank
     nraw = len(seqs)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -258,30 +297,14 @@ def main():
         res = multi.sharded_resident(seqs, ab, None, q, device=local_rank)
     else:
         res = dada2_b200.Resident(seqs, ab, None, q, device=local_rank)
-    last = None
     sampler = ClockSampler(local_rank)
-    sampler.start()                      # nvidia-smi's start-up takes ~1 s of driver calls: keep it out of the timed region
-    for _ in range(args.warmup):
-        last = res.run(err)
-        flush.zero_()
+    sampler.start()                      # NVML start-up takes ~1 s of driver calls: keep it out of the timed region
+    res.run(err)
     t_wait = time.time()
     while not sampler.rows and time.time() - t_wait < (0 if os.environ.get("DADA2B_BENCH_NOCLOCKS") else 10):
         time.sleep(0.05)
     sampler.rows.clear()
-    barrier()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    step_ms, step_host = [], []
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        ts = time.perf_counter()
-        last = res.run(err)
-        step_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
-        step_host.append([round(last["stats"][k], 2) for k in ("ms_setup", "ms_loop", "ms_final")])
-        dev_ms += last["stats"]["ms_device"]
-    barrier()
-    t_val = time.perf_counter() - t0
+    t_val, step_ms, step_host, dev_ms, last = measure(res, err, args.steps, max(0, args.warmup - 1), flush, barrier, torch)
     st = last["stats"]
 
     # ---------------- e2e: host buffers in, host buffers out, through the C-ABI ----------------
@@ -305,9 +328,8 @@ def main():
             e2e_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
         barrier()
         t_e2e = time.perf_counter() - t0
-        L0 = len(seqs[0])
         est = dict(est)
-        est["h2d_bytes"] += nraw * ((((L0 + 15) // 16 + 3) & ~3) * 4 + ((L0 + 15) & ~15) + 7)   # packed upload of dada2b_reupload
+        est["h2d_bytes"] += int(res.upload_h2d_bytes()) if hasattr(res, "upload_h2d_bytes") else 0
     else:
         call = dada2_b200.PackedCall(seqs, ab, None, err, q)
         for _ in range(max(1, args.warmup // 2)):
@@ -328,102 +350,114 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_val, t_e2e = float(tt[0]), float(tt[1])
-    units = nraw if shard else world * nraw          # uniques denoised per step by the whole job
-    value = units * args.steps / t_val
-    e2e = units * args.steps / t_e2e
+    value = nraw * args.steps / t_val               # the whole job denoises the ONE sample per step
+    e2e = nraw * args.steps / t_e2e
 
+    rc = 0
     if rank == 0:
+        from tests import cases
         L = len(seqs[0])
-        bytes_per_pair = (L + 3) // 4 + 16 + L                      # SURVEY.md 8(d): S + O + Q for an aligned pair
-        pairs = st["n_nw"]                                         # loop alignments (k_nwfwd + its fallback)
-        k_ms = st["ms_k_align_nw"]
-        n_launch = st["n_rounds"] + 1                              # one k_nwfwd launch per compare round
         peak, peak_src = measured_peak_gbs()
+        # ---- roofline of the dominant kernel family (CUDA-event sums per family, measured inside the library on its stream) ----
+        bytes_per_pair = (L + 3) // 4 + 16 + L                      # SURVEY.md 8(d): S + O + Q for an aligned pair
+        pairs = st["n_nw"]
+        fam = {"nw (k_nwrow / k_nwlane / k_nwfwd: loop banded NW, bound + exact)": st["ms_k_align_nw"],
+               "screen (k_prescreen + k_classify)": st["ms_k_classify"],
+               "final pass (k_nwrow<FINAL> + k_align<FINAL>)": st["ms_k_align_final"],
+               "round control (k_tail_* / k_shuffle_* / k_p_update / k_bud_*)": st.get("ms_k_tail", 0.0)}
+        dominant = max(fam, key=fam.get)
+        k_ms = st["ms_k_align_nw"]
+        n_launch = max(1, st["n_k_align_nw"])
         achieved = (pairs * bytes_per_pair / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0
         prof = {}
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_final_k_nwfwd_metrics.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_metrics.json")))
         except Exception:
             pass
-        traffic = prof.get("dram_bytes_per_pair")
-        roofline = {"bound": "hbm", "kernel": "k_nwfwd (loop banded NW with forward-carried lambda; CUDA-event sum over its launches)",
+        cells_pair = L * 33 - 16 * 17
+        roofline = {"bound": "hbm", "kernel": "loop NW family (dd_nwrow.cu / dd_nwlane.cu): CUDA-event sum over its launches",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": (traffic * pairs / n_launch) if traffic else None,
-                    "traffic_note": "ncu dram read+write bytes per aligned pair x average pairs per launch (profiles/r1_final_k_nwfwd_full.txt)",
+                    "traffic": prof.get("nw_dram_bytes_per_launch"),
                     "peak_source": peak_src, "algorithmic_bytes_per_pair": bytes_per_pair,
                     "algorithmic_bytes_per_launch": bytes_per_pair * pairs / n_launch, "pairs_per_step": int(pairs),
-                    "kernel_ms_per_step": k_ms, "launches_per_step": int(n_launch), "avg_launch_ms": k_ms / max(1, n_launch),
-                    "nw_gcups": (pairs * (L * 33 - 16 * 17) / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0,
+                    "kernel_ms_per_step": k_ms, "launches_per_step": int(n_launch), "avg_launch_ms": k_ms / n_launch,
+                    "nw_gcups": (pairs * cells_pair / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0,
+                    "nw_bound_ms": st.get("ms_k_nw_bound"), "nw_exact_ms": st.get("ms_k_nw_exact"),
                     "kernel_share_of_device_time": k_ms / st["ms_device"] if st["ms_device"] else None,
-                    "issue_bound_evidence": prof.get("large_round"),
-                    "note": "integer DP is ALU-issue bound, not HBM-bound (DESIGN.md 4.2): the HBM fraction is low by construction"}
-        cpu = None
-        parity = None
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import ref
-            from tests import cases
-            ncores = os.cpu_count() or 1
-            kind = "reference" if ref.available() else "port"
-            n_s = args.nuniques if ncores >= 8 else min(args.nuniques, 25000)
-            if n_s == args.nuniques:
-                s_seqs, s_ab, s_q = seqs, ab, q
-            else:
-                s_seqs, s_ab, s_q, _ = workload(n_s, 12345)
-            if kind == "reference":
-                ref.set_threads(ncores)
-                t0 = time.perf_counter()
-                cres = ref.dada_uniques(s_seqs, s_ab, None, err, s_q, multithread=True)
-                dt = time.perf_counter() - t0
-            else:
-                from oracle import port
-                ncores = 1
-                t0 = time.perf_counter()
-                cres = port.dada_uniques(s_seqs, s_ab, None, err, s_q)
-                dt = time.perf_counter() - t0
-            cpu = {"value": n_s / dt, "unit": "uniques/s", "cores": ncores, "kind": kind,
-                   "sample": "%d-unique %s of the step workload, one pass, %.1f s" % (n_s, "= all" if n_s == nraw else "subsample", dt)}
-            if n_s == nraw:
-                try:
-                    cases.assert_same(last, cres, rtol=1e-10, label="bench")
-                    parity = "outputs identical to the CPU reference on this workload (ints exact, fp64 <= 1e-10)"
-                except AssertionError as e:
-                    parity = "MISMATCH: %s" % e
-        ab_res = None
-        clean_env = not any(k.startswith("DADA2B_") and k not in ("DADA2B_VERBOSE", "DADA2B_AB_TAG", "DADA2B_BENCH_NOCLOCKS") for k in os.environ)
-        if world == 1 and args.ab_seconds > 0 and clean_env:
+                    "family_ms": fam, "dominant_family": dominant,
+                    "issue_bound_evidence": prof.get("nw_large_round"),
+                    "note": "integer DP: 7 978 cells per 329 algorithmic bytes, bound by integer issue (DESIGN.md 4.2), so the HBM fraction is low "
+                            "by construction; the HBM-streaming kernel of the path is k_prescreen, reported in roofline_screen"}
+        # the DRAM-streaming kernel: one 128-byte bitmap row + 13 bytes of metadata per (centre, active raw) pair
+        ps_ms, ps_rows = st.get("ms_k_prescreen", 0.0), st.get("prescreen_rows", 0)
+        ps_bytes = 141
+        ps_ach = (ps_rows * ps_bytes / 1e9) / (ps_ms / 1e3) if ps_ms > 0 else 0.0
+        roofline_screen = {"bound": "hbm", "kernel": "k_prescreen (TMA-staged 5-mer presence bitmaps; CUDA-event sum over its launches)",
+                           "achieved": ps_ach, "peak": peak, "unit": "GB/s", "frac": ps_ach / peak,
+                           "algorithmic_bytes_per_row": ps_bytes, "rows_per_step": int(ps_rows), "kernel_ms_per_step": ps_ms,
+                           "launches_per_step": int(st.get("n_k_prescreen", 0)),
+                           "avg_launch_ms": ps_ms / max(1, st.get("n_k_prescreen", 0)),
+                           "traffic": prof.get("prescreen_dram_bytes_per_launch"),
+                           "note": "rows of this rank only (1/N of the sample); launches shorter than ~10 us are launch-latency bound"}
+        cpu, parity = None, None
+        if not args.no_cpu_baseline:
+            cres, dt, ncores, kind = cpu_reference(seqs, ab, err, q)
+            cpu = {"value": nraw / dt, "unit": "uniques/s", "cores": ncores, "kind": kind,
+                   "sample": "all %d uniques of the step workload, one pass, %.1f s" % (nraw, dt)}
             try:
-                ab_res = experimental_ab(seqs, ab, q, err, last, args.ab_seconds, local_rank)
+                cases.assert_same(last, cres, rtol=1e-10, label="bench")
+                parity = "identical: full output of rank 0 equals the CPU reference on this workload (ints exact, fp64 <= 1e-10)"
+            except AssertionError as e:
+                parity = "MISMATCH: %s" % str(e)[:400]
+                rc = 1
+        legs = {}
+        clean_env = not any(k.startswith("DADA2B_") and k not in ("DADA2B_VERBOSE", "DADA2B_BENCH_NOCLOCKS", "DADA2B_REF_BUDGET_S") for k in os.environ)
+        if world == 1 and not args.no_legs and clean_env:
+            try:
+                legs["configs1"] = configs1_leg(local_rank, flush, torch, not args.no_cpu_baseline)
+                if str(legs["configs1"].get("parity", "")).startswith("MISMATCH"):
+                    rc = 1
             except Exception as ex:
-                ab_res = {"failed": repr(ex)[:200]}
-        bim_res = None
-        if world == 1 and args.bimera_seconds > 0 and clean_env:
-            bim_res = bimera_leg(args.bimera_seconds, local_rank)
+                legs["configs1"] = {"failed": repr(ex)[:300]}
+            for tag, script, budget in (("selfconsist", "selfconsist_leg.py", 300), ("config5", "config5_leg.py", 420)):
+                if os.path.exists(os.path.join(ROOT, "tools", script)):
+                    legs[tag] = subprocess_leg(tag.upper(), [sys.executable, os.path.join(ROOT, "tools", script)], budget, local_rank)
+            if args.bimera_seconds > 0:
+                legs["bimera"] = bimera_leg(args.bimera_seconds, local_rank)
         line = {"metric": "unique-reads/sec through dada()", "value": value, "unit": "uniques/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_val / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 DP + f64 lambda/p-value",
-                "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: %d synthetic 250 nt uniques per GPU (%d in total), 100 variants (Zipf), Illumina-like quals, "
-                                       "tperr1, dada() selfConsist=FALSE, default options" % (args.nuniques, units),
-                           "per_gpu": ("ONE sample of %d uniques sharded over %d GPUs: raw r aligned on rank r %% N, one NCCL all-gather of "
-                                       "new stored comparisons per split round, final tallies all-reduced" % (nraw, world)) if shard else
-                                      "one sample per GPU (reference's per-sample loop); no data-path collective",
-                           "l2": "256 MB buffer written between timed iterations (inputs 32 MB < 126 MB L2)",
+                "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "int32 DP words (score|move|nsubs) + f64 lambda/p-value", "data": "synthetic",
+                "config": {"workload": WORKLOAD % nraw,
+                           "per_gpu": ("the ONE sample sharded over %d GPUs (strong scaling): raw r on rank r %% N, NCCL over NVLink per split round, "
+                                       "final tallies all-reduced; every rank returns the full result" % world) if shard else "one GPU",
+                           "l2": "256 MB buffer written between timed iterations (resident inputs at this size: 448 MB > 126 MB L2)",
                            "nclust": len(last["clustering"]["sequence"]), "rounds": st["n_rounds"], "shuffles": st["n_shuffles"],
-                           "experimental": sorted(k for k in os.environ if k.startswith("DADA2B_") and k not in ("DADA2B_VERBOSE", "DADA2B_AB_TAG"))},
+                           "switches": sorted(k for k in os.environ if k.startswith("DADA2B_") and k not in ("DADA2B_VERBOSE",))},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "uniques/s", "h2d_bytes_per_step": int(est["h2d_bytes"]),
-                        "d2h_bytes_per_step": int(est["d2h_bytes"]), "ms_per_step": 1e3 * t_e2e / args.steps},
+                        "d2h_bytes_per_step": int(est["d2h_bytes"]), "ms_per_step": 1e3 * t_e2e / args.steps,
+                        "ms_per_step_median": float(np.median(e2e_ms))},
                 "gpu_launches": int(st["gpu_launches"]) * args.steps,
+                "parity": parity,
+                "ms_per_step_median": float(np.median(step_ms)),
                 "device_ms_per_step": dev_ms / args.steps,
                 "step_ms": step_ms, "step_host_ms": step_host, "e2e_step_ms": e2e_ms,
-                "kernel_ms": {k: st[k] for k in ("ms_k_classify", "ms_k_align_nw", "ms_k_align_gl", "ms_k_align_final")},
+                "kernel_ms": {k: st[k] for k in st if k.startswith("ms_k_")},
                 "host_ms": {k: st[k] for k in ("ms_setup", "ms_loop", "ms_final", "ms_total")},
-                "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-                "experimental_ab": ab_res, "bimera": bim_res}
+                "roofline": roofline, "roofline_screen": roofline_screen, "cpu_baseline": cpu}
+        line.update(legs)
         print(json.dumps(line))
+        sys.stdout.flush()
     res.close()
     if world > 1:
+        flag = torch.tensor([rc], dtype=torch.int32, device=dev)
+        dist.broadcast(flag, src=0)
+        rc = int(flag[0])
         dist.destroy_process_group()
+    if rc:
+        sys.stderr.write("bench.py: parity MISMATCH against the CPU reference -- failing the run\n")
+        sys.exit(1)
 
 
 if __name__ == "__main__":

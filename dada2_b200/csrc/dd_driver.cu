@@ -160,23 +160,24 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
     cx->num_sms = sms;
     CK(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
   }
-  cx->maxq = 0; cx->bad_nt = false;
   DBG("upload: device ready, %d SMs", cx->num_sms);
+  // validate everything into locals first: a failed dada2b_reupload() must leave the live context untouched
   unsigned maxlen = 0, minlen = 9999;
-  cx->len.resize(nraw);
+  std::vector<uint16_t> len_new(nraw);
   for (unsigned i = 0; i < nraw; i++) {
     int64_t l = in->seq_off[i + 1] - in->seq_off[i];
     if (l < 0) throw Err{"Bad sequence offsets."};
     if (l >= 9999) throw Err{"Input sequences exceed the maximum allowed string length."};
-    cx->len[i] = (uint16_t)l;
+    len_new[i] = (uint16_t)l;
     maxlen = std::max<unsigned>(maxlen, (unsigned)l); minlen = std::min<unsigned>(minlen, (unsigned)l);
   }
   if (maxlen >= 9999) throw Err{"Input sequences exceed the maximum allowed string length."};
   if (minlen <= (unsigned)KMER) throw Err{"Input sequences must all be longer than the kmer-size (5)."};
-  cx->has_quals = in->maxlen > 0 && in->quals != nullptr;
-  if (!cx->has_quals)
+  if (!(in->maxlen > 0 && in->quals != nullptr))
     throw Err{"A quality matrix is required (the reference dereferences raw->qual unconditionally, error.cpp:160)."};
   if ((unsigned)in->maxlen != maxlen) throw Err{"Sequence must have associated qualities for each nucleotide position."};
+  cx->len.swap(len_new);
+  cx->maxq = 0; cx->bad_nt = false; cx->has_quals = true;
   DevIn &d = cx->in;
   d.nraw = nraw; d.maxlen = maxlen; d.minlen = minlen;
   d.SW = (((int)maxlen + 15) / 16 + 3) & ~3;
@@ -357,11 +358,15 @@ struct Run {
   DBuf<uint32_t> row_mv;                 // thread-per-pair exact NW (dd_nwrow.cu): per-thread scratch columns for the moves ...
   DBuf<uint16_t> row_sub;                // ... and the substitutions found by the traceback
   int row_grid_cap = 0;
-  bool two_phase = false;
-  // pivot pre-filter of the k-mer screen (experimental, DADA2B_PIVOT=1; dd_classify2.cu)
-  bool pivot = false;
-  DBuf<uint32_t> pv_cluster;
-  DBuf<uint16_t> pv_ms, seed_ms;
+  DBuf<uint32_t> lane_mv;                // lane-group fused NW for small rounds (dd_nwlane.cu): scratch for LANE_MAX pairs in flight
+  DBuf<uint16_t> lane_sub;
+  unsigned long long lane_max = 0;
+  // streaming tier of the k-mer screen (dd_prescreen.cu): 5-mer presence bitmaps of this rank's raws, candidates per round
+  DBuf<uint32_t> kbits, kmeta, cand_list;
+  DBuf<unsigned long long> cand_ctr;
+  bool prescreen = false;
+  int nown = 0;
+  bool two_phase = false;              // bound pass first, exact lambda for the survivors only (plain gap costs)
   // fused round tail (experimental, DADA2B_FUSED_TAIL=1; dd_round2.cu)
   bool fused_tail = false;
   // owner mode (experimental, DADA2B_OWNER=1 on top of the fused tail, sharded runs): every rank keeps the stored comparisons and
@@ -401,7 +406,8 @@ struct Run {
   struct Ev { cudaEvent_t a, b; int tag; };
   std::vector<Ev> evs;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  enum { T_CLASSIFY = 0, T_NW, T_GL, T_FINAL, T_NWB, T_N };
+  enum { T_CLASSIFY = 0, T_NW, T_GL, T_FINAL, T_NWB, T_PRE, T_TAIL, T_N };
+  long long prescreen_rows = 0;
   template <typename F> void timed(int tag, F f) {
     Ev e{cx->get_event(), cx->get_event(), tag};
     cudaEventRecord(e.a, s); f(); cudaEventRecord(e.b, s);
@@ -454,6 +460,7 @@ struct Run {
   void check_dev_error();
   void launch_compare(uint32_t i, double kdist_cutoff);
   void launch_round_tail(int first_pass, int npass);
+  void launch_round_tail_inner(int first_pass, int npass);
   void launch_shuffle_only(int pass);
   void launch_round_tail_noshuffle();
   void sync_report();
@@ -467,7 +474,7 @@ struct Run {
 
 void Run::reset_host() {
   members.clear(); slot_of.clear(); cluster_of_h.clear(); cl_center_h.clear(); cl_reads_h.clear(); birth.clear(); evs.clear();
-  n_rounds = n_shuffles = 0; tot_nw = tot_gl = 0; count_round = false; h2d_bytes = d2h_bytes = 0; cs_count = 0; est_active = 0; pending = Pending();
+  n_rounds = n_shuffles = 0; tot_nw = tot_gl = 0; prescreen_rows = 0; count_round = false; h2d_bytes = d2h_bytes = 0; cs_count = 0; est_active = 0; pending = Pending();
   st = DevState{};
 }
 void delete_run(Run *r) { delete r; }
@@ -489,7 +496,8 @@ void Run::setup_params() {
   if (P.band < 0) { lbmax = rbmax = maxlen; }
   else { lbmax = rbmax = std::min(P.band + (maxlen - minlen), maxlen); }
   const int Wmax = lbmax + rbmax + 1;
-  fwd_slots = ((lbmax + 1) & ~1) + rbmax + 1;   // band slots of dd_nwfwd.cu for the widest pair
+  // band slots of dd_nwfwd.cu for the widest pair: the length difference widens ONE side of a pair's band (nwalign_endsfree.cpp:101-111)
+  fwd_slots = P.band < 0 ? 1 << 20 : std::min(2 * P.band + (maxlen - minlen) + 3, ((lbmax + 1) & ~1) + rbmax + 1);
   const int nchunk = (((Wmax + 1) >> 1) + 31) >> 5;
   seq_bytes = (maxlen + 15) & ~15;
   H_words = (Wmax + 2 + 3) & ~3;
@@ -583,15 +591,24 @@ void Run::alloc_state() {
   ctr.alloc(CTR_N); h_ctr.alloc(CTR_N);
   DBG("alloc: ctr done");
   move_cap = (unsigned)(4 * n + 1024); fb_list.alloc(n);
-  two_phase = getenv("DADA2B_NO_TWOPHASE") == nullptr;    // bound pass first, exact lambda for the survivors only
+  const bool fallback_only = getenv("DADA2B_FALLBACK") != nullptr;   // test switch: general kernels only (no row / lane kernels, no streaming screen)
+  two_phase = !P.homo;
   if (two_phase) { surv_list.alloc(n); raw_S.alloc(n); raw_rho.alloc(n); uneq_list.alloc(n + 2); uneq_ctr.alloc(1); }
-  if (nwrow_usable(P, in.maxlen) && P.band >= 0) {
+  if (!fallback_only && nwrow_usable(P, in.maxlen) && P.band >= 0) {
     row_grid_cap = nwrow_exact_grid(cx->num_sms, nraw);
     row_mv.alloc(nwrow_mv_words(P.band, in.maxlen, row_grid_cap)); row_sub.alloc(nwrow_sub_halfwords(in.maxlen, row_grid_cap));
     if (!uneq_list.p) { uneq_list.alloc(n + 2); uneq_ctr.alloc(1); }
-  } else { row_mv.free(); row_sub.free(); }
-  pivot = getenv("DADA2B_PIVOT") != nullptr;             // off by default: not yet validated on hardware
-  if (pivot) { pv_cluster.alloc(n); pv_ms.alloc(n); CK(cudaMemsetAsync(pv_cluster.p, 0xFF, n * 4, s)); pv_ms.zero(s); }
+    {
+      lane_max = 16384;                  // rounds with at most this many NW pairs: G lanes per pair, one launch (dd_nwlane.cu)
+      lane_mv.alloc(nwlane_mv_words(P.band, in.maxlen, (int)lane_max)); lane_sub.alloc(nwlane_sub_halfwords(in.maxlen, (int)lane_max));
+    }
+  } else { row_mv.free(); row_sub.free(); lane_max = 0; }
+  prescreen = P.use_kmers && !fallback_only;
+  if (prescreen) {
+    nown = (nraw - cx->rank + cx->world - 1) / cx->world;
+    kbits.alloc((size_t)nown * 32 + 32); kmeta.alloc(nown); cand_list.alloc(nown + 32); cand_ctr.alloc(1);
+    launch_kmer_bits(in, cx->rank, cx->world, nown, kbits.p, kmeta.p, cx->num_sms, s);
+  }
   if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
   fused_tail = getenv("DADA2B_FUSED_TAIL") != nullptr;   // off by default: not yet validated on hardware
   owner = fused_tail && cx->world > 1 && getenv("DADA2B_OWNER") != nullptr;
@@ -680,20 +697,20 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   ca.greedy = o->greedy != 0; ca.lock = st.lock; ca.nw_list = st.nw_list; ca.gl_list = st.gl_list; ca.ctr = st.ctr;
   ca.kind_out = nullptr; ca.kord_words = kord_words; ca.shard_rank = cx->rank; ca.shard_world = cx->world;
   int cgrid = std::min((nraw / cx->world + 8) / 8, cx->num_sms * 4);
-  if (pivot && P.use_kmers) {
-    const int nclust_before = (int)i;                    // centres 0..i-1 exist; the seed is centre i
-    if (seed_ms.n < cl_cap) seed_ms.alloc(cl_cap);
-    PivotArgs pa{pv_cluster.p, pv_ms.p, seed_ms.p, st.cl_center, i};
-    cgrid = std::min((nraw / cx->world + 255) / 256 + 1, cx->num_sms * 4);
-    timed(T_CLASSIFY, [&]() {
-      launch_seed_dists(in, st.cl_center, nclust_before, c, seed_ms.p, cx->num_sms, s);
-      launch_classify2(ca, pa, cgrid, 256, classify_smem, s);
+  if (prescreen && kdist_cutoff < 1.0) {
+    // tier 0: stream the 128-byte bitmap rows (TMA) and settle what the presence bound can; tiers 1/2 on the rest
+    CK(cudaMemsetAsync(cand_ctr.p, 0, 8, s));
+    ca.cand_list = cand_list.p; ca.cand_count = cand_ctr.p;
+    timed(T_PRE, [&]() {
+      launch_prescreen(in, kbits.p, kmeta.p, nown, cx->rank, cx->world, c, cx->reads[c], o->greedy != 0, st.lock, kdist_cutoff, cand_list.p, cand_ctr.p,
+                       st.ctr, cx->num_sms, s);
     });
+    prescreen_rows += nown;
+    timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   } else
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   bool fwd_done = false;
-  const bool fwd_homo_ok = getenv("DADA2B_NWFWD_V2") != nullptr;       // only the restructured kernel knows homopolymer gap costs
-  if ((!P.homo || fwd_homo_ok) && P.band >= 0 && !getenv("DADA2B_NO_NWFWD")) {       // register-resident forward-carry NW (dd_nwfwd.cu)
+  if (P.band >= 0) {       // register-resident NW kernels (dd_nwrow.cu / dd_nwlane.cu / dd_nwfwd.cu); unbanded pairs: k_align below
     FwdArgs f{};
     f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
     if (owner) { f.st.shard_world = 1; f.st.shard_rank = 0; }       // this rank's comparisons go straight into its own store
@@ -701,7 +718,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes; f.mode = 0; f.job_mul = 1; f.job_add = 0;
     {  // the fast path replaces the reference's sentinel by a larger penalty: only valid while no real score can come near it
       const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::max(std::abs(P.gap), std::abs(P.hgap)) + 16;
-      f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
+      f.fast_ok = (worst < std::abs((long)P.sentinel) / 2) ? 1 : 0;
     }
     if (two_phase && i > 0 && !P.homo) {
       // pass 1: scores + substitution counts only; lambda <= S_r * rho_r^nsubs decides which pairs can pass the store rule
@@ -710,8 +727,11 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       CK(cudaMemsetAsync(ctr.p + CTR_SURV, 0, 8, s));
       CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
       // thread-per-pair row kernel (dd_nwrow.cu) for raws as long as the centre; the others come back in uneq_list
-      bool done_row = false;
-      timed(T_NWB, [&]() { done_row = launch_nwrow_bound(fbnd, uneq_list.p, uneq_ctr.p, (int)cx->len[c], (unsigned long long)nraw, cx->num_sms, s); });
+      // rounds with few pairs: one lane-group launch does bound + exact (dd_nwlane.cu); the thread-per-pair bound pass returns at once then
+      bool done_row = false, done_lane = false;
+      if (lane_max && row_mv.p) timed(T_NWB, [&]() { done_lane = launch_nwlane(fbnd, uneq_list.p, uneq_ctr.p, lane_mv.p, lane_sub.p, (int)cx->len[c], lane_max, (int)lane_max, s); });
+      if (row_mv.p)
+        timed(T_NWB, [&]() { done_row = launch_nwrow_bound(fbnd, uneq_list.p, uneq_ctr.p, (int)cx->len[c], (unsigned long long)nraw, cx->num_sms, done_lane ? lane_max : 0ull, s); });
       if (done_row) { fbnd.jobs = uneq_list.p; fbnd.njobs_ptr = uneq_ctr.p; }
       bool done_rest = done_row && in.minlen == in.maxlen;          // every raw has the centre's length: nothing was handed back
       if (!done_rest)
@@ -728,7 +748,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       if (ex_done) { f.jobs = uneq_list.p; f.njobs_ptr = uneq_ctr.p; }
     }
     if (ex_done && in.minlen == in.maxlen) fwd_done = true;       // nothing was handed back; fb_list stays empty
-    else timed(T_NW, [&]() { fwd_done = launch_nwfwd_sel(f, fwd_slots, (unsigned long long)nraw, ex_done ? 0 : (i == 0 ? (unsigned long long)nraw : est_active), cx->num_sms, s); });
+    else timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, ex_done ? 0 : (i == 0 ? (unsigned long long)nraw : est_active), cx->num_sms, s); });
   }
   for (int kind : {KIND_NW, KIND_GAPLESS}) {
     AlignArgs a = align_args(MODE_LOOP, kind);
@@ -758,6 +778,9 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
 
 // shuffle passes [first_pass, first_pass + npass) then p-update, bud scan and the report
 void Run::launch_round_tail(int first_pass, int npass) {
+  timed(T_TAIL, [&]() { launch_round_tail_inner(first_pass, npass); });
+}
+void Run::launch_round_tail_inner(int first_pass, int npass) {
   const int nclust = (int)members.size();
   const unsigned long long upper = cs_count + (unsigned long long)nraw;
   if (fused_tail) {
@@ -1046,7 +1069,7 @@ void Run::finish(dada2b_out *out) {
   if (cx->world > 1) nsubs_final.zero(s);
   {  // FinalSubsParallel: sub_new(centre, raw, use_kmers=false) for every raw
     bool split = false;
-    if (P.band > 0 && (!P.homo || getenv("DADA2B_NWFWD_V2")) && !getenv("DADA2B_NO_NWFWD")) {
+    if (P.band > 0) {
       // 1) forward-carry NW of every raw against its own centre: nsubs + "is the optimal path the pure diagonal?"
       FwdArgs f{};
       unsigned long long nn = (unsigned long long)n_owned;
@@ -1058,14 +1081,14 @@ void Run::finish(dada2b_out *out) {
       f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_NMOVE;   // (scratch counter; pairs that do not fit -> traceback list below)
       { unsigned long long z = 0; h2d(ctr.p + CTR_NMOVE, &z, 8); }
       const long worst = (long)in.maxlen * std::max(std::abs(P.mismatch), std::abs(P.match)) + std::max(std::abs(P.gap), std::abs(P.hgap)) + 16;
-      f.fast_ok = (worst < std::abs((long)P.sentinel) / 2 && !getenv("DADA2B_NO_FAST")) ? 1 : 0;
+      f.fast_ok = (worst < std::abs((long)P.sentinel) / 2) ? 1 : 0;
       bool row_done = false;
-      if (uneq_list.p) {       // thread-per-pair row kernel when every sequence has the same length (dd_nwrow.cu), else the lane-group kernel
+      if (row_mv.p) {       // thread-per-pair row kernel when every sequence has the same length (dd_nwrow.cu), else the lane-group kernel
         CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
         timed(T_FINAL, [&]() { row_done = launch_nwrow_final(f, uneq_list.p, uneq_ctr.p, (unsigned long long)nraw, cx->num_sms, s); });
       }
       if (row_done) split = true;
-      else timed(T_FINAL, [&]() { split = launch_nwfwd_sel(f, fwd_slots, (unsigned long long)nraw, (unsigned long long)nraw, cx->num_sms, s); });
+      else timed(T_FINAL, [&]() { split = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, (unsigned long long)nraw, cx->num_sms, s); });
     }
     if (split) {
       // 2) gapless column list for the pure-diagonal pairs, 3) traceback kernel for the rest (+ pairs that did not fit)
@@ -1278,10 +1301,14 @@ void Run::finish(dada2b_out *out) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
   out->ms_device = ms;
-  double sum[T_N] = {0, 0, 0, 0, 0}; int cnt[T_N] = {0, 0, 0, 0, 0};
+  double sum[T_N] = {0, 0, 0, 0, 0, 0, 0}; int cnt[T_N] = {0, 0, 0, 0, 0, 0, 0};
   for (const Ev &e : evs) { float t = 0; if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) { sum[e.tag] += t; cnt[e.tag]++; } }
   if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] loop NW: bound pass %.3f ms (%d launches), exact %.3f ms (%d launches)\n", sum[T_NWB], cnt[T_NWB], sum[T_NW], cnt[T_NW]);
+  out->ms_k_prescreen = sum[T_PRE]; out->n_k_prescreen = cnt[T_PRE]; out->prescreen_rows = prescreen_rows;
+  out->ms_k_nw_bound = sum[T_NWB]; out->n_k_nw_bound = cnt[T_NWB]; out->ms_k_nw_exact = sum[T_NW]; out->n_k_nw_exact = cnt[T_NW];
+  out->ms_k_tail = sum[T_TAIL]; out->n_k_tail = cnt[T_TAIL];
   sum[T_NW] += sum[T_NWB]; cnt[T_NW] += cnt[T_NWB];
+  sum[T_CLASSIFY] += sum[T_PRE]; cnt[T_CLASSIFY] += cnt[T_PRE];
   out->ms_k_classify = sum[T_CLASSIFY]; out->ms_k_align_nw = sum[T_NW]; out->ms_k_align_gl = sum[T_GL]; out->ms_k_align_final = sum[T_FINAL];
   out->n_k_classify = cnt[T_CLASSIFY]; out->n_k_align_nw = cnt[T_NW]; out->n_k_align_gl = cnt[T_GL]; out->n_k_align_final = cnt[T_FINAL];
   out->n_final_nw = (P.band == 0) ? 0 : nraw;
@@ -1379,8 +1406,8 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
                      R.cl_center_h[newi], now_ms() - tr, ran, R.cs_count, R.h_report->ctr[CTR_NW], R.h_report->ctr[CTR_GL],
                      R.h_report->ctr[CTR_NMOVE]);
   }
-  if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters; screened %llu, shrouded %llu (pivot bound %llu)\n", (int)R.members.size(),
-                   R.h_report->ctr[CTR_ALIGN], R.h_report->ctr[CTR_SHROUD], R.pivot ? R.h_report->ctr[CTR_GLTOT] : 0ull);
+  if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters; screened %llu, shrouded %llu\n", (int)R.members.size(),
+                   R.h_report->ctr[CTR_ALIGN], R.h_report->ctr[CTR_SHROUD]);
   R.sync();
   const double t2 = now_ms();
   dada2b_out *out = (dada2b_out *)calloc(1, sizeof(dada2b_out));

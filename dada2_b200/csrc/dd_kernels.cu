@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
   const int gw = blockIdx.x * nwarps + wid, tw = gridDim.x * nwarps;
   // mode 0 walks this rank's raws only: r = it * shard_world + shard_rank (every raw when not sharded)
   const int sw = a.mode == 0 ? max(a.shard_world, 1) : 1, sr = a.mode == 0 ? a.shard_rank : 0;
+  const bool from_list = a.mode == 0 && a.cand_list != nullptr;     // raws the streaming tier (k_prescreen) could not settle
   int r0 = a.mode == 0 ? gw : 0, rstep = a.mode == 0 ? tw : 1, rend = a.mode == 0 ? (a.in.nraw - sr + sw - 1) / sw : (wid == 0 ? 1 : 0);
+  if (from_list) rend = (int)*a.cand_count;
   // Job ids are staged per warp (one register slot per lane) and flushed 32 at a time with a single
   // atomic reservation; the diagnostic counters are accumulated per warp.  (One same-address global
   // atomic per pair costs more than the screen itself.)
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a) {
     n = 0;
   };
   for (int it = r0; it < rend; it += rstep) {
-    const uint32_t r = a.mode == 0 ? (uint32_t)(it * sw + sr) : a.pair_raw[blockIdx.x];
+    const uint32_t r = from_list ? a.cand_list[it] : (a.mode == 0 ? (uint32_t)(it * sw + sr) : a.pair_raw[blockIdx.x]);
     const uint32_t job = a.mode == 0 ? r : blockIdx.x;
     if (a.mode == 0 && a.greedy && (a.in.reads[r] > a.centre_reads || a.lock[r])) continue;   // cluster.cpp:127-131
     const int len2 = a.in.len[r];

@@ -21,17 +21,15 @@ struct ClassifyArgs {
   uint8_t *kind_out;
   int kord_words;           // words reserved for the centre's ordered 5-mers
   int shard_rank, shard_world;
+  const uint32_t *cand_list;             // mode 0: raws left undecided by k_prescreen (NULL: every raw of this rank)
+  const unsigned long long *cand_count;
 };
+// dd_prescreen.cu: streaming first tier of the k-mer screen (TMA-staged 5-mer presence bitmaps)
+void launch_kmer_bits(const DevIn &in, int rank, int world, int nown, uint32_t *kbits, uint32_t *kmeta, int num_sms, cudaStream_t s);
+void launch_prescreen(const DevIn &in, const uint32_t *kbits, const uint32_t *kmeta, int nown, int rank, int world, uint32_t centre_idx,
+                      uint32_t centre_reads, int greedy, const uint8_t *lock, double kdist_cutoff, uint32_t *cand_list, unsigned long long *cand_count,
+                      unsigned long long *ctr, int num_sms, cudaStream_t s);
 
-// pivot pre-filter of the k-mer screen (dd_classify2.cu; EXPERIMENTAL, DADA2B_PIVOT=1)
-struct PivotArgs {
-  uint32_t *pv_cluster;        // [nraw] cluster index of the raw's pivot centre, 0xFFFFFFFF = none yet
-  uint16_t *pv_ms;             // [nraw] exact 5-mer min-sum between the raw and its pivot centre
-  const uint16_t *seed_ms;     // [nclust] min-sum between every existing centre and the round's seed (k_seed_dists)
-  const uint32_t *cl_center;   // [nclust] raw index of each centre
-  uint32_t cluster_i;          // index of the cluster being seeded
-};
-void launch_seed_dists(const DevIn &in, const uint32_t *cl_center, int nclust, uint32_t seed, uint16_t *seed_ms, int num_sms, cudaStream_t s);
 
 struct AlignArgs {
   DevIn in;
@@ -80,21 +78,15 @@ struct FwdArgs {
 };
 bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s,
                   bool bound_only = false);
-// dd_nwfwd2.cu: restructured variant of the same kernel (EXPERIMENTAL, DADA2B_NWFWD_V2=1; checked on the host SIMT
-// emulator of tests/emu, not yet on hardware).
-bool launch_nwfwd2(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s,
-                   bool bound_only = false);
-inline bool launch_nwfwd_sel(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms,
-                             cudaStream_t s, bool bound_only = false) {
-  return getenv("DADA2B_NWFWD_V2") ? launch_nwfwd2(a, slots_needed, njobs_upper, njobs_hint, num_sms, s, bound_only)
-                                   : launch_nwfwd(a, slots_needed, njobs_upper, njobs_hint, num_sms, s, bound_only);
-}
-// dd_nwbound.cu: the bound pass on the 16-bit SIMD datapath, two raws per lane group (EXPERIMENTAL, DADA2B_BOUND16=1 with DADA2B_TWOPHASE=1)
-bool launch_nwbound16(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, int slots_needed, unsigned long long njobs_upper,
-                      unsigned long long njobs_hint, int num_sms, cudaStream_t s);
 // dd_nwrow.cu: thread-per-pair row kernel, bound pass over f.jobs (raws as long as the centre; the rest -> uneq_list)
 bool launch_nwrow_bound(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, int len1, unsigned long long njobs_upper, int num_sms,
-                        cudaStream_t s);
+                        unsigned long long lane_max, cudaStream_t s);
+// dd_nwlane.cu: G lanes per pair, bound + exact in one launch, for rounds with at most lane_max jobs
+int nwlane_lanes(int band);
+size_t nwlane_mv_words(int band, int maxlen, int groups);
+size_t nwlane_sub_halfwords(int maxlen, int groups);
+bool launch_nwlane(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, uint32_t *mv_scratch, uint16_t *sub_scratch, int len1,
+                   unsigned long long lane_max, int groups_cap, cudaStream_t s);
 bool launch_nwrow_final(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, unsigned long long njobs_upper, int num_sms,
                         cudaStream_t s);
 // exact pass: per-thread scratch columns for the recorded moves / substitutions; the grid is capped by what was allocated
@@ -107,7 +99,6 @@ bool launch_nwrow_exact(const FwdArgs &f, uint32_t *uneq_list, unsigned long lon
 void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, cudaStream_t s);
 void count_launch(int n);
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);
-void launch_classify2(const ClassifyArgs &a, const PivotArgs &pv, int grid, int block, size_t smem, cudaStream_t s);
 void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 cudaError_t align_set_smem(size_t bytes);
 

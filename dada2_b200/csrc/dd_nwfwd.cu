@@ -1,5 +1,8 @@
-// k_nwfwd<G, ND>: register-resident banded ends-free NW for the LOOP comparisons (b_compare),
+// k_nwfwd<G, ND, WL, HM>: register-resident banded ends-free NW for the LOOP comparisons (b_compare),
 // G lanes per (centre, raw) pair, ND diagonals per lane.  Product code (sm_100a).
+// The GENERAL loop aligner: any pair of lengths (band slots up to 256), homopolymer gap costs (HM).  Pairs as long as
+// their centre with plain gap costs -- every pair of a fixed-length amplicon run -- take the thread-per-pair row kernels
+// instead (dd_nwrow.cu / dd_nwlane.cu), which hand everything else over to this kernel through a job list.
 //
 // Replaces, for pairs that need a real alignment inside the divisive loop,
 //   nwalign_vectorized2 / nwalign_endsfree   (/root/reference/src/nwalign_vectorized.cpp:71-318,
@@ -29,7 +32,7 @@
 namespace dd2 {
 
 // DP cells of a banded alignment: sum_i [min(len2, i + rband) - max(1, i - lband) + 1], closed form.
-__device__ __forceinline__ long long band_cells(int n, int m, int l, int r) {
+__device__ __forceinline__ long long band_cells2(int n, int m, int l, int r) {
   const long long k = min(max(m - r, 0), n);
   const long long A = k * (k + 1) / 2 + k * r + (long long)(n - k) * m;
   const long long k2 = min(max(l + 1, 0), n);
@@ -37,9 +40,119 @@ __device__ __forceinline__ long long band_cells(int n, int m, int l, int r) {
   return A - B + n;
 }
 
+// One anti-diagonal step of the register-resident wavefront (cells of parity PAR), updated IN PLACE: a cell of parity
+// PAR reads its neighbours of the other parity (unchanged during this step) and its own previous value only.
+// FAST = interior step (no boundary cell, no free end gap, every pair running): branch-free, out-of-band slots kept
+// below any real score by PEN.  Otherwise every cell is checked against the matrix borders and the band.
+// select without a branch: ptxas otherwise turns the rare 'up' move into a divergent branch around the table lookup
+__device__ __forceinline__ int sel_i32(bool p, int a, int b) {
+#ifdef DADA2B_EMU
+  return p ? a : b;
+#else
+  int r;
+  asm("{.reg .pred q; setp.ne.s32 q, %3, 0; selp.s32 %0, %1, %2, q;}" : "=r"(r) : "r"(a), "r"(b), "r"((int)p));
+  return r;
+#endif
+}
+
+struct StepCtx {
+  int gl, len1, len2, tlo, thi, nsteps, SENT, match, mismatch, gap, hgap, ncol4, ONE_IDX;
+  int b2_off;            // byte offset of the pair's b2 table (entry 0) from the start of dynamic shared memory
+};
+
+// HM = homopolymer gap costs (nwalign_endsfree.cpp:220-396): a gap opposite a base that lies in a run >= 3 costs hgap; HA / HB
+// carry that flag for the centre / raw base of every slot (bit cc <-> slot cc), like A / B carry the bases.
+template <int G, int ND, bool WL, bool HM, int PAR, bool FAST>
+__device__ __forceinline__ void nw_step(int (&H)[ND], int (&NSUB)[ND], double (&LAM)[ND], const int (&PEN)[ND], uint32_t A,
+                                        uint32_t B, uint32_t HA, uint32_t HB, int I, int J, int k, const StepCtx &c) {
+  constexpr int NSL = ND / 2;
+  constexpr int BIGPEN = 1 << 20, GAPFLAG = 1 << 30, PADL = 64;
+  // neighbour exchange: identical in both paths, unconditional
+  int Hn, Nn;
+  double Ln = 1.0;
+  if (PAR == 0) {           // left neighbour of local t=0 is lane gl-1's t=ND-1
+    Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G);
+    Nn = __shfl_up_sync(0xffffffffu, NSUB[ND - 1], 1, G);
+    if (WL) Ln = __shfl_up_sync(0xffffffffu, LAM[ND - 1], 1, G);
+    if (c.gl == 0) { Hn = FAST ? -BIGPEN : c.SENT; Nn = 0; Ln = 1.0; }
+  } else {                  // up neighbour of local t=ND-1 is lane gl+1's t=0
+    Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G);
+    Nn = __shfl_down_sync(0xffffffffu, NSUB[0], 1, G);
+    if (WL) Ln = __shfl_down_sync(0xffffffffu, LAM[0], 1, G);
+    if (c.gl == G - 1) { Hn = FAST ? -BIGPEN : c.SENT; Nn = 0; Ln = 1.0; }
+  }
+  const uint32_t X = A ^ B;
+  const int Jp = J + PAR;
+  extern __shared__ uint32_t smem[];                     // named directly: no generic-to-shared address conversion per load
+  const double *s_err = (const double *)smem;             // the error table sits at offset 0
+  const uint16_t *s_b2 = (const uint16_t *)((const unsigned char *)smem + c.b2_off);
+  const uint16_t *b2p = s_b2 + (Jp - 1);
+#pragma unroll
+  for (int cc = 0; cc < NSL; cc++) {
+    const int t = 2 * cc + PAR;
+    const int hl = (PAR == 0 && cc == 0) ? Hn : H[t - 1 < 0 ? 0 : t - 1];
+    const int nl = (PAR == 0 && cc == 0) ? Nn : NSUB[t - 1 < 0 ? 0 : t - 1];
+    const double ll = (PAR == 0 && cc == 0) ? Ln : LAM[t - 1 < 0 ? 0 : t - 1];
+    const int hu = (PAR == 1 && cc == NSL - 1) ? Hn : H[t + 1 >= ND ? ND - 1 : t + 1];
+    const int nu = (PAR == 1 && cc == NSL - 1) ? Nn : NSUB[t + 1 >= ND ? ND - 1 : t + 1];
+    const double lu = (PAR == 1 && cc == NSL - 1) ? Ln : LAM[t + 1 >= ND ? ND - 1 : t + 1];
+    const uint32_t nt1 = (A >> (2 * cc)) & 3u, nt2 = (B >> (2 * cc)) & 3u;
+    const bool eq = ((X >> (2 * cc)) & 3u) == 0u;
+    if (FAST) {
+      const int gl_ = (HM && ((HB >> cc) & 1u)) ? c.hgap : c.gap, gu_ = (HM && ((HA >> cc) & 1u)) ? c.hgap : c.gap;   // :303-320
+      const int left = hl + gl_, up = hu + gu_, diag = H[t] + (eq ? c.match : c.mismatch);
+      const int m = __vimax3_s32(left, up, diag);
+      const bool isU = up == m;                      // precedence up > left > diag (nwalign_endsfree.cpp:147-156)
+      const bool isL = (left == m) && !isU;
+      if (WL) {
+        const int idx = sel_i32(isU, c.ONE_IDX, (int)b2p[cc] + (int)(isL ? nt2 : nt1) * c.ncol4);
+        const double lp = isU ? lu : (isL ? ll : LAM[t]);
+        LAM[t] = lp * s_err[idx];
+      }
+      NSUB[t] = sel_i32(isU, nu | GAPFLAG, sel_i32(isL, nl | GAPFLAG, NSUB[t] + (eq ? 0 : 1)));
+      H[t] = m + PEN[t];
+    } else {
+      const int i = I - cc, j = Jp + cc;
+      const bool valid = (t >= c.tlo) && (t <= c.thi) && i >= 0 && j >= 0 && i <= c.len1 && j <= c.len2 && k <= c.nsteps;
+      const int gl_ = (HM && ((HB >> cc) & 1u)) ? c.hgap : c.gap, gu_ = (HM && ((HA >> cc) & 1u)) ? c.hgap : c.gap;
+      const int left = hl + ((i == c.len1) ? 0 : gl_);                     // nwalign_endsfree.cpp:128-156 (homo :303-320)
+      const int up = hu + ((j == c.len2) ? 0 : gu_);
+      const int diag = H[t] + (eq ? c.match : c.mismatch);
+      const int m = max(max(left, up), diag);
+      int pmove = (up == m) ? 3 : ((left == m) ? 2 : 1);
+      int val = m;
+      if (i == 0) { val = 0; pmove = (j == 0) ? 0 : 2; }                   // top row: ends-free, p=2  (:97-101)
+      else if (j == 0) { val = 0; pmove = 0; }                             // left column: p=3, no raw base consumed
+      int np = (pmove == 3) ? nu : ((pmove == 2) ? nl : NSUB[t]);
+      if (pmove == 0) np = (i > 0) ? GAPFLAG : 0;
+      if (pmove == 1 && !eq) np++;
+      if (pmove == 2 || pmove == 3) np |= GAPFLAG;
+      if (WL) {
+        const int b2 = s_b2[min(max(j - 1, -PADL), c.len2 + PADL - 1)];
+        const int idx = (pmove == 1 || pmove == 2) ? b2 + (int)((pmove == 1) ? nt1 : nt2) * c.ncol4 : c.ONE_IDX;
+        double lp = (pmove == 3) ? lu : ((pmove == 2) ? ll : LAM[t]);
+        if (pmove == 0) lp = 1.0;
+        LAM[t] = valid ? lp * s_err[idx] : LAM[t];
+      }
+      H[t] = valid ? val : H[t];
+      NSUB[t] = valid ? np : NSUB[t];
+    }
+  }
+}
+
+// bit 2 of a staged base byte = "inside a homopolymer run of length >= 3" (nwalign_endsfree.cpp:230-255).  Writers only touch
+// bit 2 and readers of the neighbours only use bits 1:0, so the flags of one sequence can be set concurrently.
+__device__ __forceinline__ void homo_flag(uint8_t *seq, int p, int len) {
+  const int b = seq[p] & 3;
+  int L = 0, R = 0;
+  while (L < 2 && p - L - 1 >= 0 && (seq[p - L - 1] & 3) == b) L++;
+  while (R < 2 && p + R + 1 < len && (seq[p + R + 1] & 3) == b) R++;
+  if (L + R >= 2) seq[p] |= 4;
+}
+
 // WL = carry lambda (the exact kernel).  WL = false is the bound pass of the two-phase scheme: scores and
 // substitution counts only; pairs that provably fail the store rule are dropped, the rest are listed for the exact kernel.
-template <int G, int ND, bool WL>
+template <int G, int ND, bool WL, bool HM>
 __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
   constexpr int NSL = ND / 2;             // cells per lane per step
   constexpr int PPW = 32 / G;             // pairs per warp
@@ -71,6 +184,10 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
   if (!final_mode) {
     const uint32_t *crow = a.in.seq2 + (size_t)a.centre_idx * a.in.SW;
     for (int p = threadIdx.x; p < len1_shared; p += blockDim.x) s_cen_shared[p] = (uint8_t)((crow[p >> 4] >> (2 * (p & 15))) & 3u);
+    if (HM) {
+      __syncthreads();
+      for (int p = threadIdx.x; p < len1_shared; p += blockDim.x) homo_flag(s_cen_shared, p, len1_shared);
+    }
   }
   __syncthreads();
   const int ONE_IDX = 16 * ncol, ncol4 = 4 * ncol;
@@ -91,6 +208,10 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
       const uint32_t *crow = a.in.seq2 + (size_t)c * a.in.SW;
       for (int p = gl; p < len1; p += G) s_cen_own[p] = (uint8_t)((crow[p >> 4] >> (2 * (p & 15))) & 3u);
     }
+    if (HM && final_mode) {
+      __syncwarp();
+      if (act) for (int p = gl; p < len1; p += G) homo_flag(s_cen_own, p, len1);
+    }
     // ---- stage raw bases + qualities (group-cooperative) ----
     if (act) {
       const uint32_t *rrow = a.in.seq2 + (size_t)r * a.in.SW;
@@ -107,6 +228,10 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
       for (int p = gl; p < a.seq_bytes + 2 * PAD; p += G) s_b2[p - PAD] = 0;
     }
     __syncwarp();
+    if (HM) {
+      if (act) for (int p = gl; p < len2; p += G) homo_flag(s_raw, p, len2);
+      __syncwarp();
+    }
     // ---- band geometry (nwalign_endsfree.cpp:101-111) ----
     int lband, rband;
     if (len2 > len1) { lband = P.band; rband = P.band + len2 - len1; }
@@ -132,13 +257,14 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
     for (int t = 0; t < ND; t++) { H[t] = SENT; NSUB[t] = 0; LAM[t] = 1.0; }
     // windows for step k = 0: I = -D/2, J = D/2 ; slot c: s1[I-1-c], s2[J-1+c]
     int I = -(D / 2), J = D / 2;      // D even; exact
-    uint32_t A = 0, B = 0;
+    uint32_t A = 0, B = 0, HA = 0, HB = 0;
 #pragma unroll
     for (int cc = 0; cc < NSL; cc++) {
       const int i1 = I - 1 - cc, j1 = J - 1 + cc;
       const uint32_t b1 = (i1 >= 0 && i1 < len1) ? s_cen[i1] : 0u;
       const uint32_t b2 = (act && j1 >= 0 && j1 < len2) ? s_raw[j1] : 0u;
-      A |= b1 << (2 * cc); B |= b2 << (2 * cc);
+      A |= (b1 & 3u) << (2 * cc); B |= (b2 & 3u) << (2 * cc);
+      if (HM) { HA |= (b1 >> 2) << cc; HB |= (b2 >> 2) << cc; }
     }
 
     // Interior steps (no boundary cell, no free end gap, every pair still running) take a branch-free path;
@@ -153,145 +279,43 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
     constexpr int BIGPEN = 1 << 20;
     int PEN[ND];
 #pragma unroll
-    for (int t = 0; t < ND; t++) PEN[t] = (t >= tlo && t <= thi) ? 0 : -BIGPEN;
+    for (int t = 0; t < ND; t++) {
+      PEN[t] = (t >= tlo && t <= thi) ? 0 : -BIGPEN;
+      PEN[t] = __shfl_sync(0xffffffffu, PEN[t], lane);   // opaque to ptxas: stays an addend (one IADD per cell), not a predicate + select
+    }
 
-    for (int kk = 0; kk <= maxsteps; kk += 2) {
-      if (kk >= kf_lo && kk + 1 <= kf_hi) {
-#pragma unroll
-        for (int PAR = 0; PAR < 2; PAR++) {
-          int Hn, Nn; double Ln;
-          if (!WL) Ln = 1.0;
-          if (PAR == 0) {
-            Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G);
-            Nn = __shfl_up_sync(0xffffffffu, NSUB[ND - 1], 1, G);
-            if (WL) Ln = __shfl_up_sync(0xffffffffu, LAM[ND - 1], 1, G);
-            if (gl == 0) Hn = -BIGPEN;
-          } else {
-            Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G);
-            Nn = __shfl_down_sync(0xffffffffu, NSUB[0], 1, G);
-            if (WL) Ln = __shfl_down_sync(0xffffffffu, LAM[0], 1, G);
-            if (gl == G - 1) Hn = -BIGPEN;
-          }
-          const uint32_t X = A ^ B;
-          const uint16_t *b2p = s_b2 + (J + PAR - 1);
-          int Hnew[NSL], Nnew[NSL]; double Lnew[NSL];
-#pragma unroll
-          for (int cc = 0; cc < NSL; cc++) {
-            const int t = 2 * cc + PAR;
-            const int hl = (PAR == 0 && cc == 0) ? Hn : H[t - 1 < 0 ? 0 : t - 1];
-            const int nl = (PAR == 0 && cc == 0) ? Nn : NSUB[t - 1 < 0 ? 0 : t - 1];
-            const double ll = (PAR == 0 && cc == 0) ? Ln : LAM[t - 1 < 0 ? 0 : t - 1];
-            const int hu = (PAR == 1 && cc == NSL - 1) ? Hn : H[t + 1 >= ND ? ND - 1 : t + 1];
-            const int nu = (PAR == 1 && cc == NSL - 1) ? Nn : NSUB[t + 1 >= ND ? ND - 1 : t + 1];
-            const double lu = (PAR == 1 && cc == NSL - 1) ? Ln : LAM[t + 1 >= ND ? ND - 1 : t + 1];
-            const uint32_t nt1 = (A >> (2 * cc)) & 3u, nt2 = (B >> (2 * cc)) & 3u;
-            const bool eq = ((X >> (2 * cc)) & 3u) == 0u;
-            const int left = hl + gap, up = hu + gap, diag = H[t] + (eq ? match : mismatch);
-            const int m = __vimax3_s32(left, up, diag);
-            const bool isU = up == m;                      // precedence up > left > diag (nwalign_endsfree.cpp:147-156)
-            const bool isL = (left == m) && !isU;
-            const int b2 = WL ? b2p[cc] : 0;
-            const int idx = isU ? ONE_IDX : b2 + (int)(isL ? nt2 : nt1) * ncol4;
-            const double f = WL ? s_err[idx] : 1.0;
-            const double lp = isU ? lu : (isL ? ll : LAM[t]);
-            const int np = isU ? (nu | GAPFLAG) : (isL ? (nl | GAPFLAG) : NSUB[t] + (eq ? 0 : 1));
-            Hnew[cc] = m + PEN[t];
-            Nnew[cc] = np;
-            Lnew[cc] = WL ? lp * f : 1.0;
-          }
-#pragma unroll
-          for (int cc = 0; cc < NSL; cc++) { H[2 * cc + PAR] = Hnew[cc]; NSUB[2 * cc + PAR] = Nnew[cc]; LAM[2 * cc + PAR] = Lnew[cc]; }
-          if (PAR == 0) {
-            uint32_t nbB = __shfl_down_sync(0xffffffffu, B, 1, G);
-            uint32_t newb = nbB & 3u;
-            if (gl == G - 1) { const int jn = J + NSL - 1; newb = (jn >= 0 && jn < len2) ? s_raw[jn] : 0u; }
-            B = (B >> 2) | (newb << (2 * (NSL - 1)));
-          } else {
-            uint32_t nbA = __shfl_up_sync(0xffffffffu, A, 1, G);
-            uint32_t newa = (nbA >> (2 * (NSL - 1))) & 3u;
-            if (gl == 0) newa = (I >= 0 && I < len1) ? s_cen[I] : 0u;
-            A = ((A << 2) | newa) & (NSL == 16 ? 0xffffffffu : ((1u << (2 * NSL)) - 1u));
-            I += 1; J += 1;
-          }
-        }
-        continue;
-      }
-#pragma unroll
-      for (int PAR = 0; PAR < 2; PAR++) {
-        const int k = kk + PAR;
-        // ---- neighbour exchange ----
-        int Hn, Nn; double Ln;
-        if (!WL) Ln = 1.0;
-        if (PAR == 0) {           // left neighbour of local t=0 is lane gl-1's t=ND-1
-          Hn = __shfl_up_sync(0xffffffffu, H[ND - 1], 1, G);
-          Nn = __shfl_up_sync(0xffffffffu, NSUB[ND - 1], 1, G);
-          if (WL) Ln = __shfl_up_sync(0xffffffffu, LAM[ND - 1], 1, G);
-          if (gl == 0) { Hn = SENT; Nn = 0; Ln = 1.0; }
-        } else {                  // up neighbour of local t=ND-1 is lane gl+1's t=0
-          Hn = __shfl_down_sync(0xffffffffu, H[0], 1, G);
-          Nn = __shfl_down_sync(0xffffffffu, NSUB[0], 1, G);
-          if (WL) Ln = __shfl_down_sync(0xffffffffu, LAM[0], 1, G);
-          if (gl == G - 1) { Hn = SENT; Nn = 0; Ln = 1.0; }
-        }
-        const uint32_t X = A ^ B;
-        const int Jp = J + PAR;
-        int Hnew[NSL], Nnew[NSL]; double Lnew[NSL];
-#pragma unroll
-        for (int cc = 0; cc < NSL; cc++) {
-          const int t = 2 * cc + PAR;
-          const int i = I - cc, j = Jp + cc;
-          const int hl = (PAR == 0 && cc == 0) ? Hn : H[t - 1 < 0 ? 0 : t - 1];
-          const int nl = (PAR == 0 && cc == 0) ? Nn : NSUB[t - 1 < 0 ? 0 : t - 1];
-          const double ll = (PAR == 0 && cc == 0) ? Ln : LAM[t - 1 < 0 ? 0 : t - 1];
-          const int hu = (PAR == 1 && cc == NSL - 1) ? Hn : H[t + 1 >= ND ? ND - 1 : t + 1];
-          const int nu = (PAR == 1 && cc == NSL - 1) ? Nn : NSUB[t + 1 >= ND ? ND - 1 : t + 1];
-          const double lu = (PAR == 1 && cc == NSL - 1) ? Ln : LAM[t + 1 >= ND ? ND - 1 : t + 1];
-          const int nt1 = (A >> (2 * cc)) & 3, nt2 = (B >> (2 * cc)) & 3;
-          const int b2 = s_b2[min(max(j - 1, -PAD), len2 + PAD - 1)];   // nt2*ncol + quality of raw base j-1
-          const bool eq = ((X >> (2 * cc)) & 3u) == 0u;
-          const bool valid = (t >= tlo) && (t <= thi) && i >= 0 && j >= 0 && i <= len1 && j <= len2 && k <= nsteps;
-          // scores (nwalign_endsfree.cpp:128-156)
-          const int left = hl + ((i == len1) ? 0 : gap);
-          const int up = hu + ((j == len2) ? 0 : gap);
-          const int diag = H[t] + (eq ? match : mismatch);
-          const int m = max(max(left, up), diag);
-          int pmove = (up == m) ? 3 : ((left == m) ? 2 : 1);
-          int val = m;
-          if (i == 0) { val = 0; pmove = (j == 0) ? 0 : 2; }      // top row: ends-free, p=2  (:97-101)
-          else if (j == 0) { val = 0; pmove = 0; }                  // left column: p=3, no raw base consumed
-          // lambda / nsubs along the chosen predecessor (al2subs + compute_lambda_ts)
-          // err row 4*nt0+nt1 (diag) or 5*nt1 (raw base vs gap), column q:  b2 + {nt0 | nt1} * 4*ncol
-          const int idx = (pmove == 1 || pmove == 2) ? b2 + ((pmove == 1) ? nt1 : nt2) * ncol4 : ONE_IDX;
-          const double f = WL ? s_err[idx] : 1.0;
-          double lp = (pmove == 3) ? lu : ((pmove == 2) ? ll : LAM[t]);
-          int np = (pmove == 3) ? nu : ((pmove == 2) ? nl : NSUB[t]);
-          if (pmove == 0) { lp = 1.0; np = (i > 0) ? GAPFLAG : 0; }     // left column = leading gap in the raw row
-          if (pmove == 1 && !eq) np++;
-          if (pmove == 2 || pmove == 3) np |= GAPFLAG;
-          Hnew[cc] = valid ? val : H[t];
-          Nnew[cc] = valid ? np : NSUB[t];
-          Lnew[cc] = valid ? lp * f : LAM[t];
-        }
-#pragma unroll
-        for (int cc = 0; cc < NSL; cc++) { H[2 * cc + PAR] = Hnew[cc]; NSUB[2 * cc + PAR] = Nnew[cc]; LAM[2 * cc + PAR] = Lnew[cc]; }
-        // ---- advance the sequence windows ----
-        if (PAR == 0) {           // even -> odd: raw window moves one base (J -> J+1)
-          uint32_t nbB = __shfl_down_sync(0xffffffffu, B, 1, G);
-          uint32_t newb = nbB & 3u;
-          if (gl == G - 1) {
-            const int jn = J + NSL - 1;
-            const bool ok = act && jn >= 0 && jn < len2;
-            newb = ok ? s_raw[jn] : 0u;
-          }
-          B = (B >> 2) | (newb << (2 * (NSL - 1)));
-        } else {                  // odd -> even: centre window moves one base (I -> I+1), J -> J+1 completes
-          uint32_t nbA = __shfl_up_sync(0xffffffffu, A, 1, G);
-          uint32_t newa = (nbA >> (2 * (NSL - 1))) & 3u;
-          if (gl == 0) { const int in = I; newa = (in >= 0 && in < len1) ? s_cen[in] : 0u; }
-          A = ((A << 2) | newa) & (NSL == 16 ? 0xffffffffu : ((1u << (2 * NSL)) - 1u));
-          I += 1; J += 1;
-        }
-      }
+    // ---- main loop in three phases: checked prologue, branch-free interior, checked epilogue ----
+    auto advB = [&]() {            // even -> odd: raw window moves one base (J -> J+1)
+      uint32_t nbB = __shfl_down_sync(0xffffffffu, B, 1, G);
+      uint32_t newb = nbB & 3u, newh = 0;
+      if (HM) newh = __shfl_down_sync(0xffffffffu, HB, 1, G) & 1u;
+      if (gl == G - 1) { const int jn = J + NSL - 1; const uint32_t v = (act && jn >= 0 && jn < len2) ? s_raw[jn] : 0u; newb = v & 3u; newh = v >> 2; }
+      B = (B >> 2) | (newb << (2 * (NSL - 1)));
+      if (HM) HB = (HB >> 1) | (newh << (NSL - 1));
+    };
+    auto advA = [&]() {            // odd -> even: centre window moves one base (I -> I+1), J -> J+1 completes
+      uint32_t nbA = __shfl_up_sync(0xffffffffu, A, 1, G);
+      uint32_t newa = (nbA >> (2 * (NSL - 1))) & 3u, newh = 0;
+      if (HM) newh = (__shfl_up_sync(0xffffffffu, HA, 1, G) >> (NSL - 1)) & 1u;
+      if (gl == 0) { const uint32_t v = (I >= 0 && I < len1) ? s_cen[I] : 0u; newa = v & 3u; newh = v >> 2; }
+      A = ((A << 2) | newa) & (NSL == 16 ? 0xffffffffu : ((1u << (2 * NSL)) - 1u));
+      if (HM) HA = ((HA << 1) | newh) & ((1u << NSL) - 1u);
+      I += 1; J += 1;
+    };
+    const StepCtx cx{gl, len1, len2, tlo, thi, nsteps, SENT, match, mismatch, gap, P.hgap, ncol4, ONE_IDX, (int)((const unsigned char *)s_b2 - (const unsigned char *)smem)};
+    int kk = 0;
+    const int kfa = (kf_lo + 1) & ~1;                       // first even step index inside the interior range
+    for (; kk < kfa && kk <= maxsteps; kk += 2) {
+      nw_step<G, ND, WL, HM, 0, false>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk, cx); advB();
+      nw_step<G, ND, WL, HM, 1, false>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk + 1, cx); advA();
+    }
+    for (; kk + 1 <= kf_hi && kk <= maxsteps; kk += 2) {
+      nw_step<G, ND, WL, HM, 0, true>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk, cx); advB();
+      nw_step<G, ND, WL, HM, 1, true>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk + 1, cx); advA();
+    }
+    for (; kk <= maxsteps; kk += 2) {
+      nw_step<G, ND, WL, HM, 0, false>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk, cx); advB();
+      nw_step<G, ND, WL, HM, 1, false>(H, NSUB, LAM, PEN, A, B, HA, HB, I, J, kk + 1, cx); advA();
     }
     // ---- result: cell (len1, len2) on dd = len2 - len1 + LB ----
     const int ddf = len2 - len1 + LB;
@@ -300,7 +324,7 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
 #pragma unroll
     for (int t = 0; t < ND; t++) if (t == tf) { lam = LAM[t]; ns = NSUB[t]; }
     const bool owner = act && tf >= 0 && tf < ND;
-    if (owner && !a.no_cells) cells_lane += band_cells(len1, len2, lband, rband);
+    if (owner && !a.no_cells) cells_lane += band_cells2(len1, len2, lband, rband);
     if (final_mode) {
       // FinalSubsParallel (Rmain.cpp:179-236): nsubs of the final alignment; pairs whose optimal path is the pure
       // diagonal get the trivial (gapless) column list, the rest go to the traceback kernel.
@@ -354,32 +378,25 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
   if (lane == 0 && cells_lane) atomicAdd(&a.st.ctr[CTR_CELLS], (unsigned long long)cells_lane);
 }
 
-template <int G, int ND, bool WL> static void launch_one(const FwdArgs &a, int grid, size_t smem, cudaStream_t s) {
+template <int G, int ND, bool WL, bool HM> static void launch_one(const FwdArgs &a, int grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_nwfwd<G, ND, WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
-  k_nwfwd<G, ND, WL><<<grid, 128, smem, s>>>(a);
+  if (!attr_set) { cudaFuncSetAttribute(k_nwfwd<G, ND, WL, HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+  k_nwfwd<G, ND, WL, HM><<<grid, 128, smem, s>>>(a);
 }
 template <int G, int ND> static void launch_wl(const FwdArgs &a, bool bound_only, int grid, size_t smem, cudaStream_t s) {
-  if (bound_only) launch_one<G, ND, false>(a, grid, smem, s);
-  else launch_one<G, ND, true>(a, grid, smem, s);
+  if (a.P.homo) launch_one<G, ND, true, true>(a, grid, smem, s);        // homopolymer costs: exact kernel only (no bound pass)
+  else if (bound_only) launch_one<G, ND, false, false>(a, grid, smem, s);
+  else launch_one<G, ND, true, false>(a, grid, smem, s);
 }
 
 // Picks the instantiation: smallest G*ND >= needed band slots, preferring few lanes per pair for
 // large batches (throughput) and many lanes for small batches (latency).
 bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_upper, unsigned long long njobs_hint, int num_sms, cudaStream_t s,
                   bool bound_only) {
-  extern void count_launch(int);
+  if (a.P.homo && bound_only) return false;
   int G, ND;
   const bool big = njobs_hint > (unsigned long long)num_sms * 512;
-  const char *force = getenv("DADA2B_NWFWD");          // tuning override, e.g. "8x6"
-  int fg = 0, fnd = 0;
-  // EXPERIMENTAL (DADA2B_NWFWD_SMALL=<pairs>, "1" = 4096): rounds with few pairs are bound by the latency of ~500 dependent
-  // anti-diagonal steps (ncu: 6.8 % warp occupancy), so they take 16 lanes x 4 diagonals: 2 cells per lane and step instead of 3-5
-  const char *small_env = getenv("DADA2B_NWFWD_SMALL");
-  const unsigned long long small_thr = small_env ? (atoll(small_env) > 1 ? (unsigned long long)atoll(small_env) : 4096ull) : 0ull;
-  if (force && sscanf(force, "%dx%d", &fg, &fnd) == 2) { G = fg; ND = fnd; }
-  else if (small_thr && njobs_hint <= small_thr && slots_needed <= 64) { G = 16; ND = 4; }
-  else if (slots_needed <= 40) { G = big ? 4 : 8; ND = big ? 10 : 6; }
+  if (slots_needed <= 40) { G = big ? 4 : 8; ND = big ? 10 : 6; }
   else if (slots_needed <= 48) { G = 8; ND = 6; }
   else if (slots_needed <= 64) { G = 8; ND = 8; }
   else if (slots_needed <= 128) { G = 16; ND = 8; }
@@ -395,7 +412,6 @@ bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_u
   count_launch(1);
   if (G == 4 && ND == 10) launch_wl<4, 10>(a, bound_only, grid, smem, s);
   else if (G == 8 && ND == 6) launch_wl<8, 6>(a, bound_only, grid, smem, s);
-  else if (G == 16 && ND == 4) launch_wl<16, 4>(a, bound_only, grid, smem, s);
   else if (G == 8 && ND == 8) launch_wl<8, 8>(a, bound_only, grid, smem, s);
   else if (G == 16 && ND == 8) launch_wl<16, 8>(a, bound_only, grid, smem, s);
   else if (G == 32 && ND == 8) launch_wl<32, 8>(a, bound_only, grid, smem, s);

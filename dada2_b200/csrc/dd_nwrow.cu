@@ -29,6 +29,7 @@
 //   out-of-band neighbours (slot -1, slot W) are a constant far below any real score (:113-119).
 #include "dd_common.h"
 #include "dd_kernels.h"
+#include "dd_nwrow.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -37,81 +38,18 @@ namespace dd2 {
 
 namespace {
 
-constexpr int NW_CLR = (int)0xFFFF3FFFu;          // clears the prec field
-constexpr int NW_NMASK = 0x3FFF;                  // nsubs field
-constexpr int NW_SENT_H = -20000;                 // out-of-band score (biased space), far below any real score
-constexpr int NW_PREC_LEFT = 1 << 14, NW_PREC_UP = 2 << 14;
-
-struct RowConsts {
-  int cU, cU0, cL, cL0, delta, matchS;
-};
-
-__host__ __device__ inline RowConsts row_consts(const AlnParams &P) {
-  RowConsts c;
-  c.matchS = P.match * 65536;
-  c.cU = (P.gap - P.match) * 65536 + NW_PREC_UP;       // up: previous row -> one more unit of bias
-  c.cU0 = (0 - P.match) * 65536 + NW_PREC_UP;          // free end gap in column len2
-  c.cL = P.gap * 65536 + NW_PREC_LEFT;                 // left: same row
-  c.cL0 = NW_PREC_LEFT;                                // free end gap in row len1
-  c.delta = (P.mismatch - P.match) * 65536 + 1;        // mismatching diagonal move: score difference, one substitution
-  return c;
-}
-
-// mismatch bit of cell d: bit 2*(d % 16) of word d / 16 of the row's mask, as 0 / 1 through the FMA pipe
-template <int NWW> __device__ __forceinline__ int mis_bit(const uint32_t (&mm)[NWW], int d) {
-  return (int)__umulhi(mm[d >> 4] << (31 - 2 * (d & 15)), 2u);
-}
-
-// One DP row, in place.  CHECKED = false: interior row (no boundary cell).  MOVES: also return the row's 2-bit moves.
-template <int B, bool CHECKED, bool MOVES>
-__device__ __forceinline__ int nw_row(int (&S)[2 * B + 1], const uint32_t (&mm)[(2 * (2 * B + 1) + 31) / 32], const RowConsts &c, int cLrow,
-                                       int dpin, int pinval, int dfree, uint32_t (&mv)[(2 * (2 * B + 1) + 31) / 32]) {
-  constexpr int W = 2 * B + 1;
-  constexpr int SENT = NW_SENT_H * 65536;
-  int left = SENT, mB = 0;
-#pragma unroll
-  for (int w = 0; w < (2 * W + 31) / 32; w++) if (MOVES) mv[w] = 0u;
-#pragma unroll
-  for (int d = 0; d < W; d++) {
-    const int diag = S[d] + mis_bit(mm, d) * c.delta;
-    const int up = (d + 1 < W) ? S[d + 1] : SENT;
-    int cu = c.cU;
-    if (CHECKED) cu = (d == dfree) ? c.cU0 : c.cU;
-    const int t = __viaddmax_s32(up, cu, diag);
-    int m = __viaddmax_s32(left, cLrow, t);
-    if (MOVES) mv[d >> 4] |= (((uint32_t)m >> 14) & 3u) << (2 * (d & 15));
-    if (d == B) mB = m;                       // the main-diagonal cell with its prec field still in place
-    m &= NW_CLR;
-    if (CHECKED) m = (d == dpin) ? pinval : m;
-    S[d] = m; left = m;
-  }
-  return mB;
-}
-
 struct RowArgs {
   FwdArgs f;
   uint32_t *uneq_list;                 // jobs this kernel does not take (len2 != len1) -> lane-group kernels
   unsigned long long *uneq_count;
   uint32_t *mv_scratch;                // EXACT: [row][word][thread] 2-bit moves of the thread's current pair
   uint16_t *sub_scratch;               // EXACT: [k][thread] substitutions found by the traceback: raw position | centre base << 14
+  unsigned long long lane_max;         // BOUND: rounds with at most this many jobs belong to k_nwlane (dd_nwlane.cu)
 };
-
-// warp-aggregated append of r (for lanes with flag set) to list / count
-__device__ __forceinline__ void warp_append(bool flag, uint32_t r, uint32_t *list, unsigned long long *count) {
-  const unsigned m = __ballot_sync(0xffffffffu, flag);
-  if (!m) return;
-  const int lane = threadIdx.x & 31;
-  unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = r;
-}
 
 enum RowMode : int { ROW_BOUND = 0, ROW_FINAL = 1, ROW_EXACT = 2 };
 
 }  // namespace
-
-bool nwrow_applicable(const FwdArgs &f, int len1);
 
 // MODE ROW_BOUND  (loop, pass 1 of the two-phase scheme): substitution count of the traced path for every
 //                 job, then lambda <= S_r * rho_r^nsubs decides whether the pair can pass the store rule (cluster.cpp:192);
@@ -136,6 +74,7 @@ __global__ void __launch_bounds__(128) k_nwrow(RowArgs ra) {
   uint8_t *s_cen = (uint8_t *)(smem + (MODE == ROW_EXACT ? 2 * (16 * ncol) : 0));
   const unsigned long long njobs = *a.njobs_ptr;
   if ((unsigned long long)blockIdx.x * blockDim.x >= njobs) return;
+  if (MODE == ROW_BOUND && njobs <= ra.lane_max) return;
   const int L = (MODE == ROW_FINAL) ? a.in.maxlen : (int)a.in.len[a.centre_idx];
   if (MODE != ROW_FINAL) {
     const uint32_t *crow = a.in.seq2 + (size_t)a.centre_idx * a.in.SW;
@@ -227,60 +166,12 @@ __global__ void __launch_bounds__(128) k_nwrow(RowArgs ra) {
       warp_append(act && !gapped, r, a.gl_out, a.gl_count);
       warp_append(act && gapped, r, a.nw_out, a.nw_count);
     } else if (act) {
-      // ---- traceback over the recorded moves (2 = up, 1 = left, 0 = diag), substituted raw positions noted on the way ----
-      int i = L, j = L, nsub = 0;
-      while (i > 0 || j > 0) {
-        int mvv;
-        if (i == 0) mvv = 1;                    // top row: p = 2, consume the raw base (nwalign_endsfree.cpp:97-101)
-        else if (j == 0) mvv = 2;               // left column: p = 3
-        else {
-          const int d = j - i + B;
-          mvv = (int)((ra.mv_scratch[((size_t)(i - 1) * NWW + (d >> 4)) * T + tid] >> (2 * (d & 15))) & 3u);
-        }
-        if (mvv == 0) {
-          const uint32_t b1 = s_cen[i - 1], b2 = (rrow[(j - 1) >> 4] >> (2 * ((j - 1) & 15))) & 3u;
-          if (b1 != b2) { ra.sub_scratch[(size_t)nsub * T + tid] = (uint16_t)((uint32_t)(j - 1) | (b1 << 14)); nsub++; }
-          i--; j--;
-        } else if (mvv == 1) j--;
-        else i--;
-      }
-      // ---- lambda in raw-position order (pval.cpp:158-193): self transition everywhere except at the substituted positions ----
-      const uint8_t *qrow = a.in.qual + (size_t)r * a.in.QS;
-      double lam = 1.0;
-      int k = nsub - 1;
-      uint32_t nxt = k >= 0 ? ra.sub_scratch[(size_t)k * T + tid] : 0xFFFFu;
-      uint32_t bw = 0, qw = 0;
-      for (int p = 0; p < L; p++) {
-        if ((p & 15) == 0) bw = rrow[p >> 4];
-        if ((p & 3) == 0) qw = *(const uint32_t *)(qrow + p);
-        const uint32_t b = bw & 3u; bw >>= 2;
-        int q = a.P.use_quals ? (int)(qw & 0xFFu) : 0; qw >>= 8;
-        if (q > ncol - 1) { errflag = ERR_QUAL; q = ncol - 1; }               // pval.cpp:169-171
-        uint32_t t = 5u * b;
-        if ((nxt & 0x3FFFu) == (uint32_t)p) {
-          t = 4u * (nxt >> 14) + b;
-          k--;
-          nxt = k >= 0 ? ra.sub_scratch[(size_t)k * T + tid] : 0xFFFFu;
-        }
-        lam = lam * s_err[t * ncol + q];
-      }
+      // ---- traceback over the recorded moves, lambda in raw-position order, store rule (dd_nwrow.cuh) ----
+      const int nsub = trace_moves<NWW, 16, 8>(ra.mv_scratch + tid, (size_t)NWW * T, T, L, B, s_cen, rrow, ra.sub_scratch + tid, T);
+      const double lam = lambda_from_subs(rrow, a.in.qual + (size_t)r * a.in.QS, L, ncol, a.P.use_quals, s_err, ra.sub_scratch + tid, T, nsub, &errflag);
       if (nsub != ns) errflag = ERR_TRACE;      // the forward-carried count and the traced path must agree
       if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;               // pval.cpp:195
-      const double emm = a.st.E_minmax[r];                                        // cluster.cpp:192-200
-      if (lam * (double)a.total_reads > emm) {
-        const double ec = lam * (double)a.centre_reads;
-        if (ec > emm) a.st.E_minmax[r] = ec;
-        if (a.st.shard_world > 1) {
-          const unsigned long long slot = atomicAdd(&a.st.ctr[CTR_NE], 1ull);
-          a.st.ne_local[slot] = NewEntry{r, (uint32_t)ns, lam};
-        } else {
-          const unsigned long long slot = a.cluster_i == 0 ? (unsigned long long)r : atomicAdd(&a.st.ctr[CTR_CS_COUNT], 1ull);
-          if (slot < a.st.cs_cap) {
-            a.st.cs_index[slot] = r; a.st.cs_i[slot] = a.cluster_i; a.st.cs_lambda[slot] = lam; a.st.cs_ham[slot] = (uint32_t)ns;
-          }
-          if (a.cluster_i == 0 || r == a.centre_idx) { a.st.comp_lambda[r] = lam; a.st.comp_ham[r] = (uint32_t)ns; }
-        }
-      }
+      store_comparison(a, r, lam, ns);
     }
   }
   if (errflag) atomicMax(&a.st.ctr[CTR_ERR], (unsigned long long)errflag);
@@ -302,7 +193,6 @@ template <int MODE> static void launch_row_band(const RowArgs &a, int grid, size
 // plain gap costs, band narrower than the centre so that the reference fills its band boundaries)
 bool nwrow_applicable(const FwdArgs &f, int len1) {
   const AlnParams &P = f.P;
-  if (getenv("DADA2B_NO_NWROW")) return false;
   if (P.homo || P.band < 0) return false;
   if (!(P.band == 8 || P.band == 16 || P.band == 32)) return false;
   if (len1 < P.band + 2 || len1 >= 16000) return false;
@@ -321,9 +211,9 @@ static int row_grid(unsigned long long njobs_upper, int num_sms, int per_sm) {
 // Bound pass over f.jobs; jobs with len2 != len1 come back in uneq_list (count in *uneq_count, zeroed by the caller).
 // false: nothing launched (the caller falls back to the lane-group kernels for every job).
 bool launch_nwrow_bound(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, int len1, unsigned long long njobs_upper, int num_sms,
-                        cudaStream_t s) {
+                        unsigned long long lane_max, cudaStream_t s) {
   if (!nwrow_applicable(f, len1)) return false;
-  RowArgs a{f, uneq_list, uneq_count, nullptr, nullptr};
+  RowArgs a{f, uneq_list, uneq_count, nullptr, nullptr, lane_max};
   const size_t smem = (size_t)((f.in.maxlen + 15) & ~15);
   count_launch(1);
   launch_row_band<ROW_BOUND>(a, row_grid(njobs_upper, num_sms, 16), smem, s);
@@ -334,7 +224,7 @@ bool launch_nwrow_bound(const FwdArgs &f, uint32_t *uneq_list, unsigned long lon
 bool launch_nwrow_final(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, unsigned long long njobs_upper, int num_sms,
                         cudaStream_t s) {
   if (f.in.minlen != f.in.maxlen || !nwrow_applicable(f, f.in.maxlen)) return false;
-  RowArgs a{f, uneq_list, uneq_count, nullptr, nullptr};
+  RowArgs a{f, uneq_list, uneq_count, nullptr, nullptr, 0ull};
   count_launch(1);
   launch_row_band<ROW_FINAL>(a, row_grid(njobs_upper, num_sms, 16), 16, s);
   return true;
@@ -352,7 +242,7 @@ bool nwrow_usable(const AlnParams &P, int len1) { FwdArgs f{}; f.P = P; return n
 bool launch_nwrow_exact(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, uint32_t *mv_scratch, uint16_t *sub_scratch, int len1,
                         unsigned long long njobs_upper, int grid_cap, cudaStream_t s) {
   if (!nwrow_applicable(f, len1) || !mv_scratch || !sub_scratch) return false;
-  RowArgs a{f, uneq_list, uneq_count, mv_scratch, sub_scratch};
+  RowArgs a{f, uneq_list, uneq_count, mv_scratch, sub_scratch, 0ull};
   const size_t smem = (size_t)16 * f.P.ncol * 8 + (size_t)((f.in.maxlen + 15) & ~15);
   count_launch(1);
   launch_row_band<ROW_EXACT>(a, (int)std::min<unsigned long long>(std::max<unsigned long long>((njobs_upper + 127) / 128, 1ull), (unsigned long long)grid_cap), smem, s);

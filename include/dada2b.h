@@ -100,6 +100,10 @@ typedef struct {
   double ms_device;                 /* CUDA-event time, first to last device operation          */
   double ms_k_classify, ms_k_align_nw, ms_k_align_gl, ms_k_align_final;  /* CUDA-event sums per kernel family */
   int32_t n_k_classify, n_k_align_nw, n_k_align_gl, n_k_align_final;     /* launches in each sum              */
+  /* finer split (ms_k_classify = prescreen + screen; ms_k_align_nw = bound + exact) and the round-control kernels */
+  double ms_k_prescreen, ms_k_nw_bound, ms_k_nw_exact, ms_k_tail;
+  int32_t n_k_prescreen, n_k_nw_bound, n_k_nw_exact, n_k_tail;
+  int64_t prescreen_rows;           /* 5-mer bitmap rows (128 B + 13 B of per-raw metadata) streamed by k_prescreen */
 } dada2b_out;
 
 /* One-shot: host buffers in, host buffers out (what the Rcpp shim calls). */

@@ -39,6 +39,7 @@ struct dim3 {
   constexpr dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct uint3 { unsigned x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 
 typedef struct cuemu_stream_st *cudaStream_t;
 typedef struct cuemu_event_st *cudaEvent_t;

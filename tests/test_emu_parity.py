@@ -62,7 +62,7 @@ def test_emu_pair_corpus(emu):
 
 def test_emu_config1(emu):
     _gpu_tests().test_config1_bit_identical()
-    assert emu.cuemu_launches(b"k_nwfwd<") > 0 and emu.cuemu_launches(b"k_nwfwd2") == 0
+    assert emu.cuemu_launches(b"k_nwrow<") > 0 and emu.cuemu_launches(b"k_prescreen") > 0
 
 
 def test_emu_error_paths(emu):
@@ -74,21 +74,13 @@ def test_emu_e2e(emu, name):
     _gpu_tests().test_e2e_matches_reference_golden(name)
 
 
-@pytest.mark.parametrize("name", ["syn800_band8", "syn700_ragged_homo"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
-def test_emu_e2e_nwfwd_v2(emu, monkeypatch, name):
-    """The restructured loop-NW kernel (dd_nwfwd2.cu, DADA2B_NWFWD_V2=1) gives the reference's results."""
-    monkeypatch.setenv("DADA2B_NWFWD_V2", "1")
+@pytest.mark.parametrize("name", ["syn800_default", "syn800_band8", "syn800_kdist"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
+def test_emu_e2e_fallback_kernels(emu, monkeypatch, name):
+    """DADA2B_FALLBACK=1: no thread-per-pair / lane kernels, no streaming screen -- the general kernels alone (the path of
+    ragged lengths, other bands, homopolymer gap costs) reproduce the goldens on every case."""
+    monkeypatch.setenv("DADA2B_FALLBACK", "1")
     _gpu_tests().test_e2e_matches_reference_golden(name)
-    opts = cases.E2E_CASES[name][1]
-    if opts.get("band_size", 16) >= 0:          # homopolymer gap costs included (the default kernel hands those to k_align)
-        assert emu.cuemu_launches(b"k_nwfwd2") > 0 and emu.cuemu_launches(b"k_nwfwd<") == 0
-
-
-@pytest.mark.parametrize("name", ["syn800_default", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
-def test_emu_e2e_twophase(emu, monkeypatch, name):
-    """The two-phase loop NW (exact lambda bound first, DADA2B_TWOPHASE=1) gives the reference's results."""
-    monkeypatch.setenv("DADA2B_TWOPHASE", "1")
-    _gpu_tests().test_e2e_matches_reference_golden(name)
+    assert emu.cuemu_launches(b"k_nwrow<") == 0 and emu.cuemu_launches(b"k_nwlane<") == 0 and emu.cuemu_launches(b"k_prescreen") == 0
 
 
 def test_emu_long_reads_band32_homopolymer(emu, monkeypatch):
@@ -99,17 +91,13 @@ def test_emu_long_reads_band32_homopolymer(emu, monkeypatch):
     import dada2_b200
     seqs, ab, q = synth.pacbio(36, L=1500, nvar=3, seed=5)
     err = synth.extend_err(cases.tperr1(), 94)
-    for v2 in (False, True):                      # default kernels, then the restructured NW kernel (register path for homo gaps)
-        if v2:
-            monkeypatch.setenv("DADA2B_NWFWD_V2", "1")
-        for opts in (dict(band_size=32, vectorized_alignment=False, homo_gap=-1), dict(band_size=32)):
-            if v2 and "homo_gap" not in opts and not os.environ.get("DADA2B_EMU_FULL"):
-                continue
-            o = dict(opts)
-            o.setdefault("homo_gap", -8)
-            got = dada2_b200.dada_uniques(seqs, ab, None, err, q, **opts)
-            want = port.dada_uniques(seqs, ab, None, err, q, **o)
-            cases.assert_same(got, want, rtol=1e-10, label=str(opts) + (" v2" if v2 else ""))
+    for opts in (dict(band_size=32, vectorized_alignment=False, homo_gap=-1), dict(band_size=32)):
+        o = dict(opts)
+        o.setdefault("homo_gap", -8)
+        got = dada2_b200.dada_uniques(seqs, ab, None, err, q, **opts)
+        want = port.dada_uniques(seqs, ab, None, err, q, **o)
+        cases.assert_same(got, want, rtol=1e-10, label=str(opts))
+    assert emu.cuemu_launches(b"k_nwfwd<") > 0              # ragged lengths / homopolymer costs: the general lane-group kernel
 
 
 def _run_sharded(world, name, case=None):
@@ -193,37 +181,13 @@ def test_emu_large_tie_sets(emu, monkeypatch, fused):
     assert (emu.cuemu_launches(b"k_tail_final") > 0) == fused
 
 
-@pytest.mark.parametrize("name", ["syn800_kdist", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
-def test_emu_e2e_pivot_screen(emu, monkeypatch, name):
-    """The pivot pre-filter of the k-mer screen (dd_classify2.cu, DADA2B_PIVOT=1): triangle-inequality bound on the
-    5-mer min-sum from the closest centre seen so far; must classify every pair exactly like k_classify."""
-    monkeypatch.setenv("DADA2B_PIVOT", "1")
-    _gpu_tests().test_e2e_matches_reference_golden(name)
-    if cases.E2E_CASES[name][1].get("use_kmers", True):
-        assert emu.cuemu_launches(b"k_classify2") > 0
-        if cases.E2E_CASES[name][1].get("max_clust", 0) != 1:          # a run of one round never measures a seed against earlier centres
-            assert emu.cuemu_launches(b"k_seed_dists") > 0
-
-
-def test_emu_all_experimental_paths_together(emu, monkeypatch):
-    """Every experimental path at once (pivot screen, two-phase with the 16-bit SIMD bound pass + restructured NW, fused tail),
-    single rank and sharded."""
-    for k in ("DADA2B_PIVOT", "DADA2B_TWOPHASE", "DADA2B_BOUND16", "DADA2B_NWFWD_V2", "DADA2B_FUSED_TAIL"):
-        monkeypatch.setenv(k, "1")
-    _gpu_tests().test_e2e_matches_reference_golden("syn800_default")
-    _run_sharded(2, "syn700_ragged")
-    assert emu.cuemu_launches(b"k_classify2") > 0 and emu.cuemu_launches(b"k_nwfwd2") > 0 and emu.cuemu_launches(b"k_tail_final") > 0
-    assert emu.cuemu_launches(b"k_nwbound16") > 0
-
-
-@pytest.mark.parametrize("experimental", [False, True] if os.environ.get("DADA2B_EMU_FULL") else [False], ids=lambda e: "experimental" if e else "default")
-def test_emu_edge_cases(emu, monkeypatch, experimental):
+@pytest.mark.parametrize("fallback", [False, True], ids=lambda e: "fallback" if e else "default")
+def test_emu_edge_cases(emu, monkeypatch, fallback):
     """tests/cases.py:edge_cases() on the emulated library (the GPU suite runs the same table in test_gpu_zzz_edge.py),
-    with the default kernels and with every experimental path switched on."""
+    with the default kernels and with the general (fallback) kernels only."""
     import dada2_b200
-    if experimental:
-        for k in ("DADA2B_PIVOT", "DADA2B_TWOPHASE", "DADA2B_BOUND16", "DADA2B_NWFWD_V2", "DADA2B_FUSED_TAIL"):
-            monkeypatch.setenv(k, "1")
+    if fallback:
+        monkeypatch.setenv("DADA2B_FALLBACK", "1")
     for case in cases.edge_cases():
         cases.check_edge_case(case, dada2_b200.dada_uniques)
 
@@ -241,8 +205,8 @@ def test_emu_sharded_owner_mode(emu, monkeypatch, world, name):
 
 def test_emu_sharded_owner_mode_ties_and_extra_passes(emu, monkeypatch):
     """Owner mode corner paths: tie sets larger than TIE_MAX (per-rank candidate lists exchanged), and NP=1 so that rounds
-    needing more shuffle passes continue with one fused pass at a time; plus every other experimental path."""
-    for k in ("DADA2B_FUSED_TAIL", "DADA2B_OWNER", "DADA2B_NWFWD_V2", "DADA2B_PIVOT", "DADA2B_TWOPHASE"):
+    needing more shuffle passes continue with one fused pass at a time."""
+    for k in ("DADA2B_FUSED_TAIL", "DADA2B_OWNER"):
         monkeypatch.setenv(k, "1")
     monkeypatch.setenv("DADA2B_NP", "1")
     seqs, ab, q = cases.tie_case()
@@ -251,28 +215,3 @@ def test_emu_sharded_owner_mode_ties_and_extra_passes(emu, monkeypatch):
     _run_sharded(3, "syn800_maxclust5")
 
 
-@pytest.mark.parametrize("name", ["syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES))
-def test_emu_e2e_bound16(emu, monkeypatch, name):
-    """DADA2B_BOUND16=1 (dd_nwbound.cu): the bound pass of the two-phase loop NW with two raws per lane group on the 16-bit
-    SIMD datapath.  Goldens reproduced, and its survivor set equals the scalar bound pass's (same DP-cell total: the exact
-    pass aligned exactly the same pairs); ragged lengths exercise the unequal-length hand-over to the scalar pass."""
-    import dada2_b200
-    monkeypatch.setenv("DADA2B_TWOPHASE", "1")
-    seqs, ab, pri, err, q, opts = cases.build_case(name)
-    scalar = dada2_b200.dada_uniques(seqs, ab, pri, err, q, **opts)["stats"]["nw_cells"]
-    monkeypatch.setenv("DADA2B_BOUND16", "1")
-    n0 = emu.cuemu_launches(b"k_nwbound16")
-    _gpu_tests().test_e2e_matches_reference_golden(name)
-    o = cases.E2E_CASES[name][1]                 # the SIMD pass does not apply to unbanded / band 0 / homopolymer-cost / one-round runs
-    applies = o.get("band_size", 16) > 0 and o.get("max_clust", 0) != 1 and not (o.get("vectorized_alignment", True) is False and "homo_gap" in o)
-    assert emu.cuemu_launches(b"k_nwbound16") > n0 or not applies
-    assert dada2_b200.dada_uniques(seqs, ab, pri, err, q, **opts)["stats"]["nw_cells"] == scalar
-
-
-@pytest.mark.parametrize("v2", [False, True], ids=["nwfwd", "nwfwd2"])
-def test_emu_e2e_small_round_instantiation(emu, monkeypatch, v2):
-    """DADA2B_NWFWD_SMALL=1: rounds with few pairs run the <16, 4> instantiation (2 cells per lane and step) of k_nwfwd / k_nwfwd2."""
-    monkeypatch.setenv("DADA2B_NWFWD_SMALL", "1")
-    if v2:
-        monkeypatch.setenv("DADA2B_NWFWD_V2", "1")
-    _gpu_tests().test_e2e_matches_reference_golden("syn700_ragged")

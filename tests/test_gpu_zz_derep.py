@@ -1,7 +1,7 @@
 """Dereplication kernels (dd_derep.cu) on hardware through the C-ABI of include/dada2b_derep.h: the
 reference's sam1F fixture (must reproduce the committed config-1 input of dada()), chunked and synthetic inputs against
 the oracle, then 2e5 reads timed.  Written after round 1's GPU budget was spent (emulator-validated only,
-tests/test_emu_derep.py): xfail(strict=False), subprocess with a timeout -- XPASS = parity on hardware."""
+tests/test_emu_derep.py): a plain hardware gate since round 2 (XPASSed on a B200 in round 1); subprocess with a timeout."""
 import os
 import subprocess
 import sys
@@ -41,7 +41,6 @@ SCRIPT = textwrap.dedent('''
 ''') % ROOT
 
 
-@pytest.mark.xfail(strict=False, reason="new kernels, first run on hardware happens at round end")
 def test_derep_kernels_match_oracle_and_config1_input():
     out = subprocess.run([sys.executable, "-c", SCRIPT], cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "DEREP OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -1,7 +1,6 @@
 """BASELINE config 5 flavour (PacBio-like ~1.5 kb uniques, BAND_SIZE=32, homopolymer gap penalty) at a size the CPU
-oracle finishes in seconds.  The GPU budget of round 1 ran out before this configuration could be exercised on
-hardware, so it is marked xfail(strict=False): it reports XPASS/XFAIL at round end without masking the validated
-suite, and runs in a subprocess so that a device fault could not poison the other tests' CUDA context."""
+oracle finishes in seconds.  It passed on a B200 at the end of round 1 and is a plain hardware gate since round 2; it
+runs in a subprocess so that a device fault could not poison the other tests' CUDA context."""
 import os
 import subprocess
 import sys
@@ -32,7 +31,6 @@ SCRIPT = textwrap.dedent('''
 ''') % ROOT
 
 
-@pytest.mark.xfail(strict=False, reason="first exercise of the long-read configuration on hardware happens at round end")
 def test_pacbio_like_long_reads_match_oracle():
     out = subprocess.run([sys.executable, "-c", SCRIPT], cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "LONGREADS OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -1,7 +1,7 @@
 """mergePairs' fused align / evaluate / consensus kernel (dd_merge.cu) on hardware, through the C-ABI of
 include/dada2b_merge.h, against the goldens produced by the reference's own evaluate.cpp + nwalign_endsfree.cpp and, at a
 larger size, against the CPU oracle.  Written after round 1's GPU budget was spent (emulator-validated only,
-tests/test_emu_merge.py): xfail(strict=False), subprocess with a timeout -- XPASS = parity on hardware."""
+tests/test_emu_merge.py): a plain hardware gate since round 2 (XPASSed on a B200 in round 1); subprocess with a timeout."""
 import os
 import subprocess
 import sys
@@ -44,7 +44,6 @@ SCRIPT = textwrap.dedent('''
 ''') % ROOT
 
 
-@pytest.mark.xfail(strict=False, reason="new kernel, first run on hardware happens at round end")
 def test_merge_kernel_matches_reference_goldens_and_oracle():
     out = subprocess.run([sys.executable, "-c", SCRIPT], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MERGE OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
