@@ -299,9 +299,13 @@ struct BimRun {
     d_ctr.alloc(8);
     BCK(cudaMemsetAsync(d_ctr.p, 0, 8 * 8, s));
     aa.ctr = d_ctr.p;
-    // register-resident kernel (dd_bimfwd.cu; EXPERIMENTAL, off by default: not yet run on hardware)
-    use_fwd = getenv("DADA2B_BIMFWD") != nullptr && P.band >= 0;
-    use_fwd16 = use_fwd && atoi(getenv("DADA2B_BIMFWD")) == 2;       // two jobs per lane group on the 16-bit SIMD datapath (dd_bimfwd16.cu)
+    // alignment kernel: 2 (default) = two jobs per lane group on the 16-bit SIMD datapath (dd_bimfwd16.cu: 2.4x the traceback
+    // kernel on a B200, round-1 bench leg), falling back per job to 1 = register wavefront (dd_bimfwd.cu) and 0 = warp-per-pair
+    // traceback (k_bim_align).  DADA2B_BIMFWD=0|1|2 is a test hook that pins the first choice.
+    const char *bf = getenv("DADA2B_BIMFWD");
+    const int bf_mode = bf ? atoi(bf) : 2;
+    use_fwd = bf_mode >= 1 && P.band >= 0;
+    use_fwd16 = use_fwd && bf_mode == 2;
     fwd_slots = ((lbmax + 1) & ~1) + rbmax + 1;
     if (use_fwd) {
       const size_t w = bimfwd_scratch_words(fwd_slots, maxlen, num_sms);

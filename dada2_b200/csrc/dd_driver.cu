@@ -368,8 +368,8 @@ struct Run {
   int nown = 0;
   bool two_phase = false;              // bound pass first, exact lambda for the survivors only (plain gap costs)
   // fused round tail (experimental, DADA2B_FUSED_TAIL=1; dd_round2.cu)
-  bool fused_tail = false;
-  // owner mode (experimental, DADA2B_OWNER=1 on top of the fused tail, sharded runs): every rank keeps the stored comparisons and
+  bool fused_tail = false;               // dd_round2.cu: link + NP passes + final (default); dd_round.cu's split tail otherwise
+  // owner mode (sharded runs, on top of the fused tail): every rank keeps the stored comparisons and
   // runs shuffle / p-update / bud scan for its own raws only; per pass one all-reduce of the cluster read deltas, per round one
   // all-gather of the ranks' reports (bud candidates, move counts) and, when raws moved, one of the move lists.
   bool owner = false;
@@ -610,8 +610,8 @@ void Run::alloc_state() {
     launch_kmer_bits(in, cx->rank, cx->world, nown, kbits.p, kmeta.p, cx->num_sms, s);
   }
   if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
-  fused_tail = getenv("DADA2B_FUSED_TAIL") != nullptr;   // off by default: not yet validated on hardware
-  owner = fused_tail && cx->world > 1 && getenv("DADA2B_OWNER") != nullptr;
+  fused_tail = getenv("DADA2B_SPLIT_TAIL") == nullptr;   // test switch: the one-kernel-per-step tail of dd_round.cu (capacity fallback beyond 32 k clusters)
+  owner = fused_tail && cx->world > 1 && getenv("DADA2B_REPLICATED") == nullptr;   // sharded runs: every rank keeps / shuffles / scans its own raws only
   if (fused_tail) {
     const size_t g = (size_t)tail_grid(nraw);
     t_head.alloc(n); t_nmove.alloc(MAX_PASS); t_done.alloc(1); t_blk.alloc(g); t_bt.alloc(g * TIE_MAX); t_btp.alloc(g * TIE_MAX);
@@ -783,8 +783,11 @@ void Run::launch_round_tail(int first_pass, int npass) {
 void Run::launch_round_tail_inner(int first_pass, int npass) {
   const int nclust = (int)members.size();
   const unsigned long long upper = cs_count + (unsigned long long)nraw;
+  if (fused_tail && !tail_fits(nclust)) {       // per-cluster reads no longer fit shared memory: the split tail takes over for the rest of the run
+    if (owner) throw Err{"dada2b: too many clusters for a sharded run (the fused round tail holds per-cluster state in shared memory)"};
+    fused_tail = false;
+  }
   if (fused_tail) {
-    if (!tail_fits(nclust)) throw Err{"dada2b: too many clusters for the fused round tail (unset DADA2B_FUSED_TAIL)"};
     for (int p = first_pass; p < first_pass + npass; p++) {
       launch_tail_pass(st, in, ts, p, nclust, s);
       if (owner) NC(g_nccl.AllReduce(ts.rows + (size_t)p * ts.row_stride, ts.rows + (size_t)p * ts.row_stride, ts.row_stride, ncclInt32, ncclSum, cx->comm, s));

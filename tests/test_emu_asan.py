@@ -42,8 +42,7 @@ def _preload():
     return None
 
 
-@pytest.mark.parametrize("flags", [{}, {"DADA2B_NWFWD_V2": "1", "DADA2B_FUSED_TAIL": "1", "DADA2B_PIVOT": "1", "DADA2B_TWOPHASE": "1", "DADA2B_BOUND16": "1"}],
-                         ids=["default", "experimental"])
+@pytest.mark.parametrize("flags", [{}, {"DADA2B_FALLBACK": "1", "DADA2B_SPLIT_TAIL": "1"}], ids=["default", "fallback_kernels"])
 def test_kernels_are_memory_clean_under_asan(flags):
     asan = _preload()
     if asan is None:
@@ -73,7 +72,7 @@ print('ASAN RUN OK')
 """
 
 
-@pytest.mark.parametrize("flags", [{}, {"DADA2B_BIMFWD": "1"}, {"DADA2B_BIMFWD": "2"}], ids=["default", "bimfwd", "bimfwd16"])
+@pytest.mark.parametrize("flags", [{"DADA2B_BIMFWD": "0"}, {"DADA2B_BIMFWD": "1"}, {}], ids=["traceback", "bimfwd", "default_bimfwd16"])
 def test_bimera_and_merge_kernels_are_memory_clean_under_asan(flags):
     """dd_bimera.cu / dd_bimfwd.cu / dd_merge.cu / dd_derep.cu under the same memcheck stand-in."""
     asan = _preload()

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="the emul
 
 @pytest.fixture()
 def emu(monkeypatch):
-    monkeypatch.delenv("DADA2B_BIMFWD", raising=False)
+    monkeypatch.setenv("DADA2B_BIMFWD", "0")        # tests of the traceback kernel pin it; the variant tests below override
     import build_emu
     import dada2_b200.api as api
     lib = build_emu.build()

@@ -144,8 +144,8 @@ def _run_sharded(world, name, case=None):
 
 @pytest.mark.parametrize("world,name", [(2, "syn800_default"), (3, "syn700_ragged"), (8, "syn800_maxclust5")])
 def test_emu_sharded_ranks(emu, world, name):
-    """The sharded multi-GPU path (raw r aligned by rank r % world, one all-gather per split round, final all-reduces)
-    with the ranks as threads and the emulator's in-process NCCL stand-in: every rank returns the reference's result."""
+    """The sharded multi-GPU path (raw r aligned by rank r % world; owner mode) with the ranks as threads and the emulator's
+    in-process NCCL stand-in: every rank returns the reference's result."""
     _run_sharded(world, name)
 
 
@@ -155,11 +155,10 @@ FUSED_E2E = ["syn800_default", "syn800_nogreedy", "syn800_maxclust5", "syn700_ra
 @pytest.mark.parametrize("np_passes", [1, 3])
 @pytest.mark.parametrize("name", FUSED_E2E)
 def test_emu_e2e_fused_tail(emu, monkeypatch, name, np_passes):
-    """The fused round tail (dd_round2.cu, DADA2B_FUSED_TAIL=1): 1 + NP + 1 launches instead of ~17 per round.  NP=1
+    """The fused round tail (dd_round2.cu, the default): 1 + NP + 1 launches instead of ~17 per round.  NP=1
     makes every round that needs a second shuffle pass continue with one more fused pass at a time."""
     if np_passes == 1 and name not in ("syn800_default", "syn800_maxclust5") and not os.environ.get("DADA2B_EMU_FULL"):
         pytest.skip("quick subset")
-    monkeypatch.setenv("DADA2B_FUSED_TAIL", "1")
     monkeypatch.setenv("DADA2B_NP", str(np_passes))
     _gpu_tests().test_e2e_matches_reference_golden(name)
     assert emu.cuemu_launches(b"k_tail_final") > 0
@@ -169,12 +168,12 @@ def test_emu_e2e_fused_tail(emu, monkeypatch, name, np_passes):
         assert extra >= 0 and (extra > 0 or name not in ("syn800_default", "syn800_maxclust5"))      # e.g. max_clust=1: nothing ever moves
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["default", "fused_tail"])
+@pytest.mark.parametrize("fused", [False, True], ids=["split_tail", "default"])
 def test_emu_large_tie_sets(emu, monkeypatch, fused):
     """b_bud tie sets larger than TIE_MAX: the host fetches the whole set (k_bud_collect) and applies the scan order."""
     import tests.test_gpu_zz_ties as TT
-    if fused:
-        monkeypatch.setenv("DADA2B_FUSED_TAIL", "1")
+    if not fused:
+        monkeypatch.setenv("DADA2B_SPLIT_TAIL", "1")
     for opts in (dict(), dict(greedy=False), dict(max_clust=30)):
         TT.test_large_tie_sets_follow_scan_order(opts)
     assert emu.cuemu_launches(b"k_bud_collect") > 0
@@ -194,11 +193,9 @@ def test_emu_edge_cases(emu, monkeypatch, fallback):
 
 @pytest.mark.parametrize("world,name", [(2, "syn800_default"), (3, "syn700_ragged"), (8, "syn800_nogreedy")])
 def test_emu_sharded_owner_mode(emu, monkeypatch, world, name):
-    """Owner mode (DADA2B_OWNER=1 on top of the fused tail): every rank keeps the stored comparisons and runs shuffle /
+    """Owner mode (the default of sharded runs): every rank keeps the stored comparisons and runs shuffle /
     p-update / bud scan for its own raws only; per pass one all-reduce of the cluster read deltas, per round one
     all-gather of the ranks' reports and (when raws moved) of the move lists.  No exchange of comparisons at all."""
-    monkeypatch.setenv("DADA2B_FUSED_TAIL", "1")
-    monkeypatch.setenv("DADA2B_OWNER", "1")
     _run_sharded(world, name)
     assert emu.cuemu_launches(b"k_cs_append") == 0 and emu.cuemu_launches(b"k_posthoc_owned") > 0
 
@@ -206,8 +203,6 @@ def test_emu_sharded_owner_mode(emu, monkeypatch, world, name):
 def test_emu_sharded_owner_mode_ties_and_extra_passes(emu, monkeypatch):
     """Owner mode corner paths: tie sets larger than TIE_MAX (per-rank candidate lists exchanged), and NP=1 so that rounds
     needing more shuffle passes continue with one fused pass at a time."""
-    for k in ("DADA2B_FUSED_TAIL", "DADA2B_OWNER"):
-        monkeypatch.setenv(k, "1")
     monkeypatch.setenv("DADA2B_NP", "1")
     seqs, ab, q = cases.tie_case()
     _run_sharded(2, "ties", case=(seqs, ab, None, q, dict(max_clust=40)))

@@ -63,7 +63,7 @@ def test_real_kernels_are_schedule_invariant(sched):
         "T.test_e2e_matches_reference_golden('syn800_default')\n"
         "T.test_pair_corpus_kernels_match_reference()\n"
         "print('SCHED OK')\n") % (os.path.dirname(HERE), lib)
-    env = dict(os.environ, CUEMU_SCHED=str(sched), DADA2B_NWFWD_V2="1", DADA2B_FUSED_TAIL="1", DADA2B_PIVOT="1", DADA2B_TWOPHASE="1", DADA2B_BOUND16="1")
+    env = dict(os.environ, CUEMU_SCHED=str(sched))
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(HERE))
     assert out.returncode == 0 and "SCHED OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
 
@@ -87,8 +87,6 @@ def test_new_kernels_are_schedule_invariant(sched, bimfwd):
         "D.check_all(D.product_fn, sizes=(1200,))\n"
         "print('SCHED OK')\n") % (os.path.dirname(HERE), lib)
     env = dict(os.environ, CUEMU_SCHED=str(sched))
-    env.pop("DADA2B_BIMFWD", None)
-    if bimfwd != "0":
-        env["DADA2B_BIMFWD"] = bimfwd
+    env["DADA2B_BIMFWD"] = bimfwd
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(HERE))
     assert out.returncode == 0 and "SCHED OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -28,7 +28,7 @@ SCRIPT = textwrap.dedent('''
     from oracle import port
     from tools import synth
     import os
-    seqs, mat = synth.bimera_table(1500, 12, seed=9, lenvar=6) if not os.environ.get("DADA2B_BIMFWD") else synth.bimera_table(700, 8, seed=9, lenvar=6)
+    seqs, mat = synth.bimera_table(1500, 12, seed=9, lenvar=6) if os.environ.get("DADA2B_BIMFWD", "0") == "0" else synth.bimera_table(700, 8, seed=9, lenvar=6)
     for o in (dict(), dict(allow_one_off=True)):
         t0 = time.time(); want = port.table_bimera(mat, seqs, **o); t1 = time.time()
         got = bimera.C_table_bimera2(mat, seqs, return_stats=True, **o)
@@ -42,7 +42,7 @@ SCRIPT = textwrap.dedent('''
 @pytest.mark.parametrize("variant", ["traceback", "register", "simd16"])
 def test_bimera_kernels_match_reference_goldens_and_oracle(variant):
     env = dict(os.environ)
-    env.pop("DADA2B_BIMFWD", None)
+    env["DADA2B_BIMFWD"] = "0"                      # k_bim_align (warp-per-pair traceback): the kernel of last resort
     if variant == "register":                       # dd_bimfwd.cu (register-resident wavefront + per-pair traceback)
         env["DADA2B_BIMFWD"] = "1"
     if variant == "simd16":                         # dd_bimfwd16.cu (two jobs per lane group on the 16-bit SIMD datapath)

@@ -43,8 +43,9 @@ if n:
         torch.cuda.synchronize(); dist.barrier(); dt = (time.perf_counter() - t0) * 1e3
         if rank == 0:
             st = r["stats"]
-            print("sharded world=%d n=%d: %.1f ms  (loop %.1f final %.1f; k_nw %.1f k_classify %.1f k_final %.1f) nclust %d" % (
-                world, n, dt, st["ms_loop"], st["ms_final"], st["ms_k_align_nw"], st["ms_k_classify"], st["ms_k_align_final"], len(r["clustering"]["sequence"])), flush=True)
+            print("sharded world=%d n=%d: %.1f ms  (setup %.1f loop %.1f final %.1f; device %.1f; %s; launches %d) nclust %d" % (
+                world, n, dt, st["ms_setup"], st["ms_loop"], st["ms_final"], st["ms_device"], " ".join("%s %.1f" % (k[5:], st[k]) for k in st if k.startswith("ms_k_")),
+                st["gpu_launches"], len(r["clustering"]["sequence"])), flush=True)
     res.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
