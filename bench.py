@@ -214,6 +214,26 @@ def measure(res, err, steps, warmup, flush, barrier, torch):
     return time.perf_counter() - t0, step_ms, step_host, dev_ms, last
 
 
+def selfconsist_loop(runner, n):
+    """BASELINE configs[2]'s selfConsist error learning (R/dada.R:256-391; learnErrors) around `runner(err, max_clust)`:
+    pass 0 with the all-ones matrix and MAX_CLUST = 1, then loessErrfun refits (dada2_b200/errmodel.py: a restatement of R's
+    loess, parity unpinned) until the matrix repeats or MAX_CONSIST = 10.  Per-pass and whole-loop times."""
+    from dada2_b200 import errmodel
+    ms = []
+
+    def timed(e, mc):
+        t0 = time.perf_counter()
+        r = runner(e, mc)
+        ms.append(round((time.perf_counter() - t0) * 1e3, 1))
+        return r
+    t0 = time.perf_counter()
+    out = errmodel.learnErrors(timed)
+    loop_s = time.perf_counter() - t0
+    return {"passes": out["passes"], "pass_ms": ms, "loop_ms": round(loop_s * 1e3, 1), "refit_ms_total": round(loop_s * 1e3 - sum(ms), 1),
+            "uniques_per_s_whole_loop": n * out["passes"] / loop_s, "converged": out["passes"] < 11,
+            "nclust_final": len(out["dada"]["clustering"]["sequence"])}, out
+
+
 def configs1_leg(local_rank, flush, torch, do_cpu):
     """BASELINE configs[1] (1e5 uniques, one GPU) as a secondary object: value, e2e, parity against the CPU reference."""
     import dada2_b200
@@ -225,6 +245,7 @@ def configs1_leg(local_rank, flush, torch, do_cpu):
     def barrier():
         torch.cuda.synchronize()
     t_val, step_ms, _h, dev_ms, last = measure(res, err, 10, 3, flush, barrier, torch)
+    sc_gpu, sc_out = selfconsist_loop(lambda e, mc: res.run(e, max_clust=mc), n)
     res.close()
     call = dada2_b200.PackedCall(seqs, ab, None, err, q)
     call.run(unpack=False)
@@ -248,6 +269,21 @@ def configs1_leg(local_rank, flush, torch, do_cpu):
             out["parity"] = "identical"
         except AssertionError as e:
             out["parity"] = "MISMATCH: %s" % str(e)[:300]
+        # the same selfConsist loop around the reference's C++ on the host cores: same refit code, same number of passes expected
+        from oracle import ref
+        if ref.available():
+            sc_cpu, sc_cpu_out = selfconsist_loop(lambda e, mc: ref.dada_uniques(seqs, ab, None, e, q, max_clust=mc, multithread=True), n)
+            same = sc_cpu["passes"] == sc_gpu["passes"] and np.array_equal(sc_cpu_out["err_out"], sc_out["err_out"])
+            try:
+                cases.assert_same(sc_out["dada"], sc_cpu_out["dada"], rtol=1e-10, label="selfconsist")
+            except AssertionError as e:
+                same = "MISMATCH: %s" % str(e)[:200]
+            sc_gpu["cpu_reference_loop"] = {"loop_ms": sc_cpu["loop_ms"], "pass_ms": sc_cpu["pass_ms"], "passes": sc_cpu["passes"]}
+            sc_gpu["speedup_whole_loop"] = sc_cpu["loop_ms"] / sc_gpu["loop_ms"]
+            sc_gpu["identical_to_cpu_loop"] = same
+            if same is not True:
+                out["parity"] = "MISMATCH (selfConsist loop): %s" % same
+    out["selfconsist"] = sc_gpu
     return out
 
 
@@ -419,9 +455,12 @@ def main():
                     rc = 1
             except Exception as ex:
                 legs["configs1"] = {"failed": repr(ex)[:300]}
-            for tag, script, budget in (("selfconsist", "selfconsist_leg.py", 300), ("config5", "config5_leg.py", 420)):
-                if os.path.exists(os.path.join(ROOT, "tools", script)):
-                    legs[tag] = subprocess_leg(tag.upper(), [sys.executable, os.path.join(ROOT, "tools", script)], budget, local_rank)
+            try:       # BASELINE configs[2]: the whole selfConsist loop on the resident 1e6 uniques (one upload, <= 11 passes)
+                legs["selfconsist"] = dict(selfconsist_loop(lambda e, mc: res.run(e, max_clust=mc), nraw)[0],
+                                           workload="BASELINE configs[2]: learnErrors-style selfConsist loop on the resident %d uniques" % nraw)
+            except Exception as ex:
+                legs["selfconsist"] = {"failed": repr(ex)[:300]}
+            legs["config5"] = subprocess_leg("C5LEG", [sys.executable, os.path.join(ROOT, "tools", "config5_leg.py")], 420, local_rank)
             if args.bimera_seconds > 0:
                 legs["bimera"] = bimera_leg(args.bimera_seconds, local_rank)
         line = {"metric": "unique-reads/sec through dada()", "value": value, "unit": "uniques/s", "n_gpus": world,

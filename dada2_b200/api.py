@@ -44,6 +44,8 @@ def lib():
                                         P(_abi.Opts), C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int32, C.c_char_p]
+        L.dada2b_test_loop_nw.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, P(_abi.Opts),
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
         _LIB = L
     return _LIB
 
@@ -146,6 +148,23 @@ class Resident:
         if rc:
             raise Dada2bError(eb.value.decode())
         return dict(kind=kind, lam=lam, nsubs=nsubs, ops=ops, nops=nops, pos=pos, nt0=nt0, nt1=nt1, q1=q1)
+
+    def test_loop_nw(self, which, centre, raw, err, **opts):
+        """Kernel-level hook (include/dada2b_test.h): each (centre, raw) pair alone through one loop aligner
+        (0 k_nwrow<EXACT>, 1 k_nwlane, 2 k_nwfwd, 3 k_nwrow<BOUND>) -> lambda, nsubs, handled."""
+        e = _check_err(err)
+        ecm = np.asfortranarray(e)
+        o = _abi.make_opts(**_normalise_opts(dict(opts)))
+        centre = np.ascontiguousarray(centre, dtype=np.uint32)
+        raw = np.ascontiguousarray(raw, dtype=np.uint32)
+        n = len(centre)
+        lam = np.zeros(n, np.float64); nsubs = np.zeros(n, np.int32); handled = np.zeros(n, np.int32)
+        eb = C.create_string_buffer(_abi.ERRLEN)
+        rc = lib().dada2b_test_loop_nw(self._ctx, int(which), n, centre.ctypes.data, raw.ctypes.data, ecm.ctypes.data, int(e.shape[1]),
+                                       C.byref(o), lam.ctypes.data, nsubs.ctypes.data, handled.ctypes.data, eb)
+        if rc:
+            raise Dada2bError(eb.value.decode())
+        return dict(lam=lam, nsubs=nsubs, handled=handled)
 
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:

@@ -1379,13 +1379,20 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
   const int max_clust = o->max_clust < 1 ? nraw : o->max_clust;
   uint32_t wr = 0, wfrom = 0;
   int newi;
-  while ((int)R.members.size() < max_clust && (newi = R.decide_bud(&wr, &wfrom))) {
+  double h_enq = 0, h_wait = 0, h_replay = 0, h_decide = 0;      // host time per phase of a round (verbose diagnostics)
+  for (;;) {
+    const double td = now_ms();
+    if (!((int)R.members.size() < max_clust && (newi = R.decide_bud(&wr, &wfrom)))) break;
     const double tr = now_ms();
+    h_decide += tr - td;
     R.launch_compare((uint32_t)newi, o->kdist_cutoff);
     R.launch_round_tail(0, R.NP);
+    const double te = now_ms();
     R.sync_report();
+    const double tw = now_ms();
     int last = R.NP - 1;
     int ran = R.replay_moves(0, last);
+    h_enq += te - tr; h_wait += tw - te; h_replay += now_ms() - tw;
     if (!R.h_report->converged && R.fused_tail) {     // rare: more than NP passes needed: one more fused pass at a time
       while (!R.h_report->converged && last + 1 < MAX_PASS) {
         last++;
@@ -1409,8 +1416,8 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
                      R.cl_center_h[newi], now_ms() - tr, ran, R.cs_count, R.h_report->ctr[CTR_NW], R.h_report->ctr[CTR_GL],
                      R.h_report->ctr[CTR_NMOVE]);
   }
-  if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters; screened %llu, shrouded %llu\n", (int)R.members.size(),
-                   R.h_report->ctr[CTR_ALIGN], R.h_report->ctr[CTR_SHROUD]);
+  if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters; screened %llu, shrouded %llu; host ms: enqueue %.2f, wait for the device %.2f, replay moves %.2f, decide bud %.2f\n",
+                   (int)R.members.size(), R.h_report->ctr[CTR_ALIGN], R.h_report->ctr[CTR_SHROUD], h_enq, h_wait, h_replay, h_decide);
   R.sync();
   const double t2 = now_ms();
   dada2b_out *out = (dada2b_out *)calloc(1, sizeof(dada2b_out));
@@ -1478,6 +1485,59 @@ static void do_test_pairs(dada2b_ctx *cx, int npairs, const uint32_t *centre, co
   }
 }
 
+
+// Loop aligners one pair at a time (include/dada2b_test.h): the pair is compared as cluster 0 would (E_minmax = -999: always
+// stored, slot = raw index), so (lambda, hamming) can be read back from the comparison store.
+static void do_test_loop_nw(dada2b_ctx *cx, int which, int npairs, const uint32_t *centre, const uint32_t *raw, const double *err_cm, int Q,
+                            const dada2b_opts *o, double *lambda, int32_t *nsubs, int32_t *handled) {
+  CK(cudaSetDevice(cx->device));
+  if (cx->bad_nt) throw Err{"Unexpected nucleotide."};
+  Run R;
+  R.cx = cx; R.o = o; R.s = cx->stream; R.in = cx->in; R.nraw = cx->in.nraw; R.ncol = Q;
+  R.setup_params();
+  R.alloc_state();
+  cudaStream_t s = R.s;
+  std::vector<double> e((size_t)16 * Q);
+  for (int r = 0; r < 16; r++) for (int c = 0; c < Q; c++) e[(size_t)r * Q + c] = err_cm[r + 16 * (size_t)c];
+  R.h2d(R.err.p, e.data(), e.size() * 8);
+  if (R.two_phase) launch_raw_bounds(R.in, R.err.p, Q, o->use_quals != 0, R.raw_S.p, R.raw_rho.p, s);
+  DBuf<uint32_t> job, uneq, nsb; DBuf<unsigned long long> cnt;
+  job.alloc(1); uneq.alloc(4); nsb.alloc(R.nraw); cnt.alloc(4);
+  for (int k = 0; k < npairs; k++) {
+    const uint32_t c = centre[k], r = raw[k];
+    handled[k] = 0; lambda[k] = 0.0; nsubs[k] = -1;
+    if (c >= (uint32_t)R.nraw || r >= (uint32_t)R.nraw) throw Err{"dada2b_test_loop_nw: index out of range"};
+    launch_fill_f64(R.E_minmax.p, -999.0, R.nraw, s);
+    CK(cudaMemsetAsync(R.cs_ham.p + r, 0xFF, 4, s));
+    CK(cudaMemsetAsync(nsb.p + r, 0xFF, 4, s));
+    cnt.zero(s); R.ctr.zero(s);
+    const unsigned long long one = 1;
+    R.h2d(cnt.p, &one, 8);                       // cnt[0] = job count, cnt[1] = handed-back count, cnt[2] = survivors
+    R.h2d(job.p, &r, 4);
+    FwdArgs f{};
+    f.in = R.in; f.P = R.P; f.st = R.st; f.jobs = job.p; f.njobs_ptr = cnt.p;
+    f.centre_idx = c; f.centre_reads = cx->reads[c]; f.cluster_i = 0; f.total_reads = cx->total_reads;
+    f.fb_list = uneq.p; f.fb_count = cnt.p + 1; f.seq_bytes = R.seq_bytes; f.mode = 0; f.job_mul = 1; f.job_add = 0;
+    const long worst = (long)R.in.maxlen * std::max(std::abs(R.P.mismatch), std::abs(R.P.match)) + std::max(std::abs(R.P.gap), std::abs(R.P.hgap)) + 16;
+    f.fast_ok = (worst < std::abs((long)R.P.sentinel) / 2) ? 1 : 0;
+    f.raw_S = R.raw_S.p; f.raw_rho = R.raw_rho.p; f.surv_list = uneq.p + 2; f.surv_count = cnt.p + 2;
+    bool launched = false;
+    if (which == 0 && R.row_mv.p) launched = launch_nwrow_exact(f, uneq.p, cnt.p + 1, R.row_mv.p, R.row_sub.p, (int)cx->len[c], 1, R.row_grid_cap, s);
+    else if (which == 1 && R.lane_mv.p) launched = launch_nwlane(f, uneq.p, cnt.p + 1, R.lane_mv.p, R.lane_sub.p, (int)cx->len[c], R.lane_max, (int)R.lane_max, s);
+    else if (which == 2 && R.P.band >= 0) launched = launch_nwfwd(f, R.fwd_slots, 1, 1, cx->num_sms, s);
+    else if (which == 3 && R.row_mv.p && R.two_phase) launched = launch_nwrow_bound(f, uneq.p, cnt.p + 1, (int)cx->len[c], 1, cx->num_sms, 0ull, s, nsb.p);
+    if (!launched) continue;
+    unsigned long long hc[3]; double lam; uint32_t ham, nsv;
+    R.d2h(hc, cnt.p, 24); R.d2h(&lam, R.cs_lambda.p + r, 8); R.d2h(&ham, R.cs_ham.p + r, 4); R.d2h(&nsv, nsb.p + r, 4);
+    R.read_ctr();
+    R.check_dev_error();
+    if (hc[1] != 0) continue;                    // handed on to another kernel
+    handled[k] = 1;
+    if (which == 3) { nsubs[k] = (int32_t)nsv; }
+    else { lambda[k] = lam; nsubs[k] = (int32_t)ham; }
+  }
+}
+
 static void do_test_calc_pA(int n, const int32_t *reads, const double *E, const int32_t *prior, double *out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Err{"dada2b: no CUDA device available (this library has no CPU path)."};
@@ -1499,6 +1559,12 @@ int dada2b_test_pairs(dada2b_ctx *ctx, int32_t npairs, const uint32_t *centre, c
                       double *lambda, int32_t *nsubs, uint8_t *ops, int32_t *nops, int32_t opcap, uint16_t *pos,
                       uint8_t *nt0, uint8_t *nt1, uint8_t *q1, int32_t subcap, char errbuf[DADA2B_ERRLEN]) {
   try { do_test_pairs(ctx, npairs, centre, raw, err, Q, opts, use_kmers, kdist_cutoff, kind, lambda, nsubs, ops, nops, opcap, pos, nt0, nt1, q1, subcap); return 0; }
+  catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
+  catch (std::exception &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.what()); return 2; }
+}
+int dada2b_test_loop_nw(dada2b_ctx *ctx, int32_t which, int32_t npairs, const uint32_t *centre, const uint32_t *raw, const double *err,
+                        int32_t Q, const dada2b_opts *opts, double *lambda, int32_t *nsubs, int32_t *handled, char errbuf[DADA2B_ERRLEN]) {
+  try { do_test_loop_nw(ctx, which, npairs, centre, raw, err, Q, opts, lambda, nsubs, handled); return 0; }
   catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
   catch (std::exception &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.what()); return 2; }
 }

@@ -80,7 +80,7 @@ bool launch_nwfwd(const FwdArgs &a, int slots_needed, unsigned long long njobs_u
                   bool bound_only = false);
 // dd_nwrow.cu: thread-per-pair row kernel, bound pass over f.jobs (raws as long as the centre; the rest -> uneq_list)
 bool launch_nwrow_bound(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, int len1, unsigned long long njobs_upper, int num_sms,
-                        unsigned long long lane_max, cudaStream_t s);
+                        unsigned long long lane_max, cudaStream_t s, uint32_t *ns_out = nullptr);
 // dd_nwlane.cu: G lanes per pair, bound + exact in one launch, for rounds with at most lane_max jobs
 int nwlane_lanes(int band);
 size_t nwlane_mv_words(int band, int maxlen, int groups);

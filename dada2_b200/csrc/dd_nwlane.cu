@@ -35,12 +35,79 @@ struct LaneArgs {
 
 }  // namespace
 
+// Per-lane state of the pipelined sweep.
+template <int C> struct LaneState {
+  int S[C];                 // this lane's slots of the current row (clean words)
+  uint32_t win;             // 2-bit raw bases under the slots
+  uint32_t rw;              // rest of the packed raw word the next window base comes from
+  int ridx;                 // index of that base
+  int i;                    // row this lane handles in the current step
+  int pinval;               // -(i-1) * match << 16: the ends-free zero of column 0 in biased space
+  uint32_t *mvp;            // where the moves of row i go
+};
+
+// One step of one lane: row st.i of its C slots, in place.  CHECKED: boundary rules on (rows near the matrix edges);
+// GUARD: the lane may be outside rows 1..L (pipeline fill / drain) and must then leave its state alone.
+template <int B, int G, int C, bool CHECKED, bool GUARD>
+__device__ __forceinline__ void lane_step(LaneState<C> &st, const RowConsts &c, const uint8_t *s_cen, const uint32_t *rrow, int SW, int L, int g, int klast,
+                                          bool act, size_t mv_row_stride) {
+  constexpr int SENT = NW_SENT_H * 65536;
+  const int i = st.i;
+  const bool on = !GUARD || (act && i >= 1 && i <= L);
+  const uint32_t cb = s_cen[GUARD ? min(max(i - 1, 0), L - 1) : i - 1];
+  const uint32_t x = st.win ^ (cb * 0x55555555u);
+  const uint32_t mm = (x | (x >> 1)) & 0x55555555u;
+  int left = __shfl_up_sync(0xffffffffu, st.S[C - 1], 1, G);          // lane g-1 finished this row one step ago
+  if (g == 0) left = SENT;
+  const int dpin = B - i - g * C, dfree = L - i + B - g * C;            // local slot of column 0 / column L in this row
+  const int cLrow = (CHECKED && i == L) ? c.cL0 : c.cL;
+  const int pin = st.pinval - c.matchS;
+  uint32_t mv = 0;
+  int S0 = st.S[0];
+  {  // cell 0 first: the lane below needs it as its up input of this very step
+    const int diag = S0 + (int)__umulhi(mm << 31, 2u) * c.delta;
+    const int up = (0 == klast) ? SENT : st.S[1];
+    const int cu = (CHECKED && 0 == dfree) ? c.cU0 : c.cU;
+    int m = __viaddmax_s32(left, cLrow, __viaddmax_s32(up, cu, diag));
+    mv = __funnelshift_r(mv, (uint32_t)m >> 14, 2);
+    m &= NW_CLR;
+    if (CHECKED && 0 == dpin) m = pin;
+    if (on) S0 = m;
+    left = m;
+  }
+  int upin = __shfl_down_sync(0xffffffffu, S0, 1, G);                   // lane g+1's first slot of the previous row
+  if (g == G - 1) upin = SENT;
+  if (on) st.S[0] = S0;
+#pragma unroll
+  for (int k = 1; k < C; k++) {
+    const int diag = st.S[k] + (int)__umulhi(mm << (31 - 2 * k), 2u) * c.delta;
+    int up = (k + 1 < C) ? st.S[k + 1] : upin;
+    if (k == klast) up = SENT;                                            // slot W-1: the neighbour above is out of band
+    const int cu = (CHECKED && k == dfree) ? c.cU0 : c.cU;
+    int m = __viaddmax_s32(left, cLrow, __viaddmax_s32(up, cu, diag));
+    mv = __funnelshift_r(mv, (uint32_t)m >> 14, 2);                       // cell k ends at bits 32 - 2 (C - k)
+    m &= NW_CLR;
+    if (CHECKED && k == dpin) m = pin;
+    if (on) st.S[k] = m;
+    left = m;
+  }
+  if (on) {
+    st.pinval = pin;
+    *st.mvp = mv;
+    st.mvp += mv_row_stride;
+    st.win = (st.win >> 2) | ((st.rw & 3u) << (2 * (C - 1)));            // raw base ridx enters at the top slot for row i+1
+    st.rw >>= 2;
+    st.ridx++;
+    if ((st.ridx & 15) == 0) st.rw = (st.ridx >= 0 && (st.ridx >> 4) < SW) ? rrow[st.ridx >> 4] : 0u;
+  }
+  st.i = i + 1;
+}
+
 template <int B, int G>
 __global__ void __launch_bounds__(128) k_nwlane(LaneArgs la) {
   constexpr int W = 2 * B + 1;
   constexpr int C = (W + G - 1) / G;                    // slots per lane
-  constexpr int CLAST = W - 1 - (G - 1) * C;            // local index of slot W-1 in the last lane
-  static_assert(2 * C <= 32 && CLAST >= 0, "one window register per lane");
+  static_assert(C <= 16 && C >= 2, "one window register and one move word per lane and row");
   constexpr int SENT = NW_SENT_H * 65536;
   const FwdArgs &a = la.f;
   extern __shared__ uint32_t smem[];
@@ -61,6 +128,8 @@ __global__ void __launch_bounds__(128) k_nwlane(LaneArgs la) {
   const int lane = threadIdx.x & 31, g = lane % G;
   const size_t TG = (size_t)gridDim.x * GPB, grp = (size_t)blockIdx.x * GPB + threadIdx.x / G;
   const int d0 = g * C;                                 // first slot of this lane
+  const int klast = W - 1 - d0;                         // local index of slot W-1 (>= C: not in this lane; < 0: only padding here)
+  const int SW = a.in.SW;
   long long cells_lane = 0;
   const long long cells_pair = band_cells_cf(L, L, B, B);
   int errflag = 0;
@@ -72,72 +141,33 @@ __global__ void __launch_bounds__(128) k_nwlane(LaneArgs la) {
     const bool uneq = act && (int)a.in.len[r] != L;
     warp_append(uneq && g == 0, r, la.uneq_list, la.uneq_count);
     act = act && !uneq;
-    const uint32_t *rrow = a.in.seq2 + (size_t)r * a.in.SW;
+    const uint32_t *rrow = a.in.seq2 + (size_t)r * SW;
     auto raw_base = [&](int p) -> uint32_t { return (p >= 0 && p < L) ? (rrow[p >> 4] >> (2 * (p & 15))) & 3u : 0u; };
-    int S[C];
+    LaneState<C> st;
 #pragma unroll
-    for (int k = 0; k < C; k++) { const int d = d0 + k; S[k] = (d >= B && d < W) ? 0 : SENT; }      // row 0: columns 0..B are the ends-free zeros
-    uint32_t win = 0;                                   // row 1: slot d <-> raw base d - B
+    for (int k = 0; k < C; k++) { const int d = d0 + k; st.S[k] = (d >= B && d < W) ? 0 : SENT; }   // row 0: columns 0..B are the ends-free zeros
+    st.win = 0;                                         // row 1: slot d <-> raw base d - B
 #pragma unroll
-    for (int k = 0; k < C; k++) win |= raw_base(d0 + k - B) << (2 * k);
-    int pinval = 0;
-    // ---- software-pipelined row sweep: lane g handles row t - g at step t ----
-    for (int t = 1; t <= L + G - 1; t++) {
-      const int i = t - g;
-      const bool on = act && i >= 1 && i <= L;
-      const uint32_t cb = s_cen[min(max(i - 1, 0), L - 1)];
-      const uint32_t x = win ^ (cb * 0x55555555u);
-      const uint32_t mm = (x | (x >> 1)) & 0x55555555u;
-      int left = __shfl_up_sync(0xffffffffu, S[C - 1], 1, G);          // lane g-1 finished this row one step ago
-      if (g == 0) left = SENT;
-      const bool checked = (t <= B + G - 1) || (t > L - B);            // some lane of the warp is in a boundary row
-      const int dpin = B - i - d0, dfree = L - i + B - d0;             // local slot of column 0 / column L in this row
-      const int cLrow = (i == L) ? c.cL0 : c.cL;
-      const int pin = pinval - c.matchS;
-      int Sn[C];
-      uint32_t mv = 0;
-      // cell 0 first: the lane above needs it as its up input of this very step
-      {
-        const int diag = S[0] + (int)__umulhi(mm << 31, 2u) * c.delta;
-        int up = (C > 1) ? S[1] : SENT;
-        if (C > 1 && CLAST == 0 && g == G - 1) up = SENT;
-        const int cu = (checked && 0 == dfree) ? c.cU0 : c.cU;
-        int m = __viaddmax_s32(left, cLrow, __viaddmax_s32(up, cu, diag));
-        mv |= ((uint32_t)m >> 14) & 3u;
-        m &= NW_CLR;
-        if (checked && 0 == dpin) m = pin;
-        Sn[0] = m;
-      }
-      int upin = __shfl_down_sync(0xffffffffu, on ? Sn[0] : S[0], 1, G);   // lane g+1's first slot, previous row
-      if (g == G - 1) upin = SENT;
-      left = Sn[0];
-#pragma unroll
-      for (int k = 1; k < C; k++) {
-        const int diag = S[k] + (int)__umulhi(mm << (31 - 2 * k), 2u) * c.delta;
-        int up = (k + 1 < C) ? S[k + 1] : upin;
-        if (k == CLAST && g == G - 1) up = SENT;                          // slot W-1: the neighbour above is out of band
-        const int cu = (checked && k == dfree) ? c.cU0 : c.cU;
-        int m = __viaddmax_s32(left, cLrow, __viaddmax_s32(up, cu, diag));
-        mv |= (((uint32_t)m >> 14) & 3u) << (2 * k);
-        m &= NW_CLR;
-        if (checked && k == dpin) m = pin;
-        Sn[k] = m; left = m;
-      }
-      if (on) {
-#pragma unroll
-        for (int k = 0; k < C; k++) S[k] = Sn[k];
-        pinval = pin;
-        la.mv_scratch[((size_t)(i - 1) * G + g) * TG + grp] = mv;
-        win = (win >> 2) | (raw_base(i + d0 + C - 1 - B) << (2 * (C - 1)));     // slot d0+C-1 of row i+1
-      }
-    }
+    for (int k = 0; k < C; k++) st.win |= raw_base(d0 + k - B) << (2 * k);
+    st.ridx = d0 + C - B;                               // the base that enters at the top slot for row 2
+    st.rw = (st.ridx >= 0 && (st.ridx >> 4) < SW) ? rrow[st.ridx >> 4] : 0u;
+    st.rw >>= 2 * (st.ridx & 15);
+    st.pinval = 0;
+    st.i = 1 - g;                                       // software pipeline: lane g handles row t - g at step t
+    st.mvp = la.mv_scratch + (size_t)g * TG + grp;
+    const size_t mrs = (size_t)G * TG;
+    int t = 1;
+    // fill (some lanes not started), then boundary rows, interior rows, boundary rows, drain: every branch is block-uniform
+    for (; t <= min(B + G - 1, L + G - 1); t++) lane_step<B, G, C, true, true>(st, c, s_cen, rrow, SW, L, g, klast, act, mrs);
+    for (; t <= L - B; t++) lane_step<B, G, C, false, false>(st, c, s_cen, rrow, SW, L, g, klast, act, mrs);
+    for (; t <= L + G - 1; t++) lane_step<B, G, C, true, true>(st, c, s_cen, rrow, SW, L, g, klast, act, mrs);
     __syncwarp();                                       // the moves written by the other lanes are visible to the owner
     // ---- the lane holding cell (L, L) (slot B) finishes the pair on its own ----
     constexpr int GO = B / C, KO = B % C;
     const bool owner = act && g == GO;
     int ns = 0;
 #pragma unroll
-    for (int k = 0; k < C; k++) if (k == KO) ns = S[k] & NW_NMASK;
+    for (int k = 0; k < C; k++) if (k == KO) ns = st.S[k] & NW_NMASK;
     bool survive = owner;
     if (owner && a.cluster_i != 0) {
       const double bound = a.raw_S[r] * pow(a.raw_rho[r], (double)ns) * (double)a.total_reads * (1.0 + 1e-9);
@@ -146,7 +176,7 @@ __global__ void __launch_bounds__(128) k_nwlane(LaneArgs la) {
     if (owner) cells_lane += cells_pair;
     if (survive) {
       // traceback over the recorded moves, lambda in raw-position order, store rule (dd_nwrow.cuh)
-      const int nsub = trace_moves<G, C, 8>(la.mv_scratch + grp, (size_t)G * TG, TG, L, B, s_cen, rrow, la.sub_scratch + grp, TG);
+      const int nsub = trace_moves<G, C, 8, true>(la.mv_scratch + grp, (size_t)G * TG, TG, L, B, s_cen, rrow, la.sub_scratch + grp, TG);
       const double lam = lambda_from_subs(rrow, a.in.qual + (size_t)r * a.in.QS, L, ncol, a.P.use_quals, s_err, la.sub_scratch + grp, TG, nsub, &errflag);
       if (nsub != ns) errflag = ERR_TRACE;
       if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;               // pval.cpp:195
@@ -160,7 +190,7 @@ __global__ void __launch_bounds__(128) k_nwlane(LaneArgs la) {
   if (lane == 0 && cells_lane) atomicAdd(&a.st.ctr[CTR_CELLS], (unsigned long long)cells_lane);
 }
 
-int nwlane_lanes(int band) { return band == 32 ? 8 : 4; }
+int nwlane_lanes(int band) { return band == 32 ? 16 : (band == 16 ? 8 : 4); }        // 5 slots per lane in every case
 // scratch for `groups` pairs in flight
 size_t nwlane_mv_words(int band, int maxlen, int groups) { return (size_t)groups * (size_t)maxlen * nwlane_lanes(band); }
 size_t nwlane_sub_halfwords(int maxlen, int groups) { return (size_t)groups * (size_t)maxlen; }
@@ -176,9 +206,9 @@ bool launch_nwlane(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *un
   const int grid = std::max(1, groups_cap / gpb);
   const size_t smem = (size_t)16 * f.P.ncol * 8 + (size_t)((f.in.maxlen + 15) & ~15);
   count_launch(1);
-  if (f.P.band == 16) k_nwlane<16, 4><<<grid, 128, smem, s>>>(a);
+  if (f.P.band == 16) k_nwlane<16, 8><<<grid, 128, smem, s>>>(a);
   else if (f.P.band == 8) k_nwlane<8, 4><<<grid, 128, smem, s>>>(a);
-  else k_nwlane<32, 8><<<grid, 128, smem, s>>>(a);
+  else k_nwlane<32, 16><<<grid, 128, smem, s>>>(a);
   return true;
 }
 

@@ -45,6 +45,7 @@ struct RowArgs {
   uint32_t *mv_scratch;                // EXACT: [row][word][thread] 2-bit moves of the thread's current pair
   uint16_t *sub_scratch;               // EXACT: [k][thread] substitutions found by the traceback: raw position | centre base << 14
   unsigned long long lane_max;         // BOUND: rounds with at most this many jobs belong to k_nwlane (dd_nwlane.cu)
+  uint32_t *ns_out;                    // BOUND, test hook only: nsubs per raw (NULL in the product path)
 };
 
 enum RowMode : int { ROW_BOUND = 0, ROW_FINAL = 1, ROW_EXACT = 2 };
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(128) k_nwrow(RowArgs ra) {
       if (!(MODE == ROW_EXACT && a.no_cells)) cells_lane += cells_pair;
     }
     if (MODE == ROW_BOUND) {
+      if (ra.ns_out && act) ra.ns_out[r] = (uint32_t)ns;
       // lambda <= S_r * rho_r^nsubs for ANY alignment with nsubs substitutions (dd_round.cu:k_raw_bounds)
       bool survive = false;
       if (act) {
@@ -211,9 +213,9 @@ static int row_grid(unsigned long long njobs_upper, int num_sms, int per_sm) {
 // Bound pass over f.jobs; jobs with len2 != len1 come back in uneq_list (count in *uneq_count, zeroed by the caller).
 // false: nothing launched (the caller falls back to the lane-group kernels for every job).
 bool launch_nwrow_bound(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, int len1, unsigned long long njobs_upper, int num_sms,
-                        unsigned long long lane_max, cudaStream_t s) {
+                        unsigned long long lane_max, cudaStream_t s, uint32_t *ns_out) {
   if (!nwrow_applicable(f, len1)) return false;
-  RowArgs a{f, uneq_list, uneq_count, nullptr, nullptr, lane_max};
+  RowArgs a{f, uneq_list, uneq_count, nullptr, nullptr, lane_max, ns_out};
   const size_t smem = (size_t)((f.in.maxlen + 15) & ~15);
   count_launch(1);
   launch_row_band<ROW_BOUND>(a, row_grid(njobs_upper, num_sms, 16), smem, s);
@@ -224,7 +226,7 @@ bool launch_nwrow_bound(const FwdArgs &f, uint32_t *uneq_list, unsigned long lon
 bool launch_nwrow_final(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, unsigned long long njobs_upper, int num_sms,
                         cudaStream_t s) {
   if (f.in.minlen != f.in.maxlen || !nwrow_applicable(f, f.in.maxlen)) return false;
-  RowArgs a{f, uneq_list, uneq_count, nullptr, nullptr, 0ull};
+  RowArgs a{f, uneq_list, uneq_count, nullptr, nullptr, 0ull, nullptr};
   count_launch(1);
   launch_row_band<ROW_FINAL>(a, row_grid(njobs_upper, num_sms, 16), 16, s);
   return true;
@@ -242,7 +244,7 @@ bool nwrow_usable(const AlnParams &P, int len1) { FwdArgs f{}; f.P = P; return n
 bool launch_nwrow_exact(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, uint32_t *mv_scratch, uint16_t *sub_scratch, int len1,
                         unsigned long long njobs_upper, int grid_cap, cudaStream_t s) {
   if (!nwrow_applicable(f, len1) || !mv_scratch || !sub_scratch) return false;
-  RowArgs a{f, uneq_list, uneq_count, mv_scratch, sub_scratch, 0ull};
+  RowArgs a{f, uneq_list, uneq_count, mv_scratch, sub_scratch, 0ull, nullptr};
   const size_t smem = (size_t)16 * f.P.ncol * 8 + (size_t)((f.in.maxlen + 15) & ~15);
   count_launch(1);
   launch_row_band<ROW_EXACT>(a, (int)std::min<unsigned long long>(std::max<unsigned long long>((njobs_upper + 127) / 128, 1ull), (unsigned long long)grid_cap), smem, s);

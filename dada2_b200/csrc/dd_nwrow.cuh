@@ -73,13 +73,13 @@ __device__ __forceinline__ void warp_append(bool flag, uint32_t r, uint32_t *lis
 
 // ---- the tail of an exact alignment, shared by k_nwrow<EXACT> and k_nwlane: traceback, lambda, store rule ----------------
 // Moves were recorded as one word per (row, word slot): word `w` of row i (1-based) lives at mv[(i - 1) * row_stride +
-// w * word_stride]; a word holds CPW cells, cell d of the band sits in word d / CPW at bits 2 * (d % CPW).
+// w * word_stride]; a word holds CPW cells, cell d of the band sits in word d / CPW at bits 2 * (d % CPW) (TOP: counted from the top).
 // The ROW sequence of a traceback is known in advance (every diag / up move goes to row i - 1, left moves stay), so the
 // words are streamed through registers RB rows at a time: one memory latency per RB rows instead of one per move
 // (measured: ~300 ns per dependent L2 access made the naive walk 3x longer than the DP of a small round).
 // Substituted raw positions are written to `sub` ([k * sub_stride]: position | centre base << 14), last one first.
 // Returns nsubs of the traced path (al2subs, nwalign_endsfree.cpp:570-639; walk order of :169-188).
-template <int NWORDS, int CPW, int RB>
+template <int NWORDS, int CPW, int RB, bool TOP = false>
 __device__ __forceinline__ int trace_moves(const uint32_t *mv, size_t row_stride, size_t word_stride, int L, int B, const uint8_t *s_cen,
                                            const uint32_t *raw2 /* packed raw row (shared or global) */, uint16_t *sub, size_t sub_stride) {
   int i = L, j = L, nsub = 0;
@@ -101,7 +101,8 @@ __device__ __forceinline__ int trace_moves(const uint32_t *mv, size_t row_stride
         uint32_t word = buf[rr][0];
 #pragma unroll
         for (int w = 1; w < NWORDS; w++) word = (wi == w) ? buf[rr][w] : word;
-        const uint32_t mvv = (word >> (2 * (d - wi * CPW))) & 3u;
+        // TOP: the lane kernel shifts moves in from the top of the word (cell k of a lane ends at bits 32 - 2 (CPW - k))
+        const uint32_t mvv = (word >> (TOP ? 32 - 2 * (CPW - (d - wi * CPW)) : 2 * (d - wi * CPW))) & 3u;
         if (mvv == 1u) { j--; continue; }               // left: raw base against a gap (self transition)
         if (mvv == 0u) {                                // diag: centre base i-1 against raw base j-1
           const uint32_t b1 = s_cen[i - 1], b2 = (raw2[(j - 1) >> 4] >> (2 * ((j - 1) & 15))) & 3u;

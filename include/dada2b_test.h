@@ -24,6 +24,16 @@ int dada2b_test_pairs(dada2b_ctx *ctx, int32_t npairs, const uint32_t *centre, c
 int dada2b_test_calc_pA(int32_t n, const int32_t *reads, const double *E, const int32_t *prior, double *out,
                         char errbuf[DADA2B_ERRLEN]);
 
+/* Kernel-level hook for the LOOP aligners: every (centre[k], raw[k]) pair goes, alone, through one of the kernels that
+ * produce b_compare's (lambda, hamming) without an alignment string (cluster.cpp:136-143):
+ *   which = 0  k_nwrow<EXACT>   thread per pair, recorded moves + traceback        (dd_nwrow.cu)
+ *   which = 1  k_nwlane         lane group per pair, software-pipelined rows        (dd_nwlane.cu)
+ *   which = 2  k_nwfwd          lane-group anti-diagonal wavefront, carried lambda  (dd_nwfwd.cu)
+ *   which = 3  k_nwrow<BOUND>   thread per pair, substitution count only (lambda[k] is left 0)
+ * handled[k] = 0 when the kernel does not take the pair (lengths differ, band not instantiated, ...) and hands it on. */
+int dada2b_test_loop_nw(dada2b_ctx *ctx, int32_t which, int32_t npairs, const uint32_t *centre, const uint32_t *raw, const double *err,
+                        int32_t Q, const dada2b_opts *opts, double *lambda, int32_t *nsubs, int32_t *handled, char errbuf[DADA2B_ERRLEN]);
+
 #ifdef __cplusplus
 }
 #endif

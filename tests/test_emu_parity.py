@@ -60,6 +60,11 @@ def test_emu_pair_corpus(emu):
     assert emu.cuemu_launches(b"k_classify") > 0 and emu.cuemu_launches(b"k_align") > 0
 
 
+def test_emu_pair_corpus_loop_aligners(emu):
+    _gpu_tests().test_pair_corpus_loop_aligners_match_traceback_kernel()
+    assert emu.cuemu_launches(b"k_nwrow<") > 0 and emu.cuemu_launches(b"k_nwlane<") > 0 and emu.cuemu_launches(b"k_nwfwd<") > 0
+
+
 def test_emu_config1(emu):
     _gpu_tests().test_config1_bit_identical()
     assert emu.cuemu_launches(b"k_nwrow<") > 0 and emu.cuemu_launches(b"k_prescreen") > 0

@@ -93,6 +93,53 @@ def test_pair_corpus_kernels_match_reference():
     res.close()
 
 
+def test_pair_corpus_loop_aligners_match_traceback_kernel():
+    """The kernels that dominate device time never produce an alignment string, so they get their own stage test: every pair
+    of the corpus, alone, through k_nwrow<EXACT>, k_nwlane, k_nwfwd and k_nwrow<BOUND> (dada2b_test_loop_nw) must give the
+    (lambda, nsubs) of the warp-per-pair traceback kernel -- which the test above pins to the reference's alignments -- bit for
+    bit, in every option set of the corpus (bands 8 / 16 / 32 / > len, score sets, homopolymer gap costs, unequal lengths)."""
+    api = _api()
+    z, modes, a, b, qa, qb = _pairs()
+    err = cases.tperr1()
+    n = len(a)
+    seqs = a + b
+    maxlen = max(len(s) for s in seqs)
+    q = np.full((2 * n, maxlen), np.nan)
+    for i in range(n):
+        q[i, :len(a[i])] = qa[i]
+        q[n + i, :len(b[i])] = qb[i]
+    res = api.Resident(seqs, np.ones(2 * n, np.int32), None, q)
+    centre = np.arange(n, dtype=np.uint32)
+    raw = centre + n
+    took = {0: 0, 1: 0, 2: 0, 3: 0}
+    more = {"vec8": {"band_size": 8}, "vec32": {"band_size": 32}, "sc8_scores": {"band_size": 8, "match": 4, "mismatch": -5, "gap": -7}}
+    for m, o in list(modes.items()) + list(more.items()):
+        o = dict(o)
+        if o.get("band_size", 16) < 0:
+            continue                                             # unbanded: k_align only
+        want = res.test_pairs(centre, raw, err, use_kmers=False, kdist_cutoff=0.42, maxlen=maxlen, **o)
+        assert np.all(want["kind"] == (1 if o.get("band_size", 16) == 0 else 2)), m
+        if o.get("band_size", 16) == 0:
+            continue
+        for which in (0, 1, 2, 3):
+            r = res.test_loop_nw(which, centre, raw, err, **o)
+            for i in range(n):
+                if not r["handled"][i]:
+                    continue
+                took[which] += 1
+                assert r["nsubs"][i] == want["nsubs"][i], (m, which, i, r["nsubs"][i], want["nsubs"][i])
+                if which != 3:
+                    assert r["lam"][i] == want["lam"][i], (m, which, i, r["lam"][i], want["lam"][i])
+            if which in (0, 1, 3):                               # the row / lane kernels take exactly the equal-length pairs of their bands
+                homo = o.get("vectorized_alignment", True) is False and o.get("homo_gap", o.get("gap", -8)) != o.get("gap", -8)
+                ok_band = o.get("band_size", 16) in (8, 16, 32) and not homo
+                for i in range(n):
+                    fits = ok_band and len(a[i]) == len(b[i]) and len(a[i]) >= o.get("band_size", 16) + 2
+                    assert bool(r["handled"][i]) == fits, (m, which, i, len(a[i]), len(b[i]))
+    assert took[0] > 100 and took[1] > 100 and took[2] > 200 and took[3] > 100, took
+    res.close()
+
+
 def test_config1_bit_identical():
     api = _api()
     seqs, ab, q = cases.load_config1()
