@@ -55,6 +55,9 @@ struct RoundReport {
   uint32_t pad;
   uint32_t tie_r[TIE_MAX], tie_ham[TIE_MAX], tiep_r[TIE_MAX], tiep_ham[TIE_MAX];
   double tie_lam[TIE_MAX], tiep_lam[TIE_MAX];
+  // fused tail only: cluster of every tie candidate and that cluster's reads after the last pass, so that the host can open the
+  // next round before it has replayed this round's moves on its member arrays (dd_driver.cu: replay worker)
+  uint32_t tie_cl[TIE_MAX], tie_clreads[TIE_MAX], tiep_cl[TIE_MAX], tiep_clreads[TIE_MAX];
 };
 
 // A stored comparison produced by this rank in the current round (sharded runs): exchanged with one

@@ -24,6 +24,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -390,9 +393,28 @@ struct Run {
   size_t cl_cap = 0;
   unsigned long long cs_count = 0;
   // host membership (Bi::raw with slot order) and cluster records
+  // members / slot_of / cluster_of_h / cl_reads_h belong to the REPLAY side (worker thread when async_replay), cl_center_h / birth /
+  // nclust_h to the round loop.  The round loop only reads the replay side after drain_replay().
   std::vector<std::vector<uint32_t>> members;
   std::vector<uint32_t> slot_of, cluster_of_h, cl_center_h, cl_reads_h;
   std::vector<Birth> birth;
+  int nclust_h = 0;
+  // b_shuffle2's container updates and b_bud's pop / new cluster are pure host bookkeeping (O(moves), but ~30 ms of a 1e6-unique
+  // run): with the fused tail the device reports everything the next bud decision needs unless it is an exact tie, so the updates
+  // are queued to a worker and applied while the GPU runs the next round.
+  struct ReplayEvent { int kind; std::vector<uint32_t> mv; std::vector<uint32_t> pass_end; uint32_t r, from, ni; };
+  bool async_replay = false;
+  std::thread rworker;
+  std::mutex rmu;
+  std::condition_variable rcv, rdone;
+  std::deque<ReplayEvent> rq;
+  bool rbusy = false, rquit = false;
+  void apply_moves(const uint32_t *mv, size_t n);
+  void apply_bud(uint32_t r, uint32_t from);
+  void push_event(ReplayEvent &&e);
+  void drain_replay();
+  void stop_replay();
+  ~Run() { stop_replay(); }
   // align launch geometry
   int warp_words = 0, seq_bytes = 0, H_words = 0, ops_words = 0, ptr_in_smem = 0, align_grid = 0;
   unsigned long long ptr_words = 0;
@@ -473,7 +495,8 @@ struct Run {
 };
 
 void Run::reset_host() {
-  members.clear(); slot_of.clear(); cluster_of_h.clear(); cl_center_h.clear(); cl_reads_h.clear(); birth.clear(); evs.clear();
+  stop_replay();
+  members.clear(); slot_of.clear(); cluster_of_h.clear(); cl_center_h.clear(); cl_reads_h.clear(); birth.clear(); evs.clear(); nclust_h = 0;
   n_rounds = n_shuffles = 0; tot_nw = tot_gl = 0; prescreen_rows = 0; count_round = false; h2d_bytes = d2h_bytes = 0; cs_count = 0; est_active = 0; pending = Pending();
   st = DevState{};
 }
@@ -599,8 +622,10 @@ void Run::alloc_state() {
     row_mv.alloc(nwrow_mv_words(P.band, in.maxlen, row_grid_cap)); row_sub.alloc(nwrow_sub_halfwords(in.maxlen, row_grid_cap));
     if (!uneq_list.p) { uneq_list.alloc(n + 2); uneq_ctr.alloc(1); }
     {
-      lane_max = 16384;                  // rounds with at most this many NW pairs: G lanes per pair, one launch (dd_nwlane.cu)
-      lane_mv.alloc(nwlane_mv_words(P.band, in.maxlen, (int)lane_max)); lane_sub.alloc(nwlane_sub_halfwords(in.maxlen, (int)lane_max));
+      lane_max = 16384;                  // job lists of at most this many NW pairs: G lanes per pair, one launch (dd_nwlane.cu)
+      if (const char *e = getenv("DADA2B_LANE_MAX")) lane_max = (unsigned long long)std::max(0LL, std::min(16384LL, atoll(e)));   // test hook: exercises every size class on small inputs
+      lane_max = (lane_max + 31) & ~31ull;
+      if (lane_max) { lane_mv.alloc(nwlane_mv_words(P.band, in.maxlen, (int)lane_max)); lane_sub.alloc(nwlane_sub_halfwords(in.maxlen, (int)lane_max)); }
     }
   } else { row_mv.free(); row_sub.free(); lane_max = 0; }
   prescreen = P.use_kmers && !fallback_only;
@@ -687,7 +712,7 @@ void Run::launch_align_jobs(int mode, AlignArgs &a, unsigned long long upper) {
 void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   const uint32_t c = cl_center_h[i];
   ensure_cs_cap(cs_count + 2ull * (unsigned long long)nraw + 1024);
-  ensure_cluster_cap(members.size() + 2);
+  ensure_cluster_cap((size_t)nclust_h + 2);
   tail_sync_caps();
   launch_round_begin(st, pending.apply, pending.r, pending.from, pending.newi, pending.reads, s);
   pending.apply = 0;
@@ -744,7 +769,15 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     bool ex_done = false;
     if (row_mv.p) {
       CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
-      timed(T_NW, [&]() { ex_done = launch_nwrow_exact(f, uneq_list.p, uneq_ctr.p, row_mv.p, row_sub.p, (int)cx->len[c], (unsigned long long)nraw, row_grid_cap, s); });
+      // survivors of a large round are few: the lane-group kernel (lower latency) takes lists of up to lane_max jobs, the thread-per-pair
+      // kernel the rest (round 0, very large survivor sets); each returns at once when the list is not its size
+      bool lane2 = false;
+      if (lane_max && i > 0 && two_phase) {
+        FwdArgs f2 = f;
+        f2.raw_S = raw_S.p; f2.raw_rho = raw_rho.p;
+        timed(T_NW, [&]() { lane2 = launch_nwlane(f2, uneq_list.p, uneq_ctr.p, lane_mv.p, lane_sub.p, (int)cx->len[c], lane_max, (int)lane_max, s); });
+      }
+      timed(T_NW, [&]() { ex_done = launch_nwrow_exact(f, uneq_list.p, uneq_ctr.p, row_mv.p, row_sub.p, (int)cx->len[c], (unsigned long long)nraw, row_grid_cap, s, lane2 ? lane_max : 0ull); });
       if (ex_done) { f.jobs = uneq_list.p; f.njobs_ptr = uneq_ctr.p; }
     }
     if (ex_done && in.minlen == in.maxlen) fwd_done = true;       // nothing was handed back; fb_list stays empty
@@ -773,7 +806,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       launch_cs_append(st, ne_all.p, d_counts.p, (unsigned)maxc, i, c, s);
     }
   }
-  if (fused_tail) launch_tail_link(st, ts, cs_count, i, nraw, (int)members.size(), s);
+  if (fused_tail) launch_tail_link(st, ts, cs_count, i, nraw, nclust_h, s);
 }
 
 // shuffle passes [first_pass, first_pass + npass) then p-update, bud scan and the report
@@ -781,11 +814,12 @@ void Run::launch_round_tail(int first_pass, int npass) {
   timed(T_TAIL, [&]() { launch_round_tail_inner(first_pass, npass); });
 }
 void Run::launch_round_tail_inner(int first_pass, int npass) {
-  const int nclust = (int)members.size();
+  const int nclust = nclust_h;
   const unsigned long long upper = cs_count + (unsigned long long)nraw;
   if (fused_tail && !tail_fits(nclust)) {       // per-cluster reads no longer fit shared memory: the split tail takes over for the rest of the run
     if (owner) throw Err{"dada2b: too many clusters for a sharded run (the fused round tail holds per-cluster state in shared memory)"};
     fused_tail = false;
+    drain_replay(); async_replay = false;       // the split tail does not report the candidates' clusters
   }
   if (fused_tail) {
     for (int p = first_pass; p < first_pass + npass; p++) {
@@ -806,13 +840,13 @@ void Run::launch_round_tail_inner(int first_pass, int npass) {
 }
 
 void Run::launch_shuffle_only(int pass) {
-  launch_shuffle_pass(st, in, cs_count + (unsigned long long)nraw, (int)members.size(), pass, s);
+  launch_shuffle_pass(st, in, cs_count + (unsigned long long)nraw, nclust_h, pass, s);
   launch_report(st, pass, s);
 }
 void Run::launch_round_tail_noshuffle() {
   launch_p_update(st, in, o->greedy != 0, o->detect_singletons != 0, -1, s);
   BudParams bp{o->min_fold, o->min_hamming, o->min_abund};
-  launch_bud_scan(st, in, bp, (int)members.size(), -1, s);
+  launch_bud_scan(st, in, bp, nclust_h, -1, s);
   launch_report(st, -1, s);
 }
 
@@ -872,12 +906,14 @@ void Run::sync_report_owner() {
   for (int q = 0; q < W; q++) {
     if (rep[q].ctr[CTR_NTIE] && rep[q].ctr[CTR_PMIN] == a.first && rep[q].ctr[CTR_RMAX] == a.second) {
       for (unsigned long long k = 0; k < rep[q].ctr[CTR_NTIE] && k < TIE_MAX; k++)
-        if (nt + k < TIE_MAX) { h_report->tie_r[nt + k] = rep[q].tie_r[k]; h_report->tie_lam[nt + k] = rep[q].tie_lam[k]; h_report->tie_ham[nt + k] = rep[q].tie_ham[k]; }
+        if (nt + k < TIE_MAX) { h_report->tie_r[nt + k] = rep[q].tie_r[k]; h_report->tie_lam[nt + k] = rep[q].tie_lam[k]; h_report->tie_ham[nt + k] = rep[q].tie_ham[k];
+                                h_report->tie_cl[nt + k] = rep[q].tie_cl[k]; h_report->tie_clreads[nt + k] = rep[q].tie_clreads[k]; }
       nt += rep[q].ctr[CTR_NTIE];
     }
     if (rep[q].ctr[CTR_NTIE_PR] && rep[q].ctr[CTR_PMIN_PR] == b.first && rep[q].ctr[CTR_RMAX_PR] == b.second) {
       for (unsigned long long k = 0; k < rep[q].ctr[CTR_NTIE_PR] && k < TIE_MAX; k++)
-        if (ntp + k < TIE_MAX) { h_report->tiep_r[ntp + k] = rep[q].tiep_r[k]; h_report->tiep_lam[ntp + k] = rep[q].tiep_lam[k]; h_report->tiep_ham[ntp + k] = rep[q].tiep_ham[k]; }
+        if (ntp + k < TIE_MAX) { h_report->tiep_r[ntp + k] = rep[q].tiep_r[k]; h_report->tiep_lam[ntp + k] = rep[q].tiep_lam[k]; h_report->tiep_ham[ntp + k] = rep[q].tiep_ham[k];
+                                 h_report->tiep_cl[ntp + k] = rep[q].tiep_cl[k]; h_report->tiep_clreads[ntp + k] = rep[q].tiep_clreads[k]; }
       ntp += rep[q].ctr[CTR_NTIE_PR];
     }
   }
@@ -908,36 +944,96 @@ void Run::sync_report() {
 // Returns the number of passes that actually ran.
 int Run::replay_moves(int first_pass, int last_pass) {
   int ran = 0;
+  ReplayEvent ev{0, {}, {}, 0, 0, 0};
   for (int p = first_pass; p <= last_pass; p++) {
     if (p > first_pass && h_report->pinfo[p] == h_report->pinfo[p - 1]) break;   // skipped on the device (previous pass moved nothing)
     ran++; n_shuffles++;
     const uint32_t b = h_report->pinfo[p], e = h_report->pinfo[p + 1];
     if (e == b) continue;
-    struct Mv { uint32_t from, slot, r, to; };
-    std::vector<Mv> mv(e - b);
-    for (uint32_t k = b; k < e; k++) {
-      const uint32_t r = h_moves[2 * (size_t)k], to = h_moves[2 * (size_t)k + 1];
-      mv[k - b] = Mv{cluster_of_h[r], slot_of[r], r, to};
-    }
-    std::sort(mv.begin(), mv.end(), [](const Mv &a, const Mv &b2) { return a.from != b2.from ? a.from < b2.from : a.slot > b2.slot; });
-    for (const Mv &m : mv) {
-      std::vector<uint32_t> &src = members[m.from];
-      const uint32_t sl = slot_of[m.r];
-      const uint32_t last = src.back();                          // bi_pop_raw: slot <- last
-      src[sl] = last; slot_of[last] = sl; src.pop_back();
-      if (sl == 0) {                                             // only possible when slot 0 is not the centre (unsorted input)
-        const uint8_t z = 0, one = 1;
-        h2d(slot0.p + m.r, &z, 1);
-        if (last != m.r) h2d(slot0.p + last, &one, 1);
-      }
-      cl_reads_h[m.from] -= cx->reads[m.r];
-      std::vector<uint32_t> &dst = members[m.to];                // bi_add_raw: append
-      slot_of[m.r] = (uint32_t)dst.size(); dst.push_back(m.r);
-      cl_reads_h[m.to] += cx->reads[m.r];
-      cluster_of_h[m.r] = m.to;
-    }
+    if (async_replay) {
+      ev.mv.insert(ev.mv.end(), h_moves + 2 * (size_t)b, h_moves + 2 * (size_t)e);
+      ev.pass_end.push_back((uint32_t)(ev.mv.size() / 2));
+    } else apply_moves(h_moves + 2 * (size_t)b, e - b);
   }
+  if (async_replay && !ev.mv.empty()) push_event(std::move(ev));
   return ran;
+}
+
+// one shuffle pass: clusters ascending, slots descending, swap-with-last pops, appends (cluster.cpp:242-260)
+void Run::apply_moves(const uint32_t *mvp, size_t n) {
+  struct Mv { uint32_t from, slot, r, to; };
+  std::vector<Mv> mv(n);
+  for (size_t k = 0; k < n; k++) {
+    const uint32_t r = mvp[2 * k], to = mvp[2 * k + 1];
+    mv[k] = Mv{cluster_of_h[r], slot_of[r], r, to};
+  }
+  std::sort(mv.begin(), mv.end(), [](const Mv &a, const Mv &b2) { return a.from != b2.from ? a.from < b2.from : a.slot > b2.slot; });
+  for (const Mv &m : mv) {
+    std::vector<uint32_t> &src = members[m.from];
+    const uint32_t sl = slot_of[m.r];
+    const uint32_t last = src.back();                          // bi_pop_raw: slot <- last
+    src[sl] = last; slot_of[last] = sl; src.pop_back();
+    if (sl == 0 && !async_replay) {                            // only possible when slot 0 is not the centre (unsorted input: synchronous replay)
+      const uint8_t z = 0, one = 1;
+      h2d(slot0.p + m.r, &z, 1);
+      if (last != m.r) h2d(slot0.p + last, &one, 1);
+    }
+    cl_reads_h[m.from] -= cx->reads[m.r];
+    std::vector<uint32_t> &dst = members[m.to];                // bi_add_raw: append
+    slot_of[m.r] = (uint32_t)dst.size(); dst.push_back(m.r);
+    cl_reads_h[m.to] += cx->reads[m.r];
+    cluster_of_h[m.r] = m.to;
+  }
+}
+
+// bi_pop_raw(from, slot of r) + b_add_bi + bi_add_raw + bi_assign_center (cluster.cpp:315-346)
+void Run::apply_bud(uint32_t r, uint32_t from) {
+  std::vector<uint32_t> &src = members[from];
+  const uint32_t sl = slot_of[r], last = src.back();
+  src[sl] = last; slot_of[last] = sl; src.pop_back();
+  cl_reads_h[from] -= cx->reads[r];
+  const uint32_t ni = (uint32_t)members.size();
+  members.emplace_back(1, r);
+  slot_of[r] = 0; cluster_of_h[r] = ni;
+  cl_reads_h.push_back(cx->reads[r]);
+}
+
+void Run::push_event(ReplayEvent &&e) {
+  std::unique_lock<std::mutex> lk(rmu);
+  if (!rworker.joinable()) {
+    rquit = false;
+    rworker = std::thread([this]() {
+      std::unique_lock<std::mutex> lk2(rmu);
+      for (;;) {
+        rcv.wait(lk2, [&] { return rquit || !rq.empty(); });
+        if (rq.empty()) { if (rquit) return; continue; }
+        ReplayEvent ev = std::move(rq.front());
+        rq.pop_front();
+        rbusy = true;
+        lk2.unlock();
+        if (ev.kind == 0) {
+          size_t b = 0;
+          for (uint32_t e2 : ev.pass_end) { apply_moves(ev.mv.data() + 2 * b, e2 - b); b = e2; }
+        } else apply_bud(ev.r, ev.from);
+        lk2.lock();
+        rbusy = false;
+        if (rq.empty()) rdone.notify_all();
+      }
+    });
+  }
+  rq.push_back(std::move(e));
+  rcv.notify_one();
+}
+void Run::drain_replay() {
+  if (!rworker.joinable()) return;
+  std::unique_lock<std::mutex> lk(rmu);
+  rdone.wait(lk, [&] { return rq.empty() && !rbusy; });
+}
+void Run::stop_replay() {
+  if (!rworker.joinable()) return;
+  { std::unique_lock<std::mutex> lk(rmu); rquit = true; rcv.notify_all(); }
+  rworker.join();
+  rq.clear(); rbusy = false;
 }
 
 // b_bud (cluster.cpp:274-350) decision from the device scan.  Returns the new cluster index or 0.
@@ -988,7 +1084,12 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
     sync();
     tr = big.data(); trp = bigp.data();
   }
+  // The device reported the cluster and the cluster's reads of every listed candidate (fused tail): a single candidate needs nothing
+  // from the host's member arrays, so the replay worker may still be busy with this round's moves.  Exact ties do: wait for it.
+  const bool from_report = async_replay && nt <= 1 && ntp <= 1;
+  if (!from_report) drain_replay();
   auto pick = [&](const uint32_t *t, unsigned long long n) -> long {     // first in (cluster, slot) scan order
+    if (n == 1) return (long)t[0];
     long best = -1;
     for (unsigned long long k = 0; k < n; k++) {
       const uint32_t r = t[k];
@@ -1013,7 +1114,12 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
   if (pA < o->omegaA && win >= 0) { w = win; type = 'A'; pv = pA; }
   else if (pP < o->omegaP && win_pr >= 0) { w = win_pr; type = 'P'; pv = pP; }
   if (w < 0) return 0;
-  const uint32_t r = (uint32_t)w, from = cluster_of_h[r];
+  const uint32_t r = (uint32_t)w;
+  uint32_t from, from_reads;
+  if (from_report) {
+    const bool isA = type == 'A';
+    from = isA ? R.tie_cl[0] : R.tiep_cl[0]; from_reads = isA ? R.tie_clreads[0] : R.tiep_clreads[0];
+  } else { from = cluster_of_h[r]; from_reads = cl_reads_h[from]; }
   // the winner's comparison (raw->comp)
   double lam = 0; uint32_t ham = 0; bool have = false;
   for (unsigned long long k = 0; k < std::min<unsigned long long>(nt, TIE_MAX) && !have; k++)
@@ -1035,15 +1141,12 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
     d2h(&lam, comp_lambda.p + r, 8); d2h(&ham, comp_ham.p + r, 4);
     sync();
   }
-  const double expected = lam * (double)cl_reads_h[from];
-  std::vector<uint32_t> &src = members[from];                   // bi_pop_raw(from, slot)
-  const uint32_t sl = slot_of[r], last = src.back();
-  src[sl] = last; slot_of[last] = sl; src.pop_back();
-  cl_reads_h[from] -= cx->reads[r];
-  const uint32_t ni = (uint32_t)members.size();                 // b_add_bi + bi_add_raw + bi_assign_center
-  members.emplace_back(1, r);
-  slot_of[r] = 0; cluster_of_h[r] = ni;
-  cl_reads_h.push_back(cx->reads[r]); cl_center_h.push_back(r);
+  const double expected = lam * (double)from_reads;
+  const uint32_t ni = (uint32_t)nclust_h;                       // b_add_bi + bi_add_raw + bi_assign_center
+  if (async_replay) { ReplayEvent ev{1, {}, {}, r, from, ni}; push_event(std::move(ev)); }
+  else apply_bud(r, from);
+  nclust_h++;
+  cl_center_h.push_back(r);
   Birth b; b.type = type; b.from = from;                        // 'P': uninitialised in the reference (cluster.cpp:334-339)
   b.pval = pv; b.fold = (double)cx->reads[r] / expected; b.e = expected;
   b.comp_i = from; b.comp_index = r; b.comp_lambda = lam; b.comp_ham = ham;
@@ -1061,6 +1164,7 @@ template <typename T> T *dupv(const std::vector<T> &v) {
 
 // Rmain.cpp:168-295: final subs, final p, output tables
 void Run::finish(dada2b_out *out) {
+  drain_replay();
   const uint32_t nclust = (uint32_t)members.size();
   const int maxlen = in.maxlen;
   if (pending.apply) { launch_round_begin(st, 1, pending.r, pending.from, pending.newi, pending.reads, s); pending.apply = 0; }
@@ -1351,6 +1455,7 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
   const int nraw = R.nraw;
   // b_new / b_init (containers.cpp:78-137): one cluster holding every raw in index order
   R.members.emplace_back(nraw);
+  R.nclust_h = 1;
   for (int r = 0; r < nraw; r++) R.members[0][r] = r;
   R.slot_of.resize(nraw); R.cluster_of_h.assign(nraw, 0);
   for (int r = 0; r < nraw; r++) R.slot_of[r] = r;
@@ -1368,6 +1473,9 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
     R.h2d(R.cl_update_e.p, &one, 1); R.h2d(R.cl_check_locks.p, &one, 1);
     R.sync();
   }
+  // host bookkeeping off the critical path (see Run::ReplayEvent): needs the fused tail's report fields and every cluster's centre at
+  // slot 0 (abundance-sorted input, what derepFastq produces); DADA2B_SYNC_REPLAY is a test hook
+  R.async_replay = R.fused_tail && c0 == 0 && getenv("DADA2B_SYNC_REPLAY") == nullptr;
   TDBG("cluster 0 initialised");
   const double t1 = now_ms();
   const bool dbg = o->verbose || getenv("DADA2B_VERBOSE");
@@ -1382,7 +1490,7 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
   double h_enq = 0, h_wait = 0, h_replay = 0, h_decide = 0;      // host time per phase of a round (verbose diagnostics)
   for (;;) {
     const double td = now_ms();
-    if (!((int)R.members.size() < max_clust && (newi = R.decide_bud(&wr, &wfrom)))) break;
+    if (!(R.nclust_h < max_clust && (newi = R.decide_bud(&wr, &wfrom)))) break;
     const double tr = now_ms();
     h_decide += tr - td;
     R.launch_compare((uint32_t)newi, o->kdist_cutoff);
@@ -1417,7 +1525,7 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
                      R.h_report->ctr[CTR_NMOVE]);
   }
   if (dbg) fprintf(stderr, "[dada2b] loop done: %d clusters; screened %llu, shrouded %llu; host ms: enqueue %.2f, wait for the device %.2f, replay moves %.2f, decide bud %.2f\n",
-                   (int)R.members.size(), R.h_report->ctr[CTR_ALIGN], R.h_report->ctr[CTR_SHROUD], h_enq, h_wait, h_replay, h_decide);
+                   R.nclust_h, R.h_report->ctr[CTR_ALIGN], R.h_report->ctr[CTR_SHROUD], h_enq, h_wait, h_replay, h_decide);
   R.sync();
   const double t2 = now_ms();
   dada2b_out *out = (dada2b_out *)calloc(1, sizeof(dada2b_out));

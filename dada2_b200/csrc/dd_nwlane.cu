@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128) k_nwlane(LaneArgs la) {
       const double bound = a.raw_S[r] * pow(a.raw_rho[r], (double)ns) * (double)a.total_reads * (1.0 + 1e-9);
       survive = !(bound <= a.st.E_minmax[r]) || bound < 1e-280;
     }
-    if (owner) cells_lane += cells_pair;
+    if (owner && !a.no_cells) cells_lane += cells_pair;
     if (survive) {
       // traceback over the recorded moves, lambda in raw-position order, store rule (dd_nwrow.cuh)
       const int nsub = trace_moves<G, C, 8, true>(la.mv_scratch + grp, (size_t)G * TG, TG, L, B, s_cen, rrow, la.sub_scratch + grp, TG);

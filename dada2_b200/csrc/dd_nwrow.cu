@@ -44,7 +44,7 @@ struct RowArgs {
   unsigned long long *uneq_count;
   uint32_t *mv_scratch;                // EXACT: [row][word][thread] 2-bit moves of the thread's current pair
   uint16_t *sub_scratch;               // EXACT: [k][thread] substitutions found by the traceback: raw position | centre base << 14
-  unsigned long long lane_max;         // BOUND: rounds with at most this many jobs belong to k_nwlane (dd_nwlane.cu)
+  unsigned long long lane_max;         // BOUND / EXACT: job lists with at most this many entries belong to k_nwlane (dd_nwlane.cu)
   uint32_t *ns_out;                    // BOUND, test hook only: nsubs per raw (NULL in the product path)
 };
 
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) k_nwrow(RowArgs ra) {
   uint8_t *s_cen = (uint8_t *)(smem + (MODE == ROW_EXACT ? 2 * (16 * ncol) : 0));
   const unsigned long long njobs = *a.njobs_ptr;
   if ((unsigned long long)blockIdx.x * blockDim.x >= njobs) return;
-  if (MODE == ROW_BOUND && njobs <= ra.lane_max) return;
+  if (MODE != ROW_FINAL && njobs <= ra.lane_max) return;       // this many jobs or fewer: k_nwlane's launch does them
   const int L = (MODE == ROW_FINAL) ? a.in.maxlen : (int)a.in.len[a.centre_idx];
   if (MODE != ROW_FINAL) {
     const uint32_t *crow = a.in.seq2 + (size_t)a.centre_idx * a.in.SW;
@@ -242,9 +242,9 @@ size_t nwrow_sub_halfwords(int maxlen, int grid) { return (size_t)grid * 128 * (
 bool nwrow_usable(const AlnParams &P, int len1) { FwdArgs f{}; f.P = P; return nwrow_applicable(f, len1); }
 
 bool launch_nwrow_exact(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, uint32_t *mv_scratch, uint16_t *sub_scratch, int len1,
-                        unsigned long long njobs_upper, int grid_cap, cudaStream_t s) {
+                        unsigned long long njobs_upper, int grid_cap, cudaStream_t s, unsigned long long lane_max) {
   if (!nwrow_applicable(f, len1) || !mv_scratch || !sub_scratch) return false;
-  RowArgs a{f, uneq_list, uneq_count, mv_scratch, sub_scratch, 0ull, nullptr};
+  RowArgs a{f, uneq_list, uneq_count, mv_scratch, sub_scratch, lane_max, nullptr};
   const size_t smem = (size_t)16 * f.P.ncol * 8 + (size_t)((f.in.maxlen + 15) & ~15);
   count_launch(1);
   launch_row_band<ROW_EXACT>(a, (int)std::min<unsigned long long>(std::max<unsigned long long>((njobs_upper + 127) / 128, 1ull), (unsigned long long)grid_cap), smem, s);

@@ -11,8 +11,9 @@
 //
 // This is the DRAM-streaming kernel of the path (the screen is "the part that can approach the HBM roof"):
 // per round every active raw's bitmap row (128 B) + 8 B of metadata are read once.  The rows are staged to shared
-// memory by the TMA engine -- 1-D bulk copies (cp.async.bulk, dd_tma.cuh) of 64-row tiles into a 4-stage ring,
-// completion tracked by one mbarrier per stage -- and consumed 8 lanes per raw (one 16-byte shared load per lane).
+// memory by the TMA engine -- 1-D bulk copies (cp.async.bulk, dd_tma.cuh) of 128-row tiles into a 4-stage ring,
+// completion tracked by one mbarrier per stage -- and consumed one raw per thread (eight rotated 16-byte shared loads,
+// conflict-free), with the thread's 13 bytes of per-raw metadata requested before it waits on the tile.
 //
 // k_kmer_bits builds the bitmap rows of this rank's raws (row `it` <-> raw it * world + rank) once per run.
 #include "dd_common.h"
@@ -24,9 +25,9 @@
 namespace dd2 {
 
 namespace {
-constexpr int PS_TILE = 64;          // raws per TMA tile (8 KB)
-constexpr int PS_STAGES = 4;
-constexpr int PS_BLOCK = 256;        // 8 warps x 4 raws per step = 32 raws per step, two steps per tile
+constexpr int PS_TILE = 128;         // raws per TMA tile (16 KB): one raw per thread
+constexpr int PS_STAGES = 4;         // 64 KB of tiles in flight per CTA, three CTAs per SM
+constexpr int PS_BLOCK = PS_TILE;
 
 __device__ __forceinline__ unsigned kmer10(const uint32_t *row, int p) {      // same labelling as dd_kernels.cu:kmer_at
   const uint32_t w0 = row[p >> 4], w1 = row[(p + 4) >> 4];
@@ -70,11 +71,10 @@ struct PrescreenArgs {
 };
 
 __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
-  __align__(128) __shared__ uint32_t s_tile[PS_STAGES][PS_TILE * 32];
+  extern __shared__ __align__(128) uint32_t s_dyn[];         // PS_STAGES tiles of PS_TILE bitmap rows
   __align__(8) __shared__ uint64_t s_full[PS_STAGES];
   __align__(16) __shared__ uint32_t s_cen[32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int sub = lane & 7, grp = lane >> 3;                 // 8 lanes per raw, 4 raws per warp and step
+  const int tid = threadIdx.x, lane = tid & 31;
   const int ntiles = (a.nown + PS_TILE - 1) / PS_TILE;
   const int len1 = a.in.len[a.centre_idx];
   if (tid < 32) s_cen[tid] = 0u;
@@ -92,48 +92,47 @@ __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
     const uint32_t bytes = (uint32_t)rows * 128u;
     tma_fence_generic_before_async();                         // the stage was last read through the generic proxy
     mbar_expect_tx(&s_full[stage], bytes);
-    tma_load_1d(&s_tile[stage][0], a.kbits + (size_t)tile * PS_TILE * 32, bytes, &s_full[stage]);
+    tma_load_1d(s_dyn + (size_t)stage * PS_TILE * 32, a.kbits + (size_t)tile * PS_TILE * 32, bytes, &s_full[stage]);
   };
   if (tid == 0)
     for (int s = 0; s < PS_STAGES; s++) { const int t = blockIdx.x + s * gridDim.x; if (t < ntiles) issue(t, s); }
   __syncthreads();
-  const uint4 cb = *(const uint4 *)&s_cen[4 * sub];          // the centre's words this lane ANDs against
   int c_align = 0, c_shroud = 0;
   int k = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
     const int stage = k % PS_STAGES;
+    // one raw per thread; its metadata is requested before the wait on the tile so that both latencies overlap
+    const int it = tile * PS_TILE + tid;
+    const bool valid = it < a.nown;
+    const uint32_t r = (uint32_t)it * (uint32_t)a.world + (uint32_t)a.rank;
+    const uint32_t meta = valid ? a.kmeta[it] : 0u;
+    const bool skip = !valid || (a.greedy && (a.in.reads[r] > a.centre_reads || a.lock[r]));      // cluster.cpp:127-131
     mbar_wait(&s_full[stage], (uint32_t)((k / PS_STAGES) & 1));
+    const uint32_t *row = s_dyn + (size_t)stage * PS_TILE * 32 + (size_t)tid * 32;
+    int pc = 0;
 #pragma unroll
-    for (int step = 0; step < PS_TILE / 32; step++) {
-      const int rt = step * 32 + wid * 4 + grp;              // raw within the tile
-      const int it = tile * PS_TILE + rt;
-      const uint4 v = *(const uint4 *)&s_tile[stage][rt * 32 + 4 * sub];
-      int pc = __popc(v.x & cb.x) + __popc(v.y & cb.y) + __popc(v.z & cb.z) + __popc(v.w & cb.w);
-      pc += __shfl_xor_sync(0xffffffffu, pc, 1);
-      pc += __shfl_xor_sync(0xffffffffu, pc, 2);
-      pc += __shfl_xor_sync(0xffffffffu, pc, 4);
-      bool cand = false;
-      uint32_t r = 0;
-      if (sub == 0 && it < a.nown) {
-        r = (uint32_t)it * (uint32_t)a.world + (uint32_t)a.rank;
-        if (!(a.greedy && (a.in.reads[r] > a.centre_reads || a.lock[r]))) {     // cluster.cpp:127-131
-          const uint32_t meta = a.kmeta[it];
-          const int len2 = (int)(meta & 0xFFFFu), U = pc + (int)(meta >> 16);
-          const double denom = (double)(min(len1, len2) - KMER) + 1.;
-          const double kd_lb = 1. - ((double)(U & 0xFFFF)) / denom;           // kmers.cpp:24 / :91 with the bound in place of the min-sum
-          if (kd_lb > a.kdist_cutoff) { c_align++; c_shroud++; }
-          else cand = true;
-        }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, cand);
-      if (m) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.cand_count, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (cand) a.cand_list[base + __popc(m & ((1u << lane) - 1u))] = r;
-      }
+    for (int q = 0; q < 8; q++) {
+      const int ch = (q + tid) & 7;                           // rotate the 16-byte chunks over the lanes: conflict-free 128-bit shared loads
+      const uint4 v = *(const uint4 *)(row + 4 * ch);
+      const uint4 cb = *(const uint4 *)(s_cen + 4 * ch);
+      pc += __popc(v.x & cb.x) + __popc(v.y & cb.y) + __popc(v.z & cb.z) + __popc(v.w & cb.w);
     }
-    __syncthreads();                                          // every lane is done with this stage
+    bool cand = false;
+    if (!skip) {
+      const int len2 = (int)(meta & 0xFFFFu), U = pc + (int)(meta >> 16);
+      const double denom = (double)(min(len1, len2) - KMER) + 1.;
+      const double kd_lb = 1. - ((double)(U & 0xFFFF)) / denom;           // kmers.cpp:24 / :91 with the bound in place of the min-sum
+      if (kd_lb > a.kdist_cutoff) { c_align++; c_shroud++; }
+      else cand = true;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, cand);
+    if (m) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.cand_count, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (cand) a.cand_list[base + __popc(m & ((1u << lane) - 1u))] = r;
+    }
+    __syncthreads();                                          // every thread is done with this stage
     if (tid == 0) { const int t = tile + PS_STAGES * gridDim.x; if (t < ntiles) issue(t, stage); }
   }
 #pragma unroll
@@ -154,9 +153,12 @@ void launch_prescreen(const DevIn &in, const uint32_t *kbits, const uint32_t *km
                       unsigned long long *ctr, int num_sms, cudaStream_t s) {
   PrescreenArgs a{in, kbits, kmeta, nown, rank, world, centre_idx, centre_reads, greedy, lock, kdist_cutoff, cand_list, cand_count, ctr};
   const int ntiles = (nown + PS_TILE - 1) / PS_TILE;
-  const int grid = std::max(1, std::min(ntiles, num_sms * 4));
+  const int grid = std::max(1, std::min(ntiles, num_sms * 3));
+  const size_t smem = (size_t)PS_STAGES * PS_TILE * 128;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_prescreen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
   count_launch(1);
-  k_prescreen<<<grid, PS_BLOCK, 0, s>>>(a);
+  k_prescreen<<<grid, PS_BLOCK, smem, s>>>(a);
 }
 
 }  // namespace dd2

@@ -218,6 +218,8 @@ __global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, 
         for (unsigned k = 0; k < cnt && k < TIE_MAX && at + k < TIE_MAX; k++) {
           const uint32_t rr = bt[(size_t)b * TIE_MAX + k];
           st.report->tie_r[at + k] = rr; st.report->tie_lam[at + k] = st.comp_lambda[rr]; st.report->tie_ham[at + k] = st.comp_ham[rr];
+          const uint32_t cc = st.cluster_of[rr];
+          st.report->tie_cl[at + k] = cc; st.report->tie_clreads[at + k] = s_reads[cc];
         }
       }
       if (blk[b].np && blk[b].pbp == gminp && blk[b].rdp == gmaxp) {
@@ -225,6 +227,8 @@ __global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, 
         for (unsigned k = 0; k < cnt && k < TIE_MAX && at + k < TIE_MAX; k++) {
           const uint32_t rr = btp[(size_t)b * TIE_MAX + k];
           st.report->tiep_r[at + k] = rr; st.report->tiep_lam[at + k] = st.comp_lambda[rr]; st.report->tiep_ham[at + k] = st.comp_ham[rr];
+          const uint32_t cc = st.cluster_of[rr];
+          st.report->tiep_cl[at + k] = cc; st.report->tiep_clreads[at + k] = s_reads[cc];
         }
       }
     }

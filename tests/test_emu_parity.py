@@ -88,6 +88,18 @@ def test_emu_e2e_fallback_kernels(emu, monkeypatch, name):
     assert emu.cuemu_launches(b"k_nwrow<") == 0 and emu.cuemu_launches(b"k_nwlane<") == 0 and emu.cuemu_launches(b"k_prescreen") == 0
 
 
+@pytest.mark.parametrize("lane_max", ["0", "32", "96"])
+@pytest.mark.parametrize("name", ["syn800_default", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else ["syn800_default", "syn700_ragged", "syn2000_default", "syn800_band8", "syn800_priors"])
+def test_emu_e2e_every_round_size_class(emu, monkeypatch, name, lane_max):
+    """DADA2B_LANE_MAX (test hook) moves the job-count threshold between the lane-group kernel and the thread-per-pair kernels so that
+    small inputs exercise what 1e6-unique runs do: rounds above the threshold (bound pass thread-per-pair, survivors through the
+    lane kernel or, above the threshold again, the thread-per-pair exact kernel) and rounds below it (one lane-group launch)."""
+    monkeypatch.setenv("DADA2B_LANE_MAX", lane_max)
+    _gpu_tests().test_e2e_matches_reference_golden(name)
+    assert emu.cuemu_launches(b"k_nwrow<") > 0
+    assert (emu.cuemu_launches(b"k_nwlane<") > 0) == (lane_max != "0")
+
+
 def test_emu_long_reads_band32_homopolymer(emu, monkeypatch):
     """BASELINE config 5 flavour at toy size: ~1.5 kb uniques, band 32, 94 quality columns; the homopolymer-gap scalar
     path (nwalign_endsfree.cpp:220-396) and the vectorized path with ragged lengths."""
