@@ -5,3 +5,4 @@ from .api import Dada2bError, PackedCall, Resident, dada_uniques  # noqa: F401
 from . import bimera  # noqa: F401,E402
 from . import merge  # noqa: F401,E402
 from . import derep  # noqa: F401,E402
+from . import errmodel  # noqa: F401,E402

@@ -123,7 +123,18 @@ struct dada2b_ctx {
   std::vector<uint16_t> len;
   std::vector<uint32_t> reads;
   std::vector<uint8_t> prior;
-  std::string seq_concat;
+  // host copy of the sequences (the caller may free its buffers after dada2b_upload): raw bytes, filled by several threads
+  struct Bytes {
+    char *p = nullptr; size_t n = 0;
+    ~Bytes() { free(p); }
+    const char *data() const { return p; }
+    void assign(const char *b, const char *e) {
+      const size_t m = (size_t)(e - b);
+      if (m > n || !p) { free(p); p = (char *)malloc(std::max<size_t>(m, 1)); }
+      n = m;
+      parallel_for(m, [&](size_t lo, size_t hi) { memcpy(p + lo, b + lo, hi - lo); });
+    }
+  } seq_concat;
   std::vector<int64_t> seq_off;
   DBuf<uint32_t> d_seq2, d_reads;
   DBuf<uint8_t> d_qual, d_prior;
@@ -208,7 +219,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   unsigned slot = 0;
   std::vector<std::pair<size_t, size_t>> ranges;
   {
-    unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    unsigned nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
     if (nraw < 20000) nt = std::min(nt, 4u);
     size_t chunk = (nraw + nt - 1) / nt;
     std::vector<std::thread> th;
@@ -365,8 +376,9 @@ struct Run {
   DBuf<uint16_t> lane_sub;
   unsigned long long lane_max = 0;
   // streaming tier of the k-mer screen (dd_prescreen.cu): 5-mer presence bitmaps of this rank's raws, candidates per round
-  DBuf<uint32_t> kbits, kmeta, cand_list;
-  DBuf<unsigned long long> cand_ctr;
+  DBuf<uint32_t> kbits, kmeta, cand_list, old_list;
+  DBuf<uint16_t> krep, cand_ms;
+  DBuf<unsigned long long> cand_ctr;          // [0] candidates of the round, [1] raws forwarded to the warp-per-pair screen
   bool prescreen = false;
   int nown = 0;
   bool two_phase = false;              // bound pass first, exact lambda for the survivors only (plain gap costs)
@@ -631,8 +643,9 @@ void Run::alloc_state() {
   prescreen = P.use_kmers && !fallback_only;
   if (prescreen) {
     nown = (nraw - cx->rank + cx->world - 1) / cx->world;
-    kbits.alloc((size_t)nown * 32 + 32); kmeta.alloc(nown); cand_list.alloc(nown + 32); cand_ctr.alloc(1);
-    launch_kmer_bits(in, cx->rank, cx->world, nown, kbits.p, kmeta.p, cx->num_sms, s);
+    kbits.alloc((size_t)nown * 32 + 32); kmeta.alloc(nown); krep.alloc((size_t)nown * 16 + 16); cand_list.alloc(nown + 32); cand_ms.alloc(nown + 32);
+    old_list.alloc(nown + 32); cand_ctr.alloc(2);
+    launch_kmer_bits(in, cx->rank, cx->world, nown, kbits.p, kmeta.p, krep.p, cx->num_sms, s);
   }
   if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
   fused_tail = getenv("DADA2B_SPLIT_TAIL") == nullptr;   // test switch: the one-kernel-per-step tail of dd_round.cu (capacity fallback beyond 32 k clusters)
@@ -723,15 +736,21 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   ca.kind_out = nullptr; ca.kord_words = kord_words; ca.shard_rank = cx->rank; ca.shard_world = cx->world;
   int cgrid = std::min((nraw / cx->world + 8) / 8, cx->num_sms * 4);
   if (prescreen && kdist_cutoff < 1.0) {
-    // tier 0: stream the 128-byte bitmap rows (TMA) and settle what the presence bound can; tiers 1/2 on the rest
-    CK(cudaMemsetAsync(cand_ctr.p, 0, 8, s));
-    ca.cand_list = cand_list.p; ca.cand_count = cand_ctr.p;
+    // stream the 128-byte bitmap rows (TMA): every pair decided exactly (presence bound, then the exact min-sum through the raw's
+    // repeated-5-mer list); gapless / NW for the pairs that are not shrouded (k_kord); the warp-per-pair screen only sees raws
+    // whose list overflowed
+    CK(cudaMemsetAsync(cand_ctr.p, 0, 16, s));
+    ca.cand_list = old_list.p; ca.cand_count = cand_ctr.p + 1;
     timed(T_PRE, [&]() {
-      launch_prescreen(in, kbits.p, kmeta.p, nown, cx->rank, cx->world, c, cx->reads[c], o->greedy != 0, st.lock, kdist_cutoff, cand_list.p, cand_ctr.p,
-                       st.ctr, cx->num_sms, s);
+      launch_prescreen(in, kbits.p, kmeta.p, krep.p, nown, cx->rank, cx->world, c, cx->reads[c], o->greedy != 0, st.lock, kdist_cutoff, cand_list.p,
+                       cand_ms.p, cand_ctr.p, st.ctr, cx->num_sms, s);
     });
     prescreen_rows += nown;
-    timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
+    timed(T_CLASSIFY, [&]() {
+      launch_kord(in, ca.P, c, cand_list.p, cand_ms.p, cand_ctr.p, st.nw_list, st.gl_list, old_list.p, cand_ctr.p + 1, st.ctr, (unsigned long long)nown,
+                  cx->num_sms, s);
+      launch_classify(ca, std::min(cgrid, cx->num_sms), 256, classify_smem, s);
+    });
   } else
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   bool fwd_done = false;
@@ -1353,7 +1372,7 @@ void Run::finish(dada2b_out *out) {
   for (uint32_t i = 0; i < nclust; i++) {
     uint32_t max_reads = 0; long max_raw = -1;
     for (uint32_t r : members[i]) if (cx->reads[r] > max_reads) { max_raw = r; max_reads = cx->reads[r]; }
-    if (max_raw >= 0) cseq.append(cx->seq_concat, (size_t)cx->seq_off[max_raw], (size_t)cx->len[max_raw]);
+    if (max_raw >= 0) cseq.append(cx->seq_concat.data() + (size_t)cx->seq_off[max_raw], (size_t)cx->len[max_raw]);
     coff.push_back((int64_t)cseq.size());
     for (uint32_t r : members[i]) if (hcorrect[r]) {
       ab[i] += (int32_t)cx->reads[r]; nunq[i]++;

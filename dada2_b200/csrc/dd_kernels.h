@@ -25,11 +25,13 @@ struct ClassifyArgs {
   const unsigned long long *cand_count;
 };
 // dd_prescreen.cu: streaming first tier of the k-mer screen (TMA-staged 5-mer presence bitmaps)
-void launch_kmer_bits(const DevIn &in, int rank, int world, int nown, uint32_t *kbits, uint32_t *kmeta, int num_sms, cudaStream_t s);
-void launch_prescreen(const DevIn &in, const uint32_t *kbits, const uint32_t *kmeta, int nown, int rank, int world, uint32_t centre_idx,
-                      uint32_t centre_reads, int greedy, const uint8_t *lock, double kdist_cutoff, uint32_t *cand_list, unsigned long long *cand_count,
-                      unsigned long long *ctr, int num_sms, cudaStream_t s);
-
+void launch_kmer_bits(const DevIn &in, int rank, int world, int nown, uint32_t *kbits, uint32_t *kmeta, uint16_t *krep, int num_sms, cudaStream_t s);
+void launch_prescreen(const DevIn &in, const uint32_t *kbits, const uint32_t *kmeta, const uint16_t *krep, int nown, int rank, int world,
+                      uint32_t centre_idx, uint32_t centre_reads, int greedy, const uint8_t *lock, double kdist_cutoff, uint32_t *cand_list,
+                      uint16_t *cand_ms, unsigned long long *cand_count, unsigned long long *ctr, int num_sms, cudaStream_t s);
+void launch_kord(const DevIn &in, const AlnParams &P, uint32_t centre_idx, const uint32_t *cand_list, const uint16_t *cand_ms,
+                 const unsigned long long *cand_count, uint32_t *nw_list, uint32_t *gl_list, uint32_t *old_list, unsigned long long *old_count,
+                 unsigned long long *ctr, unsigned long long upper, int num_sms, cudaStream_t s);
 
 struct AlignArgs {
   DevIn in;

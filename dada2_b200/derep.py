@@ -103,7 +103,13 @@ def read_fastq(path, phred=33):
             f.readline()
             q = f.readline().strip()
             seqs.append(s)
-            quals.append(np.frombuffer(q.encode(), dtype=np.uint8) - phred)
+            qv = np.frombuffer(q.encode(), dtype=np.uint8).astype(np.int16) - phred
+            if len(qv) and (qv.min() < 0 or qv.max() > 93):        # a wrong offset (e.g. Phred+64 data) must not wrap silently
+                raise api.Dada2bError("dada2b: quality characters outside Phred+%d (0..93); only this encoding is supported "
+                                      "(the reference's qualityType = 'Auto' detection is not restated)." % phred)
+            if len(s) and any(c not in "ACGT" for c in s):
+                raise api.Dada2bError("dada2b: reads must be A/C/G/T (filter with maxN = 0 first, as the dada2 workflow does).")
+            quals.append(qv.astype(np.uint8))
     return seqs, quals
 
 
@@ -111,3 +117,40 @@ def derepFastq(path, n=1000000, device=0):
     """derepFastq(fl, n) (R/sequenceIO.R:45) for one file: host fastq parsing + dada2b_derep."""
     seqs, quals = read_fastq(path)
     return derep_reads(seqs, quals, n=n, device=device)
+
+
+def combineDereps2(dereps):
+    """combineDereps2 (R/multiSample.R:165-203), the front door of dada(pool = TRUE): a list of derep results (dicts as
+    returned by derep_reads / derepFastq) -> ONE derep whose uniques are the union in first-seen order, re-ordered by
+    decreasing pooled abundance (stable, like order(decreasing = TRUE)); quality means pooled with the abundances as
+    weights; the maps of the inputs concatenated and translated.  Host side, like the reference (it concatenates tables)."""
+    if isinstance(dereps, dict):
+        dereps = [dereps]
+    maxlen = max(d["quals"].shape[1] for d in dereps)
+    index = {}
+    for d in dereps:                                        # unique(do.call(c, lapply(dereps, getSequences))): first occurrence order
+        for s in d["uniques"]:
+            if s not in index:
+                index[s] = len(index)
+    n = len(index)
+    counts = np.zeros(n, dtype=np.int64)
+    quals = np.zeros((n, maxlen), dtype=np.float64)
+    maps = []
+    for d in dereps:
+        q = np.asarray(d["quals"], dtype=np.float64)
+        if q.shape[1] < maxlen:
+            q = np.concatenate([q, np.full((q.shape[0], maxlen - q.shape[1]), np.nan)], axis=1)
+        ab = np.asarray(d["abundances"], dtype=np.int64)
+        idx = np.fromiter((index[s] for s in d["uniques"]), dtype=np.int64, count=len(d["uniques"]))
+        np.add.at(counts, idx, ab)
+        np.add.at(quals, idx, q * ab[:, None])              # sweep(derep$quals, 1, derep$uniques, "*"): NA positions make the pooled mean NA, as in R
+        m = np.asarray(d["map"], dtype=np.int64)
+        maps.append(idx[m - 1] + 1)                         # map[derep$map], 1-based
+    quals = quals / counts[:, None]
+    order = np.argsort(-counts, kind="stable")              # order(derepCounts, decreasing = TRUE) keeps ties in input order
+    rank = np.empty(n, dtype=np.int64)
+    rank[order] = np.arange(n)
+    seqs = list(index)
+    newmap = rank[np.concatenate(maps) - 1] + 1 if maps else np.zeros(0, np.int64)
+    return {"uniques": [seqs[i] for i in order], "abundances": counts[order].astype(np.int32), "quals": quals[order],
+            "map": newmap.astype(np.int32)}

@@ -122,11 +122,12 @@ void dada2b_ctx_free(dada2b_ctx *ctx);
 int dada2b_reupload(dada2b_ctx *ctx, const dada2b_in *in, char errbuf[DADA2B_ERRLEN]);
 
 /* Sharded multi-GPU runs (one process per GPU).  Every rank uploads the same uniques and calls
- * dada2b_run_resident() with the same arguments; raw r is aligned by rank r % world, the new stored
- * comparisons of a round are exchanged with ONE NCCL all-gather per split round, everything else
- * (shuffle, p-values, bud decision) is replicated deterministically, the final tallies are all-reduced.
- * Every rank returns the complete result.  The NCCL unique id is created on rank 0 and distributed by the
- * caller (e.g. torch.distributed broadcast). */
+ * dada2b_run_resident() with the same arguments; raw r is OWNED by rank r % world: that rank alone screens and aligns
+ * it, keeps its stored comparisons and runs shuffle / p-update / bud scan for it.  Per shuffle pass one NCCL all-reduce
+ * of the per-cluster read deltas, per split round one all-gather of the ranks' reports (bud candidates, move counts)
+ * and, when raws moved, of the move lists; the final tallies are all-reduced.  Every rank returns the complete result.
+ * The NCCL unique id is created on rank 0 and distributed by the caller (e.g. torch.distributed broadcast).
+ * Threading: a dada2b_ctx is used by one thread at a time; dada2b_run() keeps one workspace per calling thread. */
 #define DADA2B_NCCL_ID_BYTES 128
 int dada2b_nccl_unique_id(char id[DADA2B_NCCL_ID_BYTES], char errbuf[DADA2B_ERRLEN]);
 int dada2b_comm_init(dada2b_ctx *ctx, int32_t rank, int32_t world, const char id[DADA2B_NCCL_ID_BYTES],

@@ -26,3 +26,27 @@ def test_chunking_only_reorders_ties_and_zero_length_reads_are_ignored():
     assert (a["map"] == na).sum() == 4 and all(seqs[i] == "" for i in np.nonzero(a["map"] == na)[0])
     for u, ab in zip(a["uniques"][:20], a["abundances"][:20]):
         assert seqs.count(u) == ab
+
+
+def test_combine_dereps_pools_like_the_reference():
+    """combineDereps2 (R/multiSample.R:165-203): pooling the per-sample dereps of a split read set gives the uniques, pooled
+    abundances and weighted quality means of dereplicating the whole set at once (the order differs only inside abundance
+    ties: first-seen order there); the translated maps point every read at its own sequence."""
+    import numpy as np
+    from oracle import derep as od
+    from dada2_b200.derep import combineDereps2
+    rng = np.random.default_rng(4)
+    base = ["".join(rng.choice(list("ACGT"), 40)) for _ in range(12)]
+    reads = [base[int(i)] for i in rng.integers(0, 12, 300)]
+    quals = [rng.integers(2, 41, 40).astype(np.uint8) for _ in reads]
+    parts = [od.derep_reads(reads[a:b], quals[a:b]) for a, b in ((0, 90), (90, 210), (210, 300))]
+    whole = od.derep_reads(reads, quals)
+    pool = combineDereps2(parts)
+    assert sorted(pool["uniques"]) == sorted(whole["uniques"])
+    w = dict(zip(whole["uniques"], whole["abundances"]))
+    assert all(w[s] == a for s, a in zip(pool["uniques"], pool["abundances"]))
+    assert list(pool["abundances"]) == sorted(pool["abundances"], reverse=True)
+    wq = dict(zip(whole["uniques"], whole["quals"]))
+    for s, q in zip(pool["uniques"], pool["quals"]):
+        assert np.allclose(q, wq[s], rtol=1e-12, atol=0)
+    assert [pool["uniques"][m - 1] for m in pool["map"]] == reads
