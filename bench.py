@@ -359,13 +359,16 @@ def main():
             flush.zero_()
             torch.cuda.synchronize()
             ts = time.perf_counter()
-            res.reupload(pin)                                   # dada2b_reupload: pack + H2D of this rank's copy
+            res.reupload(pin)                                   # dada2b_reupload: pack + H2D (all packed reads, this rank's quality rows)
             est = res.run_raw(ecm, ecm.shape[1], ostruct)       # dada2b_run_resident: loop + D2H of every output
             e2e_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
         barrier()
         t_e2e = time.perf_counter() - t0
         est = dict(est)
-        est["h2d_bytes"] += int(res.upload_h2d_bytes()) if hasattr(res, "upload_h2d_bytes") else 0
+        L0 = len(seqs[0])
+        nown = (nraw - rank + world - 1) // world
+        # dada2b_reupload on a sharded context: packed reads of every raw (any raw may become a centre), quality rows of this rank's raws only
+        est["h2d_bytes"] += nraw * ((((L0 + 15) // 16 + 3) & ~3) * 4 + 7) + nown * ((L0 + 15) & ~15)
     else:
         call = dada2_b200.PackedCall(seqs, ab, None, err, q)
         for _ in range(max(1, args.warmup // 2)):

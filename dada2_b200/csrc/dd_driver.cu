@@ -119,6 +119,8 @@ struct dada2b_ctx {
   int maxq = 0;            // largest rounded quality present
   bool has_quals = false;
   bool bad_nt = false;
+  bool qual_sharded = false;      // dada2b_reupload on a sharded context: quality rows of this rank's raws only are on the device
+  DBuf<uint8_t> d_qual_own;
   unsigned total_reads = 0;
   std::vector<uint16_t> len;
   std::vector<uint32_t> reads;
@@ -211,7 +213,12 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   // pack on the host into pinned staging, then one H2D per array
   const double tu1 = now_ms();
   PBuf<uint32_t> &h_seq = cx->st_seq; h_seq.alloc((size_t)nraw * d.SW);
-  PBuf<uint8_t> &h_qual = cx->st_qual; h_qual.alloc((size_t)nraw * d.QS);
+  // a context that already shards a sample (dada2b_reupload after dada2b_comm_init) needs the quality rows of ITS raws only:
+  // they are packed densely (row it <-> raw it * world + rank) and scattered into place on the device
+  const bool qshard = reuse && cx->comm && cx->world > 1;
+  const unsigned qworld = qshard ? (unsigned)cx->world : 1u, qrank = qshard ? (unsigned)cx->rank : 0u;
+  const size_t nqown = ((size_t)nraw + qworld - 1 - qrank) / qworld;
+  PBuf<uint8_t> &h_qual = cx->st_qual; h_qual.alloc(std::max<size_t>(nqown, 1) * d.QS);
   std::vector<int> tmaxq(64, 0), tbad(64, 0);
   const char *sc = cx->seq_concat.data();
   const double *qd = in->quals;
@@ -239,7 +246,8 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
                             case 'T': code = 3; break; default: code = 0; bad = 1; }
             row[p >> 4] |= code << (2 * (p & 15));
           }
-          uint8_t *q = h_qual.p + r * QS;
+          if (r % qworld != qrank) continue;
+          uint8_t *q = h_qual.p + (r / qworld) * QS;
           const double *src = qd + (size_t)ML * r;
           for (int p = 0; p < L; p++) {                                   // (uint8_t) round(qual[i]), containers.cpp:34
             const double x = src[p];
@@ -263,7 +271,19 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   cx->d_seq2.alloc((size_t)nraw * d.SW); cx->d_qual.alloc((size_t)nraw * d.QS);
   cx->d_len.alloc(nraw); cx->d_reads.alloc(nraw); cx->d_prior.alloc(nraw);
   CK(cudaMemcpyAsync(cx->d_seq2.p, h_seq.p, (size_t)nraw * d.SW * 4, cudaMemcpyHostToDevice, cx->stream));
-  CK(cudaMemcpyAsync(cx->d_qual.p, h_qual.p, (size_t)nraw * d.QS, cudaMemcpyHostToDevice, cx->stream));
+  if (!qshard) CK(cudaMemcpyAsync(cx->d_qual.p, h_qual.p, (size_t)nraw * d.QS, cudaMemcpyHostToDevice, cx->stream));
+  else {
+    cx->d_qual_own.alloc(nqown * d.QS);
+    CK(cudaMemcpyAsync(cx->d_qual_own.p, h_qual.p, nqown * d.QS, cudaMemcpyHostToDevice, cx->stream));
+    launch_qrows_scatter(cx->d_qual.p, d.QS, nullptr, (int)nqown, (int)qrank, (int)qworld, cx->d_qual_own.p, cx->stream);
+    // the largest quality present decides an error of the whole call (Rmain.cpp / pval.cpp:169-171): every rank must see the same value
+    DBuf<int> dq; dq.alloc(1);
+    CK(cudaMemcpyAsync(dq.p, &cx->maxq, 4, cudaMemcpyHostToDevice, cx->stream));
+    NC(g_nccl.AllReduce(dq.p, dq.p, 1, ncclInt32, ncclMax, cx->comm, cx->stream));
+    CK(cudaMemcpyAsync(&cx->maxq, dq.p, 4, cudaMemcpyDeviceToHost, cx->stream));
+    CK(cudaStreamSynchronize(cx->stream));
+  }
+  cx->qual_sharded = qshard;
   {
     cx->st_meta.alloc((size_t)nraw * 8);
     uint8_t *m = cx->st_meta.p;
@@ -277,7 +297,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   CK(cudaStreamSynchronize(cx->stream));
   if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] upload: validate+copy %.2f ms, pack %.2f ms, alloc+H2D %.2f ms\n", tu1 - tu0, tu2 - tu1, now_ms() - tu2);
   DBG("upload: H2D done");
-  cx->upload_h2d = (long long)nraw * d.SW * 4 + (long long)nraw * d.QS + (long long)nraw * 7;
+  cx->upload_h2d = (long long)nraw * d.SW * 4 + (long long)(qshard ? nqown : nraw) * d.QS + (long long)nraw * 7;
   d.seq2 = cx->d_seq2.p; d.qual = cx->d_qual.p; d.len = cx->d_len.p; d.reads = cx->d_reads.p; d.prior = cx->d_prior.p;
   if (fresh) fresh.release();
   return cx;
@@ -1252,6 +1272,13 @@ void Run::finish(dada2b_out *out) {
     pair_centre.alloc(npair); pair_raw.alloc(npair);
     h2d(pair_centre.p, pc.data(), npair * 4);
     h2d(pair_raw.p, pr.data(), npair * 4);
+    if (cx->qual_sharded) {        // the birth subs read the quality row of every centre: owners contribute theirs, one byte-sum all-reduce
+      DBuf<uint8_t> cq; cq.alloc((size_t)npair * in.QS);
+      launch_qrows_gather(in.qual, in.QS, pair_raw.p, (int)npair, cx->rank, cx->world, cq.p, s);
+      NC(g_nccl.AllReduce(cq.p, cq.p, (size_t)npair * in.QS, ncclUint8, ncclSum, cx->comm, s));
+      launch_qrows_scatter(in.qual, in.QS, pair_raw.p, (int)npair, 0, 1, cq.p, s);
+      sync();
+    }
     b_nsubs.alloc(npair); b_lambda.alloc(npair); b_pos.alloc((size_t)npair * bcap); b_nt0.alloc((size_t)npair * bcap);
     b_nt1.alloc((size_t)npair * bcap); b_q1.alloc((size_t)npair * bcap);
     DBuf<uint32_t> nwl, gll; nwl.alloc(npair); gll.alloc(npair);
@@ -1468,7 +1495,7 @@ dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opt
     std::vector<double> e((size_t)16 * Q);
     for (int r = 0; r < 16; r++) for (int c = 0; c < Q; c++) e[(size_t)r * Q + c] = err_cm[r + 16 * (size_t)c];
     R.h2d(R.err.p, e.data(), e.size() * 8);
-    if (R.two_phase) launch_raw_bounds(R.in, R.err.p, Q, o->use_quals != 0, R.raw_S.p, R.raw_rho.p, R.s);
+    if (R.two_phase) launch_raw_bounds(R.in, R.err.p, Q, o->use_quals != 0, R.raw_S.p, R.raw_rho.p, cx->rank, cx->world, R.s);
     R.sync();
   }
   const int nraw = R.nraw;
@@ -1627,7 +1654,7 @@ static void do_test_loop_nw(dada2b_ctx *cx, int which, int npairs, const uint32_
   std::vector<double> e((size_t)16 * Q);
   for (int r = 0; r < 16; r++) for (int c = 0; c < Q; c++) e[(size_t)r * Q + c] = err_cm[r + 16 * (size_t)c];
   R.h2d(R.err.p, e.data(), e.size() * 8);
-  if (R.two_phase) launch_raw_bounds(R.in, R.err.p, Q, o->use_quals != 0, R.raw_S.p, R.raw_rho.p, s);
+  if (R.two_phase) launch_raw_bounds(R.in, R.err.p, Q, o->use_quals != 0, R.raw_S.p, R.raw_rho.p, cx->rank, cx->world, s);
   DBuf<uint32_t> job, uneq, nsb; DBuf<unsigned long long> cnt;
   job.alloc(1); uneq.alloc(4); nsb.alloc(R.nraw); cnt.alloc(4);
   for (int k = 0; k < npairs; k++) {

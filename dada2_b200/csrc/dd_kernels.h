@@ -98,7 +98,9 @@ size_t nwrow_sub_halfwords(int maxlen, int grid);
 bool nwrow_usable(const AlnParams &P, int len1);
 bool launch_nwrow_exact(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, uint32_t *mv_scratch, uint16_t *sub_scratch, int len1,
                         unsigned long long njobs_upper, int grid_cap, cudaStream_t s, unsigned long long lane_max = 0);
-void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, cudaStream_t s);
+void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, int rank, int world, cudaStream_t s);
+void launch_qrows_gather(const uint8_t *qual, int QS, const uint32_t *rows, int nrows, int only_rank, int world, uint8_t *dense, cudaStream_t s);
+void launch_qrows_scatter(uint8_t *qual, int QS, const uint32_t *rows, int nrows, int rank, int world, const uint8_t *dense, cudaStream_t s);
 void count_launch(int n);
 void launch_classify(const ClassifyArgs &a, int grid, int block, size_t smem, cudaStream_t s);
 void launch_align(int mode, const AlignArgs &a, int grid, int block, size_t smem, cudaStream_t s);

@@ -210,8 +210,8 @@ __global__ void k_cs_append_commit(DevState st, const unsigned long long *counts
 
 // Two-phase loop NW: per-raw bound factors.  S_r = product over the raw's positions of its self-transition factor
 // err[5*nt][q]; rho_r = max over positions and nt0 != nt of err[4*nt0+nt][q] / err[5*nt][q].
-__global__ void k_raw_bounds(DevIn in, const double *err, int ncol, int use_quals, double *S, double *rho) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_raw_bounds(DevIn in, const double *err, int ncol, int use_quals, double *S, double *rho, int rank, int world) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) * world + rank;        // this rank's raws only (their quality rows may be the only ones uploaded)
   if (r >= in.nraw) return;
   const uint32_t *row = in.seq2 + (size_t)r * in.SW;
   const uint8_t *q = in.qual + (size_t)r * in.QS;
@@ -235,10 +235,38 @@ __global__ void k_center_cluster(int *cc, const uint32_t *cl_center, int nclust)
   if (i < nclust) cc[cl_center[i]] = i;
 }
 
+// Quality rows of a list of raws <-> a dense buffer (16-byte units).  Sharded uploads keep a raw's quality row on its owner only
+// (dd_driver.cu:do_upload); the rows of the cluster centres are exchanged before the birth subs need them.
+__global__ void k_qrows_gather(const uint8_t *qual, int QS, const uint32_t *rows, int nrows, int only_rank, int world, uint8_t *dense) {
+  const int u = QS / 16, x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= nrows * u) return;
+  const uint32_t r = rows[x / u];
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (only_rank < 0 || (int)(r % (uint32_t)world) == only_rank) v = ((const uint4 *)(qual + (size_t)r * QS))[x % u];
+  ((uint4 *)dense)[x] = v;
+}
+__global__ void k_qrows_scatter(uint8_t *qual, int QS, const uint32_t *rows, int nrows, int rank, int world, const uint8_t *dense) {
+  const int u = QS / 16, x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= nrows * u) return;
+  const uint32_t r = rows ? rows[x / u] : (uint32_t)(x / u) * (uint32_t)world + (uint32_t)rank;     // rows == NULL: the rank's own raws in order
+  ((uint4 *)(qual + (size_t)r * QS))[x % u] = ((const uint4 *)dense)[x];
+}
+
 // ------------------------------- launch wrappers --------------------------------------
-void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, cudaStream_t s) {
+void launch_qrows_gather(const uint8_t *qual, int QS, const uint32_t *rows, int nrows, int only_rank, int world, uint8_t *dense, cudaStream_t s) {
+  if (nrows <= 0) return;
   count_launch(1);
-  k_raw_bounds<<<(in.nraw + 127) / 128, 128, 0, s>>>(in, err_rowmajor, ncol, use_quals, S, rho);
+  k_qrows_gather<<<(nrows * (QS / 16) + 255) / 256, 256, 0, s>>>(qual, QS, rows, nrows, only_rank, world, dense);
+}
+void launch_qrows_scatter(uint8_t *qual, int QS, const uint32_t *rows, int nrows, int rank, int world, const uint8_t *dense, cudaStream_t s) {
+  if (nrows <= 0) return;
+  count_launch(1);
+  k_qrows_scatter<<<(nrows * (QS / 16) + 255) / 256, 256, 0, s>>>(qual, QS, rows, nrows, rank, world, dense);
+}
+void launch_raw_bounds(const DevIn &in, const double *err_rowmajor, int ncol, int use_quals, double *S, double *rho, int rank, int world, cudaStream_t s) {
+  count_launch(1);
+  const int nown = (in.nraw - rank + world - 1) / world;
+  k_raw_bounds<<<(nown + 127) / 128, 128, 0, s>>>(in, err_rowmajor, ncol, use_quals, S, rho, rank, world);
 }
 void launch_fill_f64(double *p, double v, size_t n, cudaStream_t s) {
   count_launch(1);

@@ -364,13 +364,15 @@ extern "C" int ncclAllGather(const void *send, void *recv, size_t count, int dty
   return 0;
 }
 extern "C" int ncclAllReduce(const void *send, void *recv, size_t count, int dtype, int op, void *comm, void *) {
-  if (op != 0) return 4;                                          // only ncclSum is used
+  if (op != 0 && !(op == 2 && dtype == 2)) return 4;              // ncclSum, and ncclMax on int32
   rendezvous((FakeRank *)comm, send, recv, [&](FakeComm &c) {
     const size_t eb = dtype_bytes(dtype);
     std::vector<unsigned char> acc(count * eb, 0);
+    if (op == 2) std::memcpy(acc.data(), c.src[0], acc.size());
     for (int r = 0; r < c.world; r++)
       for (size_t i = 0; i < count; i++) {
-        if (dtype == 2 || dtype == 3) ((uint32_t *)acc.data())[i] += ((const uint32_t *)c.src[r])[i];
+        if (op == 2) { int32_t &a = ((int32_t *)acc.data())[i]; a = std::max(a, ((const int32_t *)c.src[r])[i]); }
+        else if (dtype == 2 || dtype == 3) ((uint32_t *)acc.data())[i] += ((const uint32_t *)c.src[r])[i];
         else if (dtype == 4 || dtype == 5) ((uint64_t *)acc.data())[i] += ((const uint64_t *)c.src[r])[i];
         else if (dtype == 8) ((double *)acc.data())[i] += ((const double *)c.src[r])[i];
         else if (dtype <= 1) acc[i] += ((const unsigned char *)c.src[r])[i];

@@ -40,6 +40,7 @@ struct dim3 {
 };
 struct uint3 { unsigned x, y, z; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 
 typedef struct cuemu_stream_st *cudaStream_t;
 typedef struct cuemu_event_st *cudaEvent_t;

@@ -117,7 +117,7 @@ def test_emu_long_reads_band32_homopolymer(emu, monkeypatch):
     assert emu.cuemu_launches(b"k_nwfwd<") > 0              # ragged lengths / homopolymer costs: the general lane-group kernel
 
 
-def _run_sharded(world, name, case=None):
+def _run_sharded(world, name, case=None, reupload=False):
     import threading
 
     import numpy as np
@@ -139,6 +139,9 @@ def _run_sharded(world, name, case=None):
         try:
             res = api.Resident(seqs, ab, pri, q)
             res.comm_init(r, world, uid)
+            if reupload:                    # dada2b_reupload on a sharded context: only this rank's quality rows travel (bench.py's e2e at N > 1)
+                from dada2_b200 import _abi
+                res.reupload(_abi.PackedIn(seqs, ab, pri, None, q))
             results[r] = res.run(err, **opts)
             res.close()
         except Exception as e:      # surfaced below, on the main thread
@@ -164,6 +167,14 @@ def test_emu_sharded_ranks(emu, world, name):
     """The sharded multi-GPU path (raw r aligned by rank r % world; owner mode) with the ranks as threads and the emulator's
     in-process NCCL stand-in: every rank returns the reference's result."""
     _run_sharded(world, name)
+
+
+@pytest.mark.parametrize("world,name", [(2, "syn800_default"), (3, "syn700_ragged"), (4, "syn800_priors")])
+def test_emu_sharded_reupload_keeps_only_owned_quality_rows(emu, world, name):
+    """dada2b_reupload after dada2b_comm_init packs and uploads the quality rows of the rank's own raws only; the rows of the
+    cluster centres are exchanged before the birth subs; results stay the reference's on every rank."""
+    _run_sharded(world, name, reupload=True)
+    assert emu.cuemu_launches(b"k_qrows_scatter") > 0 and emu.cuemu_launches(b"k_qrows_gather") > 0
 
 
 FUSED_E2E = ["syn800_default", "syn800_nogreedy", "syn800_maxclust5", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES)
