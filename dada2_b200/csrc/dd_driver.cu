@@ -401,6 +401,7 @@ struct Run {
   DBuf<unsigned long long> cand_ctr;          // [0] candidates of the round, [1] raws forwarded to the warp-per-pair screen
   bool prescreen = false;
   int nown = 0;
+  bool fallback_only = false;          // DADA2B_FALLBACK (test switch): general kernels only
   bool two_phase = false;              // bound pass first, exact lambda for the survivors only (plain gap costs)
   // fused round tail (experimental, DADA2B_FUSED_TAIL=1; dd_round2.cu)
   bool fused_tail = false;               // dd_round2.cu: link + NP passes + final (default); dd_round.cu's split tail otherwise
@@ -646,7 +647,7 @@ void Run::alloc_state() {
   ctr.alloc(CTR_N); h_ctr.alloc(CTR_N);
   DBG("alloc: ctr done");
   move_cap = (unsigned)(4 * n + 1024); fb_list.alloc(n);
-  const bool fallback_only = getenv("DADA2B_FALLBACK") != nullptr;   // test switch: general kernels only (no row / lane kernels, no streaming screen)
+  fallback_only = getenv("DADA2B_FALLBACK") != nullptr;   // test switch: general kernels only (no row / lane kernels, no streaming screen)
   two_phase = !P.homo;
   if (two_phase) { surv_list.alloc(n); raw_S.alloc(n); raw_rho.alloc(n); uneq_list.alloc(n + 2); uneq_ctr.alloc(1); }
   if (!fallback_only && nwrow_usable(P, in.maxlen) && P.band >= 0) {
@@ -663,7 +664,7 @@ void Run::alloc_state() {
   prescreen = P.use_kmers && !fallback_only;
   if (prescreen) {
     nown = (nraw - cx->rank + cx->world - 1) / cx->world;
-    kbits.alloc((size_t)nown * 32 + 32); kmeta.alloc(nown); krep.alloc((size_t)nown * 16 + 16); cand_list.alloc(nown + 32); cand_ms.alloc(nown + 32);
+    kbits.alloc((size_t)nown * 32 + 32); kmeta.alloc(nown); krep.alloc((size_t)nown * 48 + 64); cand_list.alloc(nown + 32); cand_ms.alloc(nown + 32);
     old_list.alloc(nown + 32); cand_ctr.alloc(2);
     launch_kmer_bits(in, cx->rank, cx->world, nown, kbits.p, kmeta.p, krep.p, cx->num_sms, s);
   }
@@ -822,7 +823,16 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     if (ex_done && in.minlen == in.maxlen) fwd_done = true;       // nothing was handed back; fb_list stays empty
     else timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, ex_done ? 0 : (i == 0 ? (unsigned long long)nraw : est_active), cx->num_sms, s); });
   }
+  if (!fallback_only) {       // gapless comparisons: no DP, one thread per pair (dd_nwrow.cu:k_gapless_loop)
+    FwdArgs g{};
+    g.in = in; g.P = P; g.st = st; g.jobs = st.gl_list; g.njobs_ptr = st.ctr + CTR_GL;
+    if (owner) { g.st.shard_world = 1; g.st.shard_rank = 0; }
+    g.centre_idx = c; g.centre_reads = cx->reads[c]; g.cluster_i = i; g.total_reads = cx->total_reads;
+    g.raw_S = raw_S.p; g.raw_rho = raw_rho.p;
+    timed(T_GL, [&]() { launch_gapless_loop(g, two_phase ? 1 : 0, (unsigned long long)nraw, cx->num_sms, s); });
+  }
   for (int kind : {KIND_NW, KIND_GAPLESS}) {
+    if (kind == KIND_GAPLESS && !fallback_only) continue;
     AlignArgs a = align_args(MODE_LOOP, kind);
     a.jobs = kind == KIND_NW ? st.nw_list : st.gl_list;
     if (kind == KIND_NW && fwd_done) { a.jobs = fb_list.p; a.njobs_ptr = st.ctr + CTR_FB; }

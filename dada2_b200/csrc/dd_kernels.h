@@ -89,6 +89,8 @@ size_t nwlane_mv_words(int band, int maxlen, int groups);
 size_t nwlane_sub_halfwords(int maxlen, int groups);
 bool launch_nwlane(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, uint32_t *mv_scratch, uint16_t *sub_scratch, int len1,
                    unsigned long long lane_max, int groups_cap, cudaStream_t s);
+// loop comparisons that need no DP (gapless alignments): one thread per pair, any lengths
+void launch_gapless_loop(const FwdArgs &f, int use_bound, unsigned long long njobs_upper, int num_sms, cudaStream_t s);
 bool launch_nwrow_final(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, unsigned long long njobs_upper, int num_sms,
                         cudaStream_t s);
 // exact pass: per-thread scratch columns for the recorded moves / substitutions; the grid is capped by what was allocated

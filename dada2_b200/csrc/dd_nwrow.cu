@@ -210,6 +210,71 @@ static int row_grid(unsigned long long njobs_upper, int num_sms, int per_sm) {
   return (int)std::min<unsigned long long>(std::max<unsigned long long>(blocks, 1ull), (unsigned long long)num_sms * per_sm);
 }
 
+
+// k_gapless_loop: the loop comparisons raw_align settles WITHOUT a DP (kodist == kdist: nwalign_gapless, nwalign_endsfree.cpp:539-555:
+// position i against position i, the shorter sequence padded with '-' at its end).  One thread per pair: the substitution
+// count is the Hamming distance of the packed rows over the common length; pairs that cannot pass the store rule leave after
+// the bound test; the rest multiply lambda in raw-position order (compute_lambda_ts) and apply the store rule.  Any lengths.
+__global__ void __launch_bounds__(128) k_gapless_loop(FwdArgs a, int use_bound) {
+  extern __shared__ uint32_t smem[];
+  const int ncol = a.P.ncol;
+  double *s_err = (double *)smem;
+  uint32_t *s_crow = smem + 2 * (16 * ncol);           // the centre's packed row
+  const unsigned long long njobs = *a.njobs_ptr;
+  if ((unsigned long long)blockIdx.x * blockDim.x >= njobs) return;
+  const int SW = a.in.SW, len1 = (int)a.in.len[a.centre_idx];
+  for (int x = threadIdx.x; x < SW; x += blockDim.x) s_crow[x] = a.in.seq2[(size_t)a.centre_idx * SW + x];
+  for (int x = threadIdx.x; x < 16 * ncol; x += blockDim.x) s_err[x] = a.st.err[x];
+  __syncthreads();
+  int errflag = 0;
+  for (unsigned long long jb = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; jb < njobs; jb += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t r = a.jobs[jb];
+    const int len2 = (int)a.in.len[r], lc = min(len1, len2);
+    const uint32_t *rrow = a.in.seq2 + (size_t)r * SW;
+    int ns = 0;
+    for (int w = 0; w * 16 < lc; w++) {
+      const uint32_t x = rrow[w] ^ s_crow[w];
+      uint32_t mis = (x | (x >> 1)) & 0x55555555u;
+      const int left = lc - w * 16;
+      if (left < 16) mis &= (1u << (2 * left)) - 1u;
+      ns += __popc(mis);
+    }
+    if (use_bound && a.cluster_i != 0) {               // lambda <= S_r * rho_r^nsubs (dd_round.cu:k_raw_bounds): unstorable pairs stop here
+      const double bound = a.raw_S[r] * pow(a.raw_rho[r], (double)ns) * (double)a.total_reads * (1.0 + 1e-9);
+      if (bound <= a.st.E_minmax[r] && !(bound < 1e-280)) continue;
+    }
+    const uint8_t *qrow = a.in.qual + (size_t)r * a.in.QS;
+    double lam = 1.0;
+    uint4 qn = *(const uint4 *)qrow;
+    for (int p0 = 0; p0 < len2; p0 += 16) {
+      const uint4 qv = qn;
+      if (p0 + 16 < len2) qn = *(const uint4 *)(qrow + p0 + 16);
+      uint32_t bw = rrow[p0 >> 4], cw = s_crow[p0 >> 4];
+      const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        const int p = p0 + u;
+        if (p < len2) {
+          const uint32_t b = bw & 3u, c = (p < len1) ? (cw & 3u) : b;       // beyond the centre: raw base against a gap = self transition
+          int q = a.P.use_quals ? (int)((qq[u >> 2] >> (8 * (u & 3))) & 0xFFu) : 0;
+          if (q > ncol - 1) { errflag = ERR_QUAL; q = ncol - 1; }
+          lam = lam * s_err[(4u * c + b) * ncol + q];                        // c == b: 5 b, the self transition
+        }
+        bw >>= 2; cw >>= 2;
+      }
+    }
+    if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;               // pval.cpp:195
+    store_comparison(a, r, lam, ns);
+  }
+  if (errflag) atomicMax(&a.st.ctr[CTR_ERR], (unsigned long long)errflag);
+}
+
+void launch_gapless_loop(const FwdArgs &f, int use_bound, unsigned long long njobs_upper, int num_sms, cudaStream_t s) {
+  const size_t smem = (size_t)16 * f.P.ncol * 8 + (size_t)f.in.SW * 4;
+  count_launch(1);
+  k_gapless_loop<<<row_grid(njobs_upper, num_sms, 16), 128, smem, s>>>(f, use_bound);
+}
+
 // Bound pass over f.jobs; jobs with len2 != len1 come back in uneq_list (count in *uneq_count, zeroed by the caller).
 // false: nothing launched (the caller falls back to the lane-group kernels for every job).
 bool launch_nwrow_bound(const FwdArgs &f, uint32_t *uneq_list, unsigned long long *uneq_count, int len1, unsigned long long njobs_upper, int num_sms,

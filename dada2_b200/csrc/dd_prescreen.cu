@@ -10,7 +10,7 @@
 // Where the bound is inconclusive the SAME thread finishes the exact integer min-sum: only 5-mers that occur at least
 // twice in the raw can contribute more than their presence bit,
 //     sum_k min(c_r[k], c_c[k])  =  popc(B_r & B_c) + sum over the raw's repeated 5-mers k present in the centre of (min(c_r[k], c_c[k]) - 1),
-// and a 250-nt read has about a dozen of those: they are kept as a 16-entry list per raw (k_kmer_bits) and looked up in a
+// and a 250-nt read has about 25 of those: they are kept as a list of up to 48 entries per raw (k_kmer_bits) and looked up in a
 // count table of the centre in shared memory.  So every pair leaves this kernel decided exactly (shrouded or not); the
 // pairs that are not shrouded go to k_kord (one thread per pair: ordered 5-mer matches from the XOR of the packed rows ->
 // gapless or NW, raw_align :53-56).  Raws whose list overflows take the warp-per-pair k_classify (dd_kernels.cu) instead.
@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned kmer10(const uint32_t *row, int p) {      //
 }
 }  // namespace
 
-constexpr int KREP = 16;              // repeated-5-mer list entries per raw (u16: k-mer | (count - 1) << 10, 0xFFFF = none)
+constexpr int KREP = 48;              // repeated-5-mer list entries per raw (u16: k-mer | (count - 1) << 10, 0xFFFF = end); a 250-nt read has ~25
 constexpr uint32_t META_OVF = 1u << 31;   // kmeta flag: the list does not hold every repeated 5-mer of this raw (or a count above 64)
 
 // one warp per owned raw: bitmap row, repeated-5-mer list, meta word (overflow flag | slack << 16 | len)
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) k_kmer_bits(DevIn in, int rank, int world
     for (int o = 16; o; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
     // repeated 5-mers: lane l scans k-mers 32 l .. 32 l + 31 (the bits of its bitmap word), in k-mer order
     uint16_t *lst = krep + (size_t)it * KREP;
-    if (lane < KREP) lst[lane] = 0xFFFFu;
+    for (int x = lane; x < KREP; x += 32) lst[x] = 0xFFFFu;
     __syncwarp();
     int nrep = 0; bool ovf = false;
     for (int b = 0; b < 32; b++) {
@@ -189,15 +189,19 @@ __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
         // exact min-sum: presence bits + what the raw's repeated 5-mers add beyond their presence bit
         int ms = pc;
         const uint4 *lp = (const uint4 *)(a.krep + (size_t)(tile * PS_TILE + tid) * KREP);
-        const uint4 l0 = lp[0], l1 = lp[1];
-        const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        bool more = true;
+        for (int blk = 0; blk < KREP / 8 && more; blk++) {                    // the list is packed from the front and ends at the first 0xFFFF
+          const uint4 l4 = lp[blk];
+          const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-        for (int e = 0; e < KREP; e++) {
-          const uint32_t ent = (lw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
-          if (ent != 0xFFFFu) {
-            const uint32_t km = ent & 0x3FFu, cr = (ent >> 10) + 1u;
-            const uint32_t cc = (s_ccnt[km >> 1] >> (16 * (km & 1))) & 0xFFFFu;
-            ms += cc ? (int)min(cr, cc) - 1 : 0;
+          for (int e = 0; e < 8; e++) {
+            const uint32_t ent = (lw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+            if (ent == 0xFFFFu) more = false;
+            else {
+              const uint32_t km = ent & 0x3FFu, cr = (ent >> 10) + 1u;
+              const uint32_t cc = (s_ccnt[km >> 1] >> (16 * (km & 1))) & 0xFFFFu;
+              ms += cc ? (int)min(cr, cc) - 1 : 0;
+            }
           }
         }
         const double kdist = 1. - ((double)(ms & 0xFFFF)) / denom;          // exactly raw_align's kdist (N1: integer min-sum)
