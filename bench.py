@@ -359,7 +359,7 @@ def main():
             flush.zero_()
             torch.cuda.synchronize()
             ts = time.perf_counter()
-            res.reupload(pin)                                   # dada2b_reupload: pack + H2D (all packed reads, this rank's quality rows)
+            res.reupload(pin)                                   # dada2b_reupload: pack + H2D of this rank's reads, all-gather of the packed reads
             est = res.run_raw(ecm, ecm.shape[1], ostruct)       # dada2b_run_resident: loop + D2H of every output
             e2e_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
         barrier()
@@ -367,8 +367,9 @@ def main():
         est = dict(est)
         L0 = len(seqs[0])
         nown = (nraw - rank + world - 1) // world
-        # dada2b_reupload on a sharded context: packed reads of every raw (any raw may become a centre), quality rows of this rank's raws only
-        est["h2d_bytes"] += nraw * ((((L0 + 15) // 16 + 3) & ~3) * 4 + 7) + nown * ((L0 + 15) & ~15)
+        # dada2b_reupload on a sharded context: packed reads and quality rows of this rank's raws only (the other ranks' packed reads
+        # arrive over NVLink: one all-gather), plus lengths / abundances / priors of every raw
+        est["h2d_bytes"] += nown * ((((L0 + 15) // 16 + 3) & ~3) * 4 + ((L0 + 15) & ~15)) + nraw * 7
     else:
         call = dada2_b200.PackedCall(seqs, ab, None, err, q)
         for _ in range(max(1, args.warmup // 2)):

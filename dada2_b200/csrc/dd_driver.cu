@@ -120,7 +120,7 @@ struct dada2b_ctx {
   bool has_quals = false;
   bool bad_nt = false;
   bool qual_sharded = false;      // dada2b_reupload on a sharded context: quality rows of this rank's raws only are on the device
-  DBuf<uint8_t> d_qual_own;
+  DBuf<uint8_t> d_qual_own, d_seq_own, d_seq_all;
   unsigned total_reads = 0;
   std::vector<uint16_t> len;
   std::vector<uint32_t> reads;
@@ -212,13 +212,15 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   cx->total_reads = tot;
   // pack on the host into pinned staging, then one H2D per array
   const double tu1 = now_ms();
-  PBuf<uint32_t> &h_seq = cx->st_seq; h_seq.alloc((size_t)nraw * d.SW);
+  PBuf<uint32_t> &h_seq = cx->st_seq;
   // a context that already shards a sample (dada2b_reupload after dada2b_comm_init) needs the quality rows of ITS raws only:
   // they are packed densely (row it <-> raw it * world + rank) and scattered into place on the device
   const bool qshard = reuse && cx->comm && cx->world > 1;
   const unsigned qworld = qshard ? (unsigned)cx->world : 1u, qrank = qshard ? (unsigned)cx->rank : 0u;
   const size_t nqown = ((size_t)nraw + qworld - 1 - qrank) / qworld;
+  const size_t nqmax = ((size_t)nraw + qworld - 1) / qworld;          // rows of the largest shard (all-gather chunks are equally long)
   PBuf<uint8_t> &h_qual = cx->st_qual; h_qual.alloc(std::max<size_t>(nqown, 1) * d.QS);
+  h_seq.alloc(qshard ? nqmax * d.SW : (size_t)nraw * d.SW);          // sharded: this rank packs its own reads only, the rest arrives over NVLink
   std::vector<int> tmaxq(64, 0), tbad(64, 0);
   const char *sc = cx->seq_concat.data();
   const double *qd = in->quals;
@@ -236,9 +238,10 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
       th.emplace_back([&, b, e, t]() {
         int mq = 0, bad = 0;
         for (size_t r = b; r < e; r++) {
+          if (r % qworld != qrank) continue;                     // not this rank's read (sharded re-upload)
           const char *s = sc + cx->seq_off[r];
           const int L = cx->len[r];
-          uint32_t *row = h_seq.p + r * SW;
+          uint32_t *row = h_seq.p + (r / qworld) * SW;
           for (int w = 0; w < SW; w++) row[w] = 0;
           for (int p = 0; p < L; p++) {
             unsigned code;
@@ -246,7 +249,6 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
                             case 'T': code = 3; break; default: code = 0; bad = 1; }
             row[p >> 4] |= code << (2 * (p & 15));
           }
-          if (r % qworld != qrank) continue;
           uint8_t *q = h_qual.p + (r / qworld) * QS;
           const double *src = qd + (size_t)ML * r;
           for (int p = 0; p < L; p++) {                                   // (uint8_t) round(qual[i]), containers.cpp:34
@@ -270,18 +272,31 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   for (int v : tbad) cx->bad_nt |= (v != 0);
   cx->d_seq2.alloc((size_t)nraw * d.SW); cx->d_qual.alloc((size_t)nraw * d.QS);
   cx->d_len.alloc(nraw); cx->d_reads.alloc(nraw); cx->d_prior.alloc(nraw);
-  CK(cudaMemcpyAsync(cx->d_seq2.p, h_seq.p, (size_t)nraw * d.SW * 4, cudaMemcpyHostToDevice, cx->stream));
+  if (!qshard) CK(cudaMemcpyAsync(cx->d_seq2.p, h_seq.p, (size_t)nraw * d.SW * 4, cudaMemcpyHostToDevice, cx->stream));
+  else {          // own packed reads up, everybody's over NVLink (one all-gather), rows scattered into raw order
+    const size_t chunk = nqmax * d.SW * 4;
+    cx->d_seq_own.alloc(chunk); cx->d_seq_all.alloc(chunk * qworld);
+    CK(cudaMemsetAsync(cx->d_seq_own.p, 0, chunk, cx->stream));
+    CK(cudaMemcpyAsync(cx->d_seq_own.p, h_seq.p, nqown * d.SW * 4, cudaMemcpyHostToDevice, cx->stream));
+    NC(g_nccl.AllGather(cx->d_seq_own.p, cx->d_seq_all.p, chunk, ncclChar, cx->comm, cx->stream));
+    for (unsigned q = 0; q < qworld; q++) {
+      const size_t nq = ((size_t)nraw + qworld - 1 - q) / qworld;
+      launch_qrows_scatter((uint8_t *)cx->d_seq2.p, d.SW * 4, nullptr, (int)nq, (int)q, (int)qworld, cx->d_seq_all.p + chunk * q, cx->stream);
+    }
+  }
   if (!qshard) CK(cudaMemcpyAsync(cx->d_qual.p, h_qual.p, (size_t)nraw * d.QS, cudaMemcpyHostToDevice, cx->stream));
   else {
     cx->d_qual_own.alloc(nqown * d.QS);
     CK(cudaMemcpyAsync(cx->d_qual_own.p, h_qual.p, nqown * d.QS, cudaMemcpyHostToDevice, cx->stream));
     launch_qrows_scatter(cx->d_qual.p, d.QS, nullptr, (int)nqown, (int)qrank, (int)qworld, cx->d_qual_own.p, cx->stream);
     // the largest quality present decides an error of the whole call (Rmain.cpp / pval.cpp:169-171): every rank must see the same value
-    DBuf<int> dq; dq.alloc(1);
-    CK(cudaMemcpyAsync(dq.p, &cx->maxq, 4, cudaMemcpyHostToDevice, cx->stream));
-    NC(g_nccl.AllReduce(dq.p, dq.p, 1, ncclInt32, ncclMax, cx->comm, cx->stream));
-    CK(cudaMemcpyAsync(&cx->maxq, dq.p, 4, cudaMemcpyDeviceToHost, cx->stream));
+    DBuf<int> dq; dq.alloc(2);
+    int hq[2] = {cx->maxq, cx->bad_nt ? 1 : 0};                  // ... and so does an unexpected nucleotide in anybody's reads
+    CK(cudaMemcpyAsync(dq.p, hq, 8, cudaMemcpyHostToDevice, cx->stream));
+    NC(g_nccl.AllReduce(dq.p, dq.p, 2, ncclInt32, ncclMax, cx->comm, cx->stream));
+    CK(cudaMemcpyAsync(hq, dq.p, 8, cudaMemcpyDeviceToHost, cx->stream));
     CK(cudaStreamSynchronize(cx->stream));
+    cx->maxq = hq[0]; cx->bad_nt = hq[1] != 0;
   }
   cx->qual_sharded = qshard;
   {
@@ -297,7 +312,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   CK(cudaStreamSynchronize(cx->stream));
   if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] upload: validate+copy %.2f ms, pack %.2f ms, alloc+H2D %.2f ms\n", tu1 - tu0, tu2 - tu1, now_ms() - tu2);
   DBG("upload: H2D done");
-  cx->upload_h2d = (long long)nraw * d.SW * 4 + (long long)(qshard ? nqown : nraw) * d.QS + (long long)nraw * 7;
+  cx->upload_h2d = (long long)(qshard ? nqown : nraw) * (d.SW * 4 + d.QS) + (long long)nraw * 7;
   d.seq2 = cx->d_seq2.p; d.qual = cx->d_qual.p; d.len = cx->d_len.p; d.reads = cx->d_reads.p; d.prior = cx->d_prior.p;
   if (fresh) fresh.release();
   return cx;
