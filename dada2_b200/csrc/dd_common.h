@@ -60,9 +60,6 @@ struct RoundReport {
   uint32_t tie_cl[TIE_MAX], tie_clreads[TIE_MAX], tiep_cl[TIE_MAX], tiep_clreads[TIE_MAX];
 };
 
-// A stored comparison produced by this rank in the current round (sharded runs): exchanged with one
-// all-gather per round, then appended to every rank's comparison store in rank-major order.
-struct NewEntry { uint32_t index, ham; double lambda; };
 
 // Mutable per-run state.
 struct DevState {
@@ -88,7 +85,6 @@ struct DevState {
   double *err;
   // sharded runs (one process per GPU): raw r is owned by rank r % shard_world
   int shard_rank, shard_world;
-  NewEntry *ne_local;               // this rank's new stored comparisons of the round (count in ctr[CTR_NE])
   // per-round control block (device) + host-mapped report / move list
   uint32_t *pinfo;                  // [MAX_PASS + 2]
   uint32_t *moves;                  // mapped pinned host memory: (raw, to) pairs

@@ -388,10 +388,6 @@ struct Run {
   DBuf<int> trans, center_cluster, pa_reads, pa_prior;
   PBuf<unsigned long long> h_ctr;
   DBuf<uint32_t> cl_reads_next, pinfo;
-  DBuf<NewEntry> ne_local, ne_all;       // sharded runs: staged / all-gathered new comparisons
-  DBuf<unsigned long long> d_counts;
-  PBuf<unsigned long long> h_counts;
-  unsigned shard_cap = 0;
   DBuf<RoundReport> d_report;
   DBuf<uint32_t> d_moves;
   PBuf<RoundReport> h_report_buf;
@@ -685,7 +681,8 @@ void Run::alloc_state() {
   }
   if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
   fused_tail = getenv("DADA2B_SPLIT_TAIL") == nullptr;   // test switch: the one-kernel-per-step tail of dd_round.cu (capacity fallback beyond 32 k clusters)
-  owner = fused_tail && cx->world > 1 && getenv("DADA2B_REPLICATED") == nullptr;   // sharded runs: every rank keeps / shuffles / scans its own raws only
+  owner = cx->world > 1;           // sharded runs: every rank keeps / shuffles / scans its own raws only (needs the fused tail)
+  if (owner && !fused_tail) throw Err{"dada2b: sharded runs need the fused round tail (unset DADA2B_SPLIT_TAIL)"};
   if (fused_tail) {
     const size_t g = (size_t)tail_grid(nraw);
     t_head.alloc(n); t_nmove.alloc(MAX_PASS); t_done.alloc(1); t_blk.alloc(g); t_bt.alloc(g * TIE_MAX); t_btp.alloc(g * TIE_MAX);
@@ -709,12 +706,7 @@ void Run::alloc_state() {
   st.emax_bits = emax_bits.p; st.best_entry = best_entry.p; st.nw_list = nw_list.p; st.gl_list = gl_list.p;
   st.ctr = ctr.p; st.err = err.p; st.nsubs_final = nsubs_final.p;
   st.pinfo = pinfo.p; st.move_cap = move_cap;
-  st.shard_rank = cx->rank; st.shard_world = cx->world; st.ne_local = nullptr;
-  if (cx->world > 1) {
-    shard_cap = (unsigned)((n + cx->world - 1) / cx->world + 32);
-    ne_local.alloc(shard_cap); ne_all.alloc((size_t)shard_cap * cx->world); d_counts.alloc(cx->world); h_counts.alloc(cx->world);
-    st.ne_local = ne_local.p;
-  }
+  st.shard_rank = cx->rank; st.shard_world = cx->world;
   st.report = d_report.p; st.moves = d_moves.p;
   emax_bits.zero(s);                                               // shuffle scratch starts clean
   CK(cudaMemsetAsync(best_entry.p, 0xFF, n * 4, s));
@@ -793,7 +785,6 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   if (P.band >= 0) {       // register-resident NW kernels (dd_nwrow.cu / dd_nwlane.cu / dd_nwfwd.cu); unbanded pairs: k_align below
     FwdArgs f{};
     f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
-    if (owner) { f.st.shard_world = 1; f.st.shard_rank = 0; }       // this rank's comparisons go straight into its own store
     f.centre_idx = c; f.centre_reads = cx->reads[c]; f.cluster_i = i; f.total_reads = cx->total_reads;
     f.fb_list = fb_list.p; f.fb_count = st.ctr + CTR_FB; f.seq_bytes = seq_bytes; f.mode = 0; f.job_mul = 1; f.job_add = 0;
     {  // the fast path replaces the reference's sentinel by a larger penalty: only valid while no real score can come near it
@@ -841,7 +832,6 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
   if (!fallback_only) {       // gapless comparisons: no DP, one thread per pair (dd_nwrow.cu:k_gapless_loop)
     FwdArgs g{};
     g.in = in; g.P = P; g.st = st; g.jobs = st.gl_list; g.njobs_ptr = st.ctr + CTR_GL;
-    if (owner) { g.st.shard_world = 1; g.st.shard_rank = 0; }
     g.centre_idx = c; g.centre_reads = cx->reads[c]; g.cluster_i = i; g.total_reads = cx->total_reads;
     g.raw_S = raw_S.p; g.raw_rho = raw_rho.p;
     timed(T_GL, [&]() { launch_gapless_loop(g, two_phase ? 1 : 0, (unsigned long long)nraw, cx->num_sms, s); });
@@ -853,22 +843,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     if (kind == KIND_NW && fwd_done) { a.jobs = fb_list.p; a.njobs_ptr = st.ctr + CTR_FB; }
     else a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
     a.centre_idx = c; a.centre_reads = cx->reads[c]; a.cluster_i = i; a.total_reads = cx->total_reads;
-    if (owner) { a.st.shard_world = 1; a.st.shard_rank = 0; }
     timed(kind == KIND_NW ? T_NW : T_GL, [&]() { launch_align_jobs(MODE_LOOP, a, (unsigned long long)nraw); });
-  }
-  if (cx->world > 1 && !owner) {
-    // The one collective of a split round: all-gather of the new stored comparisons (count first, then the
-    // payload padded to the largest count), appended on every rank in rank-major order.
-    NC(g_nccl.AllGather(ctr.p + CTR_NE, d_counts.p, 1, ncclUint64, cx->comm, s));
-    d2h_pinned(h_counts.p, d_counts.p, (size_t)cx->world * 8);
-    sync();
-    unsigned long long maxc = 0;
-    for (int q = 0; q < cx->world; q++) maxc = std::max(maxc, h_counts.p[q]);
-    if (maxc > shard_cap) throw Err{"dada2b: shard staging overflow"};
-    if (maxc) {
-      NC(g_nccl.AllGather(ne_local.p, ne_all.p, (size_t)maxc * sizeof(NewEntry), ncclChar, cx->comm, s));
-      launch_cs_append(st, ne_all.p, d_counts.p, (unsigned)maxc, i, c, s);
-    }
   }
   if (fused_tail) launch_tail_link(st, ts, cs_count, i, nraw, nclust_h, s);
 }

@@ -267,10 +267,7 @@ __global__ void __launch_bounds__(128) k_align(AlignArgs a) {
         if (lambda * (double)a.total_reads > emm) {
           const double ec = lambda * (double)a.centre_reads;
           if (ec > emm) a.st.E_minmax[r] = ec;
-          if (a.st.shard_world > 1) {          // sharded: stage, exchange with one all-gather, append on every rank
-            const unsigned long long slot = atomicAdd(&a.st.ctr[CTR_NE], 1ull);
-            a.st.ne_local[slot] = NewEntry{r, (uint32_t)nsubs, lambda};
-          } else {
+          {                                    // sharded runs: every rank stores the comparisons of its own raws (owner mode)
             unsigned long long slot = a.cluster_i == 0 ? (unsigned long long)r : atomicAdd(&a.st.ctr[CTR_CS_COUNT], 1ull);
             if (slot < a.st.cs_cap) {
               a.st.cs_index[slot] = r; a.st.cs_i[slot] = a.cluster_i; a.st.cs_lambda[slot] = lambda; a.st.cs_ham[slot] = (uint32_t)nsubs;

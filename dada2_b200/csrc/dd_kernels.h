@@ -142,7 +142,6 @@ void launch_shuffle_pass(const DevState &st, const DevIn &in, unsigned long long
 void launch_p_update(const DevState &st, const DevIn &in, int greedy, int detect_singletons, int last_pass, cudaStream_t s);
 void launch_bud_scan(const DevState &st, const DevIn &in, const BudParams &bp, int nclust, int last_pass, cudaStream_t s);
 void launch_report(const DevState &st, int last_pass, cudaStream_t s);
-void launch_cs_append(const DevState &st, const NewEntry *all, const unsigned long long *counts, unsigned cap, uint32_t cluster_i, uint32_t centre, cudaStream_t s);
 void launch_fill_f64(double *p, double v, size_t n, cudaStream_t s);
 void launch_center_cluster(int *cc, const uint32_t *cl_center, int nclust, cudaStream_t s);
 void launch_bud_collect_big(const DevState &st, const DevIn &in, const BudParams &bp, uint32_t *ties, uint32_t *ties_pr, unsigned cap, cudaStream_t s);

@@ -358,10 +358,7 @@ __global__ void __launch_bounds__(128) k_nwfwd(FwdArgs a) {
       if (lam * (double)a.total_reads > emm) {
         const double ec = lam * (double)a.centre_reads;
         if (ec > emm) a.st.E_minmax[r] = ec;
-        if (a.st.shard_world > 1) {
-          const unsigned long long slot = atomicAdd(&a.st.ctr[CTR_NE], 1ull);
-          a.st.ne_local[slot] = NewEntry{r, (uint32_t)ns, lam};
-        } else {
+        {
           const unsigned long long slot = a.cluster_i == 0 ? (unsigned long long)r : atomicAdd(&a.st.ctr[CTR_CS_COUNT], 1ull);
           if (slot < a.st.cs_cap) {
             a.st.cs_index[slot] = r; a.st.cs_i[slot] = a.cluster_i; a.st.cs_lambda[slot] = lam; a.st.cs_ham[slot] = (uint32_t)ns;

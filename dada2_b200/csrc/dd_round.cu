@@ -27,7 +27,7 @@ __global__ void k_round_begin(DevState st, int apply, uint32_t r, uint32_t from,
       st.cl_reads[newi] = reads_r; st.cl_reads_next[newi] = reads_r;
       st.cl_update_e[from] = 1; st.cl_update_e[newi] = 1; st.cl_check_locks[newi] = 1;
     }
-    st.ctr[CTR_NW] = 0; st.ctr[CTR_GL] = 0; st.ctr[CTR_FB] = 0; st.ctr[CTR_NMOVE] = 0; st.ctr[CTR_NE] = 0;
+    st.ctr[CTR_NW] = 0; st.ctr[CTR_GL] = 0; st.ctr[CTR_FB] = 0; st.ctr[CTR_NMOVE] = 0;
   }
   if (threadIdx.x < MAX_PASS + 2) st.pinfo[threadIdx.x] = 0;
 }
@@ -184,30 +184,6 @@ __global__ void k_report(DevState st, int last_pass) {
   if (threadIdx.x == 0) st.report->converged = (last_pass < 0 || converged_after(st, last_pass)) ? 1u : 0u;
 }
 
-// Sharded runs: append the all-gathered new comparisons of every rank (rank-major, so all ranks build
-// the same store) and apply the raw->comp rule of cluster.cpp:197-199.
-__global__ void k_cs_append(DevState st, const NewEntry *all, const unsigned long long *counts, unsigned cap, uint32_t cluster_i,
-                            uint32_t centre) {
-  const int q = blockIdx.y;
-  const unsigned long long cnt = counts[q];
-  unsigned long long prefix = 0;
-  for (int t = 0; t < q; t++) prefix += counts[t];
-  const unsigned long long base = st.ctr[CTR_CS_COUNT];
-  for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < cnt; j += (unsigned long long)gridDim.x * blockDim.x) {
-    const NewEntry e = all[(size_t)q * cap + j];
-    const unsigned long long slot = cluster_i == 0 ? (unsigned long long)e.index : base + prefix + j;
-    if (slot < st.cs_cap) { st.cs_index[slot] = e.index; st.cs_i[slot] = cluster_i; st.cs_lambda[slot] = e.lambda; st.cs_ham[slot] = e.ham; }
-    if (cluster_i == 0 || e.index == centre) { st.comp_lambda[e.index] = e.lambda; st.comp_ham[e.index] = e.ham; }
-  }
-}
-__global__ void k_cs_append_commit(DevState st, const unsigned long long *counts, int world, uint32_t cluster_i) {
-  if (threadIdx.x == 0 && cluster_i != 0) {
-    unsigned long long tot = 0;
-    for (int t = 0; t < world; t++) tot += counts[t];
-    st.ctr[CTR_CS_COUNT] += tot;
-  }
-}
-
 // Two-phase loop NW: per-raw bound factors.  S_r = product over the raw's positions of its self-transition factor
 // err[5*nt][q]; rho_r = max over positions and nt0 != nt of err[4*nt0+nt][q] / err[5*nt][q].
 __global__ void k_raw_bounds(DevIn in, const double *err, int ncol, int use_quals, double *S, double *rho, int rank, int world) {
@@ -275,13 +251,6 @@ void launch_fill_f64(double *p, double v, size_t n, cudaStream_t s) {
 void launch_center_cluster(int *cc, const uint32_t *cl_center, int nclust, cudaStream_t s) {
   count_launch(1);
   k_center_cluster<<<(nclust + 127) / 128, 128, 0, s>>>(cc, cl_center, nclust);
-}
-void launch_cs_append(const DevState &st, const NewEntry *all, const unsigned long long *counts, unsigned cap, uint32_t cluster_i,
-                      uint32_t centre, cudaStream_t s) {
-  count_launch(2);
-  dim3 g((cap + 255) / 256 > 0 ? std::min<unsigned>((cap + 255) / 256, 1024u) : 1u, st.shard_world);
-  k_cs_append<<<g, 256, 0, s>>>(st, all, counts, cap, cluster_i, centre);
-  k_cs_append_commit<<<1, 32, 0, s>>>(st, counts, st.shard_world, cluster_i);
 }
 void launch_round_begin(const DevState &st, int apply, uint32_t r, uint32_t from, uint32_t newi, uint32_t reads_r, cudaStream_t s) {
   count_launch(1);

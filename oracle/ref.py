@@ -6,6 +6,8 @@ may import this module.
 """
 import ctypes as C
 import os
+import time
+
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -74,6 +76,9 @@ def _svec(h, outer, inner):
     return [L.ref_field_str(h, outer, inner, i).decode() for i in range(max(n, 0))]
 
 
+last_native_s = 0.0
+
+
 def dada_uniques(seqs, abundances, priors, err, quals, **opts):
     """Run the reference's dada_uniques (Rmain.cpp:30).  quals: float64 [nraw, maxlen] (NaN pad)
     or None; err: float64 [16, Q].  Returns a dict mirroring the R list."""
@@ -94,6 +99,8 @@ def dada_uniques(seqs, abundances, priors, err, quals, **opts):
         q = None
         maxlen = 0
         qp = None
+    global last_native_s
+    _t0 = time.perf_counter()
     h = L.ref_run(C.c_int(nraw), arr, ab.ctypes.data_as(C.c_void_p), pr.ctypes.data_as(C.c_void_p),
                   err_cm.ctypes.data_as(C.c_void_p), C.c_int(err.shape[1]), qp, C.c_int(maxlen),
                   C.c_int(o["match"]), C.c_int(o["mismatch"]), C.c_int(o["gap"]), C.c_int(o["use_kmers"]),
@@ -103,6 +110,8 @@ def dada_uniques(seqs, abundances, priors, err, quals, **opts):
                   C.c_int(o["min_abund"]), C.c_int(o["use_quals"]), C.c_int(o["final_consensus"]),
                   C.c_int(o["vectorized_alignment"]), C.c_int(o["homo_gap"]), C.c_int(o["multithread"]),
                   C.c_int(o["verbose"]), C.c_int(o["SSE"]), C.c_int(o["gapless"]), C.c_int(o["greedy"]))
+    last_native_s = time.perf_counter() - _t0          # the native call alone (what .Call('_dada2_dada_uniques') costs); marshalling of the
+                                                       # Python lists above and of the result below is not the reference's time
     h = C.c_void_p(h)
     try:
         e = L.ref_error(h)
