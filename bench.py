@@ -48,7 +48,7 @@ class ClockSampler(threading.Thread):
     `nvidia-smi -lms` child was observed to stall the stream synchronisations of this latency-bound loop
     for hundreds of ms at a time).  Falls back to one nvidia-smi query per second."""
 
-    def __init__(self, index, period=0.5):
+    def __init__(self, index, period=2.0):      # NVML queries contend with CUDA API calls for driver locks (profiles/r2_host_stalls.md): sample sparsely
         super().__init__(daemon=True)
         self.index = index
         self.period = period
