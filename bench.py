@@ -139,10 +139,39 @@ def bimera_leg(budget_s, device, cmd=None):
     return subprocess_leg("BIMLEG", cmd or [sys.executable, os.path.join(ROOT, "tools", "bimera_leg.py")], budget_s, device)
 
 
+def host_cpus():
+    """CPUs this process may really use: the affinity mask, capped by the cgroup's CPU quota (the GPU boxes show 128 hardware threads
+    under `cpu.max = 1600000 100000`, i.e. 16 CPUs: 128 runnable threads there are stopped for 7/8 of every 100 ms period).
+    DADA2B_REF_THREADS overrides."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            f = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if f[0] != "max":
+                    quota = float(f[0]) / float(f[1])
+            else:
+                per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if float(f[0]) > 0:
+                    quota = float(f[0]) / per
+            break
+        except Exception:
+            continue
+    if quota:
+        n = max(1, min(n, int(quota + 0.5)))
+    if os.environ.get("DADA2B_REF_THREADS"):
+        n = max(1, int(os.environ["DADA2B_REF_THREADS"]))
+    return n
+
+
 def cpu_reference(seqs, ab, err, q):
     """One pass of the reference's own C++ (or of the port when oracle/_ref is absent) on all host cores."""
     from oracle import ref
-    ncores = os.cpu_count() or 1
+    ncores = host_cpus()
     if ref.available():
         ref.set_threads(ncores)
         cres = ref.dada_uniques(seqs, ab, None, err, q, multithread=True)
@@ -160,7 +189,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import ref
-    ncores = os.cpu_count() or 1
+    ncores = host_cpus()
     ref.set_threads(ncores)
     seqs, ab, q, err = workload(args.nuniques, 12345)
     budget = float(os.environ.get("DADA2B_REF_BUDGET_S", 1400 if world == 1 else 420))

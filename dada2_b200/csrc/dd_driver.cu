@@ -35,7 +35,26 @@ using namespace dd2;
 namespace {
 
 struct Err { std::string msg; };
-#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw Err{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x}; } while (0)
+double now_ms();
+// DADA2B_STALLWATCH=<ms> (diagnostics, profiles/r2_host_stalls.md): report every CUDA runtime call of the driver that takes longer
+// than <ms>, and every stretch of host code between two calls that does
+struct StallWatch {
+  double thr = 0, last_end = 0;
+  StallWatch() { if (const char *e = getenv("DADA2B_STALLWATCH")) thr = atof(e); }
+  double begin(const char *what) {
+    const double t = now_ms();
+    if (last_end != 0 && t - last_end > thr) fprintf(stderr, "[dada2b] stall: %.1f ms of host time before %s\n", t - last_end, what);
+    return t;
+  }
+  void end(const char *what, double t0) {
+    const double t = now_ms();
+    if (t - t0 > thr) fprintf(stderr, "[dada2b] stall: %.1f ms inside %s\n", t - t0, what);
+    last_end = t;
+  }
+};
+static StallWatch g_watch;
+#define CK(x) do { const double w0_ = g_watch.thr > 0 ? g_watch.begin(#x) : 0.0; cudaError_t e_ = (x); if (g_watch.thr > 0) g_watch.end(#x, w0_); \
+                   if (e_ != cudaSuccess) throw Err{std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x}; } while (0)
 
 #define TDBG(msg) do { if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] t=%.3f ms %s\n", now_ms() - g_t0, msg); } while (0)
 #define DBG(...) do { if (getenv("DADA2B_SYNCDEBUG")) { fprintf(stderr, "[dada2b] " __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
@@ -52,6 +71,7 @@ template <typename T> struct DBuf {   // device buffer (grow-only: reused across
   }
   void free() { if (p) cudaFree(p); p = nullptr; n = cap = 0; }
   void zero(cudaStream_t s) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void swap(DBuf &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
   ~DBuf() { free(); }
 };
 template <typename T> struct PBuf {   // pinned host buffer (grow-only)
@@ -146,6 +166,7 @@ struct dada2b_ctx {
   PBuf<uint8_t> st_meta;          // len (u16) | reads (u32) | prior (u8), pinned
   int num_sms = 148;
   long long upload_h2d = 0;
+  unsigned long long upload_gen = 0;   // bumped by every (re)upload: per-sequence tables derived on the device are rebuilt when it changes
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   cudaEvent_t get_event() {
@@ -313,6 +334,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] upload: validate+copy %.2f ms, pack %.2f ms, alloc+H2D %.2f ms\n", tu1 - tu0, tu2 - tu1, now_ms() - tu2);
   DBG("upload: H2D done");
   cx->upload_h2d = (long long)(qshard ? nqown : nraw) * (d.SW * 4 + d.QS) + (long long)nraw * 7;
+  cx->upload_gen++;
   d.seq2 = cx->d_seq2.p; d.qual = cx->d_qual.p; d.len = cx->d_len.p; d.reads = cx->d_reads.p; d.prior = cx->d_prior.p;
   if (fresh) fresh.release();
   return cx;
@@ -410,7 +432,14 @@ struct Run {
   DBuf<uint32_t> kbits, kmeta, cand_list, old_list;
   DBuf<uint16_t> krep, cand_ms;
   DBuf<unsigned long long> cand_ctr;          // [0] candidates of the round, [1] raws forwarded to the warp-per-pair screen
+  // scratch of the rare paths and of finish(): members, so that a steady-state pass makes no cudaMalloc / cudaFree (those go through the
+  // kernel driver and wait behind whatever else holds its lock, e.g. a monitoring agent polling the GPU: profiles/r2_host_stalls.md)
+  DBuf<uint32_t> tie_d1, tie_d2, tie_g1, tie_g2, fin_nwl, fin_gll, fin_sij, fin_gij;
+  DBuf<unsigned long long> win_buf, fin_dcount, fin_dall;
+  DBuf<uint8_t> fin_cq;
+  DBuf<double> fin_sv, fin_gv;
   bool prescreen = false;
+  unsigned long long kbits_gen = ~0ull;   // dada2b_ctx::upload_gen the k-mer tables were built for
   int nown = 0;
   bool fallback_only = false;          // DADA2B_FALLBACK (test switch): general kernels only
   bool two_phase = false;              // bound pass first, exact lambda for the survivors only (plain gap costs)
@@ -591,7 +620,7 @@ void Run::tail_sync_caps() {
     np.alloc(st.cs_cap);
     if (cs_count && t_prev.p) CK(cudaMemcpyAsync(np.p, t_prev.p, cs_count * 4, cudaMemcpyDeviceToDevice, s));
     sync();
-    std::swap(t_prev.p, np.p); std::swap(t_prev.n, np.n); std::swap(t_prev.cap, np.cap);
+    t_prev.swap(np);
   }
   const size_t stride = 2 * cl_cap + 4;
   if (t_delta.n < (size_t)MAX_PASS * stride) { t_delta.alloc((size_t)MAX_PASS * stride); t_delta.zero(s); }   // cleared every round by k_tail_link
@@ -614,11 +643,7 @@ void Run::ensure_cluster_cap(size_t n) {
     CK(cudaMemcpyAsync(k2.p, cl_check_locks.p, cl_cap, cudaMemcpyDeviceToDevice, s));
   }
   sync();
-  std::swap(cl_reads.p, r2.p); std::swap(cl_reads.n, r2.n);
-  std::swap(cl_reads_next.p, rn2.p); std::swap(cl_reads_next.n, rn2.n);
-  std::swap(cl_center.p, c2.p); std::swap(cl_center.n, c2.n);
-  std::swap(cl_update_e.p, u2.p); std::swap(cl_update_e.n, u2.n);
-  std::swap(cl_check_locks.p, k2.p); std::swap(cl_check_locks.n, k2.n);
+  cl_reads.swap(r2); cl_reads_next.swap(rn2); cl_center.swap(c2); cl_update_e.swap(u2); cl_check_locks.swap(k2);
   cl_cap = nc;
   st.cl_reads = cl_reads.p; st.cl_reads_next = cl_reads_next.p; st.cl_center = cl_center.p;
   st.cl_update_e = cl_update_e.p; st.cl_check_locks = cl_check_locks.p;
@@ -640,10 +665,7 @@ void Run::ensure_cs_cap(unsigned long long need) {
     CK(cudaMemcpyAsync(l.p, cs_lambda.p, cs_count * 8, cudaMemcpyDeviceToDevice, s));
   }
   sync();
-  std::swap(cs_index.p, a.p); std::swap(cs_index.n, a.n);
-  std::swap(cs_i.p, b.p); std::swap(cs_i.n, b.n);
-  std::swap(cs_ham.p, c.p); std::swap(cs_ham.n, c.n);
-  std::swap(cs_lambda.p, l.p); std::swap(cs_lambda.n, l.n);
+  cs_index.swap(a); cs_i.swap(b); cs_ham.swap(c); cs_lambda.swap(l);
   st.cs_index = cs_index.p; st.cs_i = cs_i.p; st.cs_ham = cs_ham.p; st.cs_lambda = cs_lambda.p; st.cs_cap = nc;
 }
 
@@ -677,7 +699,10 @@ void Run::alloc_state() {
     nown = (nraw - cx->rank + cx->world - 1) / cx->world;
     kbits.alloc((size_t)nown * 32 + 32); kmeta.alloc(nown); krep.alloc((size_t)nown * 48 + 64); cand_list.alloc(nown + 32); cand_ms.alloc(nown + 32);
     old_list.alloc(nown + 32); cand_ctr.alloc(2);
-    launch_kmer_bits(in, cx->rank, cx->world, nown, kbits.p, kmeta.p, krep.p, cx->num_sms, s);
+    if (kbits_gen != cx->upload_gen) {       // the bitmaps and repeat lists depend on the sequences only: kept across the runs of a resident sample
+      launch_kmer_bits(in, cx->rank, cx->world, nown, kbits.p, kmeta.p, krep.p, cx->num_sms, s);
+      kbits_gen = cx->upload_gen;
+    }
   }
   if (const char *e = getenv("DADA2B_NP")) NP = std::max(1, std::min(MAX_PASS, atoi(e)));      // tuning / test override
   fused_tail = getenv("DADA2B_SPLIT_TAIL") == nullptr;   // test switch: the one-kernel-per-step tail of dd_round.cu (capacity fallback beyond 32 k clusters)
@@ -795,6 +820,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       // pass 1: scores + substitution counts only; lambda <= S_r * rho_r^nsubs decides which pairs can pass the store rule
       FwdArgs fbnd = f;
       fbnd.raw_S = raw_S.p; fbnd.raw_rho = raw_rho.p; fbnd.surv_list = surv_list.p; fbnd.surv_count = st.ctr + CTR_SURV;
+      if (!fallback_only && !getenv("DADA2B_NO_DIAG_SPLIT")) { fbnd.gl_out = st.gl_list; fbnd.gl_count = st.ctr + CTR_GL; }   // diagonal-path survivors -> k_gapless_loop
       CK(cudaMemsetAsync(ctr.p + CTR_SURV, 0, 8, s));
       CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
       // thread-per-pair row kernel (dd_nwrow.cu) for raws as long as the centre; the others come back in uneq_list
@@ -1092,7 +1118,7 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
       if (rep[q].ctr[CTR_NTIE_PR] && rep[q].ctr[CTR_PMIN_PR] == R.ctr[CTR_PMIN_PR] && rep[q].ctr[CTR_RMAX_PR] == R.ctr[CTR_RMAX_PR]) np[q] = rep[q].ctr[CTR_NTIE_PR];
       maxn = std::max(maxn, std::max(na[q], np[q]));
     }
-    DBuf<uint32_t> d1, d2, g1, g2;
+    DBuf<uint32_t> &d1 = tie_d1, &d2 = tie_d2, &g1 = tie_g1, &g2 = tie_g2;       // members: no cudaMalloc / cudaFree in a steady-state pass
     d1.alloc(maxn); d2.alloc(maxn); g1.alloc(maxn * W); g2.alloc(maxn * W);
     unsigned long long gl[6] = {R.ctr[CTR_PMIN], R.ctr[CTR_RMAX], 0ull, R.ctr[CTR_PMIN_PR], R.ctr[CTR_RMAX_PR], 0ull};
     static_assert(CTR_RMAX == CTR_PMIN + 1 && CTR_NTIE == CTR_PMIN + 2 && CTR_PMIN_PR == CTR_PMIN + 3 && CTR_NTIE_PR == CTR_PMIN + 5, "counter layout");
@@ -1112,7 +1138,7 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
     tr = big.data(); trp = bigp.data();
   } else if (nt > TIE_MAX || ntp > TIE_MAX) {                          // pathological tie set: fetch all of it
     const unsigned cap = (unsigned)std::max(nt, ntp);
-    DBuf<uint32_t> d1, d2; d1.alloc(cap); d2.alloc(cap);
+    DBuf<uint32_t> &d1 = tie_d1, &d2 = tie_d2; d1.alloc(cap); d2.alloc(cap);
     unsigned long long z[2] = {0ull, 0ull};
     h2d(ctr.p + CTR_NTIE, &z[0], 8); h2d(ctr.p + CTR_NTIE_PR, &z[1], 8);
     BudParams bp{o->min_fold, o->min_hamming, o->min_abund};
@@ -1166,7 +1192,7 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
   for (unsigned long long k = 0; k < std::min<unsigned long long>(ntp, TIE_MAX) && !have; k++)
     if (R.tiep_r[k] == r && type == 'P') { lam = R.tiep_lam[k]; ham = R.tiep_ham[k]; have = true; }
   if (!have && owner) {            // only the winner's owner holds its comparison: sum all-reduce of (lambda bits, hamming) with zeros elsewhere
-    DBuf<unsigned long long> w2; w2.alloc(2); w2.zero(s);
+    DBuf<unsigned long long> &w2 = win_buf; w2.alloc(2); w2.zero(s);
     if ((int)(r % (uint32_t)cx->world) == cx->rank) {
       CK(cudaMemcpyAsync(w2.p, comp_lambda.p + r, 8, cudaMemcpyDeviceToDevice, s));
       CK(cudaMemcpyAsync(w2.p + 1, comp_ham.p + r, 4, cudaMemcpyDeviceToDevice, s));
@@ -1273,7 +1299,7 @@ void Run::finish(dada2b_out *out) {
     h2d(pair_centre.p, pc.data(), npair * 4);
     h2d(pair_raw.p, pr.data(), npair * 4);
     if (cx->qual_sharded) {        // the birth subs read the quality row of every centre: owners contribute theirs, one byte-sum all-reduce
-      DBuf<uint8_t> cq; cq.alloc((size_t)npair * in.QS);
+      DBuf<uint8_t> &cq = fin_cq; cq.alloc((size_t)npair * in.QS);
       launch_qrows_gather(in.qual, in.QS, pair_raw.p, (int)npair, cx->rank, cx->world, cq.p, s);
       NC(g_nccl.AllReduce(cq.p, cq.p, (size_t)npair * in.QS, ncclUint8, ncclSum, cx->comm, s));
       launch_qrows_scatter(in.qual, in.QS, pair_raw.p, (int)npair, 0, 1, cq.p, s);
@@ -1281,7 +1307,7 @@ void Run::finish(dada2b_out *out) {
     }
     b_nsubs.alloc(npair); b_lambda.alloc(npair); b_pos.alloc((size_t)npair * bcap); b_nt0.alloc((size_t)npair * bcap);
     b_nt1.alloc((size_t)npair * bcap); b_q1.alloc((size_t)npair * bcap);
-    DBuf<uint32_t> nwl, gll; nwl.alloc(npair); gll.alloc(npair);
+    DBuf<uint32_t> &nwl = fin_nwl, &gll = fin_gll; nwl.alloc(npair); gll.alloc(npair);
     CK(cudaMemsetAsync(ctr.p + CTR_NW, 0, 2 * 8, s));
     ClassifyArgs ca{};
     ca.in = in; ca.P = P; ca.P.kdist_cutoff = 1.0; ca.mode = 1; ca.pair_centre = pair_centre.p; ca.pair_raw = pair_raw.p;
@@ -1318,7 +1344,7 @@ void Run::finish(dada2b_out *out) {
     launch_center_cluster(center_cluster.p, st.cl_center, (int)nclust, s);
     unsigned cap = std::max<unsigned>(4096, nclust * 8);
     std::vector<uint32_t> tij; std::vector<double> tv; unsigned long long cnt = 0;
-    DBuf<unsigned long long> dcount; dcount.alloc(1);
+    DBuf<unsigned long long> &dcount = fin_dcount; dcount.alloc(1);
     for (;;) {
       trip_ij.alloc((size_t)cap * 2); trip_v.alloc(cap); dcount.zero(s);
       if (owner) launch_posthoc_owned(st, nraw, cs_count, center_cluster.p, trip_ij.p, trip_v.p, cap, dcount.p, cx->rank, cx->world, s);
@@ -1330,14 +1356,14 @@ void Run::finish(dada2b_out *out) {
     }
     if (owner) {       // every rank found the triples of the centres it owns: exchange them (counts first, then padded payloads)
       const int W = cx->world;
-      DBuf<unsigned long long> dall; dall.alloc(W);
+      DBuf<unsigned long long> &dall = fin_dall; dall.alloc(W);
       NC(g_nccl.AllGather(dcount.p, dall.p, 1, ncclUint64, cx->comm, s));
       std::vector<unsigned long long> cq(W);
       d2h(cq.data(), dall.p, (size_t)W * 8);
       sync();
       unsigned long long maxc = 1, tot = 0;
       for (int q = 0; q < W; q++) { maxc = std::max(maxc, cq[q]); tot += cq[q]; }
-      DBuf<uint32_t> sij, gij; DBuf<double> sv, gv;
+      DBuf<uint32_t> &sij = fin_sij, &gij = fin_gij; DBuf<double> &sv = fin_sv, &gv = fin_gv;
       sij.alloc((size_t)maxc * 2); sv.alloc((size_t)maxc); sij.zero(s); sv.zero(s);
       if (cnt) {
         CK(cudaMemcpyAsync(sij.p, trip_ij.p, cnt * 8, cudaMemcpyDeviceToDevice, s));
@@ -1472,6 +1498,7 @@ void Run::finish(dada2b_out *out) {
 dada2b_out *do_run(dada2b_ctx *cx, const double *err_cm, int Q, const dada2b_opts *o) {
   const double t0 = now_ms();
   g_t0 = t0;
+  g_watch.last_end = 0;
   CK(cudaSetDevice(cx->device));
   if (Q < 1) throw Err{"Error matrix must have 16 rows."};
   if (cx->bad_nt) throw Err{o->use_kmers ? "Unexpected nucleotide." : "Non-ACGT sequences in compute_lambda."};
@@ -1753,14 +1780,14 @@ int dada2b_nccl_unique_id(char id[DADA2B_NCCL_ID_BYTES], char errbuf[DADA2B_ERRL
 int dada2b_comm_init(dada2b_ctx *ctx, int32_t rank, int32_t world, const char id[DADA2B_NCCL_ID_BYTES], char errbuf[DADA2B_ERRLEN]) {
   try {
     if (world < 1 || rank < 0 || rank >= world) throw Err{"dada2b: bad rank/world"};
-    if (world == 1) { ctx->rank = 0; ctx->world = 1; return 0; }
+    if (world == 1) { ctx->rank = 0; ctx->world = 1; ctx->upload_gen++; return 0; }
     std::string why;
     if (!g_nccl.load(why)) throw Err{why};
     CK(cudaSetDevice(ctx->device));
     ncclUniqueId u;
     memcpy(&u, id, sizeof u);
     NC(g_nccl.CommInitRank(&ctx->comm, world, u, rank));
-    ctx->rank = rank; ctx->world = world;
+    ctx->rank = rank; ctx->world = world; ctx->upload_gen++;      // the owned rows changed
     return 0;
   } catch (Err &e) { snprintf(errbuf, DADA2B_ERRLEN, "%s", e.msg.c_str()); return 1; }
 }

@@ -54,7 +54,8 @@ enum RowMode : int { ROW_BOUND = 0, ROW_FINAL = 1, ROW_EXACT = 2 };
 
 // MODE ROW_BOUND  (loop, pass 1 of the two-phase scheme): substitution count of the traced path for every
 //                 job, then lambda <= S_r * rho_r^nsubs decides whether the pair can pass the store rule (cluster.cpp:192);
-//                 survivors are listed for the exact pass.
+//                 survivors whose path leaves the main diagonal are listed for the exact pass, the others (every main-diagonal
+//                 cell took the diagonal move strictly: the traced path IS the gapless alignment) for k_gapless_loop.
 // MODE ROW_EXACT  (loop): the moves of every row go to a per-thread scratch column, the thread walks its path back
 //                 (nwalign_endsfree.cpp:169-188), notes the substituted raw positions (al2subs) and multiplies lambda in
 //                 raw-position order (compute_lambda_ts, pval.cpp:190-193: bit-identical), then applies the store rule
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(128) k_nwrow(RowArgs ra) {
         int mB;
         if (i > B && i <= L - B) mB = nw_row<B, false, MODE == ROW_EXACT>(S, mm, c, c.cL, -1, 0, -1, mv);
         else mB = nw_row<B, true, MODE == ROW_EXACT>(S, mm, c, i == L ? c.cL0 : c.cL, B - i, pinval, L - i + B, mv);
-        if (MODE == ROW_FINAL) gacc |= (uint32_t)mB;          // prec of the main-diagonal cell: non-zero = the path leaves the diagonal here
+        if (MODE != ROW_EXACT) gacc |= (uint32_t)mB;          // prec of the main-diagonal cell: non-zero = the path leaves the diagonal here
         if (MODE == ROW_EXACT) {
 #pragma unroll
           for (int w = 0; w < NWW; w++) ra.mv_scratch[((size_t)(i - 1) * NWW + w) * T + tid] = mv[w];
@@ -162,7 +163,11 @@ __global__ void __launch_bounds__(128) k_nwrow(RowArgs ra) {
         const double bound = a.raw_S[r] * pow(a.raw_rho[r], (double)ns) * (double)a.total_reads * (1.0 + 1e-9);
         survive = !(bound <= a.st.E_minmax[r]) || bound < 1e-280;     // near underflow the fp product is not a safe bound: keep
       }
-      warp_append(survive, r, a.surv_list, a.surv_count);
+      // a survivor whose traced path is the pure diagonal is the gapless alignment (same columns, same lambda): it joins the
+      // gapless jobs of this round (k_gapless_loop) instead of the exact pass, which then only records moves for real gaps
+      const bool diag = survive && !gapped && a.gl_out != nullptr;
+      warp_append(diag, r, a.gl_out, a.gl_count);
+      warp_append(survive && !diag, r, a.surv_list, a.surv_count);
     } else if (MODE == ROW_FINAL) {
       if (act) a.st.nsubs_final[r] = (uint32_t)ns;
       warp_append(act && !gapped, r, a.gl_out, a.gl_count);

@@ -48,7 +48,8 @@ def main():
     os.environ.pop("DADA2B_BIMFWD", None)
     try:
         from oracle import ref, port
-        ncores = os.cpu_count() or 1
+        from bench import host_cpus
+        ncores = host_cpus()
         if ref.available():
             ref.set_threads(ncores)
             dts = []
