@@ -939,7 +939,11 @@ void Run::sync_report_owner() {
   for (int q = 0; q < W && last >= 0; q++) maxM = std::max(maxM, rep[q].pinfo[last + 1]);
   uint32_t gp[MAX_PASS + 2] = {0};
   if (maxM) {
-    d_moves_all.alloc((size_t)W * maxM * 2); h_moves_all.alloc((size_t)W * maxM * 2);
+    if ((size_t)W * maxM * 2 > d_moves_all.cap || !d_moves_all.p) {     // grown in powers of two and kept across runs: allocation calls stall behind the kernel driver's lock
+      size_t m = 65536;
+      while (m < maxM) m *= 2;
+      d_moves_all.alloc((size_t)W * m * 2); h_moves_all.alloc((size_t)W * m * 2);
+    }
     NC(g_nccl.AllGather(d_moves.p, d_moves_all.p, (size_t)maxM * 8, ncclChar, cx->comm, s));
     d2h_pinned(h_moves_all.p, d_moves_all.p, (size_t)W * maxM * 8);
     sync();
@@ -1402,16 +1406,18 @@ void Run::finish(dada2b_out *out) {
     launch_calc_pA_vec(pa_reads.p, pa_E.p, pa_prior.p, pa_out.p, (int)nclust, s);
     d2h(cpval.data(), pa_out.p, nclust * 8);
   }
-  // per-raw results
-  std::vector<double> hp(nraw); std::vector<uint8_t> hcorrect(nraw); std::vector<uint32_t> hns(nraw);
+  // per-raw results: staged in the pinned arena and written straight into the output arrays by several threads
   std::vector<int> htrans((size_t)16 * ncol); std::vector<unsigned long long> hsum((size_t)nclust * maxlen), hcnt((size_t)nclust * maxlen);
-  d2h(hp.data(), p.p, (size_t)nraw * 8);
-  d2h(hcorrect.data(), correct.p, nraw);
-  d2h(hns.data(), nsubs_final.p, (size_t)nraw * 4);
   d2h(htrans.data(), trans.p, htrans.size() * 4);
   d2h(hsum.data(), cq_sum.p, hsum.size() * 8);
   d2h(hcnt.data(), cq_cnt.p, hcnt.size() * 8);
-  read_ctr();
+  sync();                                         // the arena is empty from here on
+  if ((size_t)nraw * 13 + 256 > arena.cap) arena.alloc((size_t)nraw * 13 + 256);
+  auto stage = [&](const void *d, size_t n) { d2h_bytes += (long long)n; uint8_t *q = arena_get(n); CK(cudaMemcpyAsync(q, d, n, cudaMemcpyDeviceToHost, s)); return q; };
+  const double *hp = (const double *)stage(p.p, (size_t)nraw * 8);
+  const uint32_t *hns = (const uint32_t *)stage(nsubs_final.p, (size_t)nraw * 4);
+  const uint8_t *hcorrect = stage(correct.p, nraw);
+  read_ctr();                                     // synchronises; nothing below touches the arena
   check_dev_error();
 
   out->nclust = nclust; out->nraw = nraw; out->maxlen = maxlen; out->Q = ncol;
@@ -1422,16 +1428,30 @@ void Run::finish(dada2b_out *out) {
   std::string cseq; std::vector<int64_t> coff(1, 0);
   std::vector<int32_t> ab(nclust, 0), n0(nclust, 0), n1(nclust, 0), nunq(nclust, 0), bfrom(nclust), bham(nclust);
   std::vector<double> bpval(nclust), bfold(nclust), bqave(nclust);
+  std::vector<uint32_t> mxr(nclust, 0);            // largest abundance among a cluster's members (correct or not)
+  {
+    std::mutex mu;
+    parallel_for((size_t)nraw, [&](size_t lo, size_t hi) {       // integer tallies: order-independent
+      std::vector<int32_t> a(nclust, 0), z0(nclust, 0), z1(nclust, 0), nu(nclust, 0);
+      std::vector<uint32_t> mx(nclust, 0);
+      for (size_t r = lo; r < hi; r++) {
+        const uint32_t i = cluster_of_h[r], rd = cx->reads[r];
+        mx[i] = std::max(mx[i], rd);
+        if (hcorrect[r]) {
+          a[i] += (int32_t)rd; nu[i]++;
+          if (hns[r] == 0) z0[i] += (int32_t)rd;
+          if (hns[r] == 1) z1[i] += (int32_t)rd;
+        }
+      }
+      std::lock_guard<std::mutex> lk(mu);
+      for (uint32_t i = 0; i < nclust; i++) { ab[i] += a[i]; n0[i] += z0[i]; n1[i] += z1[i]; nunq[i] += nu[i]; mxr[i] = std::max(mxr[i], mx[i]); }
+    });
+  }
   for (uint32_t i = 0; i < nclust; i++) {
-    uint32_t max_reads = 0; long max_raw = -1;
-    for (uint32_t r : members[i]) if (cx->reads[r] > max_reads) { max_raw = r; max_reads = cx->reads[r]; }
+    long max_raw = -1;                             // error.cpp:20-27: the first member (Bi::raw order) holding the largest abundance
+    if (mxr[i] > 0) for (uint32_t r : members[i]) if (cx->reads[r] == mxr[i]) { max_raw = r; break; }
     if (max_raw >= 0) cseq.append(cx->seq_concat.data() + (size_t)cx->seq_off[max_raw], (size_t)cx->len[max_raw]);
     coff.push_back((int64_t)cseq.size());
-    for (uint32_t r : members[i]) if (hcorrect[r]) {
-      ab[i] += (int32_t)cx->reads[r]; nunq[i]++;
-      if (hns[r] == 0) n0[i] += (int32_t)cx->reads[r];
-      if (hns[r] == 1) n1[i] += (int32_t)cx->reads[r];
-    }
     if (i == 0) { bpval[i] = na_real(); bfrom[i] = INT_MIN; bfold[i] = na_real(); bham[i] = INT_MIN; bqave[i] = na_real(); }
     else {
       bfrom[i] = (int32_t)birth[i].from + 1; bpval[i] = birth[i].pval; bfold[i] = birth[i].fold; bham[i] = (int32_t)birth[i].comp_ham;
@@ -1471,9 +1491,12 @@ void Run::finish(dada2b_out *out) {
   }
   out->clusterquals = dupv(cq);
   // ---- $map, $pval (Rmain.cpp:239-279)
-  std::vector<int32_t> map(nraw);
-  for (int r = 0; r < nraw; r++) map[r] = hcorrect[r] ? (int32_t)cluster_of_h[r] + 1 : INT_MIN;
-  out->map = dupv(map); out->pval = dupv(hp);
+  out->map = (int32_t *)malloc(std::max<size_t>(1, nraw) * sizeof(int32_t));
+  out->pval = (double *)malloc(std::max<size_t>(1, nraw) * sizeof(double));
+  parallel_for((size_t)nraw, [&](size_t lo, size_t hi) {
+    for (size_t r = lo; r < hi; r++) out->map[r] = hcorrect[r] ? (int32_t)cluster_of_h[r] + 1 : INT_MIN;
+    memcpy(out->pval + lo, hp + lo, (hi - lo) * sizeof(double));
+  });
   // ---- timing / traffic diagnostics
   CK(cudaEventRecord(ev_end, s));
   CK(cudaEventSynchronize(ev_end));

@@ -56,7 +56,7 @@ __device__ __forceinline__ void lane_step(LaneState<C> &st, const RowConsts &c, 
   const bool on = !GUARD || (act && i >= 1 && i <= L);
   const uint32_t cb = s_cen[GUARD ? min(max(i - 1, 0), L - 1) : i - 1];
   const uint32_t x = st.win ^ (cb * 0x55555555u);
-  const uint32_t mm = (x | (x >> 1)) & 0x55555555u;
+  const uint32_t mm = x | (x >> 1);                    // even bits: mismatch flags (only those are read below)
   int left = __shfl_up_sync(0xffffffffu, st.S[C - 1], 1, G);          // lane g-1 finished this row one step ago
   if (g == 0) left = SENT;
   const int dpin = B - i - g * C, dfree = L - i + B - g * C;            // local slot of column 0 / column L in this row

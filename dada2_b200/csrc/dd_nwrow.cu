@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(128) k_nwrow(RowArgs ra) {
         else cb = s_cen[i - 1];
         const uint32_t cen = cb * 0x55555555u;
 #pragma unroll
-        for (int w = 0; w < NWW; w++) { const uint32_t x = win[w] ^ cen; mm[w] = (x | (x >> 1)) & 0x55555555u; }
+        for (int w = 0; w < NWW; w++) { const uint32_t x = win[w] ^ cen; mm[w] = x | (x >> 1); }   // even bits: mismatch flags (mis_bit reads nothing else; an
+                                                                                                   // `& 0x55555555` here is sunk by the compiler into one LOP3 per cell)
         pinval -= c.matchS;
         int mB;
         if (i > B && i <= L - B) mB = nw_row<B, false, MODE == ROW_EXACT>(S, mm, c, c.cL, -1, 0, -1, mv);

@@ -27,7 +27,7 @@ __host__ __device__ inline RowConsts row_consts(const AlnParams &P) {
   return c;
 }
 
-// mismatch bit of cell d: bit 2*(d % 16) of word d / 16 of the row's mask, as 0 / 1 through the FMA pipe
+// mismatch bit of cell d: bit 2*(d % 16) of word d / 16 of the row's mask (odd bits: don't care), as 0 / 1 through the FMA pipe
 template <int NWW> __device__ __forceinline__ int mis_bit(const uint32_t (&mm)[NWW], int d) {
   return (int)__umulhi(mm[d >> 4] << (31 - 2 * (d & 15)), 2u);
 }
