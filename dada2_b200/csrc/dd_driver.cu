@@ -893,6 +893,10 @@ void Run::launch_round_tail_inner(int first_pass, int npass) {
     }
     tail_last = first_pass + npass - 1;
     BudParams bp{o->min_fold, o->min_hamming, o->min_abund};
+    bp.skip_log = log(o->omegaA / (double)(unsigned)nraw) + 1.0;                       // decide_bud: pA = p * nraw < omegaA
+    bp.skip_log_prior = log(std::max(o->omegaA / (double)(unsigned)nraw, o->omegaP)) + 1.0;   // ... or p < omegaP
+    if (!(bp.skip_log == bp.skip_log)) bp.skip_log = 1e300;                              // non-positive thresholds: no shortcut
+    if (!(bp.skip_log_prior == bp.skip_log_prior)) bp.skip_log_prior = 1e300;
     launch_tail_final(st, in, ts, bp, o->greedy != 0, o->detect_singletons != 0, tail_last, nclust, tail_last == MAX_PASS - 1 ? 2 : 0, s);
     return;
   }

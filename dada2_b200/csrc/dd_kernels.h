@@ -136,7 +136,12 @@ void launch_posthoc_owned(const DevState &st, int nraw, unsigned long long n_ent
                           unsigned cap, unsigned long long *count, int rank, int world, cudaStream_t s);
 
 // per-round control kernels (dd_round.cu)
-struct BudParams { double min_fold; int min_hamming, min_abund; };
+struct BudParams {
+  double min_fold; int min_hamming, min_abund;
+  // k_tail_final: log of the smallest p-value b_bud could still act on, plus a safety margin (raws without / with a prior);
+  // +inf = always evaluate the exact tail
+  double skip_log = 1e300, skip_log_prior = 1e300;
+};
 void launch_round_begin(const DevState &st, int apply, uint32_t r, uint32_t from, uint32_t newi, uint32_t reads_r, cudaStream_t s);
 void launch_shuffle_pass(const DevState &st, const DevIn &in, unsigned long long n_entries_upper, int nclust, int pass, cudaStream_t s);
 void launch_p_update(const DevState &st, const DevIn &in, int greedy, int detect_singletons, int last_pass, cudaStream_t s);

@@ -44,6 +44,7 @@ template <int C> struct LaneState {
   int i;                    // row this lane handles in the current step
   int pinval;               // -(i-1) * match << 16: the ends-free zero of column 0 in biased space
   uint32_t *mvp;            // where the moves of row i go
+  uint32_t gacc;            // OR of the main-diagonal cells' words (prec field in place): non-zero prec = the traced path leaves the diagonal
 };
 
 // One step of one lane: row st.i of its C slots, in place.  CHECKED: boundary rules on (rows near the matrix edges);
@@ -62,7 +63,8 @@ __device__ __forceinline__ void lane_step(LaneState<C> &st, const RowConsts &c, 
   const int dpin = B - i - g * C, dfree = L - i + B - g * C;            // local slot of column 0 / column L in this row
   const int cLrow = (CHECKED && i == L) ? c.cL0 : c.cL;
   const int pin = st.pinval - c.matchS;
-  uint32_t mv = 0;
+  uint32_t mv = 0, mdiag = 0;
+  constexpr int GO = B / C, KO = B % C;                                   // lane / local slot of the main diagonal (slot B)
   int S0 = st.S[0];
   {  // cell 0 first: the lane below needs it as its up input of this very step
     const int diag = S0 + (int)__umulhi(mm << 31, 2u) * c.delta;
@@ -70,6 +72,7 @@ __device__ __forceinline__ void lane_step(LaneState<C> &st, const RowConsts &c, 
     const int cu = (CHECKED && 0 == dfree) ? c.cU0 : c.cU;
     int m = __viaddmax_s32(left, cLrow, __viaddmax_s32(up, cu, diag));
     mv = __funnelshift_r(mv, (uint32_t)m >> 14, 2);
+    if (KO == 0) mdiag = (uint32_t)m;
     m &= NW_CLR;
     if (CHECKED && 0 == dpin) m = pin;
     if (on) S0 = m;
@@ -86,12 +89,14 @@ __device__ __forceinline__ void lane_step(LaneState<C> &st, const RowConsts &c, 
     const int cu = (CHECKED && k == dfree) ? c.cU0 : c.cU;
     int m = __viaddmax_s32(left, cLrow, __viaddmax_s32(up, cu, diag));
     mv = __funnelshift_r(mv, (uint32_t)m >> 14, 2);                       // cell k ends at bits 32 - 2 (C - k)
+    if (k == KO) mdiag = (uint32_t)m;
     m &= NW_CLR;
     if (CHECKED && k == dpin) m = pin;
     if (on) st.S[k] = m;
     left = m;
   }
   if (on) {
+    if (g == GO) st.gacc |= mdiag;
     st.pinval = pin;
     *st.mvp = mv;
     st.mvp += mv_row_stride;
@@ -153,6 +158,7 @@ __global__ void __launch_bounds__(128) k_nwlane(LaneArgs la) {
     st.rw = (st.ridx >= 0 && (st.ridx >> 4) < SW) ? rrow[st.ridx >> 4] : 0u;
     st.rw >>= 2 * (st.ridx & 15);
     st.pinval = 0;
+    st.gacc = 0u;
     st.i = 1 - g;                                       // software pipeline: lane g handles row t - g at step t
     st.mvp = la.mv_scratch + (size_t)g * TG + grp;
     const size_t mrs = (size_t)G * TG;
@@ -174,7 +180,23 @@ __global__ void __launch_bounds__(128) k_nwlane(LaneArgs la) {
       survive = !(bound <= a.st.E_minmax[r]) || bound < 1e-280;
     }
     if (owner && !a.no_cells) cells_lane += cells_pair;
-    if (survive) {
+    if (survive && !(st.gacc & 0xC000u)) {
+      // every main-diagonal cell took the diagonal move strictly: the traced path is the gapless alignment, no walk needed
+      int ham = 0;
+      for (int w = 0; w * 16 < L; w++) {
+        uint32_t x = rrow[w];
+        uint32_t cw = 0;
+        for (int u = 0; u < 16 && w * 16 + u < L; u++) cw |= (uint32_t)s_cen[w * 16 + u] << (2 * u);
+        x ^= cw;
+        uint32_t mis = (x | (x >> 1)) & 0x55555555u;
+        if (L - w * 16 < 16) mis &= (1u << (2 * (L - w * 16))) - 1u;
+        ham += __popc(mis);
+      }
+      const double lam = lambda_diag(rrow, s_cen, a.in.qual + (size_t)r * a.in.QS, L, ncol, a.P.use_quals, s_err, &errflag);
+      if (ham != ns) errflag = ERR_TRACE;       // the forward-carried count and the diagonal's Hamming distance must agree
+      if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;               // pval.cpp:195
+      store_comparison(a, r, lam, ns);
+    } else if (survive) {
       // traceback over the recorded moves, lambda in raw-position order, store rule (dd_nwrow.cuh)
       const int nsub = trace_moves<G, C, 8, true>(la.mv_scratch + grp, (size_t)G * TG, TG, L, B, s_cen, rrow, la.sub_scratch + grp, TG);
       const double lam = lambda_from_subs(rrow, a.in.qual + (size_t)r * a.in.QS, L, ncol, a.P.use_quals, s_err, la.sub_scratch + grp, TG, nsub, &errflag);

@@ -152,6 +152,32 @@ __device__ __forceinline__ double lambda_from_subs(const uint32_t *raw2, const u
   return lam;
 }
 
+// lambda of the gapless alignment of two equally long sequences (the traced path is the main diagonal): position p of the raw against
+// position p of the centre, in raw-position order -- the same product compute_lambda_ts forms from that alignment's subs
+__device__ __forceinline__ double lambda_diag(const uint32_t *raw2, const uint8_t *s_cen, const uint8_t *qrow, int L, int ncol, int use_quals,
+                                              const double *s_err, int *errflag) {
+  double lam = 1.0;
+  uint4 qn = *(const uint4 *)qrow;
+  for (int p0 = 0; p0 < L; p0 += 16) {
+    const uint4 qv = qn;
+    if (p0 + 16 < L) qn = *(const uint4 *)(qrow + p0 + 16);
+    uint32_t bw = raw2[p0 >> 4];
+    const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int p = p0 + u;
+      if (p < L) {
+        const uint32_t b = bw & 3u, cb = s_cen[p];
+        int q = use_quals ? (int)((qq[u >> 2] >> (8 * (u & 3))) & 0xFFu) : 0;
+        if (q > ncol - 1) { *errflag = ERR_QUAL; q = ncol - 1; }
+        lam = lam * s_err[(4u * cb + b) * ncol + q];
+      }
+      bw >>= 2;
+    }
+  }
+  return lam;
+}
+
 // the "selectively store" step of b_compare (cluster.cpp:179-201) for one exact comparison
 __device__ __forceinline__ void store_comparison(const FwdArgs &a, uint32_t r, double lam, int ns) {
   const double emm = a.st.E_minmax[r];

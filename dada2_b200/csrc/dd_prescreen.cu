@@ -152,7 +152,10 @@ __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
   __syncthreads();
   int c_align = 0, c_shroud = 0;
   int k = 0;
-  // one raw per thread; the 13 bytes of per-raw metadata are fetched ONE TILE AHEAD, so that neither their latency nor the tile's is exposed
+  // One raw per thread.  No global load of the loop is waited for in the iteration that issues it: the 13 bytes of per-raw
+  // metadata are requested TWO tiles ahead, and a raw whose presence bound is inconclusive requests its whole repeated-5-mer
+  // list (six independent 16-byte loads) and is only resolved in the NEXT iteration, after that iteration's tile has been
+  // waited for and scanned -- a warp otherwise pays the slowest lane's chain of dependent DRAM round trips on every tile.
   auto fetch_meta = [&](int tile, uint32_t &meta, bool &skip) {
     const int it = tile * PS_TILE + tid;
     const bool valid = tile < ntiles && it < a.nown;
@@ -160,13 +163,58 @@ __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
     meta = valid ? a.kmeta[it] : 0u;
     skip = !valid || (a.greedy && (a.in.reads[r] > a.centre_reads || a.lock[r]));      // cluster.cpp:127-131
   };
-  uint32_t meta_n; bool skip_n;
-  fetch_meta(blockIdx.x, meta_n, skip_n);
+  auto append = [&](bool cand, uint32_t r, uint32_t msv) {
+    const unsigned m = __ballot_sync(0xffffffffu, cand);
+    if (m) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.cand_count, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (cand) { const unsigned long long at = base + __popc(m & ((1u << lane) - 1u)); a.cand_list[at] = r; a.cand_ms[at] = (uint16_t)msv; }
+    }
+  };
+  // the raw of the previous tile that still waits for its exact min-sum: its list (in registers), presence count and denominator
+  bool pend = false;
+  uint32_t pend_r = 0;
+  int pend_pc = 0;
+  double pend_denom = 1.;
+  uint4 L[KREP / 8];
+  auto resolve = [&]() {
+    bool cand = false;
+    uint32_t msv = 0;
+    if (pend) {
+      // exact min-sum: presence bits + what the raw's repeated 5-mers add beyond their presence bit
+      int ms = pend_pc;
+      bool more = true;
+#pragma unroll
+      for (int blk = 0; blk < KREP / 8; blk++) {                              // the list is packed from the front and ends at the first 0xFFFF
+        const uint32_t lw[4] = {L[blk].x, L[blk].y, L[blk].z, L[blk].w};
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const uint32_t ent = (lw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+          if (ent == 0xFFFFu) more = false;
+          if (more) {
+            const uint32_t km = ent & 0x3FFu, cr = (ent >> 10) + 1u;
+            const uint32_t cc = (s_ccnt[km >> 1] >> (16 * (km & 1))) & 0xFFFFu;
+            ms += cc ? (int)min(cr, cc) - 1 : 0;
+          }
+        }
+      }
+      const double kdist = 1. - ((double)(ms & 0xFFFF)) / pend_denom;         // exactly raw_align's kdist (N1: integer min-sum)
+      if (kdist > a.kdist_cutoff) { c_align++; c_shroud++; }
+      else { cand = true; msv = (uint32_t)ms; }
+    }
+    append(cand, pend_r, msv);
+    pend = false;
+  };
+  uint32_t meta_n1, meta_n2; bool skip_n1, skip_n2;
+  fetch_meta(blockIdx.x, meta_n1, skip_n1);
+  fetch_meta(blockIdx.x + gridDim.x, meta_n2, skip_n2);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
     const int stage = k % PS_STAGES;
-    const uint32_t meta = meta_n; const bool skip = skip_n;
+    const uint32_t meta = meta_n1; const bool skip = skip_n1;
+    meta_n1 = meta_n2; skip_n1 = skip_n2;
     const uint32_t r = (uint32_t)(tile * PS_TILE + tid) * (uint32_t)a.world + (uint32_t)a.rank;
-    fetch_meta(tile + gridDim.x, meta_n, skip_n);
+    fetch_meta(tile + 2 * gridDim.x, meta_n2, skip_n2);
     mbar_wait(&s_full[stage], (uint32_t)((k / PS_STAGES) & 1));
     const uint32_t *row = s_dyn + (size_t)stage * PS_TILE * 32 + (size_t)tid * 32;
     int pc = 0;
@@ -177,8 +225,8 @@ __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
       const uint4 cb = *(const uint4 *)(s_cen + 4 * ch);
       pc += __popc(v.x & cb.x) + __popc(v.y & cb.y) + __popc(v.z & cb.z) + __popc(v.w & cb.w);
     }
+    resolve();                                                // the previous tile's inconclusive raw: its list has landed by now
     bool cand = false;
-    uint32_t msv = 0xFFFFu;
     if (!skip) {
       const int len2 = (int)(meta & 0xFFFFu), U = pc + (int)((meta >> 16) & 0x3FFFu);
       const double denom = (double)(min(len1, len2) - KMER) + 1.;
@@ -186,39 +234,17 @@ __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
       if (kd_lb > a.kdist_cutoff) { c_align++; c_shroud++; }
       else if (meta & META_OVF) cand = true;                                // list overflow: the warp-per-pair screen decides
       else {
-        // exact min-sum: presence bits + what the raw's repeated 5-mers add beyond their presence bit
-        int ms = pc;
         const uint4 *lp = (const uint4 *)(a.krep + (size_t)(tile * PS_TILE + tid) * KREP);
-        bool more = true;
-        for (int blk = 0; blk < KREP / 8 && more; blk++) {                    // the list is packed from the front and ends at the first 0xFFFF
-          const uint4 l4 = lp[blk];
-          const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-          for (int e = 0; e < 8; e++) {
-            const uint32_t ent = (lw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
-            if (ent == 0xFFFFu) more = false;
-            else {
-              const uint32_t km = ent & 0x3FFu, cr = (ent >> 10) + 1u;
-              const uint32_t cc = (s_ccnt[km >> 1] >> (16 * (km & 1))) & 0xFFFFu;
-              ms += cc ? (int)min(cr, cc) - 1 : 0;
-            }
-          }
-        }
-        const double kdist = 1. - ((double)(ms & 0xFFFF)) / denom;          // exactly raw_align's kdist (N1: integer min-sum)
-        if (kdist > a.kdist_cutoff) { c_align++; c_shroud++; }
-        else { cand = true; msv = (uint32_t)ms; }
+        for (int blk = 0; blk < KREP / 8; blk++) L[blk] = lp[blk];
+        pend = true; pend_r = r; pend_pc = pc; pend_denom = denom;
       }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, cand);
-    if (m) {
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(a.cand_count, (unsigned long long)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (cand) { const unsigned long long at = base + __popc(m & ((1u << lane) - 1u)); a.cand_list[at] = r; a.cand_ms[at] = (uint16_t)msv; }
-    }
+    append(cand, r, 0xFFFFu);
     __syncthreads();                                          // every thread is done with this stage
     if (tid == 0) { const int t = tile + PS_STAGES * gridDim.x; if (t < ntiles) issue(t, stage); }
   }
+  resolve();
 #pragma unroll
   for (int o = 16; o; o >>= 1) { c_align += __shfl_xor_sync(0xffffffffu, c_align, o); c_shroud += __shfl_xor_sync(0xffffffffu, c_shroud, o); }
   if (lane == 0 && c_align) { atomicAdd(&a.ctr[CTR_ALIGN], (unsigned long long)c_align); atomicAdd(&a.ctr[CTR_SHROUD], (unsigned long long)c_shroud); }

@@ -63,33 +63,58 @@ __device__ __forceinline__ void stage_reads(const DevState &st, const TailState 
   __syncthreads();
 }
 
+// TAIL_RPT raws per thread, their chains walked in lockstep: the walk is a chain of dependent DRAM round trips (head -> entry ->
+// previous entry ...), so what one thread can overlap is what counts (one raw per thread: 3.3 waves of 2048 threads per SM, each
+// as long as the chain; profiles/r2_tail_screen_lane_metrics.txt: 80 % occupancy, 21 % issue, long-scoreboard bound)
+constexpr int TAIL_RPT = 4;
 __global__ void k_tail_pass(DevState st, DevIn in, TailState ts, int pass, int nclust) {
   extern __shared__ uint32_t s_reads[];
   if (pass > 0 && row_nmove(ts, pass - 1) == 0) return;             // previous pass moved nothing (anywhere): b_shuffle2 returned false
   stage_reads(st, ts, pass, nclust, s_reads);
-  const long long rl = tail_raw(ts, blockIdx.x * (long long)blockDim.x + threadIdx.x);
-  if (rl >= in.nraw) return;
-  const int r = (int)rl;
-  double best_e = -1.0;
-  uint32_t best_x = CHAIN_END;
-  for (uint32_t x = ts.head[r]; x != CHAIN_END; x = ts.cs_prev[x]) {   // clusters descending: '>=' keeps the lowest index among ties
-    const double e = st.cs_lambda[x] * (double)s_reads[st.cs_i[x]];
-    if (e >= best_e) { best_e = e; best_x = x; }
+  int r[TAIL_RPT];
+  uint32_t x[TAIL_RPT], best_x[TAIL_RPT];
+  double best_e[TAIL_RPT];
+#pragma unroll
+  for (int u = 0; u < TAIL_RPT; u++) {
+    const long long rl = tail_raw(ts, ((long long)blockIdx.x * TAIL_RPT + u) * blockDim.x + threadIdx.x);
+    r[u] = rl < in.nraw ? (int)rl : -1;
+    best_e[u] = -1.0; best_x[u] = CHAIN_END;
   }
-  if (best_x == CHAIN_END) return;
-  const uint32_t to = st.cs_i[best_x], from = st.cluster_of[r];
-  if (to != from && !st.is_center[r]) {                                 // cluster.cpp:248-260
-    const unsigned long long s = atomicAdd(&st.ctr[CTR_NMOVE], 1ull);
-    if (s < st.move_cap) { st.moves[2 * s] = (uint32_t)r; st.moves[2 * s + 1] = to; }
-    atomicAdd(&ts.nmove_pass[pass], 1u);                                // this rank's moves of the pass (splits the local move list)
-    atomicAdd(&row_nmove(ts, pass), 1);                                 // all ranks' after the all-reduce
-    st.cluster_of[r] = to;
-    st.comp_lambda[r] = st.cs_lambda[best_x];
-    st.comp_ham[r] = st.cs_ham[best_x];
-    const int rd = (int)in.reads[r];
-    atomicAdd(&row_delta(ts, pass, from), -rd);
-    atomicAdd(&row_delta(ts, pass, to), rd);
-    row_touched(ts, pass, from) = 1; row_touched(ts, pass, to) = 1;     // -> cl_update_e (bi_pop_raw / bi_add_raw set update_e)
+#pragma unroll
+  for (int u = 0; u < TAIL_RPT; u++) x[u] = r[u] >= 0 ? ts.head[r[u]] : CHAIN_END;
+  for (;;) {                                                            // clusters descending: '>=' keeps the lowest index among ties
+    bool any = false;
+    double lam[TAIL_RPT]; uint32_t ci[TAIL_RPT], nx[TAIL_RPT];
+#pragma unroll
+    for (int u = 0; u < TAIL_RPT; u++)
+      if (x[u] != CHAIN_END) { lam[u] = st.cs_lambda[x[u]]; ci[u] = st.cs_i[x[u]]; nx[u] = ts.cs_prev[x[u]]; any = true; }
+    if (!any) break;
+#pragma unroll
+    for (int u = 0; u < TAIL_RPT; u++)
+      if (x[u] != CHAIN_END) {
+        const double e = lam[u] * (double)s_reads[ci[u]];
+        if (e >= best_e[u]) { best_e[u] = e; best_x[u] = x[u]; }
+        x[u] = nx[u];
+      }
+  }
+#pragma unroll
+  for (int u = 0; u < TAIL_RPT; u++) {
+    if (best_x[u] == CHAIN_END) continue;
+    const int rr = r[u];
+    const uint32_t to = st.cs_i[best_x[u]], from = st.cluster_of[rr];
+    if (to != from && !st.is_center[rr]) {                              // cluster.cpp:248-260
+      const unsigned long long s = atomicAdd(&st.ctr[CTR_NMOVE], 1ull);
+      if (s < st.move_cap) { st.moves[2 * s] = (uint32_t)rr; st.moves[2 * s + 1] = to; }
+      atomicAdd(&ts.nmove_pass[pass], 1u);                              // this rank's moves of the pass (splits the local move list)
+      atomicAdd(&row_nmove(ts, pass), 1);                               // all ranks' after the all-reduce
+      st.cluster_of[rr] = to;
+      st.comp_lambda[rr] = st.cs_lambda[best_x[u]];
+      st.comp_ham[rr] = st.cs_ham[best_x[u]];
+      const int rd = (int)in.reads[rr];
+      atomicAdd(&row_delta(ts, pass, from), -rd);
+      atomicAdd(&row_delta(ts, pass, to), rd);
+      row_touched(ts, pass, from) = 1; row_touched(ts, pass, to) = 1;   // -> cl_update_e (bi_pop_raw / bi_add_raw set update_e)
+    }
   }
 }
 
@@ -141,7 +166,16 @@ __global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, 
       if (rd == 1 && !prior && !detect_singletons) pval = 1.;
       else if (ham == 0) pval = 1.;
       else if (lambda == 0) pval = 0.;
-      else pval = calc_pA((int)rd, lambda * (double)s_reads[ci], prior || detect_singletons);
+      else {
+        // b_bud only ever asks whether p * nraw < omegaA (or p < omegaP for a raw with a prior), cluster.cpp:313-316, and the
+        // p-values of the output are recomputed after the loop (k_final_p).  p >= P(X = reads) = exp(-E) E^reads / reads!  for
+        // either normalisation of calc_pA: when that lower bound is already above the threshold (by a factor e), the raw cannot
+        // be budded whatever its exact p is, and the bound is stored in its place -- no incomplete-gamma evaluation.
+        const double E = lambda * (double)s_reads[ci];
+        const double lg = -E + (double)rd * log(E) - lgamma((double)rd + 1.0);
+        if (lg >= (prior ? bp.skip_log_prior : bp.skip_log)) pval = exp(lg);
+        else pval = calc_pA((int)rd, E, prior || detect_singletons);
+      }
       st.p[r] = pval;
     }
     if (greedy && st.cl_check_locks[ci]) {                             // pval.cpp:29-38
@@ -304,7 +338,7 @@ void launch_tail_pass(const DevState &st, const DevIn &in, const TailState &ts, 
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_tail_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX); attr_set = true; }
   count_launch(1);
-  k_tail_pass<<<tail_grid_owned(in, ts), TAIL_BLOCK, (size_t)nclust * 4, s>>>(st, in, ts, pass, nclust);
+  k_tail_pass<<<(tail_grid_owned(in, ts) + TAIL_RPT - 1) / TAIL_RPT, TAIL_BLOCK, (size_t)nclust * 4, s>>>(st, in, ts, pass, nclust);
 }
 void launch_tail_final(const DevState &st, const DevIn &in, const TailState &ts, const BudParams &bp, int greedy, int detect_singletons,
                        int last_pass, int nclust, int mode, cudaStream_t s) {

@@ -1,6 +1,6 @@
 import sys, time, os
 sys.path.insert(0,'.')
-import faulthandler; faulthandler.dump_traceback_later(100, exit=True)
+import faulthandler; faulthandler.dump_traceback_later(int(os.environ.get("RUN_ONCE_WATCHDOG", "400")), exit=True)
 import numpy as np
 from tools import synth
 from tests import cases
