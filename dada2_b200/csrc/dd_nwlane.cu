@@ -180,22 +180,41 @@ __global__ void __launch_bounds__(128) k_nwlane(LaneArgs la) {
       survive = !(bound <= a.st.E_minmax[r]) || bound < 1e-280;
     }
     if (owner && !a.no_cells) cells_lane += cells_pair;
-    if (survive && !(st.gacc & 0xC000u)) {
-      // every main-diagonal cell took the diagonal move strictly: the traced path is the gapless alignment, no walk needed
-      int ham = 0;
-      for (int w = 0; w * 16 < L; w++) {
-        uint32_t x = rrow[w];
-        uint32_t cw = 0;
-        for (int u = 0; u < 16 && w * 16 + u < L; u++) cw |= (uint32_t)s_cen[w * 16 + u] << (2 * u);
-        x ^= cw;
-        uint32_t mis = (x | (x >> 1)) & 0x55555555u;
-        if (L - w * 16 < 16) mis &= (1u << (2 * (L - w * 16))) - 1u;
-        ham += __popc(mis);
+    // Every main-diagonal cell took the diagonal move strictly: the traced path is the gapless alignment, no walk
+    // needed -- and its lambda is formed by the whole lane group: lane g looks up the factor of position p0 + g (bases, quality,
+    // table: ~20 instructions), the group then multiplies the G factors IN POSITION ORDER through shuffles, so the owner's chain
+    // is one DMUL per position instead of the ~22 dependent instructions of a one-lane loop (x * 1.0 pads the tail exactly).
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const int gbase = lane & ~(G - 1);
+    const int diag_grp = __shfl_sync(gmask, (int)(survive && !(st.gacc & 0xC000u)), gbase + GO);
+    if (diag_grp) {
+      const uint32_t rg = __shfl_sync(gmask, r, gbase + GO);
+      const uint32_t *rr2 = a.in.seq2 + (size_t)rg * SW;
+      const uint8_t *qrow = a.in.qual + (size_t)rg * a.in.QS;
+      auto factor = [&](int p, int &mis) -> double {
+        if (p >= L) return 1.0;
+        const uint32_t b = (rr2[p >> 4] >> (2 * (p & 15))) & 3u, cb = s_cen[p];
+        int q = a.P.use_quals ? (int)qrow[p] : 0;
+        if (q > ncol - 1) { errflag = ERR_QUAL; q = ncol - 1; }
+        mis += (b != cb) ? 1 : 0;
+        return s_err[(4u * cb + b) * ncol + q];                               // cb == b: 5 b, the self transition (pval.cpp:158-193)
+      };
+      double lam = 1.0;
+      int mis = 0;
+      double f = factor(g, mis);
+      for (int p0 = 0; p0 < L; p0 += G) {
+        const double fn = factor(p0 + G + g, mis);                           // next block's factor: its loads overlap this block's products
+#pragma unroll
+        for (int k = 0; k < G; k++) lam = lam * __shfl_sync(gmask, f, gbase + k);
+        f = fn;
       }
-      const double lam = lambda_diag(rrow, s_cen, a.in.qual + (size_t)r * a.in.QS, L, ncol, a.P.use_quals, s_err, &errflag);
-      if (ham != ns) errflag = ERR_TRACE;       // the forward-carried count and the diagonal's Hamming distance must agree
-      if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;               // pval.cpp:195
-      store_comparison(a, r, lam, ns);
+#pragma unroll
+      for (int o = G / 2; o; o >>= 1) mis += __shfl_xor_sync(gmask, mis, o);
+      if (survive) {
+        if (mis != ns) errflag = ERR_TRACE;     // the forward-carried count and the diagonal's Hamming distance must agree
+        if (lam < 0 || lam > 1 || lam != lam) errflag = ERR_LAMBDA;             // pval.cpp:195
+        store_comparison(a, r, lam, ns);
+      }
     } else if (survive) {
       // traceback over the recorded moves, lambda in raw-position order, store rule (dd_nwrow.cuh)
       const int nsub = trace_moves<G, C, 8, true>(la.mv_scratch + grp, (size_t)G * TG, TG, L, B, s_cen, rrow, la.sub_scratch + grp, TG);

@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned kmer10(const uint32_t *row, int p) {      //
 }
 }  // namespace
 
-constexpr int KREP = 48;              // repeated-5-mer list entries per raw (u16: k-mer | (count - 1) << 10, 0xFFFF = end); a 250-nt read has ~25
+constexpr int KREP = 48;              // repeated-5-mer list entries per raw (u16: k-mer | (count - 1) << 10, packed from the front, 0 = padding); a 250-nt read has ~25
 constexpr uint32_t META_OVF = 1u << 31;   // kmeta flag: the list does not hold every repeated 5-mer of this raw (or a count above 64)
 
 // one warp per owned raw: bitmap row, repeated-5-mer list, meta word (overflow flag | slack << 16 | len)
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) k_kmer_bits(DevIn in, int rank, int world
     for (int o = 16; o; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
     // repeated 5-mers: lane l scans k-mers 32 l .. 32 l + 31 (the bits of its bitmap word), in k-mer order
     uint16_t *lst = krep + (size_t)it * KREP;
-    for (int x = lane; x < KREP; x += 32) lst[x] = 0xFFFFu;
+    for (int x = lane; x < KREP; x += 32) lst[x] = 0u;                 // padding: count field 0 (a real entry has count - 1 >= 1)
     __syncwarp();
     int nrep = 0; bool ovf = false;
     for (int b = 0; b < 32; b++) {
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
   __align__(8) __shared__ uint64_t s_full[PS_STAGES];
   __align__(16) __shared__ uint32_t s_cen[32];
   __shared__ uint32_t s_ccnt[512];                           // the centre's 5-mer counts, 1024 x u16
+  __shared__ uint8_t s_t1[1024];                             // max(count - 1, 0): what a repeated 5-mer of the raw can add beyond its presence bit
   const int tid = threadIdx.x, lane = tid & 31;
   const int ntiles = (a.nown + PS_TILE - 1) / PS_TILE;
   const int len1 = a.in.len[a.centre_idx];
@@ -149,6 +150,11 @@ __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
   };
   if (tid == 0)
     for (int s = 0; s < PS_STAGES; s++) { const int t = blockIdx.x + s * gridDim.x; if (t < ntiles) issue(t, s); }
+  __syncthreads();
+  for (int x = tid; x < 1024; x += blockDim.x) {
+    const uint32_t cc = (s_ccnt[x >> 1] >> (16 * (x & 1))) & 0xFFFFu;
+    s_t1[x] = (uint8_t)(cc ? min(cc - 1u, 255u) : 0u);       // list counts stop at 63: the cap never binds
+  }
   __syncthreads();
   int c_align = 0, c_shroud = 0;
   int k = 0;
@@ -182,22 +188,19 @@ __global__ void __launch_bounds__(PS_BLOCK) k_prescreen(PrescreenArgs a) {
     bool cand = false;
     uint32_t msv = 0;
     if (pend) {
-      // exact min-sum: presence bits + what the raw's repeated 5-mers add beyond their presence bit
+      // exact min-sum: presence bits + what the raw's repeated 5-mers add beyond their presence bit: for an entry (k, count - 1),
+      // min(count, c_centre[k]) - 1 = min(count - 1, max(c_centre[k] - 1, 0)) when the 5-mer is in the centre, 0 when not -- the
+      // same expression with the table holding max(c - 1, 0); padding entries (count field 0) add nothing
       int ms = pend_pc;
-      bool more = true;
 #pragma unroll
-      for (int blk = 0; blk < KREP / 8; blk++) {                              // the list is packed from the front and ends at the first 0xFFFF
+      for (int blk = 0; blk < KREP / 8; blk++) {
         const uint32_t lw[4] = {L[blk].x, L[blk].y, L[blk].z, L[blk].w};
 #pragma unroll
         for (int e = 0; e < 8; e++) {
           const uint32_t ent = (lw[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
-          if (ent == 0xFFFFu) more = false;
-          if (more) {
-            const uint32_t km = ent & 0x3FFu, cr = (ent >> 10) + 1u;
-            const uint32_t cc = (s_ccnt[km >> 1] >> (16 * (km & 1))) & 0xFFFFu;
-            ms += cc ? (int)min(cr, cc) - 1 : 0;
-          }
+          ms += (int)min(ent >> 10, (uint32_t)s_t1[ent & 0x3FFu]);
         }
+        if ((lw[3] >> 26) == 0u) break;                                       // the block's last entry is padding: the list ended here
       }
       const double kdist = 1. - ((double)(ms & 0xFFFF)) / pend_denom;         // exactly raw_align's kdist (N1: integer min-sum)
       if (kdist > a.kdist_cutoff) { c_align++; c_shroud++; }

@@ -129,6 +129,9 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
   return v;
 }
 
+// one copy of the incomplete-gamma code for the TAIL_RPT unrolled raws of a thread
+__device__ __noinline__ double calc_pA_call(int reads, double E_reads, bool prior) { return calc_pA(reads, E_reads, prior); }
+
 // blockDim.x must be TAIL_BLOCK (a multiple of 32, at most 1024)
 // mode 0: p-update + bud scan only if the last launched pass moved nothing (anywhere); otherwise just report and leave the
 //         state for further k_tail_pass launches
@@ -150,43 +153,58 @@ __global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, 
     s_upd[c] = u ? 1 : 0;
   }
   stage_reads(st, ts, last_pass + 1, nclust, s_reads);               // also the barrier behind s_n / s_np / s_upd
-  const long long rl = tail_raw(ts, blockIdx.x * (long long)blockDim.x + tid);
-  const int r = (int)(rl < in.nraw ? rl : in.nraw);
-  unsigned long long pb = ~0ull, pbp = ~0ull;
-  uint32_t rd = 0;
-  bool elig = false, prior = false;
-  if (converged && r < in.nraw) {
-    const uint32_t ci = st.cluster_of[r];
-    rd = in.reads[r];
-    prior = in.prior[r] != 0;
-    const double lambda = st.comp_lambda[r];
-    const uint32_t ham = st.comp_ham[r];
-    double pval = st.p[r];
-    if (s_upd[ci]) {                                                   // get_pA pval.cpp:67-89
-      if (rd == 1 && !prior && !detect_singletons) pval = 1.;
-      else if (ham == 0) pval = 1.;
-      else if (lambda == 0) pval = 0.;
-      else {
-        // b_bud only ever asks whether p * nraw < omegaA (or p < omegaP for a raw with a prior), cluster.cpp:313-316, and the
-        // p-values of the output are recomputed after the loop (k_final_p).  p >= P(X = reads) = exp(-E) E^reads / reads!  for
-        // either normalisation of calc_pA: when that lower bound is already above the threshold (by a factor e), the raw cannot
-        // be budded whatever its exact p is, and the bound is stored in its place -- no incomplete-gamma evaluation.
-        const double E = lambda * (double)s_reads[ci];
-        const double lg = -E + (double)rd * log(E) - lgamma((double)rd + 1.0);
-        if (lg >= (prior ? bp.skip_log_prior : bp.skip_log)) pval = exp(lg);
-        else pval = calc_pA((int)rd, E, prior || detect_singletons);
+  // TAIL_RPT raws per thread: the per-CTA work around them (staging, five barriers, the block reductions: two thirds of the
+  // kernel's instructions with one raw per thread, profiles/r2_tail_screen_lane_metrics.txt) is paid once per 1024 raws
+  int rA[TAIL_RPT];
+  unsigned long long pbA[TAIL_RPT];
+  uint32_t rdA[TAIL_RPT];
+  unsigned eligm = 0, priorm = 0;
+  unsigned long long pb = ~0ull, pbp = ~0ull;                           // this thread's minima
+#pragma unroll
+  for (int u = 0; u < TAIL_RPT; u++) {
+    const long long rl = tail_raw(ts, ((long long)blockIdx.x * TAIL_RPT + u) * blockDim.x + tid);
+    const int r = (int)(rl < in.nraw ? rl : in.nraw);
+    rA[u] = r; pbA[u] = ~0ull; rdA[u] = 0;
+    if (converged && r < in.nraw) {
+      const uint32_t ci = st.cluster_of[r];
+      const uint32_t rd = in.reads[r];
+      const bool prior = in.prior[r] != 0;
+      const double lambda = st.comp_lambda[r];
+      const uint32_t ham = st.comp_ham[r];
+      double pval = st.p[r];
+      if (s_upd[ci]) {                                                   // get_pA pval.cpp:67-89
+        if (rd == 1 && !prior && !detect_singletons) pval = 1.;
+        else if (ham == 0) pval = 1.;
+        else if (lambda == 0) pval = 0.;
+        else {
+          // b_bud only ever asks whether p * nraw < omegaA (or p < omegaP for a raw with a prior), cluster.cpp:313-316, and the
+          // p-values of the output are recomputed after the loop (k_final_p).  p >= P(X = reads) = exp(-E) E^reads / reads!  for
+          // either normalisation of calc_pA: when that lower bound is already above the threshold (by a factor e), the raw cannot
+          // be budded whatever its exact p is, and the bound is stored in its place -- no incomplete-gamma evaluation.
+          const double E = lambda * (double)s_reads[ci];
+          const double lg = -E + (double)rd * log(E) - lgamma((double)rd + 1.0);
+          if (lg >= (prior ? bp.skip_log_prior : bp.skip_log)) pval = exp(lg);
+          else pval = calc_pA_call((int)rd, E, prior || detect_singletons);
+        }
+        st.p[r] = pval;
       }
-      st.p[r] = pval;
+      if (greedy && st.cl_check_locks[ci]) {                             // pval.cpp:29-38
+        const uint32_t cen = st.cl_center[ci];
+        if ((double)in.reads[cen] * lambda > (double)rd) st.lock[r] = 1;
+        if ((uint32_t)r == cen) st.lock[r] = 1;
+      }
+      // b_bud candidate (cluster.cpp:285-294)
+      const bool elig = !st.slot0[r] && (int)rd >= bp.min_abund && (int)ham >= bp.min_hamming &&
+                        (bp.min_fold <= 1 || ((double)rd) >= bp.min_fold * lambda * (double)s_reads[ci]);
+      rdA[u] = rd;
+      if (prior) priorm |= 1u << u;
+      if (elig) {
+        eligm |= 1u << u;
+        pbA[u] = (unsigned long long)__double_as_longlong(pval);
+        pb = pbA[u] < pb ? pbA[u] : pb;
+        if (prior) pbp = pbA[u] < pbp ? pbA[u] : pbp;
+      }
     }
-    if (greedy && st.cl_check_locks[ci]) {                             // pval.cpp:29-38
-      const uint32_t cen = st.cl_center[ci];
-      if ((double)in.reads[cen] * lambda > (double)rd) st.lock[r] = 1;
-      if ((uint32_t)r == cen) st.lock[r] = 1;
-    }
-    // b_bud candidate (cluster.cpp:285-294)
-    elig = !st.slot0[r] && (int)rd >= bp.min_abund && (int)ham >= bp.min_hamming &&
-           (bp.min_fold <= 1 || ((double)rd) >= bp.min_fold * lambda * (double)s_reads[ci]);
-    if (elig) { pb = (unsigned long long)__double_as_longlong(pval); if (prior) pbp = pb; }
   }
   // block minimum of p, then maximum of reads among the raws attaining it; all of those are tie candidates
   unsigned long long w = warp_min_u64(pb), wp = warp_min_u64(pbp);
@@ -194,14 +212,24 @@ __global__ void k_tail_final(DevState st, DevIn in, TailState ts, BudParams bp, 
   __syncthreads();
   unsigned long long bmin = ~0ull, bminp = ~0ull;
   for (int k = 0; k < nwarp; k++) { bmin = s_pb[k] < bmin ? s_pb[k] : bmin; bminp = s_pbp[k] < bminp ? s_pbp[k] : bminp; }
-  const bool ca = elig && pb == bmin, cp = elig && prior && pb == bminp;
-  uint32_t wr = warp_max_u32(ca ? rd : 0u), wrp = warp_max_u32(cp ? rd : 0u);
+  uint32_t tr = 0, trp = 0;                                             // this thread's largest reads among its candidates
+  unsigned cam = 0, cpm = 0;
+#pragma unroll
+  for (int u = 0; u < TAIL_RPT; u++) {
+    const bool elig = (eligm >> u) & 1u, prior = (priorm >> u) & 1u;
+    if (elig && pbA[u] == bmin) { cam |= 1u << u; tr = rdA[u] > tr ? rdA[u] : tr; }
+    if (elig && prior && pbA[u] == bminp) { cpm |= 1u << u; trp = rdA[u] > trp ? rdA[u] : trp; }
+  }
+  uint32_t wr = warp_max_u32(tr), wrp = warp_max_u32(trp);
   if (lane == 0) { s_rd[wid] = wr; s_rdp[wid] = wrp; }
   __syncthreads();
   uint32_t bmax = 0, bmaxp = 0;
   for (int k = 0; k < nwarp; k++) { bmax = s_rd[k] > bmax ? s_rd[k] : bmax; bmaxp = s_rdp[k] > bmaxp ? s_rdp[k] : bmaxp; }
-  if (ca && rd == bmax) { const unsigned k = atomicAdd(&s_n, 1u); if (k < TIE_MAX) ts.blk_ties[(size_t)blockIdx.x * TIE_MAX + k] = (uint32_t)r; }
-  if (cp && rd == bmaxp) { const unsigned k = atomicAdd(&s_np, 1u); if (k < TIE_MAX) ts.blk_ties_pr[(size_t)blockIdx.x * TIE_MAX + k] = (uint32_t)r; }
+#pragma unroll
+  for (int u = 0; u < TAIL_RPT; u++) {
+    if (((cam >> u) & 1u) && rdA[u] == bmax) { const unsigned k = atomicAdd(&s_n, 1u); if (k < TIE_MAX) ts.blk_ties[(size_t)blockIdx.x * TIE_MAX + k] = (uint32_t)rA[u]; }
+    if (((cpm >> u) & 1u) && rdA[u] == bmaxp) { const unsigned k = atomicAdd(&s_np, 1u); if (k < TIE_MAX) ts.blk_ties_pr[(size_t)blockIdx.x * TIE_MAX + k] = (uint32_t)rA[u]; }
+  }
   __syncthreads();
   if (tid == 0) {
     BlkBest b;
@@ -345,7 +373,7 @@ void launch_tail_final(const DevState &st, const DevIn &in, const TailState &ts,
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_tail_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX); attr_set = true; }
   count_launch(1);
-  k_tail_final<<<tail_grid_owned(in, ts), TAIL_BLOCK, (size_t)nclust * 5 + 16, s>>>(st, in, ts, bp, greedy, detect_singletons, last_pass, nclust, mode);
+  k_tail_final<<<(tail_grid_owned(in, ts) + TAIL_RPT - 1) / TAIL_RPT, TAIL_BLOCK, (size_t)nclust * 5 + 16, s>>>(st, in, ts, bp, greedy, detect_singletons, last_pass, nclust, mode);
 }
 
 void launch_bud_collect_owned(const DevState &st, const DevIn &in, const TailState &ts, const BudParams &bp, uint32_t *ties, uint32_t *ties_pr,

@@ -58,11 +58,22 @@ constexpr size_t STACK_BYTES = 256 * 1024;
 constexpr int MAX_THREADS = 1024;
 constexpr size_t SMEM_BYTES = 232448;     // 227 KB
 
+// a rendezvous of part of a warp (collectives with a partial mask: lane groups that diverged from each other)
+struct SubWarp {
+  uint32_t mask;                       // 0: free
+  uint64_t slot[2][32];
+  uint32_t valid[2];
+  int kind[2];
+  int gen, arrived;
+};
+constexpr int MAX_SUB = 8;
 struct Warp {
   uint64_t slot[2][32];
   uint32_t valid[2];
   int kind[2];
   int gen, arrived, live;
+  uint32_t live_mask;
+  SubWarp sub[MAX_SUB];
 };
 struct Fiber {
   void *sp;
@@ -142,7 +153,10 @@ void reorder(std::vector<int> &order, int sched, uint64_t &rng) {
   R.progress++;
   Warp &w = *f->warp;
   w.live--;
+  w.live_mask &= ~(1u << f->lane);
   if (w.arrived > 0 && w.arrived == w.live) { w.arrived = 0; w.gen++; }        // the rest of the warp was waiting for us
+  for (SubWarp &q : w.sub)
+    if (q.mask && q.arrived > 0 && q.arrived == __builtin_popcount(q.mask & w.live_mask)) { q.arrived = 0; q.gen++; }
   R.blive--;
   if (R.barrived > 0 && R.barrived == R.blive) { R.barrived = 0; R.bgen++; }
   for (;;) to_main(f);
@@ -165,6 +179,36 @@ const uint64_t *warp_publish(uint64_t v, uint32_t *valid, int kind) {
   else park(&w.gen, g);
   *valid = w.valid[b];
   return w.slot[b];
+}
+
+// collective among the lanes of `mask` only (the named lanes must all reach it, like on hardware; lanes outside it are free to be
+// anywhere else, e.g. in another group's collective).  Masks in flight at the same time must be equal or disjoint.
+const uint64_t *warp_publish_masked(unsigned mask, uint64_t v, uint32_t *valid, int kind) {
+  if (mask == 0xffffffffu) return warp_publish(v, valid, kind);
+  Fiber *f = R.cur;
+  Warp &w = *f->warp;
+  if (!((mask >> f->lane) & 1u)) { std::fprintf(stderr, "cuda_emu: lane %d calls a collective whose mask %08x does not name it\n", f->lane, mask); std::abort(); }
+  SubWarp *q = nullptr;
+  for (SubWarp &c : w.sub) if (c.mask == mask) { q = &c; break; }
+  if (!q) for (SubWarp &c : w.sub) {         // a slot belongs to one mask for the whole block (parked lanes keep pointers into it)
+    if (c.mask && (c.mask & mask)) { std::fprintf(stderr, "cuda_emu: overlapping partial masks %08x / %08x\n", c.mask, mask); std::abort(); }
+    if (!q && c.mask == 0) q = &c;
+  }
+  if (!q) { std::fprintf(stderr, "cuda_emu: more than %d partial-mask groups in one warp\n", MAX_SUB); std::abort(); }
+  if (q->mask != mask) { q->mask = mask; q->gen = 0; q->arrived = 0; }
+  const int g = q->gen, b = g & 1;
+  if (q->arrived == 0) { q->valid[b] = 0; q->kind[b] = kind; }
+  else if (q->kind[b] != kind) {
+    std::fprintf(stderr, "cuda_emu: divergent group collective (kind %d vs %d, mask %08x) in block %u thread %u\n", q->kind[b], kind, mask, t_blockIdx.x, f->tid.x);
+    std::abort();
+  }
+  q->slot[b][f->lane] = v;
+  q->valid[b] |= 1u << f->lane;
+  R.progress++;
+  if (++q->arrived == __builtin_popcount(mask & w.live_mask)) { q->arrived = 0; q->gen++; }
+  else park(&q->gen, g);
+  *valid = q->valid[b];
+  return q->slot[b];
 }
 
 void block_barrier() {
@@ -245,7 +289,9 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, void (*tramp)(void *), void
 #if CUEMU_ASAN
         __asan_poison_memory_region(t_smem + smem, SMEM_BYTES - smem);               // beyond what this launch asked for
 #endif
-        for (int w = 0; w < nwarps; w++) { R.warps[w].gen = 0; R.warps[w].arrived = 0; R.warps[w].live = std::min(32, nthreads - 32 * w); }
+        for (int w = 0; w < nwarps; w++) { R.warps[w].gen = 0; R.warps[w].arrived = 0; R.warps[w].live = std::min(32, nthreads - 32 * w);
+          R.warps[w].live_mask = R.warps[w].live >= 32 ? 0xffffffffu : ((1u << R.warps[w].live) - 1u);
+          for (SubWarp &q : R.warps[w].sub) { q.mask = 0; q.arrived = 0; q.gen = 0; } }
         R.bgen = 0; R.barrived = 0; R.blive = nthreads; R.progress = 0;
         for (int t = 0; t < nthreads; t++) {
           Fiber &f = R.fibers[t];

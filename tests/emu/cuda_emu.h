@@ -29,6 +29,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
 #define __constant__ static
@@ -58,6 +59,7 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, void (*tramp)(void *), void
 unsigned char *dyn_smem();
 // Publishes one 64-bit value per lane and waits for the warp; returns the 32 published values and which lanes were live.
 const uint64_t *warp_publish(uint64_t v, uint32_t *valid, int kind);
+const uint64_t *warp_publish_masked(unsigned mask, uint64_t v, uint32_t *valid, int kind);
 void block_barrier();
 void *dev_alloc(size_t bytes);
 void dev_free(void *p);
@@ -81,9 +83,7 @@ template <class T> inline T from_slot(const uint64_t *s, uint32_t valid, int src
   std::memcpy(&v, &r, sizeof(T));
   return v;
 }
-inline void need_full(unsigned mask) {
-  if (mask != 0xffffffffu) { std::fprintf(stderr, "cuda_emu: only full-mask warp collectives are supported\n"); std::abort(); }
-}
+inline void need_full(unsigned) {}      // partial masks: the lanes of the mask meet among themselves (warp_publish_masked)
 }  // namespace cuemu
 
 #define threadIdx (cuemu::t_threadIdx)
@@ -96,35 +96,35 @@ static const int warpSize = 32;
 template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
   cuemu::need_full(mask);
   uint32_t valid;
-  const uint64_t *s = cuemu::warp_publish(cuemu::to_raw(v), &valid, cuemu::K_SHFL_UP);
+  const uint64_t *s = cuemu::warp_publish_masked(mask, cuemu::to_raw(v), &valid, cuemu::K_SHFL_UP);
   const int lane = cuemu::t_lane, l = lane % width;
   return (l - (int)delta < 0) ? v : cuemu::from_slot<T>(s, valid, lane - (int)delta);
 }
 template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32) {
   cuemu::need_full(mask);
   uint32_t valid;
-  const uint64_t *s = cuemu::warp_publish(cuemu::to_raw(v), &valid, cuemu::K_SHFL_DOWN);
+  const uint64_t *s = cuemu::warp_publish_masked(mask, cuemu::to_raw(v), &valid, cuemu::K_SHFL_DOWN);
   const int lane = cuemu::t_lane, l = lane % width;
   return (l + (int)delta >= width) ? v : cuemu::from_slot<T>(s, valid, lane + (int)delta);
 }
 template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
   cuemu::need_full(mask);
   uint32_t valid;
-  const uint64_t *s = cuemu::warp_publish(cuemu::to_raw(v), &valid, cuemu::K_SHFL_XOR);
+  const uint64_t *s = cuemu::warp_publish_masked(mask, cuemu::to_raw(v), &valid, cuemu::K_SHFL_XOR);
   const int lane = cuemu::t_lane, src = lane ^ lanemask;
   return (src / width != lane / width) ? v : cuemu::from_slot<T>(s, valid, src);
 }
 template <class T> inline T __shfl_sync(unsigned mask, T v, int srclane, int width = 32) {
   cuemu::need_full(mask);
   uint32_t valid;
-  const uint64_t *s = cuemu::warp_publish(cuemu::to_raw(v), &valid, cuemu::K_SHFL_IDX);
+  const uint64_t *s = cuemu::warp_publish_masked(mask, cuemu::to_raw(v), &valid, cuemu::K_SHFL_IDX);
   const int lane = cuemu::t_lane, src = (lane / width) * width + (((srclane % width) + width) % width);
   return cuemu::from_slot<T>(s, valid, src);
 }
 inline unsigned __ballot_sync(unsigned mask, int pred) {
   cuemu::need_full(mask);
   uint32_t valid;
-  const uint64_t *s = cuemu::warp_publish(pred ? 1u : 0u, &valid, cuemu::K_BALLOT);
+  const uint64_t *s = cuemu::warp_publish_masked(mask, pred ? 1u : 0u, &valid, cuemu::K_BALLOT);
   unsigned r = 0;
   for (int i = 0; i < 32; i++) if (((valid >> i) & 1u) && s[i]) r |= 1u << i;
   return r;
@@ -134,7 +134,7 @@ inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pre
 inline void __syncwarp(unsigned mask = 0xffffffffu) {
   cuemu::need_full(mask);
   uint32_t valid;
-  cuemu::warp_publish(0, &valid, cuemu::K_SYNCWARP);
+  cuemu::warp_publish_masked(mask, 0, &valid, cuemu::K_SYNCWARP);
 }
 inline void __syncthreads() { cuemu::block_barrier(); }
 inline void __threadfence() {}
