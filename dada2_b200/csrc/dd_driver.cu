@@ -141,6 +141,7 @@ struct dada2b_ctx {
   bool bad_nt = false;
   bool qual_sharded = false;      // dada2b_reupload on a sharded context: quality rows of this rank's raws only are on the device
   DBuf<uint8_t> d_qual_own, d_seq_own, d_seq_all;
+  DBuf<int> d_flags;
   unsigned total_reads = 0;
   std::vector<uint16_t> len;
   std::vector<uint32_t> reads;
@@ -311,7 +312,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
     CK(cudaMemcpyAsync(cx->d_qual_own.p, h_qual.p, nqown * d.QS, cudaMemcpyHostToDevice, cx->stream));
     launch_qrows_scatter(cx->d_qual.p, d.QS, nullptr, (int)nqown, (int)qrank, (int)qworld, cx->d_qual_own.p, cx->stream);
     // the largest quality present decides an error of the whole call (Rmain.cpp / pval.cpp:169-171): every rank must see the same value
-    DBuf<int> dq; dq.alloc(2);
+    DBuf<int> &dq = cx->d_flags; dq.alloc(2);                    // member: no cudaMalloc / cudaFree per re-upload
     int hq[2] = {cx->maxq, cx->bad_nt ? 1 : 0};                  // ... and so does an unexpected nucleotide in anybody's reads
     CK(cudaMemcpyAsync(dq.p, hq, 8, cudaMemcpyHostToDevice, cx->stream));
     NC(g_nccl.AllReduce(dq.p, dq.p, 2, ncclInt32, ncclMax, cx->comm, cx->stream));
@@ -820,7 +821,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       // pass 1: scores + substitution counts only; lambda <= S_r * rho_r^nsubs decides which pairs can pass the store rule
       FwdArgs fbnd = f;
       fbnd.raw_S = raw_S.p; fbnd.raw_rho = raw_rho.p; fbnd.surv_list = surv_list.p; fbnd.surv_count = st.ctr + CTR_SURV;
-      if (!fallback_only && !getenv("DADA2B_NO_DIAG_SPLIT")) { fbnd.gl_out = st.gl_list; fbnd.gl_count = st.ctr + CTR_GL; }   // diagonal-path survivors -> k_gapless_loop
+      if (!fallback_only) { fbnd.gl_out = st.gl_list; fbnd.gl_count = st.ctr + CTR_GL; }   // diagonal-path survivors -> k_gapless_loop
       CK(cudaMemsetAsync(ctr.p + CTR_SURV, 0, 8, s));
       CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
       // thread-per-pair row kernel (dd_nwrow.cu) for raws as long as the centre; the others come back in uneq_list

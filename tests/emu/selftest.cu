@@ -26,6 +26,24 @@ __global__ void k_collectives(int *out) {
   out[2 * 128 + blockIdx.x * blockDim.x + t] = bc;
 }
 
+// Lane groups of 8 that diverged from each other: every group runs its own number of group-wide collectives (partial masks), as
+// k_nwlane's group-wide lambda does; groups 1 and 3 skip the block entirely.
+__global__ void k_group_collectives(int *out) {
+  const int lane = threadIdx.x & 31, g = lane & 7, grp = lane >> 3;
+  const unsigned gmask = 0xFFu << (lane & ~7);
+  int acc = 0;
+  if (grp == 0 || grp == 2) {
+    const int rounds = grp == 0 ? 3 : 5;
+    for (int k = 0; k < rounds; k++) {
+      int v = lane * 10 + k;
+      for (int o = 4; o; o >>= 1) v += __shfl_xor_sync(gmask, v, o);       // sum over the group
+      acc += __shfl_sync(gmask, v, (lane & ~7) + ((g + 1) & 7));            // every lane reads a neighbour's copy of the sum
+    }
+  }
+  __syncwarp();
+  out[threadIdx.x] = acc;
+}
+
 // Each lane writes its slot, then reads its neighbour's WITHOUT a __syncwarp(): undefined on the GPU, order dependent here.
 __global__ void k_missing_syncwarp(int *out) {
   __shared__ int slot[32];
@@ -48,6 +66,15 @@ int main() {
       if (d[b * 128 + t] != exp) { bad++; std::printf("collectives: block %d thread %d got %d expected %d\n", b, t, d[b * 128 + t], exp); }
       if (t < 96 && d[2 * 128 + b * 128 + t] != bc) { bad++; std::printf("shfl width 4: thread %d got %d expected %d\n", t, d[2 * 128 + b * 128 + t], bc); }
     }
+  int *gq;
+  cudaMalloc(&gq, 64 * 4);
+  k_group_collectives<<<1, 64>>>(gq);
+  for (int t = 0; t < 64; t++) {
+    const int lane = t & 31, grp = lane >> 3, base = lane & ~7;
+    int exp = 0;
+    if (grp == 0 || grp == 2) for (int k = 0; k < (grp == 0 ? 3 : 5); k++) { int sum = 0; for (int j = 0; j < 8; j++) sum += (base + j) * 10 + k; exp += sum; }
+    if (gq[t] != exp) { bad++; std::printf("group collectives: thread %d got %d expected %d\n", t, gq[t], exp); }
+  }
   std::printf("collectives bad=%d\n", bad);
   int *e;
   cudaMalloc(&e, 32 * 4);
