@@ -40,6 +40,7 @@ enum Ctr : int {
   CTR_NW, CTR_GL,     // job list lengths
   CTR_ALIGN, CTR_SHROUD, CTR_NWTOT, CTR_GLTOT, CTR_CELLS,
   CTR_NMOVE, CTR_ERR, CTR_FB, CTR_NE, CTR_PMIN, CTR_RMAX, CTR_NTIE, CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR,
+  CTR_UNEQ_B, CTR_UNEQ_X,   // raws handed on by the thread-per-pair NW kernels (not as long as the centre): bound pass / exact pass
   CTR_N
 };
 
@@ -109,6 +110,8 @@ __host__ __device__ inline long long band_cells_cf(int n, int m, int l, int r) {
 }
 
 constexpr int CTR_SURV = CTR_NWTOT;   // survivor count of the two-phase bound pass (slot otherwise unused by kernels)
+constexpr int CTR_CAND = CTR_GLTOT;   // k_prescreen: pairs of the round that are not shrouded ...
+constexpr int CTR_OLD = CTR_NE;       // ... and raws forwarded to the warp-per-pair screen (list overflow)   (all four: zeroed by k_round_begin)
 
 enum ErrCode : int { ERR_NONE = 0, ERR_LAMBDA = 1, ERR_QUAL = 2, ERR_TRACE = 3 };
 

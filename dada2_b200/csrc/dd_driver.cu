@@ -432,7 +432,6 @@ struct Run {
   // streaming tier of the k-mer screen (dd_prescreen.cu): 5-mer presence bitmaps of this rank's raws, candidates per round
   DBuf<uint32_t> kbits, kmeta, cand_list, old_list;
   DBuf<uint16_t> krep, cand_ms;
-  DBuf<unsigned long long> cand_ctr;          // [0] candidates of the round, [1] raws forwarded to the warp-per-pair screen
   // scratch of the rare paths and of finish(): members, so that a steady-state pass makes no cudaMalloc / cudaFree (those go through the
   // kernel driver and wait behind whatever else holds its lock, e.g. a monitoring agent polling the GPU: profiles/r2_host_stalls.md)
   DBuf<uint32_t> tie_d1, tie_d2, tie_g1, tie_g2, fin_nwl, fin_gll, fin_sij, fin_gij;
@@ -440,7 +439,9 @@ struct Run {
   DBuf<uint8_t> fin_cq;
   DBuf<double> fin_sv, fin_gv;
   bool prescreen = false;
-  unsigned long long kbits_gen = ~0ull;   // dada2b_ctx::upload_gen the k-mer tables were built for
+  unsigned long long kbits_gen = ~0ull;
+  unsigned n_ovf = 0;                     // this rank's raws whose repeated-5-mer list overflowed (they alone need the warp-per-pair screen)
+  DBuf<unsigned> d_novf;   // dada2b_ctx::upload_gen the k-mer tables were built for
   int nown = 0;
   bool fallback_only = false;          // DADA2B_FALLBACK (test switch): general kernels only
   bool two_phase = false;              // bound pass first, exact lambda for the survivors only (plain gap costs)
@@ -699,9 +700,11 @@ void Run::alloc_state() {
   if (prescreen) {
     nown = (nraw - cx->rank + cx->world - 1) / cx->world;
     kbits.alloc((size_t)nown * 32 + 32); kmeta.alloc(nown); krep.alloc((size_t)nown * 48 + 64); cand_list.alloc(nown + 32); cand_ms.alloc(nown + 32);
-    old_list.alloc(nown + 32); cand_ctr.alloc(2);
+    old_list.alloc(nown + 32);
     if (kbits_gen != cx->upload_gen) {       // the bitmaps and repeat lists depend on the sequences only: kept across the runs of a resident sample
-      launch_kmer_bits(in, cx->rank, cx->world, nown, kbits.p, kmeta.p, krep.p, cx->num_sms, s);
+      d_novf.alloc(1); d_novf.zero(s);
+      launch_kmer_bits(in, cx->rank, cx->world, nown, kbits.p, kmeta.p, krep.p, d_novf.p, cx->num_sms, s);
+      d2h(&n_ovf, d_novf.p, 4);            // read by the sync() at the end of alloc_state
       kbits_gen = cx->upload_gen;
     }
   }
@@ -793,21 +796,21 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     // stream the 128-byte bitmap rows (TMA): every pair decided exactly (presence bound, then the exact min-sum through the raw's
     // repeated-5-mer list); gapless / NW for the pairs that are not shrouded (k_kord); the warp-per-pair screen only sees raws
     // whose list overflowed
-    CK(cudaMemsetAsync(cand_ctr.p, 0, 16, s));
-    ca.cand_list = old_list.p; ca.cand_count = cand_ctr.p + 1;
+    ca.cand_list = old_list.p; ca.cand_count = st.ctr + CTR_OLD;      // the round's counters were zeroed by k_round_begin
     timed(T_PRE, [&]() {
       launch_prescreen(in, kbits.p, kmeta.p, krep.p, nown, cx->rank, cx->world, c, cx->reads[c], o->greedy != 0, st.lock, kdist_cutoff, cand_list.p,
-                       cand_ms.p, cand_ctr.p, st.ctr, cx->num_sms, s);
+                       cand_ms.p, st.ctr + CTR_CAND, st.ctr, cx->num_sms, s);
     });
     prescreen_rows += nown;
     timed(T_CLASSIFY, [&]() {
-      launch_kord(in, ca.P, c, cand_list.p, cand_ms.p, cand_ctr.p, st.nw_list, st.gl_list, old_list.p, cand_ctr.p + 1, st.ctr, (unsigned long long)nown,
+      launch_kord(in, ca.P, c, cand_list.p, cand_ms.p, st.ctr + CTR_CAND, st.nw_list, st.gl_list, old_list.p, st.ctr + CTR_OLD, st.ctr, (unsigned long long)nown,
                   cx->num_sms, s);
-      launch_classify(ca, std::min(cgrid, cx->num_sms), 256, classify_smem, s);
+      if (n_ovf) launch_classify(ca, std::min(cgrid, cx->num_sms), 256, classify_smem, s);      // only raws whose list overflowed can be forwarded
     });
   } else
   timed(T_CLASSIFY, [&]() { launch_classify(ca, cgrid, 256, classify_smem, s); });
   bool fwd_done = false;
+  bool fb_possible = false;   // only k_nwfwd hands pairs back (those that do not fit its register band)
   if (P.band >= 0) {       // register-resident NW kernels (dd_nwrow.cu / dd_nwlane.cu / dd_nwfwd.cu); unbanded pairs: k_align below
     FwdArgs f{};
     f.in = in; f.P = P; f.st = st; f.jobs = st.nw_list; f.njobs_ptr = st.ctr + CTR_NW;
@@ -822,18 +825,16 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
       FwdArgs fbnd = f;
       fbnd.raw_S = raw_S.p; fbnd.raw_rho = raw_rho.p; fbnd.surv_list = surv_list.p; fbnd.surv_count = st.ctr + CTR_SURV;
       if (!fallback_only) { fbnd.gl_out = st.gl_list; fbnd.gl_count = st.ctr + CTR_GL; }   // diagonal-path survivors -> k_gapless_loop
-      CK(cudaMemsetAsync(ctr.p + CTR_SURV, 0, 8, s));
-      CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
       // thread-per-pair row kernel (dd_nwrow.cu) for raws as long as the centre; the others come back in uneq_list
       // rounds with few pairs: one lane-group launch does bound + exact (dd_nwlane.cu); the thread-per-pair bound pass returns at once then
       bool done_row = false, done_lane = false;
-      if (lane_max && row_mv.p) timed(T_NWB, [&]() { done_lane = launch_nwlane(fbnd, uneq_list.p, uneq_ctr.p, lane_mv.p, lane_sub.p, (int)cx->len[c], lane_max, (int)lane_max, s); });
+      if (lane_max && row_mv.p) timed(T_NWB, [&]() { done_lane = launch_nwlane(fbnd, uneq_list.p, st.ctr + CTR_UNEQ_B, lane_mv.p, lane_sub.p, (int)cx->len[c], lane_max, (int)lane_max, s); });
       if (row_mv.p)
-        timed(T_NWB, [&]() { done_row = launch_nwrow_bound(fbnd, uneq_list.p, uneq_ctr.p, (int)cx->len[c], (unsigned long long)nraw, cx->num_sms, done_lane ? lane_max : 0ull, s); });
-      if (done_row) { fbnd.jobs = uneq_list.p; fbnd.njobs_ptr = uneq_ctr.p; }
+        timed(T_NWB, [&]() { done_row = launch_nwrow_bound(fbnd, uneq_list.p, st.ctr + CTR_UNEQ_B, (int)cx->len[c], (unsigned long long)nraw, cx->num_sms, done_lane ? lane_max : 0ull, s); });
+      if (done_row) { fbnd.jobs = uneq_list.p; fbnd.njobs_ptr = st.ctr + CTR_UNEQ_B; }
       bool done_rest = done_row && in.minlen == in.maxlen;          // every raw has the centre's length: nothing was handed back
       if (!done_rest)
-        timed(T_NWB, [&]() { done_rest = launch_nwfwd(fbnd, fwd_slots, (unsigned long long)nraw, done_row ? 0 : est_active, cx->num_sms, s, true); });
+        timed(T_NWB, [&]() { done_rest = launch_nwfwd(fbnd, fwd_slots, (unsigned long long)nraw, done_row ? 0 : est_active, cx->num_sms, s, true); fb_possible |= done_rest; });
       // pass 2: the exact forward-carry kernel on the survivors
       if (done_rest) { f.jobs = surv_list.p; f.njobs_ptr = st.ctr + CTR_SURV; f.no_cells = 1; }
     }
@@ -841,20 +842,19 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     // long as the centre) and every configuration it does not cover go through the lane-group forward-carry kernel
     bool ex_done = false;
     if (row_mv.p) {
-      CK(cudaMemsetAsync(uneq_ctr.p, 0, 8, s));
       // survivors of a large round are few: the lane-group kernel (lower latency) takes lists of up to lane_max jobs, the thread-per-pair
       // kernel the rest (round 0, very large survivor sets); each returns at once when the list is not its size
       bool lane2 = false;
       if (lane_max && i > 0 && two_phase) {
         FwdArgs f2 = f;
         f2.raw_S = raw_S.p; f2.raw_rho = raw_rho.p;
-        timed(T_NW, [&]() { lane2 = launch_nwlane(f2, uneq_list.p, uneq_ctr.p, lane_mv.p, lane_sub.p, (int)cx->len[c], lane_max, (int)lane_max, s); });
+        timed(T_NW, [&]() { lane2 = launch_nwlane(f2, uneq_list.p, st.ctr + CTR_UNEQ_X, lane_mv.p, lane_sub.p, (int)cx->len[c], lane_max, (int)lane_max, s); });
       }
-      timed(T_NW, [&]() { ex_done = launch_nwrow_exact(f, uneq_list.p, uneq_ctr.p, row_mv.p, row_sub.p, (int)cx->len[c], (unsigned long long)nraw, row_grid_cap, s, lane2 ? lane_max : 0ull); });
-      if (ex_done) { f.jobs = uneq_list.p; f.njobs_ptr = uneq_ctr.p; }
+      timed(T_NW, [&]() { ex_done = launch_nwrow_exact(f, uneq_list.p, st.ctr + CTR_UNEQ_X, row_mv.p, row_sub.p, (int)cx->len[c], (unsigned long long)nraw, row_grid_cap, s, lane2 ? lane_max : 0ull); });
+      if (ex_done) { f.jobs = uneq_list.p; f.njobs_ptr = st.ctr + CTR_UNEQ_X; }
     }
     if (ex_done && in.minlen == in.maxlen) fwd_done = true;       // nothing was handed back; fb_list stays empty
-    else timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, ex_done ? 0 : (i == 0 ? (unsigned long long)nraw : est_active), cx->num_sms, s); });
+    else timed(T_NW, [&]() { fwd_done = launch_nwfwd(f, fwd_slots, (unsigned long long)nraw, ex_done ? 0 : (i == 0 ? (unsigned long long)nraw : est_active), cx->num_sms, s); fb_possible |= fwd_done; });
   }
   if (!fallback_only) {       // gapless comparisons: no DP, one thread per pair (dd_nwrow.cu:k_gapless_loop)
     FwdArgs g{};
@@ -867,6 +867,7 @@ void Run::launch_compare(uint32_t i, double kdist_cutoff) {
     if (kind == KIND_GAPLESS && !fallback_only) continue;
     AlignArgs a = align_args(MODE_LOOP, kind);
     a.jobs = kind == KIND_NW ? st.nw_list : st.gl_list;
+    if (kind == KIND_NW && fwd_done && !fb_possible) continue;        // every NW job went through the row / lane kernels: nothing to hand back
     if (kind == KIND_NW && fwd_done) { a.jobs = fb_list.p; a.njobs_ptr = st.ctr + CTR_FB; }
     else a.njobs_ptr = st.ctr + (kind == KIND_NW ? CTR_NW : CTR_GL);
     a.centre_idx = c; a.centre_reads = cx->reads[c]; a.cluster_i = i; a.total_reads = cx->total_reads;

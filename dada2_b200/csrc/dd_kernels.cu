@@ -339,7 +339,9 @@ __global__ void k_posthoc(DevState st, unsigned long long n, const int *center_c
 }
 
 // ------------------------------- launch wrappers --------------------------------------
-static long long g_launches = 0;
+// kernel launches of the CALLING thread (a context is driven by one thread at a time, include/dada2b.h: per-run deltas stay
+// exact when several contexts run on several threads, e.g. the ranks of a sharded run inside one process)
+static thread_local long long g_launches = 0;
 long long launches_count() { return g_launches; }
 void count_launch(int n) { g_launches += n; }
 #define COUNT_LAUNCH(n) (g_launches += (n))

@@ -25,7 +25,7 @@ struct ClassifyArgs {
   const unsigned long long *cand_count;
 };
 // dd_prescreen.cu: streaming first tier of the k-mer screen (TMA-staged 5-mer presence bitmaps)
-void launch_kmer_bits(const DevIn &in, int rank, int world, int nown, uint32_t *kbits, uint32_t *kmeta, uint16_t *krep, int num_sms, cudaStream_t s);
+void launch_kmer_bits(const DevIn &in, int rank, int world, int nown, uint32_t *kbits, uint32_t *kmeta, uint16_t *krep, unsigned *n_overflow, int num_sms, cudaStream_t s);
 void launch_prescreen(const DevIn &in, const uint32_t *kbits, const uint32_t *kmeta, const uint16_t *krep, int nown, int rank, int world,
                       uint32_t centre_idx, uint32_t centre_reads, int greedy, const uint8_t *lock, double kdist_cutoff, uint32_t *cand_list,
                       uint16_t *cand_ms, unsigned long long *cand_count, unsigned long long *ctr, int num_sms, cudaStream_t s);

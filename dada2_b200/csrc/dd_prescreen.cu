@@ -54,7 +54,7 @@ constexpr int KREP = 48;              // repeated-5-mer list entries per raw (u1
 constexpr uint32_t META_OVF = 1u << 31;   // kmeta flag: the list does not hold every repeated 5-mer of this raw (or a count above 64)
 
 // one warp per owned raw: bitmap row, repeated-5-mer list, meta word (overflow flag | slack << 16 | len)
-__global__ void __launch_bounds__(256) k_kmer_bits(DevIn in, int rank, int world, int nown, uint32_t *kbits, uint32_t *kmeta, uint16_t *krep) {
+__global__ void __launch_bounds__(256) k_kmer_bits(DevIn in, int rank, int world, int nown, uint32_t *kbits, uint32_t *kmeta, uint16_t *krep, unsigned *n_overflow) {
   __shared__ uint32_t s_bits[8][32];
   __shared__ uint32_t s_cnt[8][512];            // 1024 u16 counters per warp
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) k_kmer_bits(DevIn in, int rank, int world
     }
     ovf = __any_sync(0xffffffffu, ovf);
     if (lane == 0) kmeta[it] = (ovf ? META_OVF : 0u) | ((uint32_t)(len - KMER + 1 - pc) << 16) | (uint32_t)len;
+    if (lane == 0 && ovf) atomicAdd(n_overflow, 1u);
     __syncwarp();
     for (int p = lane; p + KMER <= len; p += 32) s_cnt[wid][kmer10(row, p) >> 1] = 0u;       // clear what was touched
     __syncwarp();
@@ -316,10 +317,11 @@ __global__ void __launch_bounds__(128) k_kord(KordArgs a) {
   if (lane == 0 && c_align) atomicAdd(&a.ctr[CTR_ALIGN], (unsigned long long)c_align);
 }
 
-void launch_kmer_bits(const DevIn &in, int rank, int world, int nown, uint32_t *kbits, uint32_t *kmeta, uint16_t *krep, int num_sms, cudaStream_t s) {
+void launch_kmer_bits(const DevIn &in, int rank, int world, int nown, uint32_t *kbits, uint32_t *kmeta, uint16_t *krep, unsigned *n_overflow, int num_sms,
+                      cudaStream_t s) {
   count_launch(1);
   const int grid = std::max(1, std::min((nown + 7) / 8, num_sms * 8));
-  k_kmer_bits<<<grid, 256, 0, s>>>(in, rank, world, nown, kbits, kmeta, krep);
+  k_kmer_bits<<<grid, 256, 0, s>>>(in, rank, world, nown, kbits, kmeta, krep, n_overflow);
 }
 
 // Streams this rank's bitmap rows against centre `c`: every pair is decided exactly (shrouded or not), except raws whose

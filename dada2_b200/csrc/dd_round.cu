@@ -28,6 +28,7 @@ __global__ void k_round_begin(DevState st, int apply, uint32_t r, uint32_t from,
       st.cl_update_e[from] = 1; st.cl_update_e[newi] = 1; st.cl_check_locks[newi] = 1;
     }
     st.ctr[CTR_NW] = 0; st.ctr[CTR_GL] = 0; st.ctr[CTR_FB] = 0; st.ctr[CTR_NMOVE] = 0;
+    st.ctr[CTR_CAND] = 0; st.ctr[CTR_OLD] = 0; st.ctr[CTR_SURV] = 0; st.ctr[CTR_UNEQ_B] = 0; st.ctr[CTR_UNEQ_X] = 0;   // (no memsets in the round)
   }
   if (threadIdx.x < MAX_PASS + 2) st.pinfo[threadIdx.x] = 0;
 }

@@ -3,7 +3,9 @@ reference's own C++ (oracle/_ref), full output compared (ints exact, fp64 <= 1e-
   python tools/fuzz_dada_emu.py <seed> <seconds>
 Every iteration draws a sample (size, read length, variants, indel fraction, ragged ends, low-complexity stretches, priors) and
 options (band, omegaA, greedy, detect_singletons, min_abund / min_fold / min_hamming, kdist_cutoff, max_clust), and the size class
-switches (DADA2B_LANE_MAX) so that the thread-per-pair, the lane-group and the general kernels all take turns."""
+switches (DADA2B_LANE_MAX) so that the thread-per-pair, the lane-group and the general kernels all take turns; two iterations in
+five shard the sample over 2-3 ranks (owner mode; ranks as threads, the emulator's in-process NCCL stand-in), half of those through
+dada2b_reupload."""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
 import numpy as np
@@ -54,7 +56,34 @@ while time.time() < t_end:
     if os.environ.get("FUZZ_VERBOSE"): print("it", it, "n", len(seqs), "L", L, "nvar", nvar, opts, "lane_max", os.environ["DADA2B_LANE_MAX"], "priors", priors is not None, flush=True)
     want = ref.dada_uniques(seqs, ab, priors, err, q, homo_gap=-8, **opts)
     if os.environ.get("FUZZ_VERBOSE"): print("   reference done", flush=True)
-    got = dada2_b200.dada_uniques(seqs, ab, priors, err, q, **opts)
+    world = int(rng.choice([1, 1, 1, 2, 3])) if os.environ.get("FUZZ_SHARDED", "1") != "0" else 1
+    if world == 1:
+        got = dada2_b200.dada_uniques(seqs, ab, priors, err, q, **opts)
+    else:                                       # owner-mode sharding: the ranks are threads, NCCL is the emulator's in-process stand-in
+        import threading
+        uid = api.nccl_unique_id()
+        results = [None] * world
+        reup = bool(rng.integers(0, 2))
+        def rank_main(r):
+            try:
+                res = api.Resident(seqs, ab, priors, q)
+                res.comm_init(r, world, uid)
+                if reup:
+                    from dada2_b200 import _abi
+                    res.reupload(_abi.PackedIn(seqs, ab, priors, None, q))
+                results[r] = res.run(err, **opts)
+                res.close()
+            except Exception as e:
+                results[r] = e
+        th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in th: t.start()
+        for t in th: t.join()
+        for r in range(world):
+            if isinstance(results[r], Exception): raise results[r]
+        got = results[0]
+        for r in range(1, world):
+            cases.assert_same(results[r], got, rtol=0, prior_born=None, label="fuzz seed %d it %d: rank %d vs rank 0" % (seed, it, r))
+        n_sharded = globals().get("n_sharded", 0) + 1
     pb = None
     if priors is not None:                      # prior-born clusters: the reference leaves birth_from uninitialised (cluster.cpp:334-339)
         pb = np.zeros(len(want["clustering"]["sequence"]), dtype=bool)
@@ -68,4 +97,4 @@ while time.time() < t_end:
     nraw_tot += len(seqs); nclust_tot += len(got["clustering"]["sequence"])
     if it % 10 == 0:
         print("it %d: %d uniques, %d clusters so far, all identical" % (it, nraw_tot, nclust_tot), flush=True)
-print("DONE seed %d: %d iterations, %d uniques, %d clusters: all identical" % (seed, it, nraw_tot, nclust_tot))
+print("DONE seed %d: %d iterations (%d sharded over 2-3 ranks), %d uniques, %d clusters: all identical" % (seed, it, globals().get("n_sharded", 0), nraw_tot, nclust_tot))
