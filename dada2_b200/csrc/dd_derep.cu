@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(256) k_dr_to_ctx(DrToCtx a) {
     uint8_t q = 0;
     if (p < len) {
       const double xq = a.quals[(size_t)r * a.maxlen + p];
-      int rv = (int)(xq + 0.5);
-      if ((double)rv - xq > 0.5) rv--;
+      int rv = (int)xq;                                  // mean qualities are >= 0: trunc + (fraction >= 0.5), both exact
+      if (xq - (double)rv >= 0.5) rv++;
       q = (uint8_t)rv;
       atomicMax(a.maxq, (unsigned long long)q);
     }

@@ -24,6 +24,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -84,6 +89,84 @@ template <typename T> struct PBuf {   // pinned host buffer (grow-only)
   void free() { if (p) cudaFreeHost(p); p = nullptr; n = cap = 0; }
   ~PBuf() { free(); }
 };
+
+// (uint8_t) round(x) of a row of qualities (containers.cpp:34), returns the row's largest value.  For x >= 0: t = trunc(x) and
+// x - t are both exact in fp64, and round() (half away from zero) is t + (x - t >= 0.5) -- unlike (int)(x + 0.5), whose sum rounds
+// up to 1.0 for the double just below 0.5.  Negative / NaN / out-of-int-range values go through round() and the cast themselves.
+// 2 GB of doubles per 1e6 uniques pass through here on every upload: eight at a time with SSE2 (baseline x86-64; cvttpd2dq has
+// cvttsd2si's semantics per lane, so the out-of-range cases agree with the scalar cast as well).
+inline uint8_t round_qual(double x) {
+  int rv = (int)x;
+  if (x - (double)rv >= 0.5) rv++;
+  if (!(x >= 0 && x < 2147483648.0)) rv = (int)round(x);           // negative, NaN, beyond int: whatever the plain cast gives
+  return (uint8_t)rv;
+}
+inline int round_quals_row(const double *src, uint8_t *q, int L) {
+  int mq = 0, p = 0;
+#if defined(__SSE2__)
+  const __m128d half = _mm_set1_pd(0.5), zero = _mm_setzero_pd(), big = _mm_set1_pd(2147483648.0);
+  __m128i vmax = _mm_setzero_si128();
+  for (; p + 8 <= L; p += 8) {
+    __m128i r[4];
+    int ok = 3;
+    for (int k = 0; k < 4; k++) {
+      const __m128d x = _mm_loadu_pd(src + p + 2 * k);
+      ok &= _mm_movemask_pd(_mm_and_pd(_mm_cmpge_pd(x, zero), _mm_cmplt_pd(x, big)));   // false for negative, NaN and huge lanes
+      const __m128i rv = _mm_cvttpd_epi32(x);                           // two int32 in the low half
+      const __m128d f = _mm_sub_pd(x, _mm_cvtepi32_pd(rv));
+      const __m128i up = _mm_castpd_si128(_mm_cmpge_pd(f, half));       // all-ones 64-bit lanes where the fraction is >= 0.5
+      r[k] = _mm_sub_epi32(rv, _mm_shuffle_epi32(up, _MM_SHUFFLE(3, 3, 2, 0)));     // - (-1) in the matching 32-bit lanes 0 and 1
+    }
+    if (ok != 3) { for (int u = 0; u < 8; u++) { const uint8_t v = round_qual(src[p + u]); q[p + u] = v; if (v > mq) mq = v; } continue; }
+    const __m128i lo = _mm_unpacklo_epi64(r[0], r[1]), hi = _mm_unpacklo_epi64(r[2], r[3]);
+    const __m128i m = _mm_set1_epi32(0xFF);                              // (uint8_t) truncation
+    const __m128i w = _mm_packs_epi32(_mm_and_si128(lo, m), _mm_and_si128(hi, m));
+    const __m128i b = _mm_packus_epi16(w, w);
+    _mm_storel_epi64((__m128i *)(q + p), b);
+    vmax = _mm_max_epu8(vmax, b);
+  }
+  uint8_t tmp[16];
+  _mm_storeu_si128((__m128i *)tmp, vmax);
+  for (int u = 0; u < 8; u++) if (tmp[u] > mq) mq = tmp[u];
+#endif
+  for (; p < L; p++) { const uint8_t v = round_qual(src[p]); q[p] = v; if (v > mq) mq = v; }
+  return mq;
+}
+
+// 2-bit packing of one read (DevIn::seq2: base b at bits 2(b%16) of word b/16; A,C,G,T = 0..3), returns 1 when a character
+// other than ACGT was seen (it packs as A; the caller turns the flag into the reference's error, misc.cpp:6-24).
+// 250 MB of bases per 1e6 uniques: sixteen at a time with SSE2 -- (c >> 1) & 3 maps A,C,G,T to 0,1,3,2 and t ^ (t >> 1) to
+// 0,1,2,3; the sixteen 2-bit fields are then folded together by shift-or steps.  A per-character switch costs a mispredicted
+// branch on most bases.
+inline int pack_bases_row(const char *s, uint32_t *row, int L, int SW) {
+  int p = 0, w = 0, bad = 0;
+#if defined(__SSE2__)
+  const __m128i cA = _mm_set1_epi8('A'), cC = _mm_set1_epi8('C'), cG = _mm_set1_epi8('G'), cT = _mm_set1_epi8('T');
+  const __m128i m3 = _mm_set1_epi8(3), m1 = _mm_set1_epi8(1), mF = _mm_set1_epi16(0x000F);
+  for (; p + 16 <= L; p += 16, w++) {
+    const __m128i v = _mm_loadu_si128((const __m128i *)(s + p));
+    const __m128i okv = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, cA), _mm_cmpeq_epi8(v, cC)), _mm_or_si128(_mm_cmpeq_epi8(v, cG), _mm_cmpeq_epi8(v, cT)));
+    if (_mm_movemask_epi8(okv) != 0xFFFF) break;                         // finish this read character by character
+    const __m128i t = _mm_and_si128(_mm_srli_epi16(v, 1), m3);
+    const __m128i c = _mm_xor_si128(t, _mm_and_si128(_mm_srli_epi16(t, 1), m1));          // one 2-bit code per byte
+    const __m128i n = _mm_and_si128(_mm_or_si128(c, _mm_srli_epi16(c, 6)), mF);           // two codes per 16-bit lane
+    const __m128i b = _mm_packus_epi16(n, n);                                             // eight bytes, a nibble each
+    uint64_t q = (uint64_t)_mm_cvtsi128_si64(b);
+    q = (q | (q >> 4)) & 0x00FF00FF00FF00FFull;
+    q = (q | (q >> 8)) & 0x0000FFFF0000FFFFull;
+    q = (q | (q >> 16));
+    row[w] = (uint32_t)q;
+  }
+#endif
+  for (int x = w; x < SW; x++) row[x] = 0;
+  for (; p < L; p++) {
+    unsigned code;
+    switch (s[p]) { case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break;
+                    case 'T': code = 3; break; default: code = 0; bad = 1; }
+    row[p >> 4] |= code << (2 * (p & 15));
+  }
+  return bad;
+}
 
 template <typename F> void parallel_for(size_t n, F f) {
   unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -146,19 +229,6 @@ struct dada2b_ctx {
   std::vector<uint16_t> len;
   std::vector<uint32_t> reads;
   std::vector<uint8_t> prior;
-  // host copy of the sequences (the caller may free its buffers after dada2b_upload): raw bytes, filled by several threads
-  struct Bytes {
-    char *p = nullptr; size_t n = 0;
-    ~Bytes() { free(p); }
-    const char *data() const { return p; }
-    void assign(const char *b, const char *e) {
-      const size_t m = (size_t)(e - b);
-      if (m > n || !p) { free(p); p = (char *)malloc(std::max<size_t>(m, 1)); }
-      n = m;
-      parallel_for(m, [&](size_t lo, size_t hi) { memcpy(p + lo, b + lo, hi - lo); });
-    }
-  } seq_concat;
-  std::vector<int64_t> seq_off;
   DBuf<uint32_t> d_seq2, d_reads;
   DBuf<uint8_t> d_qual, d_prior;
   DBuf<uint16_t> d_len;
@@ -220,10 +290,6 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   d.nraw = nraw; d.maxlen = maxlen; d.minlen = minlen;
   d.SW = (((int)maxlen + 15) / 16 + 3) & ~3;
   d.QS = ((int)maxlen + 15) & ~15;
-  cx->seq_off.assign(in->seq_off, in->seq_off + nraw + 1);
-  cx->seq_concat.assign(in->seq_concat + in->seq_off[0], in->seq_concat + in->seq_off[nraw]);
-  const int64_t off0 = in->seq_off[0];
-  for (auto &o : cx->seq_off) o -= off0;
   cx->reads.resize(nraw); cx->prior.resize(nraw);
   unsigned tot = 0;
   for (unsigned i = 0; i < nraw; i++) {
@@ -244,72 +310,79 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   PBuf<uint8_t> &h_qual = cx->st_qual; h_qual.alloc(std::max<size_t>(nqown, 1) * d.QS);
   h_seq.alloc(qshard ? nqmax * d.SW : (size_t)nraw * d.SW);          // sharded: this rank packs its own reads only, the rest arrives over NVLink
   std::vector<int> tmaxq(64, 0), tbad(64, 0);
-  const char *sc = cx->seq_concat.data();
+  const char *sc = in->seq_concat;                                    // read in place: no host copy of the strings is kept (finish() decodes the packed rows)
+  const int64_t *soff = in->seq_off;
   const double *qd = in->quals;
   const int SW = d.SW, QS = d.QS, ML = in->maxlen;
-  unsigned slot = 0;
-  std::vector<std::pair<size_t, size_t>> ranges;
+  cx->d_seq2.alloc((size_t)nraw * d.SW); cx->d_qual.alloc((size_t)nraw * d.QS);
+  cx->d_len.alloc(nraw); cx->d_reads.alloc(nraw); cx->d_prior.alloc(nraw);
+  const size_t seq_chunk = nqmax * d.SW * 4;                          // sharded: bytes of one rank's all-gather chunk
+  uint8_t *seq_dst = (uint8_t *)cx->d_seq2.p, *qual_dst = cx->d_qual.p;
+  if (qshard) {
+    cx->d_seq_own.alloc(seq_chunk); cx->d_seq_all.alloc(seq_chunk * qworld); cx->d_qual_own.alloc(nqown * d.QS);
+    CK(cudaMemsetAsync(cx->d_seq_own.p, 0, seq_chunk, cx->stream));
+    seq_dst = cx->d_seq_own.p; qual_dst = cx->d_qual_own.p;
+  }
+  // Packing and the H2D copies are pipelined: worker threads take blocks of PACK_BLK raws from a counter, the calling thread
+  // sends every group of PACK_GRP finished blocks on its way while the later ones are still being packed (pinned staging, one
+  // stream: the copies arrive in order).  own(x) = how many of the raws below x are packed by this rank = their staging row.
+  auto own = [&](size_t x) { return (x + qworld - 1 - qrank) / qworld; };
+  size_t PACK_BLK = 4096; const size_t PACK_GRP = 16;
+  if (const char *e = getenv("DADA2B_PACK_BLK")) PACK_BLK = (size_t)std::max(1, atoi(e));      // test hook: many blocks / groups on small inputs
+  const size_t nblk = ((size_t)nraw + PACK_BLK - 1) / PACK_BLK;
+  std::unique_ptr<std::atomic<int>[]> blk_done(new std::atomic<int>[nblk]);
+  for (size_t k = 0; k < nblk; k++) blk_done[k].store(0, std::memory_order_relaxed);
+  std::atomic<size_t> blk_next{0};
   {
     unsigned nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
     if (nraw < 20000) nt = std::min(nt, 4u);
-    size_t chunk = (nraw + nt - 1) / nt;
+    nt = (unsigned)std::min<size_t>(nt, nblk);
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nt; t++) {
-      size_t b = t * chunk, e = std::min<size_t>(nraw, b + chunk);
-      if (b >= e) break;
-      th.emplace_back([&, b, e, t]() {
+      th.emplace_back([&, t]() {
         int mq = 0, bad = 0;
-        for (size_t r = b; r < e; r++) {
-          if (r % qworld != qrank) continue;                     // not this rank's read (sharded re-upload)
-          const char *s = sc + cx->seq_off[r];
-          const int L = cx->len[r];
-          uint32_t *row = h_seq.p + (r / qworld) * SW;
-          for (int w = 0; w < SW; w++) row[w] = 0;
-          for (int p = 0; p < L; p++) {
-            unsigned code;
-            switch (s[p]) { case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break;
-                            case 'T': code = 3; break; default: code = 0; bad = 1; }
-            row[p >> 4] |= code << (2 * (p & 15));
+        for (;;) {
+          const size_t k = blk_next.fetch_add(1, std::memory_order_relaxed);
+          if (k >= nblk) break;
+          const size_t b = k * PACK_BLK, e = std::min<size_t>(nraw, b + PACK_BLK);
+          for (size_t r = b; r < e; r++) {
+            if (r % qworld != qrank) continue;                     // not this rank's read (sharded re-upload)
+            const char *s = sc + soff[r];
+            const int L = cx->len[r];
+            bad |= pack_bases_row(s, h_seq.p + (r / qworld) * SW, L, SW);
+            uint8_t *q = h_qual.p + (r / qworld) * QS;
+            mq = std::max(mq, round_quals_row(qd + (size_t)ML * r, q, L));      // (uint8_t) round(qual[i]), containers.cpp:34
+            for (int p = L; p < QS; p++) q[p] = 0;
           }
-          uint8_t *q = h_qual.p + (r / qworld) * QS;
-          const double *src = qd + (size_t)ML * r;
-          for (int p = 0; p < L; p++) {                                   // (uint8_t) round(qual[i]), containers.cpp:34
-            const double x = src[p];
-            int rv = (int)(x + 0.5);                                      // == round(x) for x >= 0 except when x+0.5 rounds up
-            if ((double)rv - x > 0.5) rv--;
-            if (!(x >= 0)) rv = (int)round(x);
-            const uint8_t v = (uint8_t)rv; q[p] = v; if (v > mq) mq = v;
-          }
-          for (int p = L; p < QS; p++) q[p] = 0;
+          blk_done[k].store(1, std::memory_order_release);
         }
         tmaxq[t] = mq; tbad[t] = bad;
       });
     }
+    cudaError_t copy_err = cudaSuccess;
+    for (size_t g = 0; g < nblk; g += PACK_GRP) {
+      const size_t ge = std::min(nblk, g + PACK_GRP);
+      for (size_t k = g; k < ge; k++)
+        while (!blk_done[k].load(std::memory_order_acquire)) std::this_thread::sleep_for(std::chrono::microseconds(50));
+      const size_t r0 = own(g * PACK_BLK), r1 = own(std::min<size_t>(nraw, ge * PACK_BLK));
+      if (r1 == r0 || copy_err != cudaSuccess) continue;             // (after an error: only wait for the workers)
+      copy_err = cudaMemcpyAsync(seq_dst + r0 * SW * 4, h_seq.p + r0 * SW, (r1 - r0) * SW * 4, cudaMemcpyHostToDevice, cx->stream);
+      if (copy_err == cudaSuccess)
+        copy_err = cudaMemcpyAsync(qual_dst + r0 * QS, h_qual.p + r0 * QS, (r1 - r0) * QS, cudaMemcpyHostToDevice, cx->stream);
+    }
     for (auto &x : th) x.join();
-    (void)slot;
+    CK(copy_err);
   }
   const double tu2 = now_ms();
   DBG("upload: packed on host");
   for (int v : tmaxq) cx->maxq = std::max(cx->maxq, v);
   for (int v : tbad) cx->bad_nt |= (v != 0);
-  cx->d_seq2.alloc((size_t)nraw * d.SW); cx->d_qual.alloc((size_t)nraw * d.QS);
-  cx->d_len.alloc(nraw); cx->d_reads.alloc(nraw); cx->d_prior.alloc(nraw);
-  if (!qshard) CK(cudaMemcpyAsync(cx->d_seq2.p, h_seq.p, (size_t)nraw * d.SW * 4, cudaMemcpyHostToDevice, cx->stream));
-  else {          // own packed reads up, everybody's over NVLink (one all-gather), rows scattered into raw order
-    const size_t chunk = nqmax * d.SW * 4;
-    cx->d_seq_own.alloc(chunk); cx->d_seq_all.alloc(chunk * qworld);
-    CK(cudaMemsetAsync(cx->d_seq_own.p, 0, chunk, cx->stream));
-    CK(cudaMemcpyAsync(cx->d_seq_own.p, h_seq.p, nqown * d.SW * 4, cudaMemcpyHostToDevice, cx->stream));
-    NC(g_nccl.AllGather(cx->d_seq_own.p, cx->d_seq_all.p, chunk, ncclChar, cx->comm, cx->stream));
+  if (qshard) {   // own packed reads are up: everybody's over NVLink (one all-gather), rows scattered into raw order
+    NC(g_nccl.AllGather(cx->d_seq_own.p, cx->d_seq_all.p, seq_chunk, ncclChar, cx->comm, cx->stream));
     for (unsigned q = 0; q < qworld; q++) {
       const size_t nq = ((size_t)nraw + qworld - 1 - q) / qworld;
-      launch_qrows_scatter((uint8_t *)cx->d_seq2.p, d.SW * 4, nullptr, (int)nq, (int)q, (int)qworld, cx->d_seq_all.p + chunk * q, cx->stream);
+      launch_qrows_scatter((uint8_t *)cx->d_seq2.p, d.SW * 4, nullptr, (int)nq, (int)q, (int)qworld, cx->d_seq_all.p + seq_chunk * q, cx->stream);
     }
-  }
-  if (!qshard) CK(cudaMemcpyAsync(cx->d_qual.p, h_qual.p, (size_t)nraw * d.QS, cudaMemcpyHostToDevice, cx->stream));
-  else {
-    cx->d_qual_own.alloc(nqown * d.QS);
-    CK(cudaMemcpyAsync(cx->d_qual_own.p, h_qual.p, nqown * d.QS, cudaMemcpyHostToDevice, cx->stream));
     launch_qrows_scatter(cx->d_qual.p, d.QS, nullptr, (int)nqown, (int)qrank, (int)qworld, cx->d_qual_own.p, cx->stream);
     // the largest quality present decides an error of the whole call (Rmain.cpp / pval.cpp:169-171): every rank must see the same value
     DBuf<int> &dq = cx->d_flags; dq.alloc(2);                    // member: no cudaMalloc / cudaFree per re-upload
@@ -357,15 +430,11 @@ dada2b_ctx *ctx_create_device(int device, int nraw, int maxlen, int minlen, cons
     CK(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
     cx->has_quals = true; cx->bad_nt = false; cx->maxq = 0;
     cx->len.resize(nraw); cx->reads.resize(nraw); cx->prior.assign(nraw, 0);
-    cx->seq_off.assign(seq_off, seq_off + nraw + 1);
-    cx->seq_concat.assign(seq_concat + seq_off[0], seq_concat + seq_off[nraw]);
-    const int64_t off0 = seq_off[0];
     unsigned tot = 0;
     for (int i = 0; i < nraw; i++) {
       cx->len[i] = (uint16_t)(seq_off[i + 1] - seq_off[i]);
       cx->reads[i] = (uint32_t)abund[i]; tot += cx->reads[i];
     }
-    for (auto &o : cx->seq_off) o -= off0;
     cx->total_reads = tot;
     DevIn &d = cx->in;
     d.nraw = nraw; d.maxlen = maxlen; d.minlen = minlen;
@@ -436,7 +505,9 @@ struct Run {
   // kernel driver and wait behind whatever else holds its lock, e.g. a monitoring agent polling the GPU: profiles/r2_host_stalls.md)
   DBuf<uint32_t> tie_d1, tie_d2, tie_g1, tie_g2, fin_nwl, fin_gll, fin_sij, fin_gij;
   DBuf<unsigned long long> win_buf, fin_dcount, fin_dall;
-  DBuf<uint8_t> fin_cq;
+  DBuf<uint8_t> fin_cq, fin_rep_d;
+  DBuf<uint32_t> fin_rep_rows;
+  PBuf<uint8_t> fin_rep_h;          // representative sequences of the clusters: row list up, packed rows back
   DBuf<double> fin_sv, fin_gv;
   bool prescreen = false;
   unsigned long long kbits_gen = ~0ull;
@@ -1453,10 +1524,33 @@ void Run::finish(dada2b_out *out) {
       for (uint32_t i = 0; i < nclust; i++) { ab[i] += a[i]; n0[i] += z0[i]; n1[i] += z1[i]; nunq[i] += nu[i]; mxr[i] = std::max(mxr[i], mx[i]); }
     });
   }
+  // The representative sequences are read back from the packed rows on the device (a run that gets here saw nothing but ACGT,
+  // nt2int would have stopped it): no host copy of the input strings is kept.  Pinned buffer of its own -- the arena is in use.
+  std::vector<long> max_raw(nclust, -1);           // error.cpp:20-27: the first member (Bi::raw order) holding the largest abundance
+  uint32_t nrep = 0;
+  for (uint32_t i = 0; i < nclust; i++)
+    if (mxr[i] > 0) for (uint32_t r : members[i]) if (cx->reads[r] == mxr[i]) { max_raw[i] = r; nrep++; break; }
+  const size_t rowb = (size_t)in.SW * 4;
+  if (nrep) {
+    fin_rep_h.alloc((size_t)nrep * (4 + rowb) + 64);
+    uint32_t *rows_h = (uint32_t *)fin_rep_h.p;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < nclust; i++) if (max_raw[i] >= 0) rows_h[k++] = (uint32_t)max_raw[i];
+    fin_rep_rows.alloc(nrep); fin_rep_d.alloc((size_t)nrep * rowb);
+    h2d_bytes += (long long)nrep * 4; d2h_bytes += (long long)(nrep * rowb);
+    CK(cudaMemcpyAsync(fin_rep_rows.p, rows_h, (size_t)nrep * 4, cudaMemcpyHostToDevice, s));
+    launch_qrows_gather((const uint8_t *)in.seq2, (int)rowb, fin_rep_rows.p, (int)nrep, -1, 1, fin_rep_d.p, s);
+    CK(cudaMemcpyAsync(fin_rep_h.p + (((size_t)nrep * 4 + 63) & ~(size_t)63), fin_rep_d.p, (size_t)nrep * rowb, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  const uint32_t *rep_words = (const uint32_t *)(fin_rep_h.p + (((size_t)nrep * 4 + 63) & ~(size_t)63));
+  uint32_t rep_k = 0;
   for (uint32_t i = 0; i < nclust; i++) {
-    long max_raw = -1;                             // error.cpp:20-27: the first member (Bi::raw order) holding the largest abundance
-    if (mxr[i] > 0) for (uint32_t r : members[i]) if (cx->reads[r] == mxr[i]) { max_raw = r; break; }
-    if (max_raw >= 0) cseq.append(cx->seq_concat.data() + (size_t)cx->seq_off[max_raw], (size_t)cx->len[max_raw]);
+    if (max_raw[i] >= 0) {
+      const uint32_t *w = rep_words + (size_t)rep_k++ * in.SW;
+      const int L = cx->len[max_raw[i]];
+      for (int b = 0; b < L; b++) cseq.push_back("ACGT"[(w[b >> 4] >> (2 * (b & 15))) & 3]);
+    }
     coff.push_back((int64_t)cseq.size());
     if (i == 0) { bpval[i] = na_real(); bfrom[i] = INT_MIN; bfold[i] = na_real(); bham[i] = INT_MIN; bqave[i] = na_real(); }
     else {

@@ -177,6 +177,20 @@ def test_emu_sharded_reupload_keeps_only_owned_quality_rows(emu, world, name):
     assert emu.cuemu_launches(b"k_qrows_scatter") > 0 and emu.cuemu_launches(b"k_qrows_gather") > 0
 
 
+@pytest.mark.parametrize("blk", [1, 7, 100])
+def test_emu_upload_pipeline_many_blocks(emu, monkeypatch, blk):
+    """do_upload packs blocks of raws on worker threads and sends every group of 16 finished blocks to the device while the
+    later ones are still being packed: DADA2B_PACK_BLK (test hook) makes 800 raws span many blocks and groups, on one
+    context and on sharded re-uploads (rows of the rank's own raws only, groups that start at any raw index)."""
+    import dada2_b200
+    from tests.test_oracle import load_golden
+    monkeypatch.setenv("DADA2B_PACK_BLK", str(blk))
+    for name in ("syn800_default", "syn700_ragged"):
+        seqs, ab, pri, err, q, opts = cases.build_case(name)
+        cases.assert_same(dada2_b200.dada_uniques(seqs, ab, pri, err, q, **opts), load_golden(name), rtol=1e-10, label=name)
+    _run_sharded(3, "syn700_ragged", reupload=True)
+
+
 FUSED_E2E = ["syn800_default", "syn800_nogreedy", "syn800_maxclust5", "syn700_ragged"] if not os.environ.get("DADA2B_EMU_FULL") else list(cases.E2E_CASES)
 
 

@@ -162,6 +162,23 @@ def test_e2e_matches_reference_golden(name):
     cases.assert_same(got, want, rtol=1e-10, prior_born=pb, label=name)
 
 
+@pytest.mark.parametrize("blk", [1, 100])
+def test_upload_pipeline_many_blocks(monkeypatch, blk):
+    """do_upload pipelines packing (worker threads, blocks of raws) with grouped H2D copies from the pinned staging buffers:
+    DADA2B_PACK_BLK (test hook) makes 800 raws span many blocks and copy groups; one-shot call and re-upload."""
+    api = _api()
+    monkeypatch.setenv("DADA2B_PACK_BLK", str(blk))
+    for name in ("syn800_default", "syn700_ragged"):
+        seqs, ab, pri, err, q, opts = cases.build_case(name)
+        want = load_golden(name)
+        cases.assert_same(api.dada_uniques(seqs, ab, pri, err, q, **opts), want, rtol=1e-10, label=name)
+        from dada2_b200 import _abi
+        r = api.Resident(seqs[::-1], ab[::-1].copy(), None, q[::-1].copy())
+        r.reupload(_abi.PackedIn(seqs, ab, pri, None, q))
+        cases.assert_same(r.run(err, **opts), want, rtol=1e-10, label=name + " after reupload")
+        r.close()
+
+
 def test_resident_rerun_is_deterministic_and_err_swappable():
     api = _api()
     seqs, ab, pri, err, q, opts = cases.build_case("syn800_default")
