@@ -386,7 +386,7 @@ def main():
         pin = _abi.PackedIn(seqs, ab, None, None, q)
         ecm = np.asfortranarray(np.asarray(err, dtype=np.float64))
         ostruct = _abi.make_opts(homo_gap=-8)
-        for _ in range(max(1, args.warmup // 2)):
+        for _ in range(max(1, args.warmup)):
             res.reupload(pin); res.run_raw(ecm, ecm.shape[1], ostruct)
         barrier()
         t0 = time.perf_counter()
@@ -407,7 +407,7 @@ def main():
         est["h2d_bytes"] += nown * ((((L0 + 15) // 16 + 3) & ~3) * 4 + ((L0 + 15) & ~15)) + nraw * 7
     else:
         call = dada2_b200.PackedCall(seqs, ab, None, err, q)
-        for _ in range(max(1, args.warmup // 2)):
+        for _ in range(max(1, args.warmup)):
             call.run(unpack=False)
         barrier()
         t0 = time.perf_counter()
