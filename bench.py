@@ -212,7 +212,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "unique-reads/sec through dada()", "value": val, "unit": "uniques/s",
             "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
             "ms_per_step": 1e3 * tsum / len(times),
-            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "int16/int32 + f64",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16/int32 + f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD % args.nuniques},
             "cpu_baseline": {"value": val, "unit": "uniques/s", "cores": ncores, "kind": "reference", "hardware_threads": os.cpu_count(),
@@ -504,7 +504,7 @@ def main():
                 legs["bimera"] = bimera_leg(args.bimera_seconds, local_rank)
         line = {"metric": "unique-reads/sec through dada()", "value": value, "unit": "uniques/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_val / args.steps,
-                "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "int32 DP words (score|move|nsubs) + f64 lambda/p-value", "data": "synthetic",
                 "config": {"workload": WORKLOAD % nraw,
                            "per_gpu": ("the ONE sample sharded over %d GPUs (strong scaling): raw r on rank r %% N, NCCL over NVLink per split round, "
