@@ -3,7 +3,8 @@ reference's own C++ (oracle/_ref), full output compared (ints exact, fp64 <= 1e-
   python tools/fuzz_dada_emu.py <seed> <seconds>
 Every iteration draws a sample (size, read length, variants, indel fraction, ragged ends, low-complexity stretches, priors) and
 options (band, omegaA, greedy, detect_singletons, min_abund / min_fold / min_hamming, kdist_cutoff, max_clust), and the size class
-switches (DADA2B_LANE_MAX) so that the thread-per-pair, the lane-group and the general kernels all take turns; two iterations in
+switches (DADA2B_LANE_MAX) so that the thread-per-pair, the lane-group and the general kernels all take turns, DADA2B_PACK_BLK the
+upload pipeline's block size, some quality matrices sit on exact halves and their neighbouring doubles; two iterations in
 five shard the sample over 2-3 ranks (owner mode; ranks as threads, the emulator's in-process NCCL stand-in), half of those through
 dada2b_reupload."""
 import sys, os, time
@@ -43,6 +44,11 @@ while time.time() < t_end:
         for i in rng.choice(len(seqs), size=max(1, len(seqs) // 10), replace=False):
             s = seqs[i]
             if len(s) > k + 24: seqs[i] = s[:k] + rep[:24] + s[k + 24:]
+    if rng.random() < 0.15:                     # mean qualities on exact halves and the doubles next to them ((uint8_t) round(q), containers.cpp:34)
+        near = rng.random(q.shape)
+        h = np.minimum(np.floor(q), 39.0) + 0.5          # 40.5 would round to 41, beyond the 41 columns of tperr1 (the reference reads past its table there)
+        q = np.where(np.isnan(q), q, np.where(near < 0.25, np.nextafter(h, 0.0), np.where(near < 0.5, np.nextafter(h, 100.0), np.where(near < 0.75, h, q))))
+        q[:, 0] = np.where(np.isnan(q[:, 0]), q[:, 0], 0.49999999999999994)
     priors = (rng.random(len(seqs)) < 0.05).astype(np.uint8) if rng.random() < 0.3 else None
     opts = dict(band_size=int(rng.choice([16, 16, 8, 32])), omegaA=float(rng.choice([1e-40, 1e-40, 1e-10, 1e-3])),
                 greedy=int(rng.integers(0, 2)), detect_singletons=int(rng.random() < 0.2), min_abund=int(rng.choice([1, 1, 2, 8])),
@@ -52,6 +58,9 @@ while time.time() < t_end:
     if (opts["detect_singletons"] or opts["omegaA"] >= 1e-10) and opts["max_clust"] == 0 and len(seqs) > 400:
         opts["max_clust"] = 25                  # permissive thresholds bud hundreds of clusters: bound the emulated rounds
     os.environ["DADA2B_LANE_MAX"] = str(int(rng.choice([0, 32, 256, 16384])))
+    blk = int(rng.choice([0, 0, 1, 13, 64]))    # upload pipeline: raws per packing block (0: the default, one block here)
+    if blk: os.environ["DADA2B_PACK_BLK"] = str(blk)
+    else: os.environ.pop("DADA2B_PACK_BLK", None)
     if it < int(os.environ.get("FUZZ_SKIP_UNTIL", "0")): continue          # replay a campaign up to a given iteration (the draws above are all that matters)
     if os.environ.get("FUZZ_VERBOSE"): print("it", it, "n", len(seqs), "L", L, "nvar", nvar, opts, "lane_max", os.environ["DADA2B_LANE_MAX"], "priors", priors is not None, flush=True)
     want = ref.dada_uniques(seqs, ab, priors, err, q, homo_gap=-8, **opts)
