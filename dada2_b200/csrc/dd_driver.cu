@@ -1038,16 +1038,15 @@ void Run::sync_report_owner() {
   for (int p = 0; p <= last + 1 && p < MAX_PASS + 2; p++) h_report->pinfo[p] = gp[p];
   h_report->ctr[CTR_NMOVE] = last >= 0 ? gp[last + 1] : 0;
   // ---- bud candidates: lexicographic (p asc, reads desc) over the ranks' local optima ----
-  auto merge = [&](int iP, int iR, int iN, uint32_t RoundReport::*tr, uint32_t RoundReport::*th, double RoundReport::*tl, int tie_off) {
-    (void)tr; (void)th; (void)tl; (void)tie_off;
-    unsigned long long gmin = ~0ull, gmax = 0, n = 0;
+  auto merge = [&](int iP, int iR, int iN) {
+    unsigned long long gmin = ~0ull, gmax = 0;
     for (int q = 0; q < W; q++) if (rep[q].ctr[iN]) gmin = std::min(gmin, rep[q].ctr[iP]);
     for (int q = 0; q < W; q++) if (rep[q].ctr[iN] && rep[q].ctr[iP] == gmin) gmax = std::max(gmax, rep[q].ctr[iR]);
     h_report->ctr[iP] = gmin; h_report->ctr[iR] = gmax;
     return std::make_pair(gmin, gmax);
   };
-  auto a = merge(CTR_PMIN, CTR_RMAX, CTR_NTIE, nullptr, nullptr, nullptr, 0);
-  auto b = merge(CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR, nullptr, nullptr, nullptr, 0);
+  auto a = merge(CTR_PMIN, CTR_RMAX, CTR_NTIE);
+  auto b = merge(CTR_PMIN_PR, CTR_RMAX_PR, CTR_NTIE_PR);
   unsigned long long nt = 0, ntp = 0;
   for (int q = 0; q < W; q++) {
     if (rep[q].ctr[CTR_NTIE] && rep[q].ctr[CTR_PMIN] == a.first && rep[q].ctr[CTR_RMAX] == a.second) {
