@@ -9,6 +9,7 @@
 #include <atomic>
 #include <algorithm>
 #include <condition_variable>
+#include <exception>
 #include <functional>
 #include <mutex>
 
@@ -94,14 +95,24 @@ inline void parallelFor(std::size_t begin, std::size_t end, Worker &w, std::size
   std::size_t n = end - begin;
   std::size_t chunk = std::max<std::size_t>(grainSize, (n + (std::size_t)nt * 8 - 1) / ((std::size_t)nt * 8));
   std::atomic<std::size_t> next(begin);
+  // An exception of a chunk (Rcpp::stop inside b_compare_parallel, say) is carried to the calling thread once every worker has
+  // left the loop, as TBB does: thrown through run() it would unwind `next` and `body` under the workers still using them.
+  std::exception_ptr first;
+  std::mutex first_mu;
   const std::function<void()> body = [&]() {
     for (;;) {
       std::size_t b = next.fetch_add(chunk);
       if (b >= end) break;
-      w(b, std::min(end, b + chunk));
+      try { w(b, std::min(end, b + chunk)); }
+      catch (...) {
+        std::lock_guard<std::mutex> lk(first_mu);
+        if (!first) first = std::current_exception();
+        next.store(end);                       // no new chunks
+      }
     }
   };
   Pool::get().run(nt, body);
+  if (first) std::rethrow_exception(first);
 }
 }  // namespace RcppParallel
 #endif
