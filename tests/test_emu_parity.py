@@ -177,7 +177,7 @@ def test_emu_sharded_reupload_keeps_only_owned_quality_rows(emu, world, name):
     assert emu.cuemu_launches(b"k_qrows_scatter") > 0 and emu.cuemu_launches(b"k_qrows_gather") > 0
 
 
-@pytest.mark.parametrize("blk", [1, 7, 100])
+@pytest.mark.parametrize("blk", [1, 100])
 def test_emu_upload_pipeline_many_blocks(emu, monkeypatch, blk):
     """do_upload packs blocks of raws on worker threads and sends every group of 16 finished blocks to the device while the
     later ones are still being packed: DADA2B_PACK_BLK (test hook) makes 800 raws span many blocks and groups, on one
