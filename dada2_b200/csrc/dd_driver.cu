@@ -482,6 +482,16 @@ struct Run {
   DBuf<uint32_t> cl_reads_next, pinfo;
   DBuf<RoundReport> d_report;
   DBuf<uint32_t> d_moves;
+  // Owner mode: report and move list share ONE device buffer [RoundReport | moves], so that the round's all-gather carries the report
+  // together with the first `eager_sh` moves of every rank: the move lists need a collective of their own only in the few rounds that
+  // move more (one NCCL call + one host synchronisation less per round).
+  DBuf<uint8_t> d_repmv, d_gather_all;
+  PBuf<uint8_t> h_gather_all;
+  static constexpr size_t RR_PAD = (sizeof(RoundReport) + 15) & ~(size_t)15;
+  unsigned eager_sh = 1024;
+  RoundReport *rep_dev = nullptr;        // where the device writes the report / the moves (views of d_repmv in owner mode)
+  uint32_t *mv_dev = nullptr;
+  std::vector<const RoundReport *> rep_all;   // owner mode: every rank's report of the round (pinned host copy)
   PBuf<RoundReport> h_report_buf;
   PBuf<uint32_t> h_moves_buf;
   RoundReport *h_report = nullptr;       // pinned host copy, refreshed once per round
@@ -523,8 +533,6 @@ struct Run {
   // all-gather of the ranks' reports (bud candidates, move counts) and, when raws moved, one of the move lists.
   bool owner = false;
   int tail_last = -1;                    // last shuffle pass launched in the current round
-  DBuf<RoundReport> d_report_all;
-  PBuf<RoundReport> h_report_all;
   DBuf<uint32_t> d_moves_all;
   PBuf<uint32_t> h_moves_all;
   void sync_report_owner();
@@ -790,7 +798,16 @@ void Run::alloc_state() {
     ts.head = t_head.p; ts.nmove_pass = t_nmove.p; ts.done = t_done.p; ts.blk = t_blk.p; ts.blk_ties = t_bt.p; ts.blk_ties_pr = t_btp.p;
   }
   pinfo.alloc(MAX_PASS + 2); pinfo.zero(s);
-  d_report.alloc(1); d_moves.alloc((size_t)move_cap * 2);
+  if (owner) {
+    d_repmv.alloc(RR_PAD + (size_t)move_cap * 8);
+    rep_dev = (RoundReport *)d_repmv.p; mv_dev = (uint32_t *)(d_repmv.p + RR_PAD);
+    eager_sh = 1024;
+    if (const char *e = getenv("DADA2B_MOVES_EAGER")) eager_sh = (unsigned)std::max(0, atoi(e));      // test hook: 0 = every move list through its own all-gather
+    eager_sh = std::min(eager_sh, move_cap);
+  } else {
+    d_report.alloc(1); d_moves.alloc((size_t)move_cap * 2);
+    rep_dev = d_report.p; mv_dev = d_moves.p;
+  }
   h_report_buf.alloc(1); h_moves_buf.alloc((size_t)move_cap * 2);
   h_report = h_report_buf.p; h_moves = h_moves_buf.p;
   memset(h_report, 0, sizeof(RoundReport));
@@ -807,7 +824,7 @@ void Run::alloc_state() {
   st.ctr = ctr.p; st.err = err.p; st.nsubs_final = nsubs_final.p;
   st.pinfo = pinfo.p; st.move_cap = move_cap;
   st.shard_rank = cx->rank; st.shard_world = cx->world;
-  st.report = d_report.p; st.moves = d_moves.p;
+  st.report = rep_dev; st.moves = mv_dev;
   emax_bits.zero(s);                                               // shuffle scratch starts clean
   CK(cudaMemsetAsync(best_entry.p, 0xFF, n * 4, s));
   { unsigned long long nn = n; h2d(ctr.p + CTR_CS_COUNT, &nn, 8); }  // cluster 0 owns entries [0, nraw)
@@ -996,11 +1013,14 @@ void Run::launch_round_tail_noshuffle() {
 // replay_moves / decide_bud see exactly what a single-GPU run would have reported.  Every rank computes the same merge.
 void Run::sync_report_owner() {
   const int W = cx->world;
-  d_report_all.alloc(W); h_report_all.alloc(W);
-  NC(g_nccl.AllGather(d_report.p, d_report_all.p, sizeof(RoundReport), ncclChar, cx->comm, s));
-  d2h_pinned(h_report_all.p, d_report_all.p, (size_t)W * sizeof(RoundReport));
+  const size_t G = RR_PAD + (size_t)eager_sh * 8;                  // per rank: the report and the head of its move list
+  d_gather_all.alloc((size_t)W * G); h_gather_all.alloc((size_t)W * G);
+  NC(g_nccl.AllGather(d_repmv.p, d_gather_all.p, G, ncclChar, cx->comm, s));
+  d2h_pinned(h_gather_all.p, d_gather_all.p, (size_t)W * G);
   sync();
-  const RoundReport *rep = h_report_all.p;
+  rep_all.resize(W);
+  for (int q = 0; q < W; q++) rep_all[q] = (const RoundReport *)(h_gather_all.p + (size_t)q * G);
+  struct RepView { const std::vector<const RoundReport *> &v; const RoundReport &operator[](int q) const { return *v[q]; } } rep{rep_all};
   *h_report = rep[cx->rank];
   memcpy(h_ctr.p, h_report->ctr, sizeof(unsigned long long) * CTR_N);
   for (int q = 0; q < W; q++) h_ctr.p[CTR_ERR] = std::max(h_ctr.p[CTR_ERR], rep[q].ctr[CTR_ERR]);
@@ -1016,20 +1036,25 @@ void Run::sync_report_owner() {
   for (int q = 0; q < W && last >= 0; q++) maxM = std::max(maxM, rep[q].pinfo[last + 1]);
   uint32_t gp[MAX_PASS + 2] = {0};
   if (maxM) {
-    if ((size_t)W * maxM * 2 > d_moves_all.cap || !d_moves_all.p) {     // grown in powers of two and kept across runs: allocation calls stall behind the kernel driver's lock
-      size_t m = 65536;
-      while (m < maxM) m *= 2;
-      d_moves_all.alloc((size_t)W * m * 2); h_moves_all.alloc((size_t)W * m * 2);
+    const uint32_t *src = (const uint32_t *)(h_gather_all.p + RR_PAD);      // rank q's moves: src + q * stride (u32 units)
+    size_t stride = G / 4;
+    if (maxM > eager_sh) {     // a round that moved more than the report's gather carries: the whole lists, padded to the longest one
+      if ((size_t)W * maxM * 2 > d_moves_all.cap || !d_moves_all.p) {     // grown in powers of two and kept across runs: allocation calls stall behind the kernel driver's lock
+        size_t m = 65536;
+        while (m < maxM) m *= 2;
+        d_moves_all.alloc((size_t)W * m * 2); h_moves_all.alloc((size_t)W * m * 2);
+      }
+      NC(g_nccl.AllGather(mv_dev, d_moves_all.p, (size_t)maxM * 8, ncclChar, cx->comm, s));
+      d2h_pinned(h_moves_all.p, d_moves_all.p, (size_t)W * maxM * 8);
+      sync();
+      src = h_moves_all.p; stride = (size_t)maxM * 2;
     }
-    NC(g_nccl.AllGather(d_moves.p, d_moves_all.p, (size_t)maxM * 8, ncclChar, cx->comm, s));
-    d2h_pinned(h_moves_all.p, d_moves_all.p, (size_t)W * maxM * 8);
-    sync();
     size_t at = 0;
     for (int p = 0; p <= last; p++) {
       for (int q = 0; q < W; q++) {
         const uint32_t b = rep[q].pinfo[p], e = rep[q].pinfo[p + 1];
         if (at + (e - b) > move_cap) throw Err{"dada2b: move list overflow"};
-        memcpy(h_moves + 2 * at, h_moves_all.p + 2 * ((size_t)q * maxM + b), (size_t)(e - b) * 8);
+        memcpy(h_moves + 2 * at, src + (size_t)q * stride + 2 * (size_t)b, (size_t)(e - b) * 8);
         at += e - b;
       }
       gp[p + 1] = (uint32_t)at;
@@ -1067,12 +1092,12 @@ void Run::sync_report_owner() {
 
 void Run::sync_report() {
   if (owner) { sync_report_owner(); return; }
-  d2h_pinned(h_report, d_report.p, sizeof(RoundReport));
+  d2h_pinned(h_report, rep_dev, sizeof(RoundReport));
   const unsigned eager = std::min<unsigned>(MOVES_EAGER, move_cap);
-  d2h_pinned(h_moves, d_moves.p, (size_t)eager * 8);
+  d2h_pinned(h_moves, mv_dev, (size_t)eager * 8);
   sync();
   if (h_report->ctr[CTR_NMOVE] > eager && h_report->ctr[CTR_NMOVE] <= move_cap) {
-    d2h_pinned(h_moves + 2 * (size_t)eager, d_moves.p + 2 * (size_t)eager, (size_t)(h_report->ctr[CTR_NMOVE] - eager) * 8);
+    d2h_pinned(h_moves + 2 * (size_t)eager, mv_dev + 2 * (size_t)eager, (size_t)(h_report->ctr[CTR_NMOVE] - eager) * 8);
     sync();
   }
   memcpy(h_ctr.p, h_report->ctr, sizeof(unsigned long long) * CTR_N);
@@ -1190,7 +1215,7 @@ int Run::decide_bud(uint32_t *r_out, uint32_t *from_out) {
   if (owner && (nt > TIE_MAX || ntp > TIE_MAX)) {
     // every rank lists its own candidates at the global optimum; the lists are exchanged padded to the longest one
     const int W = cx->world;
-    const RoundReport *rep = h_report_all.p;
+    struct RepView { const std::vector<const RoundReport *> &v; const RoundReport &operator[](int q) const { return *v[q]; } } rep{rep_all};
     std::vector<unsigned long long> na(W, 0), np(W, 0);
     unsigned long long maxn = 1;
     for (int q = 0; q < W; q++) {

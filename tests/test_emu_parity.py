@@ -242,6 +242,16 @@ def test_emu_sharded_owner_mode(emu, monkeypatch, world, name):
     assert emu.cuemu_launches(b"k_cs_append") == 0 and emu.cuemu_launches(b"k_posthoc_owned") > 0
 
 
+@pytest.mark.parametrize("eager", [0, 3, 100000])
+def test_emu_sharded_report_gather_carries_the_head_of_the_move_lists(emu, monkeypatch, eager):
+    """Owner mode: the round's all-gather carries every rank's report AND the first DADA2B_MOVES_EAGER (test hook; default 1024)
+    moves of its list; only rounds in which some rank moved more exchange the whole lists in a second all-gather.  0: always the
+    second exchange; 3: rounds of both kinds; 100000: never."""
+    monkeypatch.setenv("DADA2B_MOVES_EAGER", str(eager))
+    _run_sharded(3, "syn800_nogreedy")
+    _run_sharded(2, "syn700_ragged", reupload=True)
+
+
 def test_emu_sharded_owner_mode_ties_and_extra_passes(emu, monkeypatch):
     """Owner mode corner paths: tie sets larger than TIE_MAX (per-rank candidate lists exchanged), and NP=1 so that rounds
     needing more shuffle passes continue with one fused pass at a time."""

@@ -58,6 +58,9 @@ while time.time() < t_end:
     if (opts["detect_singletons"] or opts["omegaA"] >= 1e-10) and opts["max_clust"] == 0 and len(seqs) > 400:
         opts["max_clust"] = 25                  # permissive thresholds bud hundreds of clusters: bound the emulated rounds
     os.environ["DADA2B_LANE_MAX"] = str(int(rng.choice([0, 32, 256, 16384])))
+    eag = int(rng.choice([-1, -1, 0, 5, 64]))   # sharded runs: moves carried by the report's all-gather (-1: the default, 1024)
+    if eag >= 0: os.environ["DADA2B_MOVES_EAGER"] = str(eag)
+    else: os.environ.pop("DADA2B_MOVES_EAGER", None)
     blk = int(rng.choice([0, 0, 1, 13, 64]))    # upload pipeline: raws per packing block (0: the default, one block here)
     if blk: os.environ["DADA2B_PACK_BLK"] = str(blk)
     else: os.environ.pop("DADA2B_PACK_BLK", None)
