@@ -290,14 +290,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   d.nraw = nraw; d.maxlen = maxlen; d.minlen = minlen;
   d.SW = (((int)maxlen + 15) / 16 + 3) & ~3;
   d.QS = ((int)maxlen + 15) & ~15;
-  cx->reads.resize(nraw); cx->prior.resize(nraw);
-  unsigned tot = 0;
-  for (unsigned i = 0; i < nraw; i++) {
-    cx->reads[i] = (uint32_t)in->abund[i];
-    cx->prior[i] = in->prior ? (in->prior[i] != 0) : 0;
-    tot += cx->reads[i];                                      // unsigned int accumulation, containers.cpp:100
-  }
-  cx->total_reads = tot;
+  cx->reads.resize(nraw); cx->prior.resize(nraw);             // filled below, by the calling thread while the workers pack
   // pack on the host into pinned staging, then one H2D per array
   const double tu1 = now_ms();
   PBuf<uint32_t> &h_seq = cx->st_seq;
@@ -316,6 +309,7 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
   const int SW = d.SW, QS = d.QS, ML = in->maxlen;
   cx->d_seq2.alloc((size_t)nraw * d.SW); cx->d_qual.alloc((size_t)nraw * d.QS);
   cx->d_len.alloc(nraw); cx->d_reads.alloc(nraw); cx->d_prior.alloc(nraw);
+  cx->st_meta.alloc((size_t)nraw * 8);                                // reads (u32) | len (u16) | prior (u8), pinned
   const size_t seq_chunk = nqmax * d.SW * 4;                          // sharded: bytes of one rank's all-gather chunk
   uint8_t *seq_dst = (uint8_t *)cx->d_seq2.p, *qual_dst = cx->d_qual.p;
   if (qshard) {
@@ -360,6 +354,22 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
       });
     }
     cudaError_t copy_err = cudaSuccess;
+    {  // meanwhile: abundances / priors / lengths (7 bytes per raw) from the calling thread
+      unsigned tot = 0;
+      uint8_t *m = cx->st_meta.p;
+      uint32_t *m_reads = (uint32_t *)m; uint8_t *m_prior = m + (size_t)nraw * 6;
+      for (unsigned i = 0; i < nraw; i++) {
+        const uint32_t rd = (uint32_t)in->abund[i];
+        const uint8_t pr = in->prior ? (in->prior[i] != 0) : 0;
+        cx->reads[i] = rd; cx->prior[i] = pr; m_reads[i] = rd; m_prior[i] = pr;
+        tot += rd;                                              // unsigned int accumulation, containers.cpp:100
+      }
+      cx->total_reads = tot;
+      memcpy(m + (size_t)nraw * 4, cx->len.data(), (size_t)nraw * 2);
+      copy_err = cudaMemcpyAsync(cx->d_reads.p, m, (size_t)nraw * 4, cudaMemcpyHostToDevice, cx->stream);
+      if (copy_err == cudaSuccess) copy_err = cudaMemcpyAsync(cx->d_len.p, m + (size_t)nraw * 4, (size_t)nraw * 2, cudaMemcpyHostToDevice, cx->stream);
+      if (copy_err == cudaSuccess) copy_err = cudaMemcpyAsync(cx->d_prior.p, m + (size_t)nraw * 6, nraw, cudaMemcpyHostToDevice, cx->stream);
+    }
     for (size_t g = 0; g < nblk; g += PACK_GRP) {
       const size_t ge = std::min(nblk, g + PACK_GRP);
       for (size_t k = g; k < ge; k++)
@@ -394,16 +404,6 @@ static dada2b_ctx *do_upload(const dada2b_in *in, int device, dada2b_ctx *reuse 
     cx->maxq = hq[0]; cx->bad_nt = hq[1] != 0;
   }
   cx->qual_sharded = qshard;
-  {
-    cx->st_meta.alloc((size_t)nraw * 8);
-    uint8_t *m = cx->st_meta.p;
-    memcpy(m, cx->reads.data(), (size_t)nraw * 4);
-    memcpy(m + (size_t)nraw * 4, cx->len.data(), (size_t)nraw * 2);
-    memcpy(m + (size_t)nraw * 6, cx->prior.data(), nraw);
-    CK(cudaMemcpyAsync(cx->d_reads.p, m, (size_t)nraw * 4, cudaMemcpyHostToDevice, cx->stream));
-    CK(cudaMemcpyAsync(cx->d_len.p, m + (size_t)nraw * 4, (size_t)nraw * 2, cudaMemcpyHostToDevice, cx->stream));
-    CK(cudaMemcpyAsync(cx->d_prior.p, m + (size_t)nraw * 6, nraw, cudaMemcpyHostToDevice, cx->stream));
-  }
   CK(cudaStreamSynchronize(cx->stream));
   if (getenv("DADA2B_VERBOSE")) fprintf(stderr, "[dada2b] upload: validate+copy %.2f ms, pack %.2f ms, alloc+H2D %.2f ms\n", tu1 - tu0, tu2 - tu1, now_ms() - tu2);
   DBG("upload: H2D done");
