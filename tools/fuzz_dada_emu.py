@@ -55,6 +55,20 @@ while time.time() < t_end:
                 min_fold=float(rng.choice([1.0, 1.0, 2.0])), min_hamming=int(rng.choice([1, 1, 2])),
                 kdist_cutoff=float(rng.choice([0.42, 0.42, 0.3, 0.6])), max_clust=int(rng.choice([0, 0, 0, 5])))
     if rng.random() < 0.15: opts["use_quals"] = 0
+    if os.environ.get("FUZZ_RARE_OPTS"):        # the options the e2e goldens cover once each, a few at a time
+        if rng.random() < 0.15: opts["gapless"] = 0
+        if rng.random() < 0.15: opts["use_kmers"] = 0
+        if rng.random() < 0.2: opts["SSE"] = int(rng.integers(0, 3))
+        if rng.random() < 0.2:
+            opts["vectorized_alignment"] = 0
+            if rng.random() < 0.6: opts["homo_gap"] = int(rng.choice([-1, -4, -8]))
+        if rng.random() < 0.2:
+            m, mm, g = [(4, -5, -7), (5, -4, -4), (1, -1, -2), (5, -4, -16)][int(rng.integers(0, 4))]
+            opts.update(match=m, mismatch=mm, gap=g)
+            if "homo_gap" not in opts and not opts.get("vectorized_alignment", 1): opts["homo_gap"] = g
+        if rng.random() < 0.15: opts["omegaC"] = float(rng.choice([1e-5, 0.0, 1.0]))
+        if rng.random() < 0.15: opts["omegaP"] = float(rng.choice([1e-2, 0.5, 1e-10]))
+        if rng.random() < 0.1: opts["band_size"] = int(rng.choice([0, 64] + ([-1] if L <= 90 else [])))
     if (opts["detect_singletons"] or opts["omegaA"] >= 1e-10) and opts["max_clust"] == 0 and len(seqs) > 400:
         opts["max_clust"] = 25                  # permissive thresholds bud hundreds of clusters: bound the emulated rounds
     os.environ["DADA2B_LANE_MAX"] = str(int(rng.choice([0, 32, 256, 16384])))
@@ -66,7 +80,7 @@ while time.time() < t_end:
     else: os.environ.pop("DADA2B_PACK_BLK", None)
     if it < int(os.environ.get("FUZZ_SKIP_UNTIL", "0")): continue          # replay a campaign up to a given iteration (the draws above are all that matters)
     if os.environ.get("FUZZ_VERBOSE"): print("it", it, "n", len(seqs), "L", L, "nvar", nvar, opts, "lane_max", os.environ["DADA2B_LANE_MAX"], "priors", priors is not None, flush=True)
-    want = ref.dada_uniques(seqs, ab, priors, err, q, homo_gap=-8, **opts)
+    want = ref.dada_uniques(seqs, ab, priors, err, q, **dict(dict(homo_gap=opts.get("gap", -8)), **opts))
     if os.environ.get("FUZZ_VERBOSE"): print("   reference done", flush=True)
     world = int(rng.choice([1, 1, 1, 2, 3])) if os.environ.get("FUZZ_SHARDED", "1") != "0" else 1
     if world == 1:
